@@ -1,0 +1,947 @@
+// fcb200.cu — hand-written sm_100a kernels + C ABI for the ensemble-batched
+// IMEX Navier-Stokes step of FlowControl (see include/fcb200.h for the entry
+// points and the reference call sites they replace).
+//
+// Data layout: every ensemble field is X[row * ldb + b] (dof-major, trajectory
+// innermost, FP64), ldb = B rounded up to a multiple of 32; padding columns are
+// kept at zero.  In every kernel a warp owns 32 consecutive trajectories of one
+// row / cell / tile, so indices, geometry and matrix values are warp-uniform
+// (broadcast loads) and all state traffic is 256-byte coalesced.
+//
+// One time step (reference: FlowSolver.step, flowsolver.py:703-799):
+//   k_rhs_build   rhs = a_n + b_{n-1} (BDF2) | a_n/2 (BDF1) + sum_k u_ctrl_k (f_k - l_k)   [solver row order]
+//   k_block_rows  forward sweep  (one launch per elimination-tree height)
+//   k_block_rows  backward sweep (one launch per elimination-tree depth)
+//   k_post        un-permute, Dirichlet values, non-finite flag
+//   k_element     per cell: convection N(u) (7-point Radon rule) + mass M u, coloured scatter into
+//                 a = (2/dt) M u - 2 N(u),  b = -(1/2dt) M u + N(u);  energy partials u.(M u)
+//   k_measure     sensors (sparse rows) + energy reduction (fixed order)
+// Closed loop adds k_controller before and k_log after, all inside one CUDA graph.
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "fcb200.h"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+// ----------------------------------------------------------------------------------------------
+// constant tables (filled by fcb_create): Radon 7-point rule and P2 shape functions
+// ----------------------------------------------------------------------------------------------
+__constant__ double c_phi[7][6];      // phi_a(q)
+__constant__ double c_dphi[7][6][2];  // reference gradients
+__constant__ double c_w[7];           // quadrature weights (sum = 1/2)
+__constant__ double c_mass[6][6];     // reference mass matrix (int phi_a phi_b over the unit triangle)
+
+struct Tile {
+    int out, self, nrows, K;
+    long long kptr, vptr;
+};
+
+// ----------------------------------------------------------------------------------------------
+// kernels
+// ----------------------------------------------------------------------------------------------
+constexpr int ELEM_WARPS = 4;  // warps (cells in flight) per CTA
+constexpr int ELEM_CPW = 4;    // cells per warp (sequential)
+
+struct ElemArgs {
+    const int* cells;       // cells of this colour
+    int ncells;
+    const int* cell_nodes;  // [nT*6]
+    const double* Jinv;     // [nT*4]
+    const double* detJ;     // [nT]
+    const double* u;        // [2nN, ldb]
+    double* a;              // [2nN, ldb] accumulated
+    double* b;              // [2nN, ldb] accumulated
+    double* epart;          // [nblk_total, ldb]
+    int blk_offset;
+    int nN;
+    int ldb;
+    double ca, cb;          // mass coefficients: a += ca*Mu - 2 N ; b += cb*Mu + N
+};
+
+template <bool NONLINEAR>
+__global__ void __launch_bounds__(32 * ELEM_WARPS) k_element(const ElemArgs p) {
+    const int b = blockIdx.y * 32 + threadIdx.x;
+    const size_t ldb = (size_t)p.ldb;
+    double e_acc = 0.0;
+#pragma unroll 1
+    for (int c = 0; c < ELEM_CPW; ++c) {
+        const int ci = (blockIdx.x * ELEM_WARPS + threadIdx.y) * ELEM_CPW + c;
+        if (ci >= p.ncells) break;  // warp-uniform
+        const int cell = __ldg(p.cells + ci);
+        int nd[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) nd[i] = __ldg(p.cell_nodes + cell * 6 + i);
+        const double g00 = __ldg(p.Jinv + cell * 4 + 0), g01 = __ldg(p.Jinv + cell * 4 + 1);
+        const double g10 = __ldg(p.Jinv + cell * 4 + 2), g11 = __ldg(p.Jinv + cell * 4 + 3);
+        const double det = __ldg(p.detJ + cell);
+        double ux[6], uy[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            ux[i] = p.u[(size_t)nd[i] * ldb + b];
+            uy[i] = p.u[(size_t)(nd[i] + p.nN) * ldb + b];
+        }
+        double rx[6], ry[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { rx[i] = 0.0; ry[i] = 0.0; }
+        if (NONLINEAR) {
+#pragma unroll
+            for (int q = 0; q < 7; ++q) {
+                double vx = 0.0, vy = 0.0, ax0 = 0.0, ax1 = 0.0, ay0 = 0.0, ay1 = 0.0;
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                    vx = fma(c_phi[q][i], ux[i], vx);
+                    vy = fma(c_phi[q][i], uy[i], vy);
+                    ax0 = fma(c_dphi[q][i][0], ux[i], ax0);
+                    ax1 = fma(c_dphi[q][i][1], ux[i], ax1);
+                    ay0 = fma(c_dphi[q][i][0], uy[i], ay0);
+                    ay1 = fma(c_dphi[q][i][1], uy[i], ay1);
+                }
+                // physical gradients: d_j u = sum_k (d_ref_k u) Jinv[k][j]
+                const double dux_dx = ax0 * g00 + ax1 * g10, dux_dy = ax0 * g01 + ax1 * g11;
+                const double duy_dx = ay0 * g00 + ay1 * g10, duy_dy = ay0 * g01 + ay1 * g11;
+                const double wq = c_w[q] * det;
+                const double cx = wq * (vx * dux_dx + vy * dux_dy);
+                const double cy = wq * (vx * duy_dx + vy * duy_dy);
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                    rx[i] = fma(c_phi[q][i], cx, rx[i]);
+                    ry[i] = fma(c_phi[q][i], cy, ry[i]);
+                }
+            }
+        }
+        // mass product and energy
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            double mx = 0.0, my = 0.0;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                mx = fma(c_mass[i][j], ux[j], mx);
+                my = fma(c_mass[i][j], uy[j], my);
+            }
+            mx *= det;
+            my *= det;
+            e_acc = fma(ux[i], mx, e_acc);
+            e_acc = fma(uy[i], my, e_acc);
+            const size_t ox = (size_t)nd[i] * ldb + b;
+            const size_t oy = (size_t)(nd[i] + p.nN) * ldb + b;
+            // same-colour cells share no node: plain read-modify-write, no atomics
+            p.a[ox] += p.ca * mx - 2.0 * rx[i];
+            p.a[oy] += p.ca * my - 2.0 * ry[i];
+            p.b[ox] += p.cb * mx + rx[i];
+            p.b[oy] += p.cb * my + ry[i];
+        }
+    }
+    __shared__ double se[ELEM_WARPS][32];
+    se[threadIdx.y][threadIdx.x] = e_acc;
+    __syncthreads();
+    if (threadIdx.y == 0) {
+        double s = se[0][threadIdx.x];
+#pragma unroll
+        for (int w = 1; w < ELEM_WARPS; ++w) s += se[w][threadIdx.x];
+        p.epart[(size_t)(p.blk_offset + blockIdx.x) * ldb + b] = s;
+    }
+}
+
+// rhs in solver row order.  grid = (ceil(n/8), ldb/32), block = (32, 8)
+__global__ void __launch_bounds__(256) k_rhs_build(int n, int Nv, const int* __restrict__ perm,
+                                                  const double* __restrict__ a, const double* __restrict__ bprev,
+                                                  int order, int na, const double* __restrict__ ctrl_rhs,
+                                                  const double* __restrict__ uctrl, double* __restrict__ Z, int ldb) {
+    const int r = blockIdx.x * blockDim.y + threadIdx.y;
+    const int b = blockIdx.y * 32 + threadIdx.x;
+    if (r >= n) return;
+    const int dof = __ldg(perm + r);
+    double v = 0.0;
+    if (dof < Nv) {
+        const size_t o = (size_t)dof * ldb + b;
+        v = (order == 2) ? (a[o] + bprev[o]) : 0.5 * a[o];
+    }
+    for (int k = 0; k < na; ++k) {
+        const double c = __ldg(ctrl_rhs + (size_t)k * n + r);
+        if (c != 0.0) v = fma(c, uctrl[(size_t)k * ldb + b], v);
+    }
+    Z[(size_t)r * ldb + b] = v;
+}
+
+// Dense block-row products of the multifrontal sweeps (see multifrontal.py: SolvePlan).
+// grid = (tiles in launch, ceil(ldb/128)), block = 64 threads, 2 trajectories per thread.
+template <int RT>
+__global__ void __launch_bounds__(64) k_block_rows(const Tile* __restrict__ tiles, const int* __restrict__ cols,
+                                                   const double* __restrict__ vals, double* Z, int ldb) {
+    const Tile t = tiles[blockIdx.x];
+    const int b0 = blockIdx.y * 128 + threadIdx.x;
+    if (b0 >= ldb) return;
+    const bool two = (b0 + 64) < ldb;
+    const int b1 = two ? b0 + 64 : b0;
+    double acc0[RT], acc1[RT];
+#pragma unroll
+    for (int r = 0; r < RT; ++r) { acc0[r] = 0.0; acc1[r] = 0.0; }
+    const int* c = cols + t.kptr;
+    const double2* v = reinterpret_cast<const double2*>(vals + t.vptr);
+#pragma unroll 4
+    for (int k = 0; k < t.K; ++k) {
+        const double* zr = Z + (size_t)__ldg(c + k) * ldb;
+        const double x0 = zr[b0];
+        const double x1 = zr[b1];
+#pragma unroll
+        for (int r = 0; r < RT; r += 2) {
+            const double2 w = __ldg(v + (size_t)k * (RT / 2) + r / 2);
+            acc0[r] = fma(w.x, x0, acc0[r]);
+            acc0[r + 1] = fma(w.y, x0, acc0[r + 1]);
+            acc1[r] = fma(w.x, x1, acc1[r]);
+            acc1[r + 1] = fma(w.y, x1, acc1[r + 1]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+        if (r < t.nrows) {
+            double s0 = acc0[r], s1 = acc1[r];
+            if (t.self >= 0) {
+                const double* zs = Z + (size_t)(t.self + r) * ldb;
+                s0 += zs[b0];
+                s1 += zs[b1];
+            }
+            double* zo = Z + (size_t)(t.out + r) * ldb;
+            zo[b0] = s0;
+            if (two) zo[b1] = s1;
+        }
+    }
+}
+
+// un-permute the solution into canonical numbering, apply Dirichlet values, flag non-finite velocity.
+// grid = (ceil(N/8), ldb/32), block = (32, 8)
+__global__ void __launch_bounds__(256) k_post(int N, int Nv, int n, const int* __restrict__ iperm,
+                                             const double* __restrict__ Z, int na, int nbc,
+                                             const double* __restrict__ bc_shape, const double* __restrict__ uctrl,
+                                             double* __restrict__ up, int* __restrict__ diverged, int ldb) {
+    const int i = blockIdx.x * blockDim.y + threadIdx.y;
+    const int b = blockIdx.y * 32 + threadIdx.x;
+    if (i >= N) return;
+    const int r = __ldg(iperm + i);
+    double v;
+    if (r >= 0) {
+        v = Z[(size_t)(n + r) * ldb + b];
+    } else {
+        const int j = -1 - r;
+        v = 0.0;
+        for (int k = 0; k < na; ++k) {
+            const double s = __ldg(bc_shape + (size_t)k * nbc + j);
+            if (s != 0.0) v = fma(s, uctrl[(size_t)k * ldb + b], v);
+        }
+    }
+    up[(size_t)i * ldb + b] = v;
+    if (i < Nv && !isfinite(v)) diverged[b] = 1;
+}
+
+// sensors + energy.  grid = ldb/32, block = (32, 8)
+__global__ void __launch_bounds__(256) k_measure(int ns, const int* __restrict__ sptr, const int* __restrict__ sidx,
+                                                const double* __restrict__ sval, const double* __restrict__ up,
+                                                double* __restrict__ y, const double* __restrict__ epart, int nblk,
+                                                double* __restrict__ dE, int ldb) {
+    const int b = blockIdx.x * 32 + threadIdx.x;
+    const int ty = threadIdx.y;
+    for (int s = ty; s < ns; s += blockDim.y) {
+        double acc = 0.0;
+        for (int j = __ldg(sptr + s); j < __ldg(sptr + s + 1); ++j)
+            acc = fma(__ldg(sval + j), up[(size_t)__ldg(sidx + j) * ldb + b], acc);
+        y[(size_t)s * ldb + b] = acc;
+    }
+    // energy: strided partial sums, then a fixed-order combine (deterministic)
+    double e = 0.0;
+    for (int k = ty; k < nblk; k += blockDim.y) e += epart[(size_t)k * ldb + b];
+    __shared__ double se[8][32];
+    se[ty][threadIdx.x] = e;
+    __syncthreads();
+    if (ty == 0) {
+        double s = 0.0;
+        for (int w = 0; w < 8; ++w) s += se[w][threadIdx.x];
+        dE[b] = 0.5 * s;
+    }
+}
+
+// One LTI controller per trajectory (controller.py:157-158): uses the PRE-update state for the output.
+// grid = ldb/32... one thread per trajectory.
+__global__ void k_controller(int nx, int ny, int nu, int ns, int na, const double* __restrict__ Ad,
+                             const double* __restrict__ Bd, const double* __restrict__ Cd,
+                             const double* __restrict__ Dd, const double* __restrict__ Ky,
+                             const double* __restrict__ Fu, const double* __restrict__ y,
+                             const double* __restrict__ xin, double* __restrict__ xout, double* __restrict__ uctrl,
+                             int ldb) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= ldb) return;
+    const size_t L = (size_t)ldb;
+    double v[8], uo[8];
+    for (int i = 0; i < ny; ++i) {
+        double s = 0.0;
+        for (int j = 0; j < ns; ++j) s = fma(__ldg(Ky + i * ns + j), y[j * L + b], s);
+        v[i] = s;
+    }
+    for (int o = 0; o < nu; ++o) {
+        double s = 0.0;
+        for (int j = 0; j < nx; ++j) s = fma(Cd[(size_t)(o * nx + j) * L + b], xin[j * L + b], s);
+        for (int j = 0; j < ny; ++j) s = fma(Dd[(size_t)(o * ny + j) * L + b], v[j], s);
+        uo[o] = s;
+    }
+    for (int i = 0; i < nx; ++i) {
+        double s = 0.0;
+        for (int j = 0; j < nx; ++j) s = fma(Ad[(size_t)(i * nx + j) * L + b], xin[j * L + b], s);
+        for (int j = 0; j < ny; ++j) s = fma(Bd[(size_t)(i * ny + j) * L + b], v[j], s);
+        xout[i * L + b] = s;
+    }
+    for (int a = 0; a < na; ++a) {
+        double s = 0.0;
+        for (int o = 0; o < nu; ++o) s = fma(__ldg(Fu + a * nu + o), uo[o], s);
+        uctrl[a * L + b] = s;
+    }
+}
+
+// series[step][col][b], columns (dE, u_ctrl_1..na, y_1..ns); single CTA, then the step counter ticks.
+__global__ void k_log(int na, int ns, const double* __restrict__ dE, const double* __restrict__ uctrl,
+                      const double* __restrict__ y, double* __restrict__ series, int* __restrict__ counter,
+                      int capacity, int ldb) {
+    const int step = *counter;
+    const int ncol = 1 + na + ns;
+    if (step < capacity) {
+        double* row = series + (size_t)step * ncol * ldb;
+        for (int i = threadIdx.x; i < ncol * ldb; i += blockDim.x) {
+            const int col = i / ldb, b = i - col * ldb;
+            double v;
+            if (col == 0) v = dE[b];
+            else if (col <= na) v = uctrl[(size_t)(col - 1) * ldb + b];
+            else v = y[(size_t)(col - 1 - na) * ldb + b];
+            row[i] = v;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *counter = step + 1;
+}
+
+// ----------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------
+struct DevPlan {
+    int n = 0, rt = 0, ntiles = 0, nlaunch = 0;
+    Tile* tiles = nullptr;
+    int* cols = nullptr;
+    double* vals = nullptr;
+    std::vector<int> launch_ptr;
+    int n_forward = 0;
+};
+
+}  // namespace
+
+struct fcb_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string error;
+    int B = 0, ldb = 0;
+    int nT = 0, nN = 0, nV = 0, Nv = 0, N = 0, n = 0, nbc = 0, na = 0, ns = 0, ncolours = 0;
+    double dt = 0.0;
+    int nonlinear = 1;
+    // constant device data
+    int *cell_nodes = nullptr, *colour_cells = nullptr, *perm = nullptr, *iperm = nullptr;
+    double *Jinv = nullptr, *detJ = nullptr, *bc_shape = nullptr, *ctrl_rhs[2] = {nullptr, nullptr};
+    int *sensor_ptr = nullptr, *sensor_idx = nullptr;
+    double* sensor_val = nullptr;
+    std::vector<int> colour_ptr, colour_blk_offset;
+    int nblk_total = 0;
+    DevPlan plan[2];
+    // state
+    double *up[2] = {nullptr, nullptr}, *avec = nullptr, *bvec[2] = {nullptr, nullptr}, *Z = nullptr;
+    double *epart = nullptr, *uctrl = nullptr, *y = nullptr, *dE = nullptr;
+    int* diverged = nullptr;
+    int parity = 0, order = 1;
+    bool have_state = false;
+    // controllers
+    bool have_ctrl = false;
+    int nx = 0, ny = 0, nu = 0;
+    double *Ad = nullptr, *Bd = nullptr, *Cd = nullptr, *Dd = nullptr, *Ky = nullptr, *Fu = nullptr;
+    double* xk[2] = {nullptr, nullptr};
+    int xparity = 0;
+    double* series = nullptr;
+    int series_capacity = 0;
+    int* counter = nullptr;
+    // graphs: [parity] for a BDF2 step, [parity][xparity] for a closed-loop BDF2 step
+    cudaGraphExec_t g_step[2] = {nullptr, nullptr};
+    int g_step_nodes[2] = {0, 0};
+    cudaGraphExec_t g_loop[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    int g_loop_nodes[2][2] = {{0, 0}, {0, 0}};
+    long long launches = 0;
+    int phase_launches[FCB_NPHASES] = {0};
+    cudaEvent_t ev[FCB_NPHASES + 1] = {nullptr};
+};
+
+namespace {
+
+int fail(fcb_context* h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->error = buf;
+    else g_create_error = buf;
+    return code;
+}
+
+#define CK(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess)                                                                            \
+            return fail(h, FCB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+template <typename T>
+int upload(fcb_context* h, T** dst, const T* src, size_t count) {
+    *dst = nullptr;
+    if (count == 0) return FCB_OK;
+    CK(cudaMalloc((void**)dst, count * sizeof(T)));
+    if (src) CK(cudaMemcpyAsync(*dst, src, count * sizeof(T), cudaMemcpyDefault, h->stream));
+    else CK(cudaMemsetAsync(*dst, 0, count * sizeof(T), h->stream));
+    return FCB_OK;
+}
+
+#define TRY(expr)                  \
+    do {                           \
+        int rc_ = (expr);          \
+        if (rc_ != FCB_OK) return rc_; \
+    } while (0)
+
+int upload_plan(fcb_context* h, DevPlan& d, const fcb_plan& p) {
+    d.n = p.n;
+    d.rt = p.rt;
+    d.ntiles = p.ntiles;
+    d.nlaunch = p.nlaunch;
+    if (p.rt != 8 && p.rt != 16 && p.rt != 4) return fail(h, FCB_ERR_INVALID, "plan.rt must be 4, 8 or 16 (got %d)", p.rt);
+    std::vector<Tile> tiles(p.ntiles);
+    for (int i = 0; i < p.ntiles; ++i) {
+        tiles[i].out = p.tile_out[i];
+        tiles[i].self = p.tile_self[i];
+        tiles[i].nrows = p.tile_nrows[i];
+        tiles[i].K = (int)(p.tile_kptr[i + 1] - p.tile_kptr[i]);
+        tiles[i].kptr = p.tile_kptr[i];
+        tiles[i].vptr = p.tile_vptr[i];
+        if (tiles[i].vptr % 2) return fail(h, FCB_ERR_INVALID, "plan values must be 16-byte aligned per tile");
+    }
+    TRY(upload(h, &d.tiles, tiles.data(), tiles.size()));
+    CK(cudaStreamSynchronize(h->stream));  // tiles vector goes out of scope
+    const size_t ncols = (size_t)p.tile_kptr[p.ntiles];
+    TRY(upload(h, &d.cols, p.cols, ncols));
+    TRY(upload(h, &d.vals, p.vals, ncols * (size_t)p.rt));
+    d.launch_ptr.assign(p.launch_ptr, p.launch_ptr + p.nlaunch + 1);
+    // forward launches are those whose tiles carry a self row
+    d.n_forward = 0;
+    for (int l = 0; l < p.nlaunch; ++l)
+        if (p.tile_self[p.launch_ptr[l]] >= 0) d.n_forward = l + 1;
+    return FCB_OK;
+}
+
+void fill_tables(double phi[7][6], double dphi[7][6][2], double w[7], double mass[6][6]) {
+    const double s15 = std::sqrt(15.0);
+    const double a1 = (6.0 - s15) / 21.0, a2 = (6.0 + s15) / 21.0;
+    const double w1 = (155.0 - s15) / 2400.0, w2 = (155.0 + s15) / 2400.0;
+    const double xi[7] = {1.0 / 3.0, a1, 1 - 2 * a1, a1, a2, 1 - 2 * a2, a2};
+    const double eta[7] = {1.0 / 3.0, a1, a1, 1 - 2 * a1, a2, a2, 1 - 2 * a2};
+    const double ww[7] = {9.0 / 80.0, w1, w1, w1, w2, w2, w2};
+    const double dl[3][2] = {{-1, -1}, {1, 0}, {0, 1}};
+    const int ed[3][2] = {{1, 2}, {0, 2}, {0, 1}};
+    for (int q = 0; q < 7; ++q) {
+        const double l[3] = {1.0 - xi[q] - eta[q], xi[q], eta[q]};
+        w[q] = ww[q];
+        for (int i = 0; i < 3; ++i) {
+            phi[q][i] = l[i] * (2 * l[i] - 1);
+            for (int k = 0; k < 2; ++k) dphi[q][i][k] = (4 * l[i] - 1) * dl[i][k];
+        }
+        for (int e = 0; e < 3; ++e) {
+            const int i = ed[e][0], j = ed[e][1];
+            phi[q][3 + e] = 4 * l[i] * l[j];
+            for (int k = 0; k < 2; ++k) dphi[q][3 + e][k] = 4 * (l[i] * dl[j][k] + l[j] * dl[i][k]);
+        }
+    }
+    for (int a = 0; a < 6; ++a)
+        for (int b = 0; b < 6; ++b) {
+            double s = 0;
+            for (int q = 0; q < 7; ++q) s += w[q] * phi[q][a] * phi[q][b];
+            mass[a][b] = s;
+        }
+}
+
+// ---- enqueue helpers ---------------------------------------------------------------------------
+struct PhaseMark {
+    fcb_context* h;
+    bool on;
+    void mark(int i) {
+        if (on) cudaEventRecord(h->ev[i], h->stream);
+    }
+};
+
+int enqueue_element(fcb_context* h, const double* u, double* a, double* b) {
+    const size_t bytes = (size_t)h->Nv * h->ldb * sizeof(double);
+    CK(cudaMemsetAsync(a, 0, bytes, h->stream));
+    CK(cudaMemsetAsync(b, 0, bytes, h->stream));
+    h->launches += 2;
+    for (int c = 0; c < h->ncolours; ++c) {
+        ElemArgs p;
+        p.cells = h->colour_cells + h->colour_ptr[c];
+        p.ncells = h->colour_ptr[c + 1] - h->colour_ptr[c];
+        if (p.ncells == 0) continue;
+        p.cell_nodes = h->cell_nodes;
+        p.Jinv = h->Jinv;
+        p.detJ = h->detJ;
+        p.u = u;
+        p.a = a;
+        p.b = b;
+        p.epart = h->epart;
+        p.blk_offset = h->colour_blk_offset[c];
+        p.nN = h->nN;
+        p.ldb = h->ldb;
+        p.ca = 2.0 / h->dt;
+        p.cb = -0.5 / h->dt;
+        const int per_blk = ELEM_WARPS * ELEM_CPW;
+        dim3 grid((p.ncells + per_blk - 1) / per_blk, h->ldb / 32), block(32, ELEM_WARPS);
+        if (h->nonlinear) k_element<true><<<grid, block, 0, h->stream>>>(p);
+        else k_element<false><<<grid, block, 0, h->stream>>>(p);
+        h->launches += 1;
+    }
+    CK(cudaGetLastError());
+    return FCB_OK;
+}
+
+int enqueue_measure(fcb_context* h, const double* up) {
+    dim3 grid(h->ldb / 32), block(32, 8);
+    k_measure<<<grid, block, 0, h->stream>>>(h->ns, h->sensor_ptr, h->sensor_idx, h->sensor_val, up, h->y, h->epart,
+                                             h->nblk_total, h->dE, h->ldb);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    return FCB_OK;
+}
+
+int enqueue_solve(fcb_context* h, const DevPlan& pl, PhaseMark* pm) {
+    dim3 block(64);
+    for (int l = 0; l < pl.nlaunch; ++l) {
+        if (pm && l == pl.n_forward) pm->mark(FCB_PHASE_BACKWARD);
+        const int t0 = pl.launch_ptr[l], t1 = pl.launch_ptr[l + 1];
+        dim3 grid(t1 - t0, (h->ldb + 127) / 128);
+        if (pl.rt == 8) k_block_rows<8><<<grid, block, 0, h->stream>>>(pl.tiles + t0, pl.cols, pl.vals, h->Z, h->ldb);
+        else if (pl.rt == 16) k_block_rows<16><<<grid, block, 0, h->stream>>>(pl.tiles + t0, pl.cols, pl.vals, h->Z, h->ldb);
+        else k_block_rows<4><<<grid, block, 0, h->stream>>>(pl.tiles + t0, pl.cols, pl.vals, h->Z, h->ldb);
+        h->launches += 1;
+    }
+    if (pm && pl.n_forward >= pl.nlaunch) pm->mark(FCB_PHASE_BACKWARD);
+    CK(cudaGetLastError());
+    return FCB_OK;
+}
+
+// one step with the current (order, parity); u_ctrl already in h->uctrl
+int enqueue_step(fcb_context* h, int order, int parity, PhaseMark* pm) {
+    const DevPlan& pl = h->plan[order - 1];
+    double* cur = h->up[parity];
+    double* nxt = h->up[1 - parity];
+    (void)cur;
+    if (pm) pm->mark(FCB_PHASE_RHS);
+    {
+        dim3 grid((h->n + 7) / 8, h->ldb / 32), block(32, 8);
+        k_rhs_build<<<grid, block, 0, h->stream>>>(h->n, h->Nv, h->perm, h->avec, h->bvec[1 - parity], order, h->na,
+                                                   h->ctrl_rhs[order - 1], h->uctrl, h->Z, h->ldb);
+        h->launches += 1;
+    }
+    if (pm) pm->mark(FCB_PHASE_FORWARD);
+    TRY(enqueue_solve(h, pl, pm));
+    if (pm) pm->mark(FCB_PHASE_POST);
+    {
+        dim3 grid((h->N + 7) / 8, h->ldb / 32), block(32, 8);
+        k_post<<<grid, block, 0, h->stream>>>(h->N, h->Nv, h->n, h->iperm, h->Z, h->na, h->nbc, h->bc_shape, h->uctrl, nxt,
+                                              h->diverged, h->ldb);
+        h->launches += 1;
+    }
+    if (pm) pm->mark(FCB_PHASE_ELEMENT);
+    TRY(enqueue_element(h, nxt, h->avec, h->bvec[1 - parity]));
+    if (pm) pm->mark(FCB_PHASE_MEASURE);
+    TRY(enqueue_measure(h, nxt));
+    if (pm) pm->mark(FCB_NPHASES);
+    CK(cudaGetLastError());
+    return FCB_OK;
+}
+
+int enqueue_controller(fcb_context* h, int xparity) {
+    const int threads = 64;
+    k_controller<<<(h->ldb + threads - 1) / threads, threads, 0, h->stream>>>(
+        h->nx, h->ny, h->nu, h->ns, h->na, h->Ad, h->Bd, h->Cd, h->Dd, h->Ky, h->Fu, h->y, h->xk[xparity],
+        h->xk[1 - xparity], h->uctrl, h->ldb);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    return FCB_OK;
+}
+
+int enqueue_log(fcb_context* h) {
+    k_log<<<1, 256, 0, h->stream>>>(h->na, h->ns, h->dE, h->uctrl, h->y, h->series, h->counter, h->series_capacity, h->ldb);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    return FCB_OK;
+}
+
+int capture(fcb_context* h, cudaGraphExec_t* exec, int* nodes, bool loop, int parity, int xparity) {
+    const long long before = h->launches;
+    CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = FCB_OK;
+    if (loop) rc = enqueue_controller(h, xparity);
+    if (rc == FCB_OK) rc = enqueue_step(h, 2, parity, nullptr);
+    if (rc == FCB_OK && loop) rc = enqueue_log(h);
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+    *nodes = (int)(h->launches - before);
+    h->launches = before;  // capturing does not launch
+    if (rc != FCB_OK) return rc;
+    if (e != cudaSuccess) return fail(h, FCB_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+    CK(cudaGraphInstantiate(exec, graph, 0));
+    CK(cudaGraphDestroy(graph));
+    return FCB_OK;
+}
+
+// copy [rows, B] user array (host or device) into [rows, ldb] device array (or back)
+int copy_in(fcb_context* h, double* dst, const double* src, int rows) {
+    CK(cudaMemcpy2DAsync(dst, (size_t)h->ldb * sizeof(double), src, (size_t)h->B * sizeof(double),
+                         (size_t)h->B * sizeof(double), rows, cudaMemcpyDefault, h->stream));
+    return FCB_OK;
+}
+template <typename T>
+int copy_out(fcb_context* h, T* dst, const T* src, int rows) {
+    CK(cudaMemcpy2DAsync(dst, (size_t)h->B * sizeof(T), src, (size_t)h->ldb * sizeof(T), (size_t)h->B * sizeof(T), rows,
+                         cudaMemcpyDefault, h->stream));
+    return FCB_OK;
+}
+
+int run_one_step(fcb_context* h, bool loop) {
+    if (h->order == 2) {
+        cudaGraphExec_t* exec = loop ? &h->g_loop[h->parity][h->xparity] : &h->g_step[h->parity];
+        int* nodes = loop ? &h->g_loop_nodes[h->parity][h->xparity] : &h->g_step_nodes[h->parity];
+        if (!*exec) TRY(capture(h, exec, nodes, loop, h->parity, h->xparity));
+        CK(cudaGraphLaunch(*exec, h->stream));
+        h->launches += *nodes;
+    } else {
+        if (loop) TRY(enqueue_controller(h, h->xparity));
+        TRY(enqueue_step(h, h->order, h->parity, nullptr));
+        if (loop) TRY(enqueue_log(h));
+    }
+    h->parity ^= 1;
+    if (loop) h->xparity ^= 1;
+    h->order = 2;
+    return FCB_OK;
+}
+
+void destroy(fcb_context* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (int i = 0; i < 2; ++i) {
+        if (h->g_step[i]) cudaGraphExecDestroy(h->g_step[i]);
+        for (int j = 0; j < 2; ++j)
+            if (h->g_loop[i][j]) cudaGraphExecDestroy(h->g_loop[i][j]);
+    }
+    void* ptrs[] = {h->cell_nodes, h->colour_cells, h->perm, h->iperm, h->Jinv, h->detJ, h->bc_shape, h->ctrl_rhs[0],
+                    h->ctrl_rhs[1], h->sensor_ptr, h->sensor_idx, h->sensor_val, h->up[0], h->up[1], h->avec,
+                    h->bvec[0], h->bvec[1], h->Z, h->epart, h->uctrl, h->y, h->dE, h->diverged, h->Ad, h->Bd, h->Cd,
+                    h->Dd, h->Ky, h->Fu, h->xk[0], h->xk[1], h->series, h->counter};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    for (int i = 0; i < 2; ++i) {
+        if (h->plan[i].tiles) cudaFree(h->plan[i].tiles);
+        if (h->plan[i].cols) cudaFree(h->plan[i].cols);
+        if (h->plan[i].vals) cudaFree(h->plan[i].vals);
+    }
+    for (auto& e : h->ev)
+        if (e) cudaEventDestroy(e);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int create_impl(fcb_context* h, const fcb_problem* p, int B) {
+    CK(cudaSetDevice(h->device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, h->device));
+    if (prop.major < 10) return fail(h, FCB_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", h->device, prop.major, prop.minor);
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (auto& e : h->ev) CK(cudaEventCreate(&e));
+    h->B = B;
+    h->ldb = (B + 31) / 32 * 32;
+    h->nT = p->nT; h->nN = p->nN; h->nV = p->nV;
+    h->Nv = 2 * p->nN;
+    h->N = h->Nv + p->nV;
+    h->n = p->n_free; h->nbc = p->n_bc; h->na = p->na; h->ns = p->ns; h->ncolours = p->ncolours;
+    h->dt = p->dt; h->nonlinear = p->nonlinear;
+    if (h->n + h->nbc != h->N) return fail(h, FCB_ERR_INVALID, "n_free (%d) + n_bc (%d) != N (%d)", h->n, h->nbc, h->N);
+    if (p->plan[0].n != h->n || p->plan[1].n != h->n) return fail(h, FCB_ERR_INVALID, "plan size does not match n_free");
+    if (!(p->dt > 0)) return fail(h, FCB_ERR_INVALID, "dt must be positive");
+    {
+        double phi[7][6], dphi[7][6][2], w[7], mass[6][6];
+        fill_tables(phi, dphi, w, mass);
+        CK(cudaMemcpyToSymbol(c_phi, phi, sizeof phi));
+        CK(cudaMemcpyToSymbol(c_dphi, dphi, sizeof dphi));
+        CK(cudaMemcpyToSymbol(c_w, w, sizeof w));
+        CK(cudaMemcpyToSymbol(c_mass, mass, sizeof mass));
+    }
+    TRY(upload(h, &h->cell_nodes, p->cell_nodes, (size_t)p->nT * 6));
+    TRY(upload(h, &h->Jinv, p->Jinv, (size_t)p->nT * 4));
+    TRY(upload(h, &h->detJ, p->detJ, (size_t)p->nT));
+    TRY(upload(h, &h->colour_cells, p->colour_cells, (size_t)p->nT));
+    h->colour_ptr.assign(p->colour_ptr, p->colour_ptr + p->ncolours + 1);
+    h->colour_blk_offset.resize(p->ncolours);
+    h->nblk_total = 0;
+    for (int c = 0; c < p->ncolours; ++c) {
+        h->colour_blk_offset[c] = h->nblk_total;
+        const int nc = h->colour_ptr[c + 1] - h->colour_ptr[c];
+        h->nblk_total += (nc + ELEM_WARPS * ELEM_CPW - 1) / (ELEM_WARPS * ELEM_CPW);
+    }
+    TRY(upload(h, &h->perm, p->perm, (size_t)h->n));
+    {
+        std::vector<int> iperm(h->N, 0);
+        std::vector<char> seen(h->N, 0);
+        for (int r = 0; r < h->n; ++r) {
+            const int d = p->perm[r];
+            if (d < 0 || d >= h->N || seen[d]) return fail(h, FCB_ERR_INVALID, "perm is not a valid injection");
+            seen[d] = 1;
+            iperm[d] = r;
+        }
+        for (int j = 0; j < h->nbc; ++j) {
+            const int d = p->bc_dofs[j];
+            if (d < 0 || d >= h->N || seen[d]) return fail(h, FCB_ERR_INVALID, "bc_dofs overlaps perm or is out of range");
+            seen[d] = 1;
+            iperm[d] = -1 - j;
+        }
+        TRY(upload(h, &h->iperm, iperm.data(), iperm.size()));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    TRY(upload(h, &h->bc_shape, p->bc_shape, (size_t)p->na * p->n_bc));
+    for (int o = 0; o < 2; ++o) TRY(upload(h, &h->ctrl_rhs[o], p->ctrl_rhs[o], (size_t)p->na * p->n_free));
+    TRY(upload(h, &h->sensor_ptr, p->sensor_ptr, (size_t)p->ns + 1));
+    const size_t snnz = p->ns ? (size_t)p->sensor_ptr[p->ns] : 0;
+    TRY(upload(h, &h->sensor_idx, p->sensor_idx, snnz));
+    TRY(upload(h, &h->sensor_val, p->sensor_val, snnz));
+    for (int o = 0; o < 2; ++o) TRY(upload_plan(h, h->plan[o], p->plan[o]));
+    const size_t L = (size_t)h->ldb;
+    for (int i = 0; i < 2; ++i) {
+        TRY(upload<double>(h, &h->up[i], nullptr, (size_t)h->N * L));
+        TRY(upload<double>(h, &h->bvec[i], nullptr, (size_t)h->Nv * L));
+    }
+    TRY(upload<double>(h, &h->avec, nullptr, (size_t)h->Nv * L));
+    TRY(upload<double>(h, &h->Z, nullptr, (size_t)2 * h->n * L));
+    TRY(upload<double>(h, &h->epart, nullptr, (size_t)h->nblk_total * L));
+    TRY(upload<double>(h, &h->uctrl, nullptr, (size_t)(h->na > 0 ? h->na : 1) * L));
+    TRY(upload<double>(h, &h->y, nullptr, (size_t)(h->ns > 0 ? h->ns : 1) * L));
+    TRY(upload<double>(h, &h->dE, nullptr, L));
+    TRY(upload<int>(h, &h->diverged, nullptr, L));
+    TRY(upload<int>(h, &h->counter, nullptr, 1));
+    CK(cudaStreamSynchronize(h->stream));
+    return FCB_OK;
+}
+
+}  // namespace
+
+// ----------------------------------------------------------------------------------------------
+// C ABI
+// ----------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* fcb_version(void) { return "fcb200 0.1 sm_100a"; }
+
+const char* fcb_last_error(fcb_handle h) { return h ? h->error.c_str() : g_create_error.c_str(); }
+
+int fcb_create(const fcb_problem* problem, int32_t B, int32_t device, fcb_handle* out) {
+    if (!problem || !out || B <= 0) return fail(nullptr, FCB_ERR_INVALID, "fcb_create: bad arguments");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(nullptr, FCB_ERR_NO_DEVICE, "fcb_create: no CUDA device available (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(nullptr, FCB_ERR_INVALID, "fcb_create: device %d out of range [0,%d)", device, ndev);
+    fcb_context* h = new fcb_context();
+    h->device = device;
+    int rc = create_impl(h, problem, B);
+    if (rc != FCB_OK) {
+        g_create_error = h->error;
+        destroy(h);
+        *out = nullptr;
+        return rc;
+    }
+    *out = h;
+    return FCB_OK;
+}
+
+int fcb_destroy(fcb_handle h) {
+    destroy(h);
+    return FCB_OK;
+}
+
+int fcb_set_state(fcb_handle h, const double* u_n, const double* u_nn, const double* p_n, int32_t order) {
+    if (!h || !u_n) return fail(h, FCB_ERR_INVALID, "fcb_set_state: null argument");
+    if (order != 1 && order != 2) return fail(h, FCB_ERR_INVALID, "fcb_set_state: order must be 1 or 2");
+    CK(cudaSetDevice(h->device));
+    const size_t L = (size_t)h->ldb;
+    for (int i = 0; i < 2; ++i) CK(cudaMemsetAsync(h->up[i], 0, (size_t)h->N * L * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(h->diverged, 0, L * sizeof(int), h->stream));
+    h->parity = 0;
+    TRY(copy_in(h, h->up[0], u_n, h->Nv));
+    TRY(copy_in(h, h->up[1], u_nn ? u_nn : u_n, h->Nv));
+    if (p_n) TRY(copy_in(h, h->up[0] + (size_t)h->Nv * L, p_n, h->nV));
+    // b_{n-1} from u_nn, then (a_n, b_n) and the energy partials from u_n
+    TRY(enqueue_element(h, h->up[1], h->avec, h->bvec[1]));
+    TRY(enqueue_element(h, h->up[0], h->avec, h->bvec[0]));
+    TRY(enqueue_measure(h, h->up[0]));
+    CK(cudaStreamSynchronize(h->stream));
+    h->order = order;
+    h->have_state = true;
+    return FCB_OK;
+}
+
+int fcb_set_controllers(fcb_handle h, const fcb_controllers* c) {
+    if (!h || !c) return fail(h, FCB_ERR_INVALID, "fcb_set_controllers: null argument");
+    if (c->nx < 0 || c->ny < 1 || c->nu < 1 || c->ny > 8 || c->nu > 8)
+        return fail(h, FCB_ERR_INVALID, "fcb_set_controllers: need 1 <= ny,nu <= 8");
+    CK(cudaSetDevice(h->device));
+    void* old[] = {h->Ad, h->Bd, h->Cd, h->Dd, h->Ky, h->Fu, h->xk[0], h->xk[1]};
+    for (void* p : old)
+        if (p) cudaFree(p);
+    h->Ad = h->Bd = h->Cd = h->Dd = h->Ky = h->Fu = h->xk[0] = h->xk[1] = nullptr;
+    for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 2; ++j)
+            if (h->g_loop[i][j]) { cudaGraphExecDestroy(h->g_loop[i][j]); h->g_loop[i][j] = nullptr; }
+    h->nx = c->nx; h->ny = c->ny; h->nu = c->nu;
+    const size_t L = (size_t)h->ldb;
+    auto up2 = [&](double** dst, const double* src, int rows) -> int {
+        TRY(upload<double>(h, dst, nullptr, (size_t)(rows > 0 ? rows : 1) * L));
+        if (src && rows > 0) TRY(copy_in(h, *dst, src, rows));
+        return FCB_OK;
+    };
+    TRY(up2(&h->Ad, c->Ad, c->nx * c->nx));
+    TRY(up2(&h->Bd, c->Bd, c->nx * c->ny));
+    TRY(up2(&h->Cd, c->Cd, c->nu * c->nx));
+    TRY(up2(&h->Dd, c->Dd, c->nu * c->ny));
+    TRY(up2(&h->xk[0], c->x0, c->nx));
+    TRY(up2(&h->xk[1], nullptr, c->nx));
+    TRY(upload(h, &h->Ky, c->Ky, (size_t)c->ny * h->ns));
+    TRY(upload(h, &h->Fu, c->Fu, (size_t)h->na * c->nu));
+    CK(cudaStreamSynchronize(h->stream));
+    h->xparity = 0;
+    h->have_ctrl = true;
+    return FCB_OK;
+}
+
+int fcb_step(fcb_handle h, const double* u_ctrl, double* y_meas, double* dE, int32_t* diverged) {
+    if (!h) return FCB_ERR_INVALID;
+    if (!h->have_state) return fail(h, FCB_ERR_STATE, "fcb_step: call fcb_set_state first");
+    if (h->na > 0 && !u_ctrl) return fail(h, FCB_ERR_INVALID, "fcb_step: u_ctrl is NULL");
+    CK(cudaSetDevice(h->device));
+    if (h->na > 0) TRY(copy_in(h, h->uctrl, u_ctrl, h->na));
+    TRY(run_one_step(h, false));
+    if (y_meas && h->ns > 0) TRY(copy_out(h, y_meas, h->y, h->ns));
+    if (dE) TRY(copy_out(h, dE, h->dE, 1));
+    if (diverged) TRY(copy_out(h, diverged, h->diverged, 1));
+    CK(cudaStreamSynchronize(h->stream));
+    return FCB_OK;
+}
+
+int fcb_run_closed_loop(fcb_handle h, int32_t nsteps, double* series) {
+    if (!h || nsteps < 0) return FCB_ERR_INVALID;
+    if (!h->have_state) return fail(h, FCB_ERR_STATE, "fcb_run_closed_loop: call fcb_set_state first");
+    if (!h->have_ctrl) return fail(h, FCB_ERR_STATE, "fcb_run_closed_loop: call fcb_set_controllers first");
+    CK(cudaSetDevice(h->device));
+    const int ncol = 1 + h->na + h->ns;
+    const int need = series ? nsteps : 0;
+    if (need > h->series_capacity) {
+        if (h->series) cudaFree(h->series);
+        h->series = nullptr;
+        CK(cudaMalloc((void**)&h->series, (size_t)need * ncol * h->ldb * sizeof(double)));
+        // the log kernel reads series/capacity from its launch arguments: re-capture
+        for (int i = 0; i < 2; ++i)
+            for (int j = 0; j < 2; ++j)
+                if (h->g_loop[i][j]) { cudaGraphExecDestroy(h->g_loop[i][j]); h->g_loop[i][j] = nullptr; }
+        h->series_capacity = need;
+    }
+    if (!series && h->series_capacity != 0) {
+        // logging disabled for this run: counter starts beyond capacity
+        int big = h->series_capacity;
+        CK(cudaMemcpyAsync(h->counter, &big, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    } else {
+        CK(cudaMemsetAsync(h->counter, 0, sizeof(int), h->stream));
+    }
+    for (int s = 0; s < nsteps; ++s) TRY(run_one_step(h, true));
+    if (series && nsteps > 0) {
+        CK(cudaMemcpy2DAsync(series, (size_t)h->B * sizeof(double), h->series, (size_t)h->ldb * sizeof(double),
+                             (size_t)h->B * sizeof(double), (size_t)nsteps * ncol, cudaMemcpyDefault, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return FCB_OK;
+}
+
+int fcb_get_fields(fcb_handle h, int32_t which, double* up) {
+    if (!h || !up) return FCB_ERR_INVALID;
+    if (!h->have_state) return fail(h, FCB_ERR_STATE, "fcb_get_fields: no state");
+    CK(cudaSetDevice(h->device));
+    const double* src = (which == 0) ? h->up[h->parity] : h->up[1 - h->parity];
+    TRY(copy_out(h, up, src, which == 0 ? h->N : h->Nv));
+    CK(cudaStreamSynchronize(h->stream));
+    return FCB_OK;
+}
+
+int fcb_get_measurement(fcb_handle h, double* y_meas, double* dE, int32_t* diverged) {
+    if (!h) return FCB_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    if (y_meas && h->ns > 0) TRY(copy_out(h, y_meas, h->y, h->ns));
+    if (dE) TRY(copy_out(h, dE, h->dE, 1));
+    if (diverged) TRY(copy_out(h, diverged, h->diverged, 1));
+    CK(cudaStreamSynchronize(h->stream));
+    return FCB_OK;
+}
+
+int fcb_get_controller_state(fcb_handle h, double* x) {
+    if (!h || !x) return FCB_ERR_INVALID;
+    if (!h->have_ctrl) return fail(h, FCB_ERR_STATE, "no controllers set");
+    CK(cudaSetDevice(h->device));
+    if (h->nx > 0) TRY(copy_out(h, x, h->xk[h->xparity], h->nx));
+    CK(cudaStreamSynchronize(h->stream));
+    return FCB_OK;
+}
+
+int fcb_profile_step(fcb_handle h, const double* u_ctrl, float* ms, int32_t* launches) {
+    if (!h || !ms) return FCB_ERR_INVALID;
+    if (!h->have_state) return fail(h, FCB_ERR_STATE, "fcb_profile_step: call fcb_set_state first");
+    CK(cudaSetDevice(h->device));
+    if (h->na > 0 && u_ctrl) TRY(copy_in(h, h->uctrl, u_ctrl, h->na));
+    PhaseMark pm{h, true};
+    const long long l0 = h->launches;
+    const DevPlan& pl = h->plan[h->order - 1];
+    TRY(enqueue_step(h, h->order, h->parity, &pm));
+    CK(cudaStreamSynchronize(h->stream));
+    h->parity ^= 1;
+    h->order = 2;
+    for (int i = 0; i < FCB_NPHASES; ++i) CK(cudaEventElapsedTime(&ms[i], h->ev[i], h->ev[i + 1]));
+    if (launches) {
+        launches[FCB_PHASE_RHS] = 1;
+        launches[FCB_PHASE_FORWARD] = pl.n_forward;
+        launches[FCB_PHASE_BACKWARD] = pl.nlaunch - pl.n_forward;
+        launches[FCB_PHASE_POST] = 1;
+        launches[FCB_PHASE_ELEMENT] = (int)(h->launches - l0) - 3 - pl.nlaunch;
+        launches[FCB_PHASE_MEASURE] = 1;
+    }
+    return FCB_OK;
+}
+
+int64_t fcb_launch_count(fcb_handle h) { return h ? h->launches : 0; }
+void* fcb_stream(fcb_handle h) { return h ? (void*)h->stream : nullptr; }
+int fcb_synchronize(fcb_handle h) {
+    if (!h) return FCB_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    return FCB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,163 @@
+"""ctypes binding of libfcb200.so (the C ABI declared in include/fcb200.h).
+
+PyTorch is not involved here: numpy arrays (host) or raw device pointers cross
+the boundary.  The library has no CPU fallback; ``load()`` raises if the shared
+object is missing, ``fcb_create`` fails if there is no GPU.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libfcb200.so"
+
+c_i32p = C.POINTER(C.c_int32)
+c_i64p = C.POINTER(C.c_int64)
+c_f64p = C.POINTER(C.c_double)
+
+FCB_NPHASES = 6
+PHASE_NAMES = ("rhs", "forward", "backward", "post", "element", "measure")
+
+
+class fcb_plan(C.Structure):
+    _fields_ = [
+        ("n", C.c_int32), ("rt", C.c_int32), ("ntiles", C.c_int32),
+        ("tile_out", c_i32p), ("tile_self", c_i32p), ("tile_nrows", c_i32p),
+        ("tile_kptr", c_i64p), ("tile_vptr", c_i64p), ("cols", c_i32p), ("vals", c_f64p),
+        ("nlaunch", C.c_int32), ("launch_ptr", c_i32p),
+    ]
+
+
+class fcb_problem(C.Structure):
+    _fields_ = [
+        ("nT", C.c_int32), ("nN", C.c_int32), ("nV", C.c_int32),
+        ("cell_nodes", c_i32p), ("Jinv", c_f64p), ("detJ", c_f64p),
+        ("ncolours", C.c_int32), ("colour_ptr", c_i32p), ("colour_cells", c_i32p),
+        ("n_free", C.c_int32), ("perm", c_i32p),
+        ("n_bc", C.c_int32), ("bc_dofs", c_i32p),
+        ("na", C.c_int32), ("bc_shape", c_f64p), ("ctrl_rhs", c_f64p * 2),
+        ("plan", fcb_plan * 2),
+        ("ns", C.c_int32), ("sensor_ptr", c_i32p), ("sensor_idx", c_i32p), ("sensor_val", c_f64p),
+        ("dt", C.c_double), ("nonlinear", C.c_int32),
+    ]
+
+
+class fcb_controllers(C.Structure):
+    _fields_ = [
+        ("nx", C.c_int32), ("ny", C.c_int32), ("nu", C.c_int32),
+        ("Ad", c_f64p), ("Bd", c_f64p), ("Cd", c_f64p), ("Dd", c_f64p), ("x0", c_f64p),
+        ("Ky", c_f64p), ("Fu", c_f64p),
+    ]
+
+
+EXPORTS = {
+    # name: (restype, argtypes)
+    "fcb_version": (C.c_char_p, []),
+    "fcb_last_error": (C.c_char_p, [C.c_void_p]),
+    "fcb_create": (C.c_int, [C.POINTER(fcb_problem), C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "fcb_destroy": (C.c_int, [C.c_void_p]),
+    "fcb_set_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
+    "fcb_set_controllers": (C.c_int, [C.c_void_p, C.POINTER(fcb_controllers)]),
+    "fcb_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fcb_run_closed_loop": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "fcb_get_fields": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "fcb_get_measurement": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fcb_get_controller_state": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "fcb_profile_step": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
+    "fcb_launch_count": (C.c_int64, [C.c_void_p]),
+    "fcb_stream": (C.c_void_p, [C.c_void_p]),
+    "fcb_synchronize": (C.c_int, [C.c_void_p]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libfcb200.so and declare every entry point of include/fcb200.h."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). There is no CPU fallback."
+            )
+        lib = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in EXPORTS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+class FcbError(RuntimeError):
+    pass
+
+
+def _ptr(a: np.ndarray, typ):
+    return a.ctypes.data_as(typ)
+
+
+def as_voidp(x) -> C.c_void_p:
+    """numpy array, int device pointer, torch tensor (via data_ptr) or None -> void*."""
+    if x is None:
+        return C.c_void_p(0)
+    if isinstance(x, np.ndarray):
+        return C.c_void_p(x.ctypes.data)
+    if isinstance(x, int):
+        return C.c_void_p(x)
+    if hasattr(x, "data_ptr"):
+        return C.c_void_p(x.data_ptr())
+    raise TypeError(type(x))
+
+
+class ProblemPack:
+    """Keeps the numpy arrays referenced by an ``fcb_problem`` alive."""
+
+    def __init__(self, prob):
+        tab = prob.tab
+        keep = self.keep = []
+
+        def arr(a, dt):
+            a = np.ascontiguousarray(a, dtype=dt)
+            keep.append(a)
+            return a
+
+        s = fcb_problem()
+        s.nT, s.nN, s.nV = tab.nT, tab.nN, tab.nV
+        s.cell_nodes = _ptr(arr(tab.cell_nodes, np.int32), c_i32p)
+        s.Jinv = _ptr(arr(tab.Jinv.reshape(-1, 4), np.float64), c_f64p)
+        s.detJ = _ptr(arr(tab.detJ, np.float64), c_f64p)
+        s.ncolours = len(prob.colour_ptr) - 1
+        s.colour_ptr = _ptr(arr(prob.colour_ptr, np.int32), c_i32p)
+        s.colour_cells = _ptr(arr(prob.colour_cells, np.int32), c_i32p)
+        s.n_free = prob.sym.n
+        s.perm = _ptr(arr(prob.sym.perm, np.int32), c_i32p)
+        s.n_bc = len(prob.dirichlet.dofs)
+        s.bc_dofs = _ptr(arr(prob.dirichlet.dofs, np.int32), c_i32p)
+        s.na = prob.na
+        s.bc_shape = _ptr(arr(prob.dirichlet.shape, np.float64), c_f64p)
+        for o in (1, 2):
+            s.ctrl_rhs[o - 1] = _ptr(arr(prob.ctrl_rhs[o], np.float64), c_f64p)
+            p, q = prob.plans[o], s.plan[o - 1]
+            q.n, q.rt, q.ntiles = p.n, p.RT, len(p.tile_out)
+            q.tile_out = _ptr(arr(p.tile_out, np.int32), c_i32p)
+            q.tile_self = _ptr(arr(p.tile_self, np.int32), c_i32p)
+            q.tile_nrows = _ptr(arr(p.tile_nrows, np.int32), c_i32p)
+            q.tile_kptr = _ptr(arr(p.tile_kptr, np.int64), c_i64p)
+            q.tile_vptr = _ptr(arr(p.tile_vptr, np.int64), c_i64p)
+            q.cols = _ptr(arr(p.cols, np.int32), c_i32p)
+            q.vals = _ptr(arr(p.vals, np.float64), c_f64p)
+            q.nlaunch = len(p.launch_ptr) - 1
+            q.launch_ptr = _ptr(arr(p.launch_ptr, np.int32), c_i32p)
+        s.ns = prob.ns
+        s.sensor_ptr = _ptr(arr(prob.sensor_ptr, np.int32), c_i32p)
+        s.sensor_idx = _ptr(arr(prob.sensor_idx, np.int32), c_i32p)
+        s.sensor_val = _ptr(arr(prob.sensor_val, np.float64), c_f64p)
+        s.dt = prob.dt
+        s.nonlinear = int(prob.nonlinear)
+        self.struct = s

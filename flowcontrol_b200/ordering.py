@@ -1,0 +1,119 @@
+"""Element-based nested dissection of a Taylor-Hood mesh (host, setup time).
+
+The reference hands its constant LHS to MUMPS (flowsolver.py:694-697, 812-814),
+whose analysis phase orders the unknowns with METIS/SCOTCH/AMD.  This build
+needs an ordering whose elimination tree is shallow and whose supernodes are
+dense blocks the GPU solve can stream, so it bisects the *cells* geometrically
+and takes the P2 nodes shared by the two halves as the separator:
+
+    tree node t  <->  element set E_t
+    sep(t)       =   nodes shared by E_left and E_right, not owned by an ancestor
+    leaf         ->  owns the remaining (interior) nodes of its cells
+    struct(t)    =   nodes of E_t owned by strict ancestors  (= boundary of the subdomain)
+
+Each tree node becomes one supernode of the multifrontal factorisation
+(multifrontal.py); post-order over the tree is the elimination order.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from .mesh import TaylorHoodTables
+
+
+@dataclass
+class TreeNode:
+    cells: np.ndarray
+    parent: int
+    children: list = field(default_factory=list)
+    own_nodes: np.ndarray | None = None  # P2 nodes eliminated at this tree node
+    bnd_nodes: np.ndarray | None = None  # P2 nodes of cells owned by strict ancestors
+    depth: int = 0
+
+
+def _order_along_principal_axis(xy: np.ndarray) -> np.ndarray:
+    if xy.shape[0] <= 2:
+        return np.arange(xy.shape[0])
+    c = xy - xy.mean(axis=0)
+    cov = c.T @ c
+    w, v = np.linalg.eigh(cov)
+    axis = v[:, -1]
+    return np.argsort(c @ axis, kind="stable")
+
+
+_CUT_DIRECTIONS = [np.array(d) / np.linalg.norm(d) for d in ((1.0, 0.0), (0.0, 1.0), (1.0, 1.0), (1.0, -1.0))]
+
+
+def dissect(
+    tab: TaylorHoodTables, leaf_cells: int = 8, cut_fractions=(0.4, 0.45, 0.5, 0.55, 0.6)
+) -> list[TreeNode]:
+    """Return the dissection tree as a list (index 0 = root).
+
+    Every bisection tries four cut directions and a few cut positions around the
+    median and keeps the one with the fewest shared P2 nodes."""
+    cn = tab.cell_nodes
+    cent = tab.node_xy[tab.cell_nodes[:, :3]].mean(axis=1)
+    nodes: list[TreeNode] = [TreeNode(cells=np.arange(tab.nT), parent=-1, depth=0)]
+    stack = [0]
+    while stack:
+        t = stack.pop()
+        cells = nodes[t].cells
+        if len(cells) <= leaf_cells:
+            continue
+        c = cent[cells]
+        best = None
+        for direction in _CUT_DIRECTIONS:
+            proj = c @ direction
+            order = np.argsort(proj, kind="stable")
+            for frac in cut_fractions:
+                half = int(round(frac * len(cells)))
+                half = min(max(half, 1), len(cells) - 1)
+                a = np.unique(cn[cells[order[:half]]].ravel())
+                b = np.unique(cn[cells[order[half:]]].ravel())
+                nshared = np.intersect1d(a, b, assume_unique=True).size
+                # mild penalty for imbalance so that ties prefer the median cut
+                score = nshared * (1.0 + 0.5 * abs(frac - 0.5))
+                if best is None or score < best[0]:
+                    best = (score, order, half)
+        _, order, half = best
+        for part in (cells[order[:half]], cells[order[half:]]):
+            nodes.append(TreeNode(cells=part, parent=t, depth=nodes[t].depth + 1))
+            nodes[t].children.append(len(nodes) - 1)
+            stack.append(len(nodes) - 1)
+    # ownership: top-down, a node shared by both children belongs to the highest such tree node
+    owner = np.full(tab.nN, -1, dtype=np.int64)
+    cn = tab.cell_nodes
+    order_bfs = sorted(range(len(nodes)), key=lambda i: nodes[i].depth)
+    for t in order_bfs:
+        nd = nodes[t]
+        mine = np.unique(cn[nd.cells].ravel())
+        if nd.children:
+            a = np.unique(cn[nodes[nd.children[0]].cells].ravel())
+            b = np.unique(cn[nodes[nd.children[1]].cells].ravel())
+            shared = np.intersect1d(a, b, assume_unique=True)
+            own = shared[owner[shared] < 0]
+        else:
+            own = mine[owner[mine] < 0]
+        bnd = mine[(owner[mine] >= 0)]
+        owner[own] = t
+        nd.own_nodes = own[_order_along_principal_axis(tab.node_xy[own])] if len(own) else own
+        nd.bnd_nodes = bnd
+    assert np.all(owner >= 0)
+    return nodes
+
+
+def postorder(nodes: list[TreeNode]) -> list[int]:
+    out: list[int] = []
+    stack = [(0, False)]
+    while stack:
+        t, done = stack.pop()
+        if done or not nodes[t].children:
+            out.append(t)
+        else:
+            stack.append((t, True))
+            for c in reversed(nodes[t].children):
+                stack.append((c, False))
+    return out

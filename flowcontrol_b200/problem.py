@@ -1,0 +1,175 @@
+"""Host-side setup: everything constant over a run, ready for upload to the GPU.
+
+Replaces the one-time work the reference does through dolfin in
+``FlowSolver._setup`` / ``_prepare_systems``
+(/root/reference/src/flowcontrol/flowsolver.py:169-201, 665-701): Dirichlet dof
+sets and actuator profiles, the BDF1/BDF2 left-hand sides with symmetric
+Dirichlet elimination, their factorisation, the lifting/force vectors that make
+the per-step RHS linear in ``u_ctrl``, and the sensor rows.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Sequence
+
+import numpy as np
+import scipy.sparse as sp
+
+from .actuator import ACTUATOR_TYPE, Actuator
+from .fem import ScalarBlocks
+from .mesh import TaylorHoodTables
+from .multifrontal import BlockFactor, SolvePlan, SymbolicFactor, build_plan
+from .sensor import Sensor
+
+
+@dataclass
+class DirichletBC:
+    """One velocity Dirichlet condition (``dolfin.DirichletBC`` on ``W.sub(0)`` or
+    ``W.sub(0).sub(c)``): a boundary predicate ``inside(x, y) -> bool``, the constrained
+    components, and either constant values or the actuator whose profile is imposed."""
+
+    inside: Callable
+    components: tuple
+    value: object  # tuple of floats (one per component) or an Actuator
+
+
+class DirichletSet:
+    """Union of an ordered BC list; later entries override earlier ones on shared
+    dofs (dolfin behaviour)."""
+
+    def __init__(self, tab: TaylorHoodTables, bcs: Sequence[DirichletBC], actuators: Sequence[Actuator],
+                 extra_zero_dofs: Sequence[int] = ()):
+        N = tab.N
+        marked = np.zeros(N, dtype=bool)
+        const = np.zeros(N)
+        act_id = np.full(N, -1, dtype=np.int64)
+        act_val = np.zeros(N)
+        for bc in bcs:
+            nodes = tab.facet_p2_nodes(tab.mark_boundary_facets(bc.inside))
+            if nodes.size == 0:
+                continue
+            x, y = tab.node_xy[nodes, 0], tab.node_xy[nodes, 1]
+            if isinstance(bc.value, Actuator):
+                k = next(i for i, a in enumerate(actuators) if a is bc.value)
+                sx, sy = bc.value.shape(x, y)
+                prof = (sx, sy)
+                for c in bc.components:
+                    d = nodes + c * tab.nN
+                    marked[d] = True
+                    const[d] = 0.0
+                    act_id[d] = k
+                    act_val[d] = prof[c]
+            else:
+                vals = tuple(bc.value)
+                for ci, c in enumerate(bc.components):
+                    d = nodes + c * tab.nN
+                    marked[d] = True
+                    const[d] = float(vals[ci])
+                    act_id[d] = -1
+                    act_val[d] = 0.0
+        for d in extra_zero_dofs:
+            marked[d] = True
+            const[d] = 0.0
+            act_id[d] = -1
+        self.dofs = np.flatnonzero(marked).astype(np.int64)
+        self.const = const[self.dofs]
+        na = len(actuators)
+        self.shape = np.zeros((na, len(self.dofs)))
+        has = act_id[self.dofs] >= 0
+        self.shape[act_id[self.dofs][has], np.flatnonzero(has)] = act_val[self.dofs][has]
+        self.free = ~marked
+
+    def values(self, u_ctrl) -> np.ndarray:
+        return self.const + np.asarray(u_ctrl, dtype=np.float64) @ self.shape
+
+
+def sensor_matrix(tab: TaylorHoodTables, sensors: Sequence[Sensor]):
+    ptr = [0]
+    idx, val = [], []
+    for s in sensors:
+        i, v = s.row(tab)
+        s._row_cache = (i, v)
+        idx.append(np.asarray(i, dtype=np.int64))
+        val.append(np.asarray(v, dtype=np.float64))
+        ptr.append(ptr[-1] + len(i))
+    cat = (lambda xs, dt: np.concatenate(xs).astype(dt) if xs else np.zeros(0, dt))
+    return np.array(ptr, dtype=np.int32), cat(idx, np.int32), cat(val, np.float64)
+
+
+class FlowProblem:
+    """Constant data of one (mesh, Re, dt, BCs, actuators, sensors, base flow) setup."""
+
+    def __init__(
+        self,
+        tab: TaylorHoodTables,
+        blocks: ScalarBlocks,
+        Re: float,
+        dt: float,
+        bcs: Sequence[DirichletBC],
+        actuators: Sequence[Actuator],
+        sensors: Sequence[Sensor],
+        U0: np.ndarray,
+        nonlinear: bool = True,
+        shift: float = 0.0,
+        pin_pressure: bool = False,
+        leaf_cells: int = 8,
+        rows_per_tile: int = 8,
+        symbolic: SymbolicFactor | None = None,
+    ):
+        self.tab, self.blocks = tab, blocks
+        self.Re, self.dt, self.nonlinear = float(Re), float(dt), bool(nonlinear)
+        self.actuators, self.sensors = list(actuators), list(sensors)
+        na = len(self.actuators)
+        # an enclosed flow (all-Dirichlet velocity) has a constant-pressure null space: pin one dof
+        extra = [tab.Nv] if pin_pressure else []
+        self.dirichlet = DirichletSet(tab, bcs, self.actuators, extra_zero_dofs=extra)
+        dset = self.dirichlet
+        self.sym = symbolic or SymbolicFactor(tab, dset.free, leaf_cells=leaf_cells)
+        if not np.array_equal(np.sort(self.sym.perm), np.flatnonzero(dset.free)):
+            raise ValueError("symbolic factorisation was built for a different Dirichlet set")
+        # force vectors F_k = blkdiag(M,M) shape_k  (FORCE actuators), zero for BC actuators
+        force = np.zeros((na, tab.N))
+        for k, a in enumerate(self.actuators):
+            if a.actuator_type == ACTUATOR_TYPE.FORCE:
+                if hasattr(a, "normalise"):
+                    a.normalise(tab.node_xy, blocks.Mv)
+                sx, sy = a.shape(tab.node_xy[:, 0], tab.node_xy[:, 1])
+                force[k, : tab.Nv] = blocks.Mv @ np.concatenate([sx, sy])
+        U0v = np.asarray(U0[: tab.Nv], dtype=np.float64)
+        self.A_raw, self.factors, self.plans, self.ctrl_rhs = {}, {}, {}, {}
+        G = sp.csr_matrix(
+            (dset.shape.ravel(), (np.repeat(np.arange(na), len(dset.dofs)), np.tile(dset.dofs, na))),
+            shape=(na, tab.N),
+        ) if na else sp.csr_matrix((0, tab.N))
+        for order, c in ((1, 1.0 / dt), (2, 1.5 / dt)):
+            A = blocks.saddle_point(c, Re, U0v, shift=shift, linearised=True)
+            self.A_raw[order] = A
+            fac = BlockFactor(self.sym, A)
+            self.factors[order] = fac
+            self.plans[order] = build_plan(fac, RT=rows_per_tile)
+            # rhs contribution per unit u_ctrl_k in solver row order: (F_k - A[:,Gamma] shape_k)[perm]
+            lift = (A @ G.T).toarray().T if na else np.zeros((0, tab.N))
+            self.ctrl_rhs[order] = np.ascontiguousarray((force - lift)[:, self.sym.perm])
+        self.sensor_ptr, self.sensor_idx, self.sensor_val = sensor_matrix(tab, self.sensors)
+        self.colour_ptr, self.colour_cells = tab.element_colouring()
+
+    @property
+    def na(self) -> int:
+        return len(self.actuators)
+
+    @property
+    def ns(self) -> int:
+        return len(self.sensors)
+
+    def host_step_rhs(self, order: int, u_n, u_nn, u_ctrl) -> np.ndarray:
+        """Host restatement of k_rhs_build for one trajectory (setup/tests only)."""
+        b = self.blocks
+        if order == 1:
+            rv = b.Mv @ u_n / self.dt - (b.convection(u_n) if self.nonlinear else 0.0)
+        else:
+            rv = b.Mv @ (4 * u_n - u_nn) / (2 * self.dt)
+            if self.nonlinear:
+                rv = rv - 2 * b.convection(u_n) + b.convection(u_nn)
+        full = np.concatenate([rv, np.zeros(self.tab.nV)])
+        return full[self.sym.perm] + np.asarray(u_ctrl, dtype=np.float64) @ self.ctrl_rhs[order]

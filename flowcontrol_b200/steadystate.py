@@ -1,0 +1,86 @@
+"""Base-flow (steady-state) solver — one-time host setup shared by an ensemble.
+
+Restates /root/reference/src/flowcontrol/steadystate.py:60-159 (Newton through
+``dolfin.solve(F == 0, ...)`` with dolfin's NewtonSolver defaults, hand-rolled
+Picard loop) on the scalar blocks of fem.py with SciPy's SuperLU as the direct
+solver.  Not on the per-step hot path (SURVEY.md section 8(f) row f1 is the GPU
+version of this).
+"""
+
+from __future__ import annotations
+
+import logging
+
+import numpy as np
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+from .fem import ScalarBlocks
+from .mesh import TaylorHoodTables
+from .problem import DirichletSet
+
+logger = logging.getLogger(__name__)
+
+
+def _constrain_rows(A: sp.csr_matrix, dofs: np.ndarray) -> sp.csc_matrix:
+    keep = np.ones(A.shape[0])
+    keep[dofs] = 0.0
+    return (sp.diags(keep) @ A + sp.diags(1.0 - keep)).tocsc()
+
+
+class SteadyStateSolver:
+    def __init__(self, tab: TaylorHoodTables, blocks: ScalarBlocks, Re: float, dirichlet: DirichletSet,
+                 force: np.ndarray | None = None, verbose: bool = False):
+        self.tab, self.blocks, self.Re, self.dirichlet = tab, blocks, Re, dirichlet
+        self.force = np.zeros(tab.Nv) if force is None else force
+        self.verbose = verbose
+        self._Kv = sp.block_diag([blocks.K, blocks.K], format="csr")
+
+    def picard(self, UP0: np.ndarray, u_ctrl, max_iter: int = 10, tol: float = 1e-8) -> np.ndarray:
+        """Fixed-point iteration with the advection velocity frozen at the previous
+        iterate; stops on ||UP1-UP0|| / (||UP0|| + 1e-14) < tol (steadystate.py:139-157)."""
+        tab = self.tab
+        g = self.dirichlet.values(u_ctrl)
+        dofs = self.dirichlet.dofs
+        b = np.concatenate([self.force, np.zeros(tab.nV)])
+        b[dofs] = g
+        UP = np.array(UP0, dtype=np.float64)
+        for i in range(max_iter):
+            A = self.blocks.saddle_point(0.0, self.Re, UP[: tab.Nv], linearised=False)
+            UP1 = spla.splu(_constrain_rows(A, dofs)).solve(b)
+            rel = np.linalg.norm(UP1 - UP) / (np.linalg.norm(UP) + 1e-14)
+            UP = UP1
+            logger.info("Picard %d/%d  rel_err = %.3e", i + 1, max_iter, rel)
+            if rel < tol:
+                break
+        return UP
+
+    def residual(self, UP: np.ndarray) -> np.ndarray:
+        """F(UP) of nsforms.py:137-147 tested against every basis function."""
+        tab, bl = self.tab, self.blocks
+        U, P = UP[: tab.Nv], UP[tab.Nv :]
+        r = bl.convection(U) + self._Kv @ U / self.Re - self.force
+        r[: tab.nN] -= bl.Bx.T @ P
+        r[tab.nN :] -= bl.By.T @ P
+        return np.concatenate([r, -(bl.Bx @ U[: tab.nN] + bl.By @ U[tab.nN :])])
+
+    def newton(self, UP0: np.ndarray, u_ctrl, max_iter: int = 25, rtol: float = 1e-9, atol: float = 1e-10) -> np.ndarray:
+        """dolfin NewtonSolver defaults: residual criterion, relaxation 1."""
+        tab = self.tab
+        g = self.dirichlet.values(u_ctrl)
+        dofs = self.dirichlet.dofs
+        UP = np.array(UP0, dtype=np.float64)
+        r0 = None
+        for it in range(max_iter + 1):
+            b = self.residual(UP)
+            b[dofs] = UP[dofs] - g
+            r = float(np.linalg.norm(b))
+            r0 = r if r0 is None else r0
+            logger.info("Newton %d: r (abs) = %.3e  r (rel) = %.3e", it, r, r / max(r0, 1e-300))
+            if r < atol or r < rtol * r0:
+                return UP
+            if it == max_iter:
+                break
+            J = self.blocks.saddle_point(0.0, self.Re, UP[: tab.Nv], linearised=True)
+            UP = UP - spla.splu(_constrain_rows(J, dofs)).solve(b)
+        raise RuntimeError("Newton solver did not converge")

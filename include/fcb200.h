@@ -1,0 +1,163 @@
+/*
+ * fcb200.h — C ABI of the B200-native ensemble replacement for FlowControl's
+ * time-stepping hot path.
+ *
+ * The reference (williamjussiau/FlowControl) is pure Python and has no FFI of
+ * its own; its hot path crosses into third-party native code through dolfin's
+ * pybind11 layer.  Each entry point below names the reference call site(s) it
+ * replaces (paths relative to /root/reference).  INTEGRATION.md shows the
+ * ctypes stub a maintainer would add to the reference to bind them.
+ *
+ * Conventions
+ *   - plain C: opaque handle, pointers + sizes, no torch / Python types.
+ *   - every function returns 0 on success, a negative fcb_status otherwise;
+ *     fcb_last_error(h) (or fcb_last_error(NULL) for fcb_create failures)
+ *     returns a human-readable message.
+ *   - all floating-point data are IEEE binary64, all maps int32.
+ *   - ensemble arrays are "dof-major, trajectory-innermost": X[row * B + b],
+ *     b in [0,B).  Data pointers may be host (pageable or pinned) or device
+ *     pointers; the library copies with cudaMemcpyDefault (UVA).
+ *   - one handle = one GPU = one CUDA stream; a handle is not thread-safe,
+ *     independent handles are independent.
+ *   - there is NO CPU fallback: fcb_create fails if no sm_100 device is usable.
+ */
+#ifndef FCB200_H
+#define FCB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fcb_context* fcb_handle;
+
+typedef enum fcb_status {
+    FCB_OK = 0,
+    FCB_ERR_INVALID = -1,   /* bad argument / inconsistent sizes          */
+    FCB_ERR_CUDA = -2,      /* CUDA runtime error (see fcb_last_error)     */
+    FCB_ERR_NO_DEVICE = -3, /* no usable GPU                               */
+    FCB_ERR_STATE = -4      /* call order violated (e.g. step before state)*/
+} fcb_status;
+
+/* Solve plan of one factorised LHS (flowcontrol_b200/multifrontal.py: SolvePlan).
+ * Replaces the MUMPS factors held by dolfin.LUSolver after set_operator
+ * (src/flowcontrol/flowsolver.py:694-697, 812-814). */
+typedef struct fcb_plan {
+    int32_t n;               /* free unknowns                                       */
+    int32_t rt;              /* rows per tile (values are stored [K][rt] per tile)  */
+    int32_t ntiles;
+    const int32_t* tile_out;   /* [ntiles] first output row in Z (2n rows)          */
+    const int32_t* tile_self;  /* [ntiles] row added to the result, or -1           */
+    const int32_t* tile_nrows; /* [ntiles] valid rows (<= rt)                       */
+    const int64_t* tile_kptr;  /* [ntiles+1] offsets into cols                      */
+    const int64_t* tile_vptr;  /* [ntiles] offsets into vals                        */
+    const int32_t* cols;       /* [tile_kptr[ntiles]] gathered Z rows               */
+    const double* vals;        /* [sum K*rt]                                        */
+    int32_t nlaunch;
+    const int32_t* launch_ptr; /* [nlaunch+1] tile ranges; tiles of a launch are independent */
+} fcb_plan;
+
+/* Everything that is constant over a run and shared by the whole ensemble.
+ * Built on the host by flowcontrol_b200.problem.FlowProblem; replaces the
+ * objects FlowSolver._setup/_prepare_systems create through dolfin
+ * (src/flowcontrol/flowsolver.py:169-201, 665-701). */
+typedef struct fcb_problem {
+    /* mesh + P2 dof map (dolfin Mesh/FunctionSpace, flowsolver.py:233-250) */
+    int32_t nT, nN, nV;
+    const int32_t* cell_nodes; /* [nT*6] P2 node ids, local order v0 v1 v2 m12 m02 m01 */
+    const double* Jinv;        /* [nT*4] row-major d(ref)/d(phys)                      */
+    const double* detJ;        /* [nT] |det J|                                         */
+    /* atomic-free scatter schedule */
+    int32_t ncolours;
+    const int32_t* colour_ptr;   /* [ncolours+1] */
+    const int32_t* colour_cells; /* [nT] cells grouped by colour */
+    /* unknown numbering */
+    int32_t n_free;
+    const int32_t* perm;    /* [n_free] solver row -> canonical dof in [0, 2nN+nV) */
+    int32_t n_bc;
+    const int32_t* bc_dofs; /* [n_bc] canonical Dirichlet dofs (DirichletBC, <example>flowsolver._make_bcs) */
+    /* actuators (src/flowcontrol/actuator.py:184-313; flowsolver.py:278-309) */
+    int32_t na;
+    const double* bc_shape;     /* [na*n_bc] Dirichlet value per unit u_ctrl               */
+    const double* ctrl_rhs[2];  /* per BDF order: [na*n_free] (force - lifting), solver rows */
+    /* factorised LHS of BDF1 (index 0) and BDF2 (index 1) (nsforms.py:238-305) */
+    fcb_plan plan[2];
+    /* sensors as sparse rows over the canonical mixed vector (sensor.py:96-98,166-223) */
+    int32_t ns;
+    const int32_t* sensor_ptr; /* [ns+1] */
+    const int32_t* sensor_idx;
+    const double* sensor_val;
+    /* scheme */
+    double dt;
+    int32_t nonlinear; /* ParamSolver.is_eq_nonlinear (nsforms.py:249,283-284) */
+} fcb_problem;
+
+/* Controller bank: one discrete LTI controller per trajectory
+ * (src/flowcontrol/controller.py:136-159):  v = Ky*y_meas ; u = Cd x + Dd v ;
+ * x <- Ad x + Bd v ; u_ctrl = Fu*u.   Matrices are trajectory-innermost:
+ * Ad[(i*nx+j)*B + b] etc.  Ky [ny*ns] and Fu [na*nu] are shared. */
+typedef struct fcb_controllers {
+    int32_t nx, ny, nu;
+    const double* Ad; /* [nx*nx*B] */
+    const double* Bd; /* [nx*ny*B] */
+    const double* Cd; /* [nu*nx*B] */
+    const double* Dd; /* [nu*ny*B] */
+    const double* x0; /* [nx*B] or NULL (zeros) */
+    const double* Ky; /* [ny*ns] */
+    const double* Fu; /* [na*nu] */
+} fcb_controllers;
+
+/* Names of the phases timed by fcb_profile_step. */
+enum { FCB_PHASE_RHS = 0, FCB_PHASE_FORWARD = 1, FCB_PHASE_BACKWARD = 2, FCB_PHASE_POST = 3,
+       FCB_PHASE_ELEMENT = 4, FCB_PHASE_MEASURE = 5, FCB_NPHASES = 6 };
+
+/* Create an ensemble of B trajectories on CUDA device `device`.
+ * Replaces FlowSolver._prepare_systems (flowsolver.py:665-701). */
+int fcb_create(const fcb_problem* problem, int32_t B, int32_t device, fcb_handle* out);
+int fcb_destroy(fcb_handle h);
+const char* fcb_last_error(fcb_handle h);
+
+/* Load the perturbation history (u_n, u_nn: [2nN*B]) and the BDF order (1 or 2)
+ * of the next step.  Replaces FlowSolver.initialize_time_stepping
+ * (flowsolver.py:464-549, 599-663).  Also evaluates y_meas and dE of u_n. */
+int fcb_set_state(fcb_handle h, const double* u_n, const double* u_nn, const double* p_n, int32_t order);
+
+int fcb_set_controllers(fcb_handle h, const fcb_controllers* c);
+
+/* One time step of every trajectory.  u_ctrl [na*B] in; y_meas [ns*B], dE [B],
+ * diverged [B] out (any may be NULL).  Replaces FlowSolver.step
+ * (flowsolver.py:703-799): set_actuators_u_ctrl :724, assemble :728, solve :729,
+ * split/_solver_diverged :730-731, history :746-751, make_measurement :761,
+ * compute_perturbation_energy :775-779. */
+int fcb_step(fcb_handle h, const double* u_ctrl, double* y_meas, double* dE, int32_t* diverged);
+
+/* nsteps closed-loop steps without host round trips: controller -> step -> log.
+ * series (may be NULL) receives [nsteps * ncol * B] with columns
+ * (dE, u_ctrl_1..na, y_meas_1..ns) — the exporter's row minus time/runtime
+ * (src/flowcontrol/exporter.py:191-224).  Requires fcb_set_controllers. */
+int fcb_run_closed_loop(fcb_handle h, int32_t nsteps, double* series);
+
+/* Current fields in canonical numbering: up [ (2nN+nV) * B ].  which = 0: (u_, p_) of the
+ * last step; 1: u_nn, only the 2nN velocity rows are written.  Replaces fs.fields.u_/p_/u_n/u_nn reads
+ * (src/flowcontrol/flowfield.py:62-97). */
+int fcb_get_fields(fcb_handle h, int32_t which, double* up);
+int fcb_get_measurement(fcb_handle h, double* y_meas, double* dE, int32_t* diverged);
+int fcb_get_controller_state(fcb_handle h, double* x);
+
+/* Runs one step with CUDA events between phases; ms[FCB_NPHASES] receives device times,
+ * launches[FCB_NPHASES] (may be NULL) the kernel launches per phase. */
+int fcb_profile_step(fcb_handle h, const double* u_ctrl, float* ms, int32_t* launches);
+
+/* Kernel launches issued by this handle since creation (graph replays count their nodes). */
+int64_t fcb_launch_count(fcb_handle h);
+/* Raw cudaStream_t of the handle (for CUDA-event timing by the caller). */
+void* fcb_stream(fcb_handle h);
+int fcb_synchronize(fcb_handle h);
+/* Library/version string, e.g. "fcb200 0.1 sm_100a". */
+const char* fcb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FCB200_H */
