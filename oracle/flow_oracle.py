@@ -624,10 +624,16 @@ class FlowOracle:
         m, o = self.mesh, self.ops
         dt = self.case.dt
         u_ctrl = np.asarray(u_ctrl, dtype=float)
+        # N(u_nn) was N(u_n) of the previous step: reuse it (same value, half the assembly cost)
+        Nn = o.convection(self.u_n)
+        Nnn = self.N_prev if (self.N_prev is not None and self.order == 2) else None
         if self.order == 1:
-            rv = o.Mv @ self.u_n / dt - o.convection(self.u_n)
+            rv = o.Mv @ self.u_n / dt - Nn
         else:
-            rv = o.Mv @ (4.0 * self.u_n - self.u_nn) / (2.0 * dt) - 2.0 * o.convection(self.u_n) + o.convection(self.u_nn)
+            if Nnn is None:
+                Nnn = o.convection(self.u_nn)
+            rv = o.Mv @ (4.0 * self.u_n - self.u_nn) / (2.0 * dt) - 2.0 * Nn + Nnn
+        self._N_cur = Nn
         rv = rv + self.force_rhs(u_ctrl)
         b = np.concatenate([rv, np.zeros(m.nV)])
         g = self.bc_pert.values(u_ctrl)
@@ -652,6 +658,7 @@ class FlowOracle:
         self.order = 2
         self.u_nn = self.u_n
         self.u_n = x[: m.Nv].copy()
+        self.N_prev = self._N_cur
         self.up = x
         self.y_meas = self.measure(x)
         self.dE = self.energy()

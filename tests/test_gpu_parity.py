@@ -1,0 +1,326 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle — runs on the B200 box.
+
+Tolerances are BASELINE.json's: per-step velocity/pressure relative L2 error <= 1e-9 after 100
+steps, sensor time series within 1e-6 relative; integer maps bit-exact (test_host_setup.py).
+Nothing here reads /root/reference.
+"""
+import numpy as np
+import pytest
+
+from oracle import cases
+from oracle.flow_oracle import FlowOracle, ZOHController
+
+pytestmark = pytest.mark.gpu
+
+FIELD_TOL = 1e-9
+SERIES_TOL = 1e-6
+
+
+def rel(a, b):
+    return float(np.linalg.norm(np.asarray(a) - np.asarray(b)) / np.linalg.norm(np.asarray(b)))
+
+
+@pytest.fixture(scope="module")
+def cyl(root, built_lib):
+    """Cylinder Re=100 FlowSolver facade with the cached base flow + a live oracle on the same inputs."""
+    import tempfile
+    from pathlib import Path
+
+    from flowcontrol_b200.examples.cylinder import CylinderFlowSolver
+    from flowcontrol_b200.flowfield import Field
+    from flowcontrol_b200.problem import FlowProblem
+
+    UP0 = np.load(root / "tests/golden/cylinder_baseflow.npz")["UP0"]
+    fs = CylinderFlowSolver.make_default(path_out=Path(tempfile.mkdtemp()))
+    tab = fs.tables
+    fs._assign_steady_state(Field(UP0[: tab.Nv]), Field(UP0[tab.Nv :]))
+    prob = FlowProblem(tab, fs.blocks, 100.0, 0.005, fs.bc.bcu, fs.params_control.actuator_list,
+                       fs.params_control.sensor_list, UP0)
+    case = cases.cylinder(100.0)
+    xy, tri = cases.load_mesh(case.mesh_file)
+    orc = FlowOracle(case, xy, tri)
+    orc.set_base_flow(UP0)
+    orc.prepare()
+    return fs, prob, orc, UP0
+
+
+def test_cylinder_closed_loop_golden_trajectory(root, cyl):
+    """The reference's regression scenario (test_cylinder.py:78-126): 20 closed-loop steps."""
+    from flowcontrol_b200.controller import Controller
+    from flowcontrol_b200.ensemble import Ensemble
+
+    fs, prob, orc, UP0 = cyl
+    tab = prob.tab
+    gold = np.load(root / "tests/golden/cylinder_traj.npz")
+    ic = fs._default_initial_perturbation()
+    B = 32
+    ens = Ensemble(prob, B)
+    y0 = ens.set_state(ic[: tab.Nv], None, ic[tab.Nv :], order=1)
+    assert np.allclose(y0[:, 0], gold["y_meas"][0], rtol=1e-12)
+    assert np.isclose(ens.dE[0], gold["dE"][0], rtol=1e-12)
+    K = Controller.from_file(root / "tests/golden/Kopt_reduced13.npz")
+    for i in range(20):
+        u = K.step(-ens.y_meas[0, 0], prob.dt)
+        ens.step(np.full((2, B), u[0]))
+        assert np.allclose(ens.y_meas[:, 0], gold["y_meas"][i + 1], rtol=SERIES_TOL, atol=0)
+        assert np.isclose(ens.dE[0], gold["dE"][i + 1], rtol=SERIES_TOL)
+    # reference goldens themselves (test_cylinder.py:71-74)
+    assert np.allclose(ens.y_meas[:, 0], [0.011615482723602308, 0.003860524805395703, 0.0038461597025207803], rtol=1e-9)
+    assert np.isclose(ens.dE[0], 0.09462807324653322, rtol=1e-9)
+    up = ens.fields(0)
+    assert rel(up[: tab.Nv, 0], gold["up_final"][: tab.Nv]) < FIELD_TOL
+    assert rel(up[tab.Nv :, 0], gold["up_final"][tab.Nv :]) < FIELD_TOL
+    assert np.abs(up - up[:, :1]).max() == 0.0  # identical inputs -> bit-identical trajectories
+    assert not ens.diverged.any()
+    ens.close()
+
+
+def test_cylinder_100_steps_actuated_vs_oracle(cyl):
+    """100 open-loop steps with time-varying, trajectory-dependent slot actuation (BC lifting path)."""
+    from flowcontrol_b200.ensemble import Ensemble
+
+    fs, prob, orc, UP0 = cyl
+    tab = prob.tab
+    orc.case.ic = (2.0, 0.0, 0.5, 1.0)  # ParamIC of run_cylinder_example.py:55
+    orc.init_time_stepping()
+    B = 32
+    amp = np.linspace(-1.0, 1.0, B)
+    track = 7  # the oracle follows this trajectory
+    ens = Ensemble(prob, B)
+    ens.set_state(orc.ic[: tab.Nv], None, orc.ic[tab.Nv :], order=1)
+    worst_y = 0.0
+    for k in range(100):
+        t = (k + 1) * prob.dt
+        base = np.array([np.sin(40 * t), 0.5 * np.cos(25 * t)])
+        ens.step(base[:, None] * amp[None, :])
+        orc.step(base * amp[track])
+        worst_y = max(worst_y, np.abs(ens.y_meas[:, track] - orc.y_meas).max() / np.abs(orc.y_meas).max())
+    up = ens.fields(0)[:, track]
+    assert rel(up[: tab.Nv], orc.up[: tab.Nv]) < FIELD_TOL
+    assert rel(up[tab.Nv :], orc.up[tab.Nv :]) < FIELD_TOL
+    assert worst_y < SERIES_TOL
+    assert abs(ens.dE[track] - orc.dE) / orc.dE < SERIES_TOL
+    ens.close()
+
+
+def test_device_closed_loop_matches_host_loop_and_oracle(root, cyl):
+    """fcb_run_closed_loop (controller on the GPU, CUDA-graph replay) vs stepping from the host,
+    for a gain-swept family of controllers (config 2 of BASELINE.json)."""
+    from flowcontrol_b200.controller import Controller, ControllerBank
+    from flowcontrol_b200.ensemble import Ensemble
+    from flowcontrol_b200.sharding import controller_gain_sweep
+
+    fs, prob, orc, UP0 = cyl
+    tab = prob.tab
+    ic = fs._default_initial_perturbation()
+    B, nsteps = 64, 24
+    k = np.load(root / "tests/golden/Kopt_reduced13.npz")
+    gains = controller_gain_sweep(B)
+    ctrls = [Controller(k["A"], g * k["B"], k["C"], g * k["D"]) for g in gains]
+    Ky, Fu = np.array([[-1.0, 0.0, 0.0]]), np.array([[1.0], [1.0]])
+    ens = Ensemble(prob, B)
+    ens.set_state(ic[: tab.Nv], None, ic[tab.Nv :], order=1)
+    ens.set_controllers(ControllerBank(ctrls, prob.dt, Ky, Fu))
+    series = ens.run_closed_loop(nsteps)  # [nsteps, 1+na+ns, B]
+    assert series.shape == (nsteps, 6, B)
+    # (a) same thing driven from the host through fcb_step: bitwise identical
+    ens2 = Ensemble(prob, B)
+    ens2.set_state(ic[: tab.Nv], None, ic[tab.Nv :], order=1)
+    hostK = [Controller(c.A, c.B, c.C, c.D) for c in ctrls]
+    for s in range(nsteps):
+        u = np.array([hostK[b].step(-ens2.y_meas[0, b], prob.dt)[0] for b in range(B)])
+        ens2.step(np.stack([u, u]))
+        assert np.allclose(series[s, 1, :], u, rtol=1e-12, atol=1e-300)
+        assert np.allclose(series[s, 3:, :], ens2.y_meas, rtol=1e-10, atol=0)
+        assert np.allclose(series[s, 0, :], ens2.dE, rtol=1e-12)
+    # (b) oracle on three of the trajectories
+    for b in (0, 37, 63):
+        orc.case.ic = (0.0, 0.0, 1.0, 1.0)
+        orc.init_time_stepping()
+        K = ZOHController(k["A"], gains[b] * k["B"], k["C"], gains[b] * k["D"])
+        for s in range(nsteps):
+            u = K.step(-orc.y_meas[0], prob.dt)
+            orc.step([u[0], u[0]])
+            assert np.allclose(series[s, 3:, b], orc.y_meas, rtol=SERIES_TOL, atol=0)
+            assert np.isclose(series[s, 0, b], orc.dE, rtol=SERIES_TOL)
+    x = ens.controller_state()
+    assert np.allclose(x[:, 5], hostK[5].x, rtol=1e-9, atol=1e-14)
+    ens.close()
+    ens2.close()
+
+
+def test_restart_with_order2_continues_identically(cyl):
+    """set_state(order=2) from (u_n, u_nn) continues a run exactly (flowsolver.py:599-663)."""
+    from flowcontrol_b200.ensemble import Ensemble
+
+    fs, prob, orc, UP0 = cyl
+    tab = prob.tab
+    ic = fs._default_initial_perturbation()
+    B = 32
+    uc = np.full((2, B), 0.05)
+    a = Ensemble(prob, B)
+    a.set_state(ic[: tab.Nv], None, ic[tab.Nv :], order=1)
+    for _ in range(3):
+        a.step(uc)
+    u_n, u_nn = a.fields(0), a.fields(1)
+    b = Ensemble(prob, B)
+    y = b.set_state(u_n[: tab.Nv], u_nn, u_n[tab.Nv :], order=2)
+    assert np.array_equal(y, a.y_meas)
+    for _ in range(3):
+        a.step(uc)
+        b.step(uc)
+    assert np.array_equal(a.fields(0), b.fields(0))
+    assert np.array_equal(a.y_meas, b.y_meas) and np.array_equal(a.dE, b.dE)
+    a.close()
+    b.close()
+
+
+def test_divergence_is_per_trajectory(cyl):
+    from flowcontrol_b200.ensemble import Ensemble
+
+    fs, prob, orc, UP0 = cyl
+    tab = prob.tab
+    ic = fs._default_initial_perturbation()
+    B = 32
+    u0 = np.repeat(ic[: tab.Nv, None], B, axis=1)
+    u0[100, 3] = np.inf
+    ens = Ensemble(prob, B)
+    ens.set_state(u0, None, None, order=1)
+    ens.step(np.zeros((2, B)))
+    assert ens.diverged[3] == 1 and ens.diverged.sum() == 1
+    assert np.all(np.isfinite(ens.y_meas[:, np.arange(B) != 3]))
+    ens.close()
+
+
+def test_facade_regression_with_restart(root, tmp_path, cyl):
+    """Port of the reference's test_cylinder_regression: FlowSolver API, closed loop, JSON-sidecar restart."""
+    from flowcontrol_b200.controller import Controller
+    from flowcontrol_b200.examples.cylinder import CylinderFlowSolver
+    from flowcontrol_b200.exporter import write_checkpoint
+    from flowcontrol_b200.flowfield import Field
+
+    _, _, _, UP0 = cyl
+    fs = CylinderFlowSolver.make_default(Re=100, path_out=tmp_path, num_steps=10, save_every=5)
+    tab = fs.tables
+    # base flow from the fixture (computing it takes ~40 s of SuperLU; covered by the slow CPU test)
+    write_checkpoint(fs.paths.U0, "U0", UP0[: tab.Nv], 0.0, append=False)
+    write_checkpoint(fs.paths.P0, "P0", UP0[tab.Nv :], 0.0, append=False)
+    fs.load_steady_state()
+    assert np.isclose(fs.fields.U0.vector().get_local().max(), 1.1921615450014942, rtol=1e-9)
+    fs.initialize_time_stepping(ic=None)
+    Kss = Controller.from_file(root / "tests/golden/Kopt_reduced13.npz")
+    for _ in range(fs.params_time.num_steps):
+        u_ctrl = Kss.step(y=-fs.y_meas[0], dt=fs.params_time.dt)
+        fs.step(u_ctrl=[u_ctrl[0], u_ctrl[0]])
+    fs.write_timeseries()
+    fs2 = CylinderFlowSolver.make_default(Re=100, path_out=tmp_path, num_steps=10, save_every=5, Tstart=0.05)
+    fs2.load_steady_state()
+    fs2.initialize_time_stepping(Tstart=fs2.params_time.Tstart)
+    for _ in range(fs2.params_time.num_steps):
+        u_ctrl = Kss.step(y=-fs2.y_meas[0], dt=fs2.params_time.dt)
+        fs2.step(u_ctrl=np.repeat(u_ctrl, repeats=2, axis=0))
+    fs2.write_timeseries()
+    last = fs2.timeseries.iloc[-1]
+    Usave = fs2.fields.Usave.vector().get_local()
+    assert np.isclose(Usave.max(), 1.325070045534714, rtol=1e-9)
+    assert np.isclose(Usave.mean(), 0.3376859329866094, rtol=1e-9)
+    assert np.isclose(last["time"], 0.1, rtol=1e-12)
+    assert np.isclose(last["y_meas_1"], 0.011615482723602308, rtol=1e-9)
+    assert np.isclose(last["y_meas_2"], 0.003860524805395703, rtol=1e-9)
+    assert np.isclose(last["y_meas_3"], 0.0038461597025207803, rtol=1e-9)
+    assert np.isclose(last["dE"], 0.09462807324653322, rtol=1e-9)
+    assert np.all(np.isfinite(fs2.fields.u_.vector().get_local()))
+    with pytest.raises(ValueError):
+        fs2.step(u_ctrl=[0.0])
+
+
+def test_lidcavity_actuated_and_linear_superposition(root, built_lib):
+    """Lid cavity (pinned pressure): (a) non-zero lid speed vs the oracle; (b) with
+    is_eq_nonlinear=False the step is linear in (state, u_ctrl): superposition holds to round-off
+    at the full ensemble width."""
+    from flowcontrol_b200.ensemble import Ensemble
+    from flowcontrol_b200.examples import lidcavity as ex
+    from flowcontrol_b200.problem import FlowProblem
+
+    UP0 = np.load(root / "tests/golden/lidcavity_baseflow.npz")["UP0"]
+    prob = ex.make_problem(Re=1000.0, UP0=UP0)
+    tab = prob.tab
+    case = cases.lidcavity(1000.0)
+    xy, tri = cases.load_mesh(case.mesh_file)
+    orc = FlowOracle(case, xy, tri)
+    orc.set_base_flow(UP0)
+    orc.init_time_stepping()
+    B = 32
+    ens = Ensemble(prob, B)
+    ens.set_state(orc.ic[: tab.Nv], None, orc.ic[tab.Nv :], order=1)
+    for k in range(10):
+        uc = 0.1 * np.sin(0.7 * k)
+        orc.step([uc])
+        ens.step(np.full((1, B), uc))
+        assert np.allclose(ens.y_meas[:, 0], orc.y_meas, rtol=SERIES_TOL, atol=0)
+    up = ens.fields(0)[:, 0]
+    assert rel(up[: tab.Nv], orc.up[: tab.Nv]) < FIELD_TOL
+    assert rel(up[tab.Nv :], orc.up[tab.Nv :]) < 1e-8  # pressure level is pinned at dof 0 in both
+    ens.close()
+    # (b) linear mode
+    import tempfile
+    from pathlib import Path
+
+    fs = ex.LidCavityFlowSolver.make_default(Re=1000.0, path_out=Path(tempfile.mkdtemp()))
+    lin = FlowProblem(tab, fs.blocks, 1000.0, fs.params_time.dt, fs.bc.bcu, fs.params_control.actuator_list,
+                      fs.params_control.sensor_list, UP0, nonlinear=False, pin_pressure=True, symbolic=prob.sym)
+    B = 256
+    rng = np.random.default_rng(0)
+    u0 = np.zeros((tab.Nv, B))
+    u0[:, 0] = rng.standard_normal(tab.Nv)
+    u0[:, 1] = rng.standard_normal(tab.Nv)
+    u0[:, 2] = u0[:, 0] + u0[:, 1]
+    e = Ensemble(lin, B)
+    e.set_state(u0, None, None, order=1)
+    for k in range(5):
+        uc = np.zeros((1, B))
+        uc[0, 0], uc[0, 1] = 0.3 * (k + 1), -0.2
+        uc[0, 2] = uc[0, 0] + uc[0, 1]
+        e.step(uc)
+    f = e.fields(0)
+    assert rel(f[:, 2], f[:, 0] + f[:, 1]) < 1e-12
+    assert np.abs(f[:, 3:]).max() == 0.0  # untouched trajectories stay exactly zero
+    e.close()
+
+
+def test_cavity_force_actuator_golden_trajectory(root, built_lib):
+    """Open cavity Re=7500 (235 k dofs, body-force actuator, wall-shear sensor): the reference's
+    10-step regression scenario (test_cavity.py:58-90) through the CUDA path."""
+    import tempfile
+    from pathlib import Path
+
+    from flowcontrol_b200.ensemble import Ensemble
+    from flowcontrol_b200.examples.cavity import CavityFlowSolver
+    from flowcontrol_b200.flowfield import Field
+    from flowcontrol_b200.problem import FlowProblem
+
+    UP0 = np.load(root / "tests/golden/cavity_baseflow.npz")["UP0"]
+    gold = np.load(root / "tests/golden/cavity_traj.npz")
+    fs = CavityFlowSolver.make_default(path_out=Path(tempfile.mkdtemp()))
+    tab = fs.tables
+    fs._assign_steady_state(Field(UP0[: tab.Nv]), Field(UP0[tab.Nv :]))
+    prob = FlowProblem(tab, fs.blocks, 7500.0, 0.0004, fs.bc.bcu, fs.params_control.actuator_list,
+                       fs.params_control.sensor_list, UP0)
+    ic = fs._default_initial_perturbation()
+    B = 32
+    ens = Ensemble(prob, B)
+    y0 = ens.set_state(ic[: tab.Nv], None, ic[tab.Nv :], order=1)
+    assert np.allclose(y0[:, 0], gold["y_meas"][0], rtol=1e-9)
+    for i in range(10):
+        ens.step(np.zeros((1, B)))
+        assert np.allclose(ens.y_meas[:, 0], gold["y_meas"][i + 1], rtol=SERIES_TOL, atol=0)
+        assert np.isclose(ens.dE[0], gold["dE"][i + 1], rtol=SERIES_TOL)
+    assert np.allclose(ens.y_meas[:, 0], [6.0488687475121505, 0.024799707355708498], rtol=1e-9)  # test_cavity.py:52-53
+    assert np.isclose(ens.dE[0], 0.005000924582291293, rtol=1e-9)
+    up = ens.fields(0)[:, 0]
+    assert np.isclose(np.linalg.norm(up), float(gold["up_norm"]), rtol=1e-9)
+    # force actuation changes the answer linearly in u_ctrl at first order: just check it is wired
+    ens.step(np.full((1, B), 0.5))
+    y_forced = ens.y_meas[:, 0].copy()
+    assert np.all(np.isfinite(y_forced)) and not ens.diverged.any()
+    ens.close()

@@ -1,0 +1,125 @@
+"""Host-side mirror of the reference API: controller, exporter, parameters, facade validation."""
+import json
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from flowcontrol_b200 import flowsolverparameters as fsp
+from flowcontrol_b200.controller import Controller, ControllerBank
+from flowcontrol_b200.exporter import FlowExporter, read_checkpoint
+from flowcontrol_b200.flowfield import Field, FlowFieldCollection, SimPaths
+
+
+def _siso():
+    return Controller.from_matrices(
+        A=np.array([[1, 1, 1], [0.2, -1, 0], [0.0, 1.0, 1.0]]), B=np.array([[0], [1], [0.5]]),
+        C=np.array([0.5, 0.2, 0]), D=0, x0=np.array([1.0, 2.0, 3.0]),
+    )
+
+
+def test_controller_step_matches_zoh_recursion():
+    """tests/test_controller.py:182-196 of the reference: multi-step recursion vs c2d."""
+    from scipy.signal import cont2discrete
+
+    K = _siso()
+    Ad, Bd, Cd, Dd, _ = cont2discrete((K.A, K.B, K.C, K.D), 0.1, method="zoh")
+    x = K.x.copy()
+    for y in (1.2, -0.3, 0.7):
+        u = K.step(np.array([y]), 0.1)
+        assert np.allclose(u, Cd @ x + Dd @ np.array([y]))
+        x = Ad @ x + Bd @ np.array([y])
+        assert np.allclose(K.x, x)
+    K.step(np.array([0.1]), 0.05)  # dt change re-discretises (test_controller.py:198-213)
+    assert K._dt == 0.05
+    K.reset()
+    assert np.all(K.x == 0)
+
+
+def test_controller_from_npz_fixture(root):
+    K = Controller.from_file(root / "tests/golden/Kopt_reduced13.npz")
+    assert K.nstates == 13 and K.ninputs == 1 and K.noutputs == 1
+    assert np.isclose(K.D[0, 0], -7.4e-4, rtol=0.05)
+
+
+def test_controller_bank_packing_and_padding():
+    K1, K2 = _siso(), Controller.from_matrices(A=[[-1.0]], B=[[2.0]], C=[[3.0]], D=[[0.5]])
+    bank = ControllerBank([K1, K2], 0.1, Ky=np.array([[-1.0, 0, 0]]), Fu=np.array([[1.0], [1.0]]))
+    assert (bank.nx, bank.ny, bank.nu, bank.B) == (3, 1, 1, 2)
+    Ad2 = bank.Ad[:, 1].reshape(3, 3)
+    assert np.isclose(Ad2[0, 0], np.exp(-0.1)) and np.all(Ad2[1:, :] == 0) and np.all(Ad2[:, 1:] == 0)
+    assert np.allclose(bank.x0[:, 0], [1, 2, 3]) and np.all(bank.x0[:, 1] == 0)
+
+
+def _paths(tmp_path):
+    names = ["U0", "P0", "U", "P", "Uprev", "U_restart", "Uprev_restart", "P_restart"]
+    kw = {n: tmp_path / f"{n}.xdmf" for n in names}
+    return SimPaths(timeseries=tmp_path / "ts.csv", metadata=tmp_path / "meta.json", steady_meta=tmp_path / "steady.json",
+                    mesh=tmp_path / "m.xdmf", **kw)
+
+
+def test_exporter_columns_csv_and_sidecar(tmp_path):
+    """Column names/order and JSON keys of exporter.py:186-262."""
+    fields = FlowFieldCollection(U0=Field(np.ones(4)), P0=Field(np.zeros(2)))
+    ex = FlowExporter(_paths(tmp_path), fields, Tstart=0.0, dt=0.005, save_every=5)
+    ex.log_ic(0.0, np.array([0.1, 0.2]), 0.5)
+    ex.log(np.array([1.0]), np.array([0.3, 0.4]), 0.4, 0.005, 1e-3)
+    df = ex.to_dataframe()
+    assert list(df.columns) == ["time", "dE", "runtime", "y_meas_1", "y_meas_2", "u_ctrl_1"]
+    assert np.isnan(df.loc[0, "u_ctrl_1"]) and df.loc[1, "u_ctrl_1"] == 1.0
+    ex.export_xdmf(Field(np.arange(4.0)), Field(np.zeros(4)), Field(np.ones(2)), time=0.025, append=False, adjust_baseflow=1.0)
+    ex.export_xdmf(Field(2 * np.arange(4.0)), Field(np.arange(4.0)), Field(np.ones(2)), time=0.05, adjust_baseflow=1.0)
+    assert np.allclose(read_checkpoint(tmp_path / "U_restart.xdmf", 1), 2 * np.arange(4.0) + 1)
+    assert np.allclose(fields.Usave.array, 2 * np.arange(4.0) + 1)
+    ex.write_metadata(restart_order=2)
+    ex.write_timeseries()
+    meta = json.loads((tmp_path / "meta.json").read_text())
+    assert meta == {"Tstart": 0.0, "dt": 0.005, "save_every": 5, "checkpoints_written": 2, "restart_order": 2,
+                    "files": {"U": "U_restart.xdmf", "Uprev": "Uprev_restart.xdmf", "P": "P_restart.xdmf"}}
+    assert list(pd.read_csv(tmp_path / "ts.csv").columns) == list(df.columns)
+    ex.reset()
+    assert ex.to_dataframe().empty
+
+
+def test_param_defaults_match_reference():
+    assert fsp.ParamIC() == fsp.ParamIC(xloc=0.0, yloc=0.0, radius=1.0, amplitude=1.0)
+    assert fsp.ParamSolver().time_scheme == "bdf" and fsp.ParamSolver().throw_error is True
+    assert fsp.ParamTime(num_steps=10, dt=0.5, Tstart=0.0).Tfinal == 5.0
+    assert fsp.ParamSave(path_out=".", save_every=0).energy_every == 1
+    pc = fsp.ParamControl(sensor_list=[1, 2], actuator_list=[3])
+    assert (pc.sensor_number, pc.actuator_number) == (2, 1)
+
+
+def test_facade_validation_and_setup(tmp_path):
+    from flowcontrol_b200.examples.cylinder import CylinderFlowSolver
+
+    with pytest.raises(ValueError):
+        fs = CylinderFlowSolver.make_default(path_out=tmp_path)
+        fs._validate_params(fsp.ParamFlow(Re=-1), fs.params_time, fs.params_save, fs.params_solver, fs.params_mesh,
+                            fs.params_control, fs.params_ic)
+    with pytest.raises(FileNotFoundError):
+        CylinderFlowSolver.make_default(path_out=tmp_path, meshpath=tmp_path / "nope.npz")
+    fs = CylinderFlowSolver.make_default(path_out=tmp_path)
+    assert list(fs.boundaries.index) == ["inlet", "outlet", "walls", "cylinder", "actuator_up", "actuator_lo"]
+    assert fs.paths.timeseries.name == "timeseries1D_restart0,000.csv"
+    with pytest.raises(ValueError):
+        fs.set_actuators_u_ctrl([0.0])
+    fs.set_actuators_u_ctrl([0.1, 0.2])
+    assert fs.get_actuators_u_ctrl() == [0.1, 0.2]
+    with pytest.raises(RuntimeError):
+        fs.initialize_time_stepping()  # no base flow yet
+
+
+def test_mesh_reader_on_reference_files(root):
+    """hdf5_lite against the shipped XDMF/HDF5 meshes (only where /root/reference exists) and the fixtures."""
+    from pathlib import Path
+
+    from flowcontrol_b200.hdf5_lite import read_xdmf_mesh
+
+    ref = Path("/root/reference/src/examples")
+    if not ref.exists():
+        pytest.skip("reference tree not present on this machine")
+    for rel, fixture in (("cylinder/data_input/O1.xdmf", "cylinder_O1"), ("lidcavity/data_input/mesh64.xdmf", "lidcavity_mesh64")):
+        xy, tri = read_xdmf_mesh(ref / rel)
+        d = np.load(root / "data" / "meshes" / f"{fixture}.npz")
+        assert np.array_equal(xy, d["vertices"]) and np.array_equal(tri, d["triangles"])

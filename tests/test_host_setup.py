@@ -1,0 +1,207 @@
+"""Host-side setup of the product (mesh tables, FEM blocks, ordering, multifrontal plan)
+cross-checked against the independently written oracle and against SciPy's SuperLU."""
+import numpy as np
+import pytest
+import scipy.sparse.linalg as spla
+
+from flowcontrol_b200.actuator import ActuatorBCParabolicV, ActuatorBCUniformU, ActuatorForceGaussianV
+from flowcontrol_b200.fem import RADON7_ETA, RADON7_W, RADON7_XI, ScalarBlocks, p2_shape
+from flowcontrol_b200.mesh import TaylorHoodTables
+from flowcontrol_b200.multifrontal import BlockFactor, SymbolicFactor, apply_plan_host, build_plan
+from flowcontrol_b200.ordering import dissect, postorder
+from flowcontrol_b200.problem import DirichletBC, DirichletSet, FlowProblem
+from flowcontrol_b200.sensor import SENSOR_TYPE, SensorHorizontalWallShear, SensorPoint
+from oracle import flow_oracle as fo
+from util import near, unit_square_mesh
+
+
+@pytest.fixture(scope="module")
+def small():
+    xy, tri = unit_square_mesh(12, jitter=0.2, seed=3)
+    tab = TaylorHoodTables.from_arrays(xy, tri)
+    return xy, tri, tab, ScalarBlocks(tab), fo.TaylorHoodMesh(xy, tri)
+
+
+def test_integer_maps_bit_exact_vs_oracle(small):
+    xy, tri, tab, blocks, om = small
+    assert np.array_equal(tab.cell_nodes, om.cell_nodes)
+    assert np.array_equal(tab.edges, om.edges)
+    assert np.array_equal(tab.bnd_edges, om.bnd_edges)
+    assert np.array_equal(tab.bnd_cells, om.bnd_edge_cell)
+    assert tab.N == om.N and tab.nN == om.nN
+    assert np.array_equal(tab.node_xy, om.node_xy)
+
+
+def test_radon_rule_exact_to_degree_5():
+    from math import factorial
+
+    for a in range(6):
+        for b in range(6 - a):
+            exact = factorial(a) * factorial(b) / factorial(a + b + 2)
+            assert np.isclose(np.sum(RADON7_W * RADON7_XI**a * RADON7_ETA**b), exact, rtol=1e-14)
+
+
+def test_p2_shape_partition_of_unity_and_nodal():
+    phi, dphi = p2_shape(np.array([0.2, 0.7]), np.array([0.3, 0.1]))
+    assert np.allclose(phi.sum(axis=1), 1.0) and np.allclose(dphi.sum(axis=1), 0.0)
+    nodes = np.array([[0, 0], [1, 0], [0, 1], [0.5, 0.5], [0, 0.5], [0.5, 0]], dtype=float)
+    phi, _ = p2_shape(nodes[:, 0], nodes[:, 1])
+    assert np.allclose(phi, np.eye(6), atol=1e-15)
+
+
+def test_operators_match_oracle(small):
+    xy, tri, tab, blocks, om = small
+    ops = fo.Operators(om)
+    rng = np.random.default_rng(0)
+    U0 = rng.standard_normal(tab.Nv)
+    A_p = blocks.saddle_point(200.0, 100.0, U0, shift=0.3)
+    A_o = ops.lhs(200.0, 100.0, U0, shift=0.3)
+    assert abs(A_p - A_o).max() < 1e-12 * abs(A_o).max()
+    A_p = blocks.saddle_point(0.0, 50.0, U0, linearised=False)
+    A_o = ops.lhs(0.0, 50.0, U0, newton_terms=False)
+    assert abs(A_p - A_o).max() < 1e-12 * abs(A_o).max()
+    assert np.allclose(blocks.convection(U0), ops.convection(U0), rtol=0, atol=1e-13 * abs(ops.convection(U0)).max())
+
+
+def test_colouring_is_conflict_free(small):
+    _, _, tab, _, _ = small
+    cptr, cells = tab.element_colouring()
+    assert sorted(cells.tolist()) == list(range(tab.nT))
+    for c in range(len(cptr) - 1):
+        nodes = tab.cell_nodes[cells[cptr[c] : cptr[c + 1]]].ravel()
+        assert len(np.unique(nodes)) == len(nodes)
+
+
+def test_dissection_tree_invariants(small):
+    _, _, tab, _, _ = small
+    tree = dissect(tab, leaf_cells=6)
+    owned = np.concatenate([t.own_nodes for t in tree])
+    assert sorted(owned.tolist()) == list(range(tab.nN))  # every node eliminated exactly once
+    po = postorder(tree)
+    seen = set()
+    for t in po:
+        assert all(c in seen for c in tree[t].children)
+        seen.add(t)
+    # boundary nodes of a subdomain are owned by strict ancestors
+    owner = np.empty(tab.nN, dtype=int)
+    for i, t in enumerate(tree):
+        owner[t.own_nodes] = i
+    for i, t in enumerate(tree):
+        anc = set()
+        p = t.parent
+        while p >= 0:
+            anc.add(p)
+            p = tree[p].parent
+        assert set(owner[t.bnd_nodes].tolist()) <= anc
+
+
+def _bcs(acts):
+    return [
+        DirichletBC(lambda x, y: near(y, 1.0), (0, 1), acts[0]),
+        DirichletBC(lambda x, y: near(x, 0.0), (0, 1), (0.0, 0.0)),
+        DirichletBC(lambda x, y: near(y, 0.0), (1,), (0.0,)),
+    ]
+
+
+def test_dirichlet_override_semantics(small):
+    _, _, tab, _, _ = small
+    acts = [ActuatorBCUniformU()]
+    d = DirichletSet(tab, _bcs(acts), acts)
+    corner = int(np.flatnonzero(near(tab.node_xy[:, 0], 0.0) & near(tab.node_xy[:, 1], 1.0))[0])
+    j = int(np.searchsorted(d.dofs, corner))
+    assert d.dofs[j] == corner and d.shape[0, j] == 0.0  # left wall (later BC) overrides the lid
+    lid_mid = int(np.flatnonzero(near(tab.node_xy[:, 1], 1.0) & (tab.node_xy[:, 0] > 0.3) & (tab.node_xy[:, 0] < 0.7))[0])
+    assert d.shape[0, np.searchsorted(d.dofs, lid_mid)] == 1.0
+    # bottom: only u_y constrained
+    bot = int(np.flatnonzero(near(tab.node_xy[:, 1], 0.0) & (tab.node_xy[:, 0] > 0.3))[0])
+    assert bot not in set(d.dofs.tolist()) and (bot + tab.nN) in set(d.dofs.tolist())
+    assert np.allclose(d.values([2.5]), d.const + 2.5 * d.shape[0])
+
+
+def test_multifrontal_matches_superlu_and_plan_matches_factor(small):
+    _, _, tab, blocks, _ = small
+    rng = np.random.default_rng(1)
+    U0 = 0.3 * rng.standard_normal(tab.Nv)
+    acts = [ActuatorBCUniformU()]
+    d = DirichletSet(tab, _bcs(acts), acts)
+    A = blocks.saddle_point(300.0, 100.0, U0)
+    sym = SymbolicFactor(tab, d.free, leaf_cells=4)
+    assert sorted(sym.perm.tolist()) == np.flatnonzero(d.free).tolist()
+    fac = BlockFactor(sym, A)
+    b = rng.standard_normal((sym.n, 3))
+    x = fac.solve(b)
+    Aff = A[sym.perm][:, sym.perm].tocsc()
+    xref = spla.splu(Aff).solve(b)
+    assert np.linalg.norm(x - xref) / np.linalg.norm(xref) < 1e-11
+    for RT in (4, 8, 16):
+        plan = build_plan(fac, RT=RT)
+        assert np.abs(apply_plan_host(plan, b) - x).max() < 1e-12 * np.abs(x).max()
+        # every output row of Z written exactly once per sweep, tiles of a launch never read what they write
+        fw = plan.tile_self >= 0
+        rows_b = np.concatenate([np.arange(o, o + r) for o, r in zip(plan.tile_out[~fw], plan.tile_nrows[~fw])])
+        assert sorted(rows_b.tolist()) == list(range(sym.n, 2 * sym.n))
+        for l in range(len(plan.launch_ptr) - 1):
+            t0, t1 = plan.launch_ptr[l], plan.launch_ptr[l + 1]
+            written = set()
+            for t in range(t0, t1):
+                written |= set(range(plan.tile_out[t], plan.tile_out[t] + plan.tile_nrows[t]))
+            read = set(plan.cols[plan.tile_kptr[t0] : plan.tile_kptr[t1]].tolist())
+            assert not (written & read)
+
+
+def test_problem_rhs_and_lifting_match_oracle():
+    """FlowProblem.host_step_rhs + block solve == oracle step (BC actuator with u_ctrl != 0, force actuator)."""
+    xy, tri = unit_square_mesh(10, jitter=0.15, seed=5)
+    tab = TaylorHoodTables.from_arrays(xy, tri)
+    blocks = ScalarBlocks(tab)
+    rng = np.random.default_rng(2)
+    acts = [ActuatorBCUniformU(), ActuatorForceGaussianV(sigma=0.15, position=np.array([0.4, 0.5]))]
+    bcs = _bcs(acts)
+    sensors = [SensorPoint(sensor_type=SENSOR_TYPE.V, position=np.array([0.31, 0.52])),
+               SensorPoint(sensor_type=SENSOR_TYPE.P, position=np.array([0.6, 0.4])),
+               SensorHorizontalWallShear(sensor_type=SENSOR_TYPE.OTHER, x_sensor_left=0.2, x_sensor_right=0.8, y_sensor=0.0)]
+    UP0 = np.concatenate([0.5 * rng.standard_normal(tab.Nv), rng.standard_normal(tab.nV)])
+    prob = FlowProblem(tab, blocks, 80.0, 0.01, bcs, acts, sensors, UP0, leaf_cells=4)
+    case = fo.CaseSpec(
+        name="t", mesh_file="", Re=80.0, dt=0.01, uinf=1.0,
+        bcs_pert=[fo.DirichletSpec(lambda x, y: fo.near(y, 1.0), (0, 1), ("actuator", 0)),
+                  fo.DirichletSpec(lambda x, y: fo.near(x, 0.0), (0, 1), (0.0, 0.0)),
+                  fo.DirichletSpec(lambda x, y: fo.near(y, 0.0), (1,), (0.0,))],
+        bcs_full=[], actuators=[fo.ActuatorSpec("bc", fo.uniform_u()), fo.ActuatorSpec("force", fo.gaussian_v(0.15, (0.4, 0.5)))],
+        sensors=[fo.SensorSpec("point", comp=1, position=(0.31, 0.52)), fo.SensorSpec("point", comp=2, position=(0.6, 0.4)),
+                 fo.SensorSpec("wall_shear", x_left=0.2, x_right=0.8, y=0.0)],
+        initial_guess=None,
+    )
+    orc = fo.FlowOracle(case, xy, tri)
+    orc.set_base_flow(UP0)
+    ic = np.concatenate([0.1 * rng.standard_normal(tab.Nv), np.zeros(tab.nV)])
+    orc.init_time_stepping(ic=ic)
+    assert np.array_equal(prob.dirichlet.dofs, orc.bc_pert.dofs)
+    u_n, u_nn, order = ic[: tab.Nv].copy(), ic[: tab.Nv].copy(), 1
+    S = np.zeros((prob.ns, tab.N))
+    for s in range(prob.ns):
+        sl = slice(prob.sensor_ptr[s], prob.sensor_ptr[s + 1])
+        S[s, prob.sensor_idx[sl]] = prob.sensor_val[sl]
+    for step, uc in enumerate(([0.3, -0.7], [0.1, 0.4], [-0.2, 0.9])):
+        orc.step(uc)
+        b = prob.host_step_rhs(order, u_n, u_nn, uc)
+        x = np.zeros(tab.N)
+        x[prob.sym.perm] = prob.factors[order].solve(b)
+        x[prob.dirichlet.dofs] = prob.dirichlet.values(uc)
+        assert np.linalg.norm(x[: tab.Nv] - orc.up[: tab.Nv]) / np.linalg.norm(orc.up[: tab.Nv]) < 1e-10
+        assert np.linalg.norm(x[tab.Nv :] - orc.up[tab.Nv :]) / np.linalg.norm(orc.up[tab.Nv :]) < 1e-9
+        assert np.allclose(S @ x, orc.y_meas, rtol=1e-9, atol=1e-12)
+        u_nn, u_n, order = u_n, x[: tab.Nv].copy(), 2
+
+
+def test_force_actuator_unit_norm(small):
+    _, _, tab, blocks, _ = small
+    a = ActuatorForceGaussianV(sigma=0.1, position=np.array([0.5, 0.5]))
+    a.normalise(tab.node_xy, blocks.Mv)
+    sx, sy = a.shape(tab.node_xy[:, 0], tab.node_xy[:, 1])
+    s = np.concatenate([sx, sy])
+    assert np.isclose(s @ (blocks.Mv @ s), 1.0, rtol=1e-13)  # test_actuator.py:155-161 in the reference
+
+
+def test_parabolic_width_helper():
+    assert np.isclose(ActuatorBCParabolicV.angular_size_deg_to_width(10, 0.5), 0.5 * np.sin(np.deg2rad(5)))
