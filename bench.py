@@ -192,14 +192,14 @@ def run_ours(args):
     solve_ms = phase_ms["forward"] + phase_ms["backward"]
     solve_launches = prof_runs[0]["forward"]["launches"] + prof_runs[0]["backward"]["launches"]
     ldb = (B + 31) // 32 * 32
-    # algorithmic bytes of one solve (all launches of both sweeps): factor values + column indices read
-    # once, RHS read + y written (forward), y read + x written (backward)
-    solve_bytes = 8 * plan.nnz_padded + 4 * len(plan.cols) + 8 * 4 * n * ldb
+    # algorithmic bytes of one solve (all launches of both sweeps): factor values + gather indices read
+    # once; b read, y written, update vectors written and read once (forward); y read, x written (backward)
+    solve_bytes = 8 * plan.nnz_padded + 4 * len(plan.i0) + 8 * (4 * n + 2 * plan.nU) * ldb
     solve_flops = 2.0 * plan.nnz_padded * ldb
     hbm_peak, peak_src = peaks()
     achieved = solve_bytes / (solve_ms * 1e-3) / 1e9
     roofline = {
-        "kernel": "k_block_rows (multifrontal forward+backward sweeps, all launches of one solve)",
+        "kernel": "k_tile_gemm (multifrontal forward+backward sweeps, all launches of one solve)",
         "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
         "peak_source": peak_src, "traffic": None,
         "launches_per_step": solve_launches, "ms_per_launch": solve_ms / solve_launches, "ms_per_step": solve_ms,

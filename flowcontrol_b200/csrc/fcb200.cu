@@ -10,8 +10,8 @@
 //
 // One time step (reference: FlowSolver.step, flowsolver.py:703-799):
 //   k_rhs_build   rhs = a_n + b_{n-1} (BDF2) | a_n/2 (BDF1) + sum_k u_ctrl_k (f_k - l_k)   [solver row order]
-//   k_block_rows  forward sweep  (one launch per elimination-tree height)
-//   k_block_rows  backward sweep (one launch per elimination-tree depth)
+//   k_tile_gemm   forward sweep  (one launch per elimination-tree height): y_t, u_t = sum_children u_c - E_t y_t
+//   k_tile_gemm   backward sweep (one launch per elimination-tree depth):  x_t = F11^-1 y_t - G_t x_struct(t)
 //   k_post        un-permute, Dirichlet values, non-finite flag
 //   k_element     per cell: convection N(u) (7-point Radon rule) + mass M u, coloured scatter into
 //                 a = (2/dt) M u - 2 N(u),  b = -(1/2dt) M u + N(u);  energy partials u.(M u)
@@ -20,6 +20,7 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -41,9 +42,10 @@ __constant__ double c_dphi[7][6][2];  // reference gradients
 __constant__ double c_w[7];           // quadrature weights (sum = 1/2)
 __constant__ double c_mass[6][6];     // reference mass matrix (int phi_a phi_b over the unit triangle)
 
-struct Tile {
-    int out, self, nrows, K;
-    long long kptr, vptr;
+// One dense tile job of the multifrontal sweeps (multifrontal.py: SolvePlan).
+struct Job {
+    int K, MT, nr, nsrc, out0, ystore;
+    long long iptr, vptr, eptr;
 };
 
 // ----------------------------------------------------------------------------------------------
@@ -56,11 +58,12 @@ struct ElemArgs {
     const int* cells;       // cells of this colour
     int ncells;
     const int* cell_nodes;  // [nT*6]
+    const unsigned char* first;  // [nT] bit i set: this cell is the first (lowest colour) to touch local node i
     const double* Jinv;     // [nT*4]
     const double* detJ;     // [nT]
     const double* u;        // [2nN, ldb]
-    double* a;              // [2nN, ldb] accumulated
-    double* b;              // [2nN, ldb] accumulated
+    double* a;              // [2nN, ldb] written by the first colour touching a node, accumulated afterwards
+    double* b;              // [2nN, ldb] likewise
     double* epart;          // [nblk_total, ldb]
     int blk_offset;
     int nN;
@@ -69,7 +72,7 @@ struct ElemArgs {
 };
 
 template <bool NONLINEAR>
-__global__ void __launch_bounds__(32 * ELEM_WARPS) k_element(const ElemArgs p) {
+__global__ void __launch_bounds__(32 * ELEM_WARPS, 3) k_element(const ElemArgs p) {
     const int b = blockIdx.y * 32 + threadIdx.x;
     const size_t ldb = (size_t)p.ldb;
     double e_acc = 0.0;
@@ -84,6 +87,7 @@ __global__ void __launch_bounds__(32 * ELEM_WARPS) k_element(const ElemArgs p) {
         const double g00 = __ldg(p.Jinv + cell * 4 + 0), g01 = __ldg(p.Jinv + cell * 4 + 1);
         const double g10 = __ldg(p.Jinv + cell * 4 + 2), g11 = __ldg(p.Jinv + cell * 4 + 3);
         const double det = __ldg(p.detJ + cell);
+        const unsigned first = __ldg(p.first + cell);
         double ux[6], uy[6];
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
@@ -134,11 +138,20 @@ __global__ void __launch_bounds__(32 * ELEM_WARPS) k_element(const ElemArgs p) {
             e_acc = fma(uy[i], my, e_acc);
             const size_t ox = (size_t)nd[i] * ldb + b;
             const size_t oy = (size_t)(nd[i] + p.nN) * ldb + b;
-            // same-colour cells share no node: plain read-modify-write, no atomics
-            p.a[ox] += p.ca * mx - 2.0 * rx[i];
-            p.a[oy] += p.ca * my - 2.0 * ry[i];
-            p.b[ox] += p.cb * mx + rx[i];
-            p.b[oy] += p.cb * my + ry[i];
+            // same-colour cells share no node: plain (read-modify-)write, no atomics.  The lowest colour
+            // touching a node overwrites, so the vectors need no zero fill between steps.
+            double vax = p.ca * mx - 2.0 * rx[i], vay = p.ca * my - 2.0 * ry[i];
+            double vbx = p.cb * mx + rx[i], vby = p.cb * my + ry[i];
+            if (!((first >> i) & 1u)) {  // warp-uniform
+                vax += p.a[ox];
+                vay += p.a[oy];
+                vbx += p.b[ox];
+                vby += p.b[oy];
+            }
+            p.a[ox] = vax;
+            p.a[oy] = vay;
+            p.b[ox] = vbx;
+            p.b[oy] = vby;
         }
     }
     __shared__ double se[ELEM_WARPS][32];
@@ -173,48 +186,147 @@ __global__ void __launch_bounds__(256) k_rhs_build(int n, int Nv, const int* __r
     Z[(size_t)r * ldb + b] = v;
 }
 
-// Dense block-row products of the multifrontal sweeps (see multifrontal.py: SolvePlan).
-// grid = (tiles in launch, ceil(ldb/128)), block = 64 threads, 2 trajectories per thread.
-template <int RT>
-__global__ void __launch_bounds__(64) k_block_rows(const Tile* __restrict__ tiles, const int* __restrict__ cols,
-                                                   const double* __restrict__ vals, double* Z, int ldb) {
-    const Tile t = tiles[blockIdx.x];
-    const int b0 = blockIdx.y * 128 + threadIdx.x;
-    if (b0 >= ldb) return;
-    const bool two = (b0 + 64) < ldb;
-    const int b1 = two ? b0 + 64 : b0;
-    double acc0[RT], acc1[RT];
-#pragma unroll
-    for (int r = 0; r < RT; ++r) { acc0[r] = 0.0; acc1[r] = 0.0; }
-    const int* c = cols + t.kptr;
-    const double2* v = reinterpret_cast<const double2*>(vals + t.vptr);
-#pragma unroll 4
-    for (int k = 0; k < t.K; ++k) {
-        const double* zr = Z + (size_t)__ldg(c + k) * ldb;
-        const double x0 = zr[b0];
-        const double x1 = zr[b1];
-#pragma unroll
-        for (int r = 0; r < RT; r += 2) {
-            const double2 w = __ldg(v + (size_t)k * (RT / 2) + r / 2);
-            acc0[r] = fma(w.x, x0, acc0[r]);
-            acc0[r + 1] = fma(w.y, x0, acc0[r + 1]);
-            acc1[r] = fma(w.x, x1, acc1[r]);
-            acc1[r + 1] = fma(w.y, x1, acc1[r + 1]);
+// Dense tile GEMMs of the multifrontal sweeps.  One warp = one job x (32*TPT) trajectories:
+//   x_k   = Z[i0[k]] (+ Z[i1[k]] + Z[i2[k]])          gathered input rows (K of them)
+//   acc_r = sum_k V[k][r] * x_k                        r < MT, V stored k-major, warp-uniform loads
+//   Z[out0 + r] = acc_r (+ Z[e0[r]] + Z[e1[r]])        r < nr
+// The x rows of the next KC k's are prefetched into registers while the current chunk is multiplied.
+// No shared memory, no barriers, no atomics: every Z row is written by exactly one job.
+constexpr int TG_KC = 4;
+
+template <int TPT>
+__device__ __forceinline__ void tg_load_x(const double* Z, size_t ldb, int t0, bool has1, int nsrc, int r0, int r1,
+                                          int r2, double (&x)[TPT]) {
+    const double* z0 = Z + (size_t)r0 * ldb + t0;
+    x[0] = z0[0];
+    if (TPT == 2) x[TPT - 1] = has1 ? z0[32] : 0.0;
+    if (nsrc == 3) {
+        if (r1 >= 0) {
+            const double* z1 = Z + (size_t)r1 * ldb + t0;
+            x[0] += z1[0];
+            if (TPT == 2 && has1) x[TPT - 1] += z1[32];
+        }
+        if (r2 >= 0) {
+            const double* z2 = Z + (size_t)r2 * ldb + t0;
+            x[0] += z2[0];
+            if (TPT == 2 && has1) x[TPT - 1] += z2[32];
         }
     }
+}
+
+template <int MT, int TPT>
+__device__ __forceinline__ void tg_run(const Job jb, const int* __restrict__ i0, const int* __restrict__ i1,
+                                       const int* __restrict__ i2, const int* __restrict__ e0,
+                                       const int* __restrict__ e1, const double* __restrict__ vals, double* Z,
+                                       size_t ldb, int t0, bool has1) {
+    double acc[MT > 0 ? MT : 1][TPT];
 #pragma unroll
-    for (int r = 0; r < RT; ++r) {
-        if (r < t.nrows) {
-            double s0 = acc0[r], s1 = acc1[r];
-            if (t.self >= 0) {
-                const double* zs = Z + (size_t)(t.self + r) * ldb;
-                s0 += zs[b0];
-                s1 += zs[b1];
+    for (int r = 0; r < (MT > 0 ? MT : 1); ++r)
+#pragma unroll
+        for (int j = 0; j < TPT; ++j) acc[r][j] = 0.0;
+    const int* p0 = i0 + jb.iptr;
+    const int* p1 = i1 + jb.iptr;
+    const int* p2 = i2 + jb.iptr;
+    const double2* v = reinterpret_cast<const double2*>(vals + jb.vptr);
+    const int K = jb.K, nsrc = jb.nsrc;
+    double xc[TG_KC][TPT], xn[TG_KC][TPT];
+    auto load_chunk = [&](int k0, double (&x)[TG_KC][TPT]) {
+#pragma unroll
+        for (int c = 0; c < TG_KC; ++c) {
+            const int k = k0 + c;
+            if (k < K) {
+                const int r0 = __ldg(p0 + k);
+                int r1 = -1, r2 = -1;
+                if (nsrc == 3) { r1 = __ldg(p1 + k); r2 = __ldg(p2 + k); }
+                tg_load_x<TPT>(Z, ldb, t0, has1, nsrc, r0, r1, r2, x[c]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < TPT; ++j) x[c][j] = 0.0;
             }
-            double* zo = Z + (size_t)(t.out + r) * ldb;
-            zo[b0] = s0;
-            if (two) zo[b1] = s1;
         }
+    };
+    load_chunk(0, xc);
+    for (int k0 = 0; k0 < K; k0 += TG_KC) {
+        if (k0 + TG_KC < K) load_chunk(k0 + TG_KC, xn);
+        if (jb.ystore >= 0) {
+#pragma unroll
+            for (int c = 0; c < TG_KC; ++c)
+                if (k0 + c < K) {
+                    double* zy = Z + (size_t)(jb.ystore + k0 + c) * ldb + t0;
+                    zy[0] = xc[c][0];
+                    if (TPT == 2 && has1) zy[32] = xc[c][TPT - 1];
+                }
+        }
+        if (MT > 0) {
+#pragma unroll
+            for (int c = 0; c < TG_KC; ++c) {
+                if (k0 + c < K) {  // warp-uniform
+                    const double2* vk = v + (size_t)(k0 + c) * (MT / 2);
+#pragma unroll
+                    for (int r = 0; r < MT; r += 2) {
+                        const double2 w = __ldg(vk + r / 2);
+#pragma unroll
+                        for (int j = 0; j < TPT; ++j) {
+                            acc[r][j] = fma(w.x, xc[c][j], acc[r][j]);
+                            acc[r + 1][j] = fma(w.y, xc[c][j], acc[r + 1][j]);
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < TG_KC; ++c)
+#pragma unroll
+            for (int j = 0; j < TPT; ++j) xc[c][j] = xn[c][j];
+    }
+    if (MT > 0) {
+#pragma unroll
+        for (int r = 0; r < MT; ++r) {
+            if (r < jb.nr) {
+                double s0 = acc[r][0], s1 = acc[r][TPT - 1];
+                if (jb.eptr >= 0) {
+                    const int a = __ldg(e0 + jb.eptr + r), b = __ldg(e1 + jb.eptr + r);
+                    if (a >= 0) {
+                        const double* za = Z + (size_t)a * ldb + t0;
+                        s0 += za[0];
+                        if (TPT == 2 && has1) s1 += za[32];
+                    }
+                    if (b >= 0) {
+                        const double* zb = Z + (size_t)b * ldb + t0;
+                        s0 += zb[0];
+                        if (TPT == 2 && has1) s1 += zb[32];
+                    }
+                }
+                double* zo = Z + (size_t)(jb.out0 + r) * ldb + t0;
+                zo[0] = s0;
+                if (TPT == 2 && has1) zo[32] = s1;
+            }
+        }
+    }
+}
+
+// grid = (ceil(njobs / TG_WARPS), ceil(ldb / (32*TPT))), block = (32, TG_WARPS)
+constexpr int TG_WARPS = 4;
+
+template <int MAXMT, int TPT>
+__global__ void __launch_bounds__(32 * TG_WARPS) k_tile_gemm(const Job* __restrict__ jobs, int njobs,
+                                                             const int* __restrict__ i0, const int* __restrict__ i1,
+                                                             const int* __restrict__ i2, const int* __restrict__ e0,
+                                                             const int* __restrict__ e1,
+                                                             const double* __restrict__ vals, double* Z, int ldb) {
+    const int j = blockIdx.x * TG_WARPS + threadIdx.y;
+    if (j >= njobs) return;
+    const int t0 = blockIdx.y * 32 * TPT + threadIdx.x;
+    if (t0 >= ldb) return;
+    const bool has1 = (TPT == 2) && (t0 + 32 < ldb);
+    const Job jb = jobs[j];
+    switch (jb.MT) {  // warp-uniform
+        case 0: tg_run<0, TPT>(jb, i0, i1, i2, e0, e1, vals, Z, (size_t)ldb, t0, has1); break;
+        case 8: tg_run<8, TPT>(jb, i0, i1, i2, e0, e1, vals, Z, (size_t)ldb, t0, has1); break;
+        case 16: tg_run<16, TPT>(jb, i0, i1, i2, e0, e1, vals, Z, (size_t)ldb, t0, has1); break;
+        default:
+            if (MAXMT >= 32) tg_run<(MAXMT >= 32 ? 32 : 16), TPT>(jb, i0, i1, i2, e0, e1, vals, Z, (size_t)ldb, t0, has1);
+            break;
     }
 }
 
@@ -230,7 +342,7 @@ __global__ void __launch_bounds__(256) k_post(int N, int Nv, int n, const int* _
     const int r = __ldg(iperm + i);
     double v;
     if (r >= 0) {
-        v = Z[(size_t)(n + r) * ldb + b];
+        v = Z[(size_t)r * ldb + b];
     } else {
         const int j = -1 - r;
         v = 0.0;
@@ -330,9 +442,9 @@ __global__ void k_log(int na, int ns, const double* __restrict__ dE, const doubl
 // host side
 // ----------------------------------------------------------------------------------------------
 struct DevPlan {
-    int n = 0, rt = 0, ntiles = 0, nlaunch = 0;
-    Tile* tiles = nullptr;
-    int* cols = nullptr;
+    int n = 0, nU = 0, njobs = 0, nlaunch = 0, maxmt = 0;
+    Job* jobs = nullptr;
+    int *i0 = nullptr, *i1 = nullptr, *i2 = nullptr, *e0 = nullptr, *e1 = nullptr;
     double* vals = nullptr;
     std::vector<int> launch_ptr;
     int n_forward = 0;
@@ -350,6 +462,7 @@ struct fcb_context {
     int nonlinear = 1;
     // constant device data
     int *cell_nodes = nullptr, *colour_cells = nullptr, *perm = nullptr, *iperm = nullptr;
+    unsigned char* first_mask = nullptr;
     double *Jinv = nullptr, *detJ = nullptr, *bc_shape = nullptr, *ctrl_rhs[2] = {nullptr, nullptr};
     int *sensor_ptr = nullptr, *sensor_idx = nullptr;
     double* sensor_val = nullptr;
@@ -419,30 +532,35 @@ int upload(fcb_context* h, T** dst, const T* src, size_t count) {
 
 int upload_plan(fcb_context* h, DevPlan& d, const fcb_plan& p) {
     d.n = p.n;
-    d.rt = p.rt;
-    d.ntiles = p.ntiles;
+    d.nU = p.nU;
+    d.njobs = p.njobs;
     d.nlaunch = p.nlaunch;
-    if (p.rt != 8 && p.rt != 16 && p.rt != 4) return fail(h, FCB_ERR_INVALID, "plan.rt must be 4, 8 or 16 (got %d)", p.rt);
-    std::vector<Tile> tiles(p.ntiles);
-    for (int i = 0; i < p.ntiles; ++i) {
-        tiles[i].out = p.tile_out[i];
-        tiles[i].self = p.tile_self[i];
-        tiles[i].nrows = p.tile_nrows[i];
-        tiles[i].K = (int)(p.tile_kptr[i + 1] - p.tile_kptr[i]);
-        tiles[i].kptr = p.tile_kptr[i];
-        tiles[i].vptr = p.tile_vptr[i];
-        if (tiles[i].vptr % 2) return fail(h, FCB_ERR_INVALID, "plan values must be 16-byte aligned per tile");
+    d.n_forward = p.n_forward_launches;
+    std::vector<Job> jobs(p.njobs);
+    size_t nidx = 0, nvals = 0, nepi = 0;
+    d.maxmt = 0;
+    for (int i = 0; i < p.njobs; ++i) {
+        Job& j = jobs[i];
+        j.K = p.job_K[i]; j.MT = p.job_MT[i]; j.nr = p.job_nr[i]; j.nsrc = p.job_nsrc[i];
+        j.out0 = p.job_out0[i]; j.ystore = p.job_ystore[i];
+        j.iptr = p.job_iptr[i]; j.vptr = p.job_vptr[i]; j.eptr = p.job_eptr[i];
+        if (j.MT != 0 && j.MT != 8 && j.MT != 16 && j.MT != 32)
+            return fail(h, FCB_ERR_INVALID, "plan job %d: tile height %d not in {0,8,16,32}", i, j.MT);
+        if (j.nr > j.MT || j.K < 0 || (j.vptr & 1)) return fail(h, FCB_ERR_INVALID, "plan job %d is malformed", i);
+        if (j.MT > d.maxmt) d.maxmt = j.MT;
+        nidx = std::max(nidx, (size_t)(j.iptr + j.K));
+        nvals = std::max(nvals, (size_t)(j.vptr + (long long)j.K * j.MT));
+        if (j.eptr >= 0) nepi = std::max(nepi, (size_t)(j.eptr + j.nr));
     }
-    TRY(upload(h, &d.tiles, tiles.data(), tiles.size()));
-    CK(cudaStreamSynchronize(h->stream));  // tiles vector goes out of scope
-    const size_t ncols = (size_t)p.tile_kptr[p.ntiles];
-    TRY(upload(h, &d.cols, p.cols, ncols));
-    TRY(upload(h, &d.vals, p.vals, ncols * (size_t)p.rt));
+    TRY(upload(h, &d.jobs, jobs.data(), jobs.size()));
+    CK(cudaStreamSynchronize(h->stream));  // jobs vector goes out of scope
+    TRY(upload(h, &d.i0, p.i0, nidx));
+    TRY(upload(h, &d.i1, p.i1, nidx));
+    TRY(upload(h, &d.i2, p.i2, nidx));
+    TRY(upload(h, &d.e0, p.e0, nepi ? nepi : 1));
+    TRY(upload(h, &d.e1, p.e1, nepi ? nepi : 1));
+    TRY(upload(h, &d.vals, p.vals, nvals ? nvals : 2));
     d.launch_ptr.assign(p.launch_ptr, p.launch_ptr + p.nlaunch + 1);
-    // forward launches are those whose tiles carry a self row
-    d.n_forward = 0;
-    for (int l = 0; l < p.nlaunch; ++l)
-        if (p.tile_self[p.launch_ptr[l]] >= 0) d.n_forward = l + 1;
     return FCB_OK;
 }
 
@@ -486,16 +604,13 @@ struct PhaseMark {
 };
 
 int enqueue_element(fcb_context* h, const double* u, double* a, double* b) {
-    const size_t bytes = (size_t)h->Nv * h->ldb * sizeof(double);
-    CK(cudaMemsetAsync(a, 0, bytes, h->stream));
-    CK(cudaMemsetAsync(b, 0, bytes, h->stream));
-    h->launches += 2;
     for (int c = 0; c < h->ncolours; ++c) {
         ElemArgs p;
         p.cells = h->colour_cells + h->colour_ptr[c];
         p.ncells = h->colour_ptr[c + 1] - h->colour_ptr[c];
         if (p.ncells == 0) continue;
         p.cell_nodes = h->cell_nodes;
+        p.first = h->first_mask;
         p.Jinv = h->Jinv;
         p.detJ = h->detJ;
         p.u = u;
@@ -527,14 +642,21 @@ int enqueue_measure(fcb_context* h, const double* up) {
 }
 
 int enqueue_solve(fcb_context* h, const DevPlan& pl, PhaseMark* pm) {
-    dim3 block(64);
+    const bool tpt2 = (h->ldb % 64) == 0;
+    dim3 block(32, TG_WARPS);
     for (int l = 0; l < pl.nlaunch; ++l) {
         if (pm && l == pl.n_forward) pm->mark(FCB_PHASE_BACKWARD);
-        const int t0 = pl.launch_ptr[l], t1 = pl.launch_ptr[l + 1];
-        dim3 grid(t1 - t0, (h->ldb + 127) / 128);
-        if (pl.rt == 8) k_block_rows<8><<<grid, block, 0, h->stream>>>(pl.tiles + t0, pl.cols, pl.vals, h->Z, h->ldb);
-        else if (pl.rt == 16) k_block_rows<16><<<grid, block, 0, h->stream>>>(pl.tiles + t0, pl.cols, pl.vals, h->Z, h->ldb);
-        else k_block_rows<4><<<grid, block, 0, h->stream>>>(pl.tiles + t0, pl.cols, pl.vals, h->Z, h->ldb);
+        const int j0 = pl.launch_ptr[l], nj = pl.launch_ptr[l + 1] - j0;
+        if (nj <= 0) continue;
+        dim3 grid((nj + TG_WARPS - 1) / TG_WARPS, tpt2 ? h->ldb / 64 : h->ldb / 32);
+#define TG_LAUNCH(MAXMT, TPT) \
+    k_tile_gemm<MAXMT, TPT><<<grid, block, 0, h->stream>>>(pl.jobs + j0, nj, pl.i0, pl.i1, pl.i2, pl.e0, pl.e1, pl.vals, h->Z, h->ldb)
+        if (pl.maxmt >= 32) {
+            if (tpt2) TG_LAUNCH(32, 2); else TG_LAUNCH(32, 1);
+        } else {
+            if (tpt2) TG_LAUNCH(16, 2); else TG_LAUNCH(16, 1);
+        }
+#undef TG_LAUNCH
         h->launches += 1;
     }
     if (pm && pl.n_forward >= pl.nlaunch) pm->mark(FCB_PHASE_BACKWARD);
@@ -648,16 +770,17 @@ void destroy(fcb_context* h) {
         for (int j = 0; j < 2; ++j)
             if (h->g_loop[i][j]) cudaGraphExecDestroy(h->g_loop[i][j]);
     }
-    void* ptrs[] = {h->cell_nodes, h->colour_cells, h->perm, h->iperm, h->Jinv, h->detJ, h->bc_shape, h->ctrl_rhs[0],
+    void* ptrs[] = {h->first_mask, h->cell_nodes, h->colour_cells, h->perm, h->iperm, h->Jinv, h->detJ, h->bc_shape, h->ctrl_rhs[0],
                     h->ctrl_rhs[1], h->sensor_ptr, h->sensor_idx, h->sensor_val, h->up[0], h->up[1], h->avec,
                     h->bvec[0], h->bvec[1], h->Z, h->epart, h->uctrl, h->y, h->dE, h->diverged, h->Ad, h->Bd, h->Cd,
                     h->Dd, h->Ky, h->Fu, h->xk[0], h->xk[1], h->series, h->counter};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (int i = 0; i < 2; ++i) {
-        if (h->plan[i].tiles) cudaFree(h->plan[i].tiles);
-        if (h->plan[i].cols) cudaFree(h->plan[i].cols);
-        if (h->plan[i].vals) cudaFree(h->plan[i].vals);
+        void* pp[] = {h->plan[i].jobs, h->plan[i].i0, h->plan[i].i1, h->plan[i].i2, h->plan[i].e0, h->plan[i].e1,
+                      h->plan[i].vals};
+        for (void* q : pp)
+            if (q) cudaFree(q);
     }
     for (auto& e : h->ev)
         if (e) cudaEventDestroy(e);
@@ -702,6 +825,24 @@ int create_impl(fcb_context* h, const fcb_problem* p, int B) {
         const int nc = h->colour_ptr[c + 1] - h->colour_ptr[c];
         h->nblk_total += (nc + ELEM_WARPS * ELEM_CPW - 1) / (ELEM_WARPS * ELEM_CPW);
     }
+    {
+        // first-writer mask: for every P2 node the lowest colour among the cells that contain it
+        std::vector<int> colour_of(p->nT, 0), min_colour(p->nN, p->ncolours);
+        for (int c = 0; c < p->ncolours; ++c)
+            for (int k = p->colour_ptr[c]; k < p->colour_ptr[c + 1]; ++k) colour_of[p->colour_cells[k]] = c;
+        for (int e = 0; e < p->nT; ++e)
+            for (int i = 0; i < 6; ++i) {
+                const int nd = p->cell_nodes[e * 6 + i];
+                if (nd < 0 || nd >= p->nN) return fail(h, FCB_ERR_INVALID, "cell_nodes out of range");
+                min_colour[nd] = std::min(min_colour[nd], colour_of[e]);
+            }
+        std::vector<unsigned char> mask(p->nT, 0);
+        for (int e = 0; e < p->nT; ++e)
+            for (int i = 0; i < 6; ++i)
+                if (min_colour[p->cell_nodes[e * 6 + i]] == colour_of[e]) mask[e] |= (unsigned char)(1u << i);
+        TRY(upload(h, &h->first_mask, mask.data(), mask.size()));
+        CK(cudaStreamSynchronize(h->stream));
+    }
     TRY(upload(h, &h->perm, p->perm, (size_t)h->n));
     {
         std::vector<int> iperm(h->N, 0);
@@ -734,7 +875,10 @@ int create_impl(fcb_context* h, const fcb_problem* p, int B) {
         TRY(upload<double>(h, &h->bvec[i], nullptr, (size_t)h->Nv * L));
     }
     TRY(upload<double>(h, &h->avec, nullptr, (size_t)h->Nv * L));
-    TRY(upload<double>(h, &h->Z, nullptr, (size_t)2 * h->n * L));
+    {
+        const size_t zrows = (size_t)2 * h->n + (size_t)std::max(p->plan[0].nU, p->plan[1].nU);
+        TRY(upload<double>(h, &h->Z, nullptr, zrows * L));
+    }
     TRY(upload<double>(h, &h->epart, nullptr, (size_t)h->nblk_total * L));
     TRY(upload<double>(h, &h->uctrl, nullptr, (size_t)(h->na > 0 ? h->na : 1) * L));
     TRY(upload<double>(h, &h->y, nullptr, (size_t)(h->ns > 0 ? h->ns : 1) * L));
@@ -929,7 +1073,7 @@ int fcb_profile_step(fcb_handle h, const double* u_ctrl, float* ms, int32_t* lau
         launches[FCB_PHASE_FORWARD] = pl.n_forward;
         launches[FCB_PHASE_BACKWARD] = pl.nlaunch - pl.n_forward;
         launches[FCB_PHASE_POST] = 1;
-        launches[FCB_PHASE_ELEMENT] = (int)(h->launches - l0) - 3 - pl.nlaunch;
+        launches[FCB_PHASE_ELEMENT] = (int)(h->launches - l0) - 3 - (int)pl.nlaunch;
         launches[FCB_PHASE_MEASURE] = 1;
     }
     return FCB_OK;

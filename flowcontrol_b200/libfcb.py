@@ -25,10 +25,12 @@ PHASE_NAMES = ("rhs", "forward", "backward", "post", "element", "measure")
 
 class fcb_plan(C.Structure):
     _fields_ = [
-        ("n", C.c_int32), ("rt", C.c_int32), ("ntiles", C.c_int32),
-        ("tile_out", c_i32p), ("tile_self", c_i32p), ("tile_nrows", c_i32p),
-        ("tile_kptr", c_i64p), ("tile_vptr", c_i64p), ("cols", c_i32p), ("vals", c_f64p),
-        ("nlaunch", C.c_int32), ("launch_ptr", c_i32p),
+        ("n", C.c_int32), ("nU", C.c_int32), ("njobs", C.c_int32),
+        ("job_K", c_i32p), ("job_MT", c_i32p), ("job_nr", c_i32p), ("job_nsrc", c_i32p),
+        ("job_out0", c_i32p), ("job_ystore", c_i32p),
+        ("job_iptr", c_i64p), ("job_vptr", c_i64p), ("job_eptr", c_i64p),
+        ("i0", c_i32p), ("i1", c_i32p), ("i2", c_i32p), ("e0", c_i32p), ("e1", c_i32p), ("vals", c_f64p),
+        ("nlaunch", C.c_int32), ("launch_ptr", c_i32p), ("n_forward_launches", C.c_int32),
     ]
 
 
@@ -144,14 +146,13 @@ class ProblemPack:
         for o in (1, 2):
             s.ctrl_rhs[o - 1] = _ptr(arr(prob.ctrl_rhs[o], np.float64), c_f64p)
             p, q = prob.plans[o], s.plan[o - 1]
-            q.n, q.rt, q.ntiles = p.n, p.RT, len(p.tile_out)
-            q.tile_out = _ptr(arr(p.tile_out, np.int32), c_i32p)
-            q.tile_self = _ptr(arr(p.tile_self, np.int32), c_i32p)
-            q.tile_nrows = _ptr(arr(p.tile_nrows, np.int32), c_i32p)
-            q.tile_kptr = _ptr(arr(p.tile_kptr, np.int64), c_i64p)
-            q.tile_vptr = _ptr(arr(p.tile_vptr, np.int64), c_i64p)
-            q.cols = _ptr(arr(p.cols, np.int32), c_i32p)
+            q.n, q.nU, q.njobs = p.n, p.nU, len(p.job_K)
+            for name in ("job_K", "job_MT", "job_nr", "job_nsrc", "job_out0", "job_ystore", "i0", "i1", "i2", "e0", "e1"):
+                setattr(q, name, _ptr(arr(getattr(p, name), np.int32), c_i32p))
+            for name in ("job_iptr", "job_vptr", "job_eptr"):
+                setattr(q, name, _ptr(arr(getattr(p, name), np.int64), c_i64p))
             q.vals = _ptr(arr(p.vals, np.float64), c_f64p)
+            q.n_forward_launches = p.n_forward_launches
             q.nlaunch = len(p.launch_ptr) - 1
             q.launch_ptr = _ptr(arr(p.launch_ptr, np.int32), c_i32p)
         s.ns = prob.ns

@@ -193,153 +193,243 @@ class BlockFactor:
 
 @dataclass
 class SolvePlan:
-    """Flat arrays consumed by the CUDA kernel ``fcb_block_rows``.
+    """Flat job arrays consumed by the CUDA kernel ``k_tile_gemm`` (csrc/fcb200.cu).
 
-    The kernel works on one buffer Z of 2n rows x ldb columns: rows [0,n) hold y
-    (forward sweep, initially the permuted RHS), rows [n,2n) hold x.  A *tile*
-    produces ``nrows`` consecutive output rows from K gathered input rows:
+    The kernel works on one buffer Z with rows
+        [0, n)          b on entry, x on exit            (solver row order)
+        [n, 2n)         y (forward-eliminated RHS)
+        [2n, 2n + nU)   update vectors u_t of every supernode (its subdomain-boundary rows)
+    A *job* is a small dense GEMM  acc[MT x traj] = V[MT x K] . x[K x traj]  whose K input rows
+    are gathered as  x_k = Z[i0[k]] (+ Z[i1[k]] + Z[i2[k]] when nsrc == 3, -1 = absent) and whose
+    ``nr`` output rows are written to consecutive rows  Z[out0 + r] = acc[r] (+ Z[e0[r]] + Z[e1[r]]).
+    ``ystore >= 0`` additionally stores the gathered x_k rows to Z[ystore + k] (the job that owns y_t).
 
-        Z[out_row + r, :] = (self ? Z[self_row + r, :] : 0) + sum_k vals[vptr + k*RT + r] * Z[cols[kptr + k], :]
+        forward  (per supernode t, tiles over its m boundary rows, launches by tree height):
+            x_k = b_t[k] + sum_children u_c[..]            (= y_t)
+            u_t[r] = sum_children u_c[..] - (E_t y_t)[r]
+        backward (tiles over its w own rows, launches by tree depth):
+            x_t[r] = (F11^-1 y_t)[r] - (G_t x_struct(t))[r]
 
-    Tiles are grouped into launches; tiles of one launch are independent."""
+    Every output row is produced by exactly one job: no atomics, bit-reproducible."""
 
     n: int
-    RT: int
-    tile_out: np.ndarray  # int32 [ntiles] first output row in Z
-    tile_self: np.ndarray  # int32 [ntiles] row to add (or -1)
-    tile_nrows: np.ndarray  # int32 [ntiles]
-    tile_kptr: np.ndarray  # int64 [ntiles+1] offsets into cols
-    tile_vptr: np.ndarray  # int64 [ntiles] offsets into vals
-    cols: np.ndarray  # int32 [sum K]
-    vals: np.ndarray  # float64 [sum K * RT]
-    launch_ptr: np.ndarray  # int32 [nlaunch+1] tile ranges, forward launches first then backward
+    nU: int
+    job_K: np.ndarray  # int32 [njobs]
+    job_MT: np.ndarray  # int32 tile height of the value block (0 = store-only job, else 8/16/32)
+    job_nr: np.ndarray  # int32 valid output rows (<= MT)
+    job_nsrc: np.ndarray  # int32 1 or 3
+    job_out0: np.ndarray  # int32
+    job_ystore: np.ndarray  # int32 (-1 = none)
+    job_iptr: np.ndarray  # int64 offsets into i0/i1/i2
+    job_vptr: np.ndarray  # int64 offsets into vals ([K][MT] per job)
+    job_eptr: np.ndarray  # int64 offsets into e0/e1 (-1 = no epilogue gather)
+    i0: np.ndarray
+    i1: np.ndarray
+    i2: np.ndarray
+    e0: np.ndarray
+    e1: np.ndarray
+    vals: np.ndarray
+    launch_ptr: np.ndarray  # int32 [nlaunch+1] job ranges, forward launches first
     n_forward_launches: int
 
     @property
     def nnz_padded(self) -> int:
         return int(self.vals.size)
 
+    @property
+    def z_rows(self) -> int:
+        return 2 * self.n + self.nU
 
-def build_plan(fac: BlockFactor, RT: int = 8) -> SolvePlan:
+
+def _row_tiles(nrows: int, max_mt: int = 32) -> list[tuple[int, int, int]]:
+    """Split ``nrows`` into (r0, nr, MT) chunks with MT in {8,16,32} and little padding."""
+    out, r0 = [], 0
+    while nrows - r0 >= max_mt:
+        out.append((r0, max_mt, max_mt))
+        r0 += max_mt
+    rem = nrows - r0
+    while rem > 0:
+        if rem <= 8:
+            mt = 8
+        elif rem <= 16:
+            mt = 16
+        elif rem <= 24 and max_mt >= 16:
+            mt = 16
+        else:
+            mt = 32
+        mt = min(mt, max_mt)
+        nr = min(rem, mt)
+        out.append((r0, nr, mt))
+        r0 += nr
+        rem -= nr
+    return out
+
+
+def build_plan(fac: BlockFactor, max_mt: int = 32, target_jobs: int = 1200) -> SolvePlan:
+    """``max_mt``: largest tile height; levels with few rows use smaller tiles so that a launch
+    has at least ~``target_jobs`` independent warps' worth of work where possible."""
     sym = fac.sym
     sns = sym.supernodes
     n = sym.n
     nS = len(sns)
-    # ---- forward pull structure: for each target tile, the source supernodes touching it
-    # tile id of a permuted row: (supernode, (row - c0) // RT) -> flattened
-    tile_base = np.zeros(nS + 1, dtype=np.int64)
+    uoff = np.zeros(nS + 1, dtype=np.int64)
     for i, s in enumerate(sns):
-        tile_base[i + 1] = tile_base[i] + -(-(s.c1 - s.c0) // RT)
-    ntile_rows = int(tile_base[-1])
-    row_tile = np.empty(n, dtype=np.int64)
-    for i, s in enumerate(sns):
-        row_tile[s.c0 : s.c1] = tile_base[i] + (np.arange(s.c1 - s.c0) // RT)
-    fwd_sources: list[list[tuple[int, np.ndarray, np.ndarray]]] = [[] for _ in range(ntile_rows)]
-    for d, s in enumerate(sns):
-        if len(s.struct) == 0 or s.c1 == s.c0:
-            continue
-        tl = row_tile[s.struct]
-        # struct is sorted and tiles are monotone in row -> contiguous groups
-        cut = np.flatnonzero(np.diff(tl)) + 1
-        starts = np.concatenate([[0], cut])
-        stops = np.concatenate([cut, [len(tl)]])
-        for a, b in zip(starts, stops):
-            fwd_sources[tl[a]].append((d, np.arange(a, b), s.struct[a:b]))
-    tile_out, tile_self, tile_nrows, kptr, vptr = [], [], [], [0], []
-    cols_parts, vals_parts = [], []
-    launch_ptr = [0]
-    vpos = 0
+        uoff[i + 1] = uoff[i] + len(s.struct)
+    nU = int(uoff[-1])
+    UB = 2 * n  # first row of the U region
 
-    def emit(out_row, self_row, nrows, cols, vals_krt):
-        nonlocal vpos
-        tile_out.append(out_row)
-        tile_self.append(self_row)
-        tile_nrows.append(nrows)
-        cols_parts.append(cols.astype(np.int32))
-        kptr.append(kptr[-1] + len(cols))
-        vptr.append(vpos)
-        vals_parts.append(vals_krt.ravel())
-        vpos += vals_krt.size
+    def child_sources(i: int, rows: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+        """Z rows of the (at most two) children's update vectors that hit the given solver rows."""
+        srcs = [np.full(len(rows), -1, dtype=np.int64), np.full(len(rows), -1, dtype=np.int64)]
+        ch = sym.children[i]
+        if len(ch) > 2:
+            raise NotImplementedError("solve plan assumes a binary dissection tree")
+        for slot, c in enumerate(ch):
+            st = sns[c].struct
+            if len(st) == 0 or len(rows) == 0:
+                continue
+            pos = np.searchsorted(st, rows)
+            pos_c = np.minimum(pos, len(st) - 1)
+            hit = st[pos_c] == rows
+            srcs[slot][hit] = UB + uoff[c] + pos_c[hit]
+        return srcs[0], srcs[1]
+
+    jobs: list[dict] = []
+    launches: list[list[int]] = []
+
+    def tile_height_for(level_rows: int) -> int:
+        for mt in (32, 16, 8):
+            if mt <= max_mt and level_rows / mt * 4 >= target_jobs:  # x4 trajectory tiles at B=256
+                return mt
+        return 8
 
     max_h = max(s.height for s in sns)
-    # forward launches: height 1..max_h (height-0 supernodes have nothing below them)
-    for h in range(1, max_h + 1):
-        for i, s in enumerate(sns):
-            if s.height != h:
+    for h in range(max_h + 1):
+        ids = [i for i, s in enumerate(sns) if s.height == h]
+        level_rows = sum(len(sns[i].struct) for i in ids)
+        mt_cap = tile_height_for(level_rows)
+        cur: list[int] = []
+        for i in ids:
+            s = sns[i]
+            w, m = s.c1 - s.c0, len(s.struct)
+            own = np.arange(s.c0, s.c1, dtype=np.int64)
+            a1, a2 = child_sources(i, own)
+            nsrc = 3 if sym.children[i] else 1
+            E = fac.blocks[i][0]
+            if m == 0:
+                if w:
+                    jobs.append(dict(K=w, MT=0, nr=0, nsrc=nsrc, out0=0, ystore=n + s.c0, i0=own, i1=a1, i2=a2,
+                                     vals=np.zeros(0), e0=None, e1=None))
+                    cur.append(len(jobs) - 1)
                 continue
-            w = s.c1 - s.c0
-            for tix in range(-(-w // RT)):
-                src = fwd_sources[tile_base[i] + tix]
-                if not src:
-                    continue
-                r0 = s.c0 + tix * RT
-                nrows = min(RT, s.c1 - r0)
-                K = sum(sns[d].c1 - sns[d].c0 for d, _, _ in src)
-                vals = np.zeros((K, RT))
-                cols = np.empty(K, dtype=np.int64)
-                k0 = 0
-                for d, loc_in_struct, rows in src:
-                    wd = sns[d].c1 - sns[d].c0
-                    cols[k0 : k0 + wd] = np.arange(sns[d].c0, sns[d].c1)
-                    E = fac.blocks[d][0]
-                    vals[k0 : k0 + wd, rows - r0] = -E[loc_in_struct, :].T
-                    k0 += wd
-                emit(r0, r0, nrows, cols, vals)
-        if len(tile_out) > launch_ptr[-1]:
-            launch_ptr.append(len(tile_out))
-    n_fwd = len(launch_ptr) - 1
-    # backward launches: depth 0..max
+            e0, e1 = child_sources(i, s.struct)
+            for t, (r0, nr, mt) in enumerate(_row_tiles(m, mt_cap)):
+                V = np.zeros((w, mt))
+                V[:, :nr] = -E[r0 : r0 + nr, :].T
+                jobs.append(dict(K=w, MT=mt, nr=nr, nsrc=nsrc, out0=UB + int(uoff[i]) + r0,
+                                 ystore=(n + s.c0) if t == 0 else -1, i0=own, i1=a1, i2=a2, vals=V.ravel(),
+                                 e0=e0[r0 : r0 + nr] if nsrc == 3 else None, e1=e1[r0 : r0 + nr] if nsrc == 3 else None))
+                cur.append(len(jobs) - 1)
+        if cur:
+            launches.append(cur)
+    n_fwd = len(launches)
     max_d = max(s.depth for s in sns)
     for dpt in range(max_d + 1):
-        for i, s in enumerate(sns):
-            if s.depth != dpt:
-                continue
+        ids = [i for i, s in enumerate(sns) if s.depth == dpt]
+        level_rows = sum(sns[i].c1 - sns[i].c0 for i in ids)
+        mt_cap = tile_height_for(level_rows)
+        cur = []
+        for i in ids:
+            s = sns[i]
             w = s.c1 - s.c0
             if w == 0:
                 continue
-            E, Finv, G = fac.blocks[i]
-            cols = np.concatenate([np.arange(s.c0, s.c1), n + s.struct])
+            _, Finv, G = fac.blocks[i]
             full = np.concatenate([Finv, -G], axis=1)  # [w, w+m]
-            for tix in range(-(-w // RT)):
-                r0 = tix * RT
-                nrows = min(RT, w - r0)
-                vals = np.zeros((w + len(s.struct), RT))
-                vals[:, :nrows] = full[r0 : r0 + nrows, :].T
-                emit(n + s.c0 + r0, -1, nrows, cols, vals)
-        if len(tile_out) > launch_ptr[-1]:
-            launch_ptr.append(len(tile_out))
+            idx = np.concatenate([n + np.arange(s.c0, s.c1, dtype=np.int64), s.struct.astype(np.int64)])
+            for r0, nr, mt in _row_tiles(w, mt_cap):
+                V = np.zeros((full.shape[1], mt))
+                V[:, :nr] = full[r0 : r0 + nr, :].T
+                jobs.append(dict(K=full.shape[1], MT=mt, nr=nr, nsrc=1, out0=s.c0 + r0, ystore=-1, i0=idx, i1=None,
+                                 i2=None, vals=V.ravel(), e0=None, e1=None))
+                cur.append(len(jobs) - 1)
+        if cur:
+            launches.append(cur)
+    # longest jobs first inside each launch (shorter tail), then flatten
+    order: list[int] = []
+    launch_ptr = [0]
+    for cur in launches:
+        cur = sorted(cur, key=lambda j: -(jobs[j]["K"] * max(jobs[j]["MT"], 1)))
+        order += cur
+        launch_ptr.append(len(order))
+    nj = len(order)
+    K = np.array([jobs[j]["K"] for j in order], dtype=np.int32)
+    iptr = np.zeros(nj + 1, dtype=np.int64)
+    iptr[1:] = np.cumsum(K)
+    i0 = np.empty(int(iptr[-1]), dtype=np.int32)
+    i1 = np.full(int(iptr[-1]), -1, dtype=np.int32)
+    i2 = np.full(int(iptr[-1]), -1, dtype=np.int32)
+    vptr = np.zeros(nj, dtype=np.int64)
+    eptr = np.full(nj, -1, dtype=np.int64)
+    vparts, e0p, e1p = [], [], []
+    vpos = epos = 0
+    for q, j in enumerate(order):
+        jb = jobs[j]
+        sl = slice(iptr[q], iptr[q + 1])
+        i0[sl] = jb["i0"]
+        if jb["nsrc"] == 3:
+            i1[sl], i2[sl] = jb["i1"], jb["i2"]
+        vptr[q] = vpos
+        vparts.append(jb["vals"])
+        vpos += jb["vals"].size
+        if jb["e0"] is not None:
+            eptr[q] = epos
+            e0p.append(jb["e0"])
+            e1p.append(jb["e1"])
+            epos += jb["nr"]
+    cat = lambda xs, dt: np.concatenate(xs).astype(dt) if xs else np.zeros(0, dt)  # noqa: E731
     return SolvePlan(
-        n=n,
-        RT=RT,
-        tile_out=np.array(tile_out, dtype=np.int32),
-        tile_self=np.array(tile_self, dtype=np.int32),
-        tile_nrows=np.array(tile_nrows, dtype=np.int32),
-        tile_kptr=np.array(kptr, dtype=np.int64),
-        tile_vptr=np.array(vptr, dtype=np.int64),
-        cols=np.concatenate(cols_parts) if cols_parts else np.zeros(0, np.int32),
-        vals=np.concatenate(vals_parts) if vals_parts else np.zeros(0),
-        launch_ptr=np.array(launch_ptr, dtype=np.int32),
-        n_forward_launches=n_fwd,
+        n=n, nU=nU, job_K=K,
+        job_MT=np.array([jobs[j]["MT"] for j in order], dtype=np.int32),
+        job_nr=np.array([jobs[j]["nr"] for j in order], dtype=np.int32),
+        job_nsrc=np.array([jobs[j]["nsrc"] for j in order], dtype=np.int32),
+        job_out0=np.array([jobs[j]["out0"] for j in order], dtype=np.int32),
+        job_ystore=np.array([jobs[j]["ystore"] for j in order], dtype=np.int32),
+        job_iptr=iptr[:-1].copy(), job_vptr=vptr, job_eptr=eptr,
+        i0=i0, i1=i1, i2=i2, e0=cat(e0p, np.int32), e1=cat(e1p, np.int32), vals=cat(vparts, np.float64),
+        launch_ptr=np.array(launch_ptr, dtype=np.int32), n_forward_launches=n_fwd,
     )
 
 
 def apply_plan_host(plan: SolvePlan, b_perm: np.ndarray) -> np.ndarray:
-    """Numpy emulation of the CUDA sweeps (tests only; O(ntiles) python loop)."""
+    """Numpy emulation of the CUDA sweeps, job by job (tests only)."""
     b = np.asarray(b_perm, dtype=np.float64)
     squeeze = b.ndim == 1
     if squeeze:
         b = b[:, None]
-    n, RT = plan.n, plan.RT
-    Z = np.zeros((2 * n, b.shape[1]))
+    n = plan.n
+    Z = np.zeros((plan.z_rows, b.shape[1]))
     Z[:n] = b
-    for t in range(len(plan.tile_out)):
-        k0, k1 = plan.tile_kptr[t], plan.tile_kptr[t + 1]
-        K = k1 - k0
-        V = plan.vals[plan.tile_vptr[t] : plan.tile_vptr[t] + K * RT].reshape(K, RT)
-        nr = plan.tile_nrows[t]
-        acc = V[:, :nr].T @ Z[plan.cols[k0:k1]]
-        if plan.tile_self[t] >= 0:
-            acc += Z[plan.tile_self[t] : plan.tile_self[t] + nr]
-        Z[plan.tile_out[t] : plan.tile_out[t] + nr] = acc
-    x = Z[n:]
+    for q in range(len(plan.job_K)):
+        K, MT, nr = int(plan.job_K[q]), int(plan.job_MT[q]), int(plan.job_nr[q])
+        sl = slice(plan.job_iptr[q], plan.job_iptr[q] + K)
+        x = Z[plan.i0[sl]]
+        if plan.job_nsrc[q] == 3:
+            for extra in (plan.i1[sl], plan.i2[sl]):
+                has = extra >= 0
+                x = x.copy()
+                x[has] += Z[extra[has]]
+        if plan.job_ystore[q] >= 0:
+            Z[plan.job_ystore[q] : plan.job_ystore[q] + K] = x
+        if MT == 0:
+            continue
+        V = plan.vals[plan.job_vptr[q] : plan.job_vptr[q] + K * MT].reshape(K, MT)
+        acc = V[:, :nr].T @ x
+        if plan.job_eptr[q] >= 0:
+            es = slice(plan.job_eptr[q], plan.job_eptr[q] + nr)
+            for extra in (plan.e0[es], plan.e1[es]):
+                has = extra >= 0
+                acc[has] += Z[extra[has]]
+        Z[plan.job_out0[q] : plan.job_out0[q] + nr] = acc
+    x = Z[:n]
     return x[:, 0] if squeeze else x

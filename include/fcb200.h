@@ -44,18 +44,24 @@ typedef enum fcb_status {
  * Replaces the MUMPS factors held by dolfin.LUSolver after set_operator
  * (src/flowcontrol/flowsolver.py:694-697, 812-814). */
 typedef struct fcb_plan {
-    int32_t n;               /* free unknowns                                       */
-    int32_t rt;              /* rows per tile (values are stored [K][rt] per tile)  */
-    int32_t ntiles;
-    const int32_t* tile_out;   /* [ntiles] first output row in Z (2n rows)          */
-    const int32_t* tile_self;  /* [ntiles] row added to the result, or -1           */
-    const int32_t* tile_nrows; /* [ntiles] valid rows (<= rt)                       */
-    const int64_t* tile_kptr;  /* [ntiles+1] offsets into cols                      */
-    const int64_t* tile_vptr;  /* [ntiles] offsets into vals                        */
-    const int32_t* cols;       /* [tile_kptr[ntiles]] gathered Z rows               */
-    const double* vals;        /* [sum K*rt]                                        */
+    int32_t n;                /* free unknowns                                                    */
+    int32_t nU;               /* rows of the update-vector region (Z has 2n + nU rows)            */
+    int32_t njobs;
+    const int32_t* job_K;      /* [njobs] gathered input rows                                      */
+    const int32_t* job_MT;     /* [njobs] tile height of the value block: 0 (store only), 8, 16, 32 */
+    const int32_t* job_nr;     /* [njobs] valid output rows (<= MT)                                */
+    const int32_t* job_nsrc;   /* [njobs] 1: x_k = Z[i0[k]]; 3: + Z[i1[k]] + Z[i2[k]] (-1 = absent) */
+    const int32_t* job_out0;   /* [njobs] first output row in Z                                    */
+    const int32_t* job_ystore; /* [njobs] first row to store the gathered x_k to, or -1            */
+    const int64_t* job_iptr;   /* [njobs] offsets into i0/i1/i2                                    */
+    const int64_t* job_vptr;   /* [njobs] offsets into vals ([K][MT] per job, even)                */
+    const int64_t* job_eptr;   /* [njobs] offsets into e0/e1 (output-row gathers), or -1           */
+    const int32_t *i0, *i1, *i2;
+    const int32_t *e0, *e1;
+    const double* vals;
     int32_t nlaunch;
-    const int32_t* launch_ptr; /* [nlaunch+1] tile ranges; tiles of a launch are independent */
+    const int32_t* launch_ptr; /* [nlaunch+1] job ranges; jobs of a launch are independent          */
+    int32_t n_forward_launches;
 } fcb_plan;
 
 /* Everything that is constant over a run and shared by the whole ensemble.

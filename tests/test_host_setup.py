@@ -133,19 +133,34 @@ def test_multifrontal_matches_superlu_and_plan_matches_factor(small):
     Aff = A[sym.perm][:, sym.perm].tocsc()
     xref = spla.splu(Aff).solve(b)
     assert np.linalg.norm(x - xref) / np.linalg.norm(xref) < 1e-11
-    for RT in (4, 8, 16):
-        plan = build_plan(fac, RT=RT)
+    for max_mt in (8, 16, 32):
+        plan = build_plan(fac, max_mt=max_mt, target_jobs=40)
         assert np.abs(apply_plan_host(plan, b) - x).max() < 1e-12 * np.abs(x).max()
-        # every output row of Z written exactly once per sweep, tiles of a launch never read what they write
-        fw = plan.tile_self >= 0
-        rows_b = np.concatenate([np.arange(o, o + r) for o, r in zip(plan.tile_out[~fw], plan.tile_nrows[~fw])])
-        assert sorted(rows_b.tolist()) == list(range(sym.n, 2 * sym.n))
+        assert set(np.unique(plan.job_MT).tolist()) <= {0, 8, 16, 32} and plan.job_MT.max() <= max_mt
+        # every x row and every y row is produced exactly once; jobs of one launch never read rows
+        # that the same launch writes
+        n = sym.n
+        bw = np.arange(len(plan.job_K)) >= plan.launch_ptr[plan.n_forward_launches]
+        rows_x = np.concatenate([np.arange(o, o + r) for o, r in zip(plan.job_out0[bw], plan.job_nr[bw])])
+        assert sorted(rows_x.tolist()) == list(range(n))
+        ys = plan.job_ystore >= 0
+        rows_y = np.concatenate([np.arange(o, o + k) for o, k in zip(plan.job_ystore[ys], plan.job_K[ys])])
+        assert sorted(rows_y.tolist()) == list(range(n, 2 * n))
         for l in range(len(plan.launch_ptr) - 1):
-            t0, t1 = plan.launch_ptr[l], plan.launch_ptr[l + 1]
-            written = set()
-            for t in range(t0, t1):
-                written |= set(range(plan.tile_out[t], plan.tile_out[t] + plan.tile_nrows[t]))
-            read = set(plan.cols[plan.tile_kptr[t0] : plan.tile_kptr[t1]].tolist())
+            written, read = set(), set()
+            for q in range(plan.launch_ptr[l], plan.launch_ptr[l + 1]):
+                K, nr = int(plan.job_K[q]), int(plan.job_nr[q])
+                written |= set(range(plan.job_out0[q], plan.job_out0[q] + nr)) if plan.job_MT[q] else set()
+                if plan.job_ystore[q] >= 0:
+                    written |= set(range(plan.job_ystore[q], plan.job_ystore[q] + K))
+                sl = slice(plan.job_iptr[q], plan.job_iptr[q] + K)
+                read |= set(plan.i0[sl].tolist())
+                if plan.job_nsrc[q] == 3:
+                    read |= set(plan.i1[sl].tolist()) | set(plan.i2[sl].tolist())
+                if plan.job_eptr[q] >= 0:
+                    es = slice(plan.job_eptr[q], plan.job_eptr[q] + nr)
+                    read |= set(plan.e0[es].tolist()) | set(plan.e1[es].tolist())
+            read.discard(-1)
             assert not (written & read)
 
 
