@@ -10,8 +10,8 @@
 //
 // One time step (reference: FlowSolver.step, flowsolver.py:703-799):
 //   k_rhs_build   rhs = a_n + b_{n-1} (BDF2) | a_n/2 (BDF1) + sum_k u_ctrl_k (f_k - l_k)   [solver row order]
-//   k_tile_gemm   forward sweep  (one launch per elimination-tree height): y_t, u_t = sum_children u_c - E_t y_t
-//   k_tile_gemm   backward sweep (one launch per elimination-tree depth):  x_t = F11^-1 y_t - G_t x_struct(t)
+//   k_front_sweep forward sweep  (one launch per elimination-tree height): y_t, u_t = sum_children u_c - E_t y_t
+//   k_front_sweep backward sweep (one launch per elimination-tree depth):  x_t = F11^-1 y_t - G_t x_struct(t)
 //   k_post        un-permute, Dirichlet values, non-finite flag
 //   k_element     per cell: convection N(u) (7-point Radon rule) + mass M u, coloured scatter into
 //                 a = (2/dt) M u - 2 N(u),  b = -(1/2dt) M u + N(u);  energy partials u.(M u)
@@ -41,12 +41,6 @@ __constant__ double c_phi[7][6];      // phi_a(q)
 __constant__ double c_dphi[7][6][2];  // reference gradients
 __constant__ double c_w[7];           // quadrature weights (sum = 1/2)
 __constant__ double c_mass[6][6];     // reference mass matrix (int phi_a phi_b over the unit triangle)
-
-// One dense tile job of the multifrontal sweeps (multifrontal.py: SolvePlan).
-struct Job {
-    int K, MT, nr, nsrc, out0, ystore;
-    long long iptr, vptr, eptr;
-};
 
 // ----------------------------------------------------------------------------------------------
 // kernels
@@ -186,147 +180,195 @@ __global__ void __launch_bounds__(256) k_rhs_build(int n, int Nv, const int* __r
     Z[(size_t)r * ldb + b] = v;
 }
 
-// Dense tile GEMMs of the multifrontal sweeps.  One warp = one job x (32*TPT) trajectories:
-//   x_k   = Z[i0[k]] (+ Z[i1[k]] + Z[i2[k]])          gathered input rows (K of them)
-//   acc_r = sum_k V[k][r] * x_k                        r < MT, V stored k-major, warp-uniform loads
+// ----------------------------------------------------------------------------------------------
+// Multifrontal sweeps: dense tile products on the FP64 tensor cores, fed by bulk-async (TMA) copies.
+//
+// One job (multifrontal.py: SolvePlan) = 8*nrb output rows x all trajectories of the CTA's slab:
+//   x_k   = Z[i0[k]] (+ Z[i1[k]] + Z[i2[k]])          gathered input rows, k < K4
+//   acc   = sum_k V[:,k] x_k                           mma.sync m8n8k4 f64: M = rows, N = trajectories
 //   Z[out0 + r] = acc_r (+ Z[e0[r]] + Z[e1[r]])        r < nr
-// The x rows of the next KC k's are prefetched into registers while the current chunk is multiplied.
-// No shared memory, no barriers, no atomics: every Z row is written by exactly one job.
-constexpr int TG_KC = 4;
+// CTA = SV_MAXW consumer warps (32 trajectories each, up to 256 per slab) + 1 producer warp.  The
+// producer streams, per stage of a ring, up to SV_SLOTS gathered rows (one cp.async.bulk per row,
+// 8*NT bytes each) and the matching slice of V (one cp.async.bulk; the host packs V in A-fragment
+// order so a fragment is one conflict-free 256-byte shared-memory read) and signals an mbarrier;
+// consumers multiply out of shared memory and hand the stage back through a second mbarrier.
+// Row stride in shared memory is NT+8 doubles (== 8 mod 16), which makes the 4x8 B-fragment reads
+// conflict-free.  CTAs are persistent: CTA c runs jobs c, c+gridDim.x, ... of the launch and the
+// ring keeps filling across job boundaries.  Every Z row is written by exactly one job: no atomics.
+// ----------------------------------------------------------------------------------------------
+constexpr int SV_SLOTS = 12;   // gathered rows per stage (3 planes x 4 k for nsrc == 3, 12 k otherwise)
+constexpr int SV_STAGES = 4;
+constexpr int SV_MAXW = 8;     // consumer warps per CTA
+constexpr int SV_XS_MAX = 32 * SV_MAXW + 8;
+constexpr int SV_STAGE_BYTES = SV_SLOTS * SV_XS_MAX * 8 + SV_SLOTS * 32 * 8;  // rows + V slice (4 row blocks)
+constexpr int SV_SMEM_BYTES = SV_STAGES * SV_STAGE_BYTES + 2 * SV_STAGES * 8;
 
-template <int TPT>
-__device__ __forceinline__ void tg_load_x(const double* Z, size_t ldb, int t0, bool has1, int nsrc, int r0, int r1,
-                                          int r2, double (&x)[TPT]) {
-    const double* z0 = Z + (size_t)r0 * ldb + t0;
-    x[0] = z0[0];
-    if (TPT == 2) x[TPT - 1] = has1 ? z0[32] : 0.0;
-    if (nsrc == 3) {
-        if (r1 >= 0) {
-            const double* z1 = Z + (size_t)r1 * ldb + t0;
-            x[0] += z1[0];
-            if (TPT == 2 && has1) x[TPT - 1] += z1[32];
-        }
-        if (r2 >= 0) {
-            const double* z2 = Z + (size_t)r2 * ldb + t0;
-            x[0] += z2[0];
-            if (TPT == 2 && has1) x[TPT - 1] += z2[32];
-        }
-    }
+struct SolveJob {
+    int K, nrb, nr, nsrc, out0, ystore;
+    long long iptr, vptr, eptr;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c[0]), "+d"(c[1])
+                 : "d"(a), "d"(b));
 }
 
-template <int MT, int TPT>
-__device__ __forceinline__ void tg_run(const Job jb, const int* __restrict__ i0, const int* __restrict__ i1,
-                                       const int* __restrict__ i2, const int* __restrict__ e0,
-                                       const int* __restrict__ e1, const double* __restrict__ vals, double* Z,
-                                       size_t ldb, int t0, bool has1) {
-    double acc[MT > 0 ? MT : 1][TPT];
-#pragma unroll
-    for (int r = 0; r < (MT > 0 ? MT : 1); ++r)
-#pragma unroll
-        for (int j = 0; j < TPT; ++j) acc[r][j] = 0.0;
-    const int* p0 = i0 + jb.iptr;
-    const int* p1 = i1 + jb.iptr;
-    const int* p2 = i2 + jb.iptr;
-    const double2* v = reinterpret_cast<const double2*>(vals + jb.vptr);
-    const int K = jb.K, nsrc = jb.nsrc;
-    double xc[TG_KC][TPT], xn[TG_KC][TPT];
-    auto load_chunk = [&](int k0, double (&x)[TG_KC][TPT]) {
-#pragma unroll
-        for (int c = 0; c < TG_KC; ++c) {
-            const int k = k0 + c;
-            if (k < K) {
-                const int r0 = __ldg(p0 + k);
-                int r1 = -1, r2 = -1;
-                if (nsrc == 3) { r1 = __ldg(p1 + k); r2 = __ldg(p2 + k); }
-                tg_load_x<TPT>(Z, ldb, t0, has1, nsrc, r0, r1, r2, x[c]);
-            } else {
-#pragma unroll
-                for (int j = 0; j < TPT; ++j) x[c][j] = 0.0;
+// grid = (persistent CTAs, slabs of 256 trajectories), block = (32, consumer warps + 1)
+__global__ void __launch_bounds__(32 * (SV_MAXW + 1), 2)
+    k_front_sweep(const SolveJob* __restrict__ jobs, int njobs, const int* __restrict__ i0, const int* __restrict__ i1,
+                  const int* __restrict__ i2, const int* __restrict__ e0, const int* __restrict__ e1,
+                  const double* __restrict__ vals, double* Z, int ldb) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x, wid = threadIdx.y;
+    const int nwarp_c = blockDim.y - 1;  // consumer warps launched
+    const int slab0 = blockIdx.y * (32 * SV_MAXW);
+    const int NT = min(32 * nwarp_c, ldb - slab0);  // trajectories of this CTA (multiple of 32)
+    const int nact = NT >> 5;                       // active consumer warps
+    const int XS = NT + 8;                          // shared-memory row stride in doubles
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t bar_full = sbase + SV_STAGES * SV_STAGE_BYTES;
+    const uint32_t bar_empty = bar_full + SV_STAGES * 8;
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        for (int s = 0; s < SV_STAGES; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, nact);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const size_t L = (size_t)ldb;
+
+    if (wid == nwarp_c) {
+        // ---------------- producer warp ----------------
+        uint32_t it = 0;
+        for (int j = blockIdx.x; j < njobs; j += gridDim.x) {
+            const SolveJob jb = jobs[j];
+            const int K4 = (jb.K + 3) & ~3;
+            const int kc = (jb.nsrc == 3) ? SV_SLOTS / 3 : SV_SLOTS;
+            for (int k0 = 0; k0 < K4; k0 += kc, ++it) {
+                const int nk = min(kc, K4 - k0);
+                const int nrows = nk * jb.nsrc;  // <= SV_SLOTS <= 32: one row per lane
+                int row = -1, slot = 0;
+                if (lane < nrows) {
+                    const int p = lane / nk, k = lane - p * nk;
+                    const int* ip = (p == 0) ? i0 : (p == 1 ? i1 : i2);
+                    row = __ldg(ip + jb.iptr + k0 + k);
+                    slot = p * kc + k;
+                }
+                const int s = it % SV_STAGES;
+                const uint32_t full = bar_full + 8 * s;
+                mbar_wait(bar_empty + 8 * s, ((it / SV_STAGES) & 1) ^ 1);
+                const uint32_t sx = sbase + s * SV_STAGE_BYTES;
+                if (lane == 0) {
+                    const uint32_t vbytes = (uint32_t)nk * 64u * (uint32_t)jb.nrb;
+                    mbar_expect_tx(full, (uint32_t)nrows * (uint32_t)NT * 8u + vbytes);
+                    if (vbytes) bulk_g2s(sx + SV_SLOTS * SV_XS_MAX * 8, vals + jb.vptr + (size_t)k0 * 8 * jb.nrb, vbytes, full);
+                }
+                __syncwarp();
+                if (row >= 0) bulk_g2s(sx + (uint32_t)(slot * XS) * 8u, Z + (size_t)row * L + slab0, (uint32_t)NT * 8u, full);
             }
         }
-    };
-    load_chunk(0, xc);
-    for (int k0 = 0; k0 < K; k0 += TG_KC) {
-        if (k0 + TG_KC < K) load_chunk(k0 + TG_KC, xn);
-        if (jb.ystore >= 0) {
+        return;
+    }
+    if (wid >= nact) return;
+
+    // ---------------- consumer warps ----------------
+    const int gid = lane >> 2, tig = lane & 3;
+    const int t0 = slab0 + wid * 32;  // first trajectory of this warp
+    uint32_t it = 0;
+    for (int j = blockIdx.x; j < njobs; j += gridDim.x) {
+        const SolveJob jb = jobs[j];
+        const int K4 = (jb.K + 3) & ~3;
+        const int nrb = jb.nrb;
+        const int kc = (jb.nsrc == 3) ? SV_SLOTS / 3 : SV_SLOTS;
+        double acc[4][4][2];
 #pragma unroll
-            for (int c = 0; c < TG_KC; ++c)
-                if (k0 + c < K) {
-                    double* zy = Z + (size_t)(jb.ystore + k0 + c) * ldb + t0;
-                    zy[0] = xc[c][0];
-                    if (TPT == 2 && has1) zy[32] = xc[c][TPT - 1];
-                }
-        }
-        if (MT > 0) {
+        for (int rb = 0; rb < 4; ++rb)
 #pragma unroll
-            for (int c = 0; c < TG_KC; ++c) {
-                if (k0 + c < K) {  // warp-uniform
-                    const double2* vk = v + (size_t)(k0 + c) * (MT / 2);
+            for (int nb = 0; nb < 4; ++nb) acc[rb][nb][0] = acc[rb][nb][1] = 0.0;
+        if (jb.eptr >= 0) {
+            // the children's update rows that land on these output rows seed the accumulators
 #pragma unroll
-                    for (int r = 0; r < MT; r += 2) {
-                        const double2 w = __ldg(vk + r / 2);
+            for (int rb = 0; rb < 4; ++rb) {
+                const int r = rb * 8 + gid;
+                if (rb < nrb && r < jb.nr) {
+                    const int ea = __ldg(e0 + jb.eptr + r), eb = __ldg(e1 + jb.eptr + r);
 #pragma unroll
-                        for (int j = 0; j < TPT; ++j) {
-                            acc[r][j] = fma(w.x, xc[c][j], acc[r][j]);
-                            acc[r + 1][j] = fma(w.y, xc[c][j], acc[r + 1][j]);
+                    for (int nb = 0; nb < 4; ++nb) {
+                        const int col = t0 + nb * 8 + 2 * tig;
+                        if (ea >= 0) {
+                            const double2 v = *reinterpret_cast<const double2*>(Z + (size_t)ea * L + col);
+                            acc[rb][nb][0] += v.x;
+                            acc[rb][nb][1] += v.y;
+                        }
+                        if (eb >= 0) {
+                            const double2 v = *reinterpret_cast<const double2*>(Z + (size_t)eb * L + col);
+                            acc[rb][nb][0] += v.x;
+                            acc[rb][nb][1] += v.y;
                         }
                     }
                 }
             }
         }
+        for (int k0 = 0; k0 < K4; k0 += kc, ++it) {
+            const int nk = min(kc, K4 - k0);
+            const int s = it % SV_STAGES;
+            mbar_wait(bar_full + 8 * s, (it / SV_STAGES) & 1);
+            const double* xs = reinterpret_cast<const double*>(smem + s * SV_STAGE_BYTES) + wid * 32 + gid;
+            const double* vs = reinterpret_cast<const double*>(smem + s * SV_STAGE_BYTES + SV_SLOTS * SV_XS_MAX * 8) + lane;
+            for (int g = 0; g < nk; g += 4) {
+                double a[4];
 #pragma unroll
-        for (int c = 0; c < TG_KC; ++c)
+                for (int rb = 0; rb < 4; ++rb) a[rb] = (rb < nrb) ? vs[((g >> 2) * nrb + rb) * 32] : 0.0;
+                const double* xr = xs + (g + tig) * XS;
 #pragma unroll
-            for (int j = 0; j < TPT; ++j) xc[c][j] = xn[c][j];
-    }
-    if (MT > 0) {
+                for (int nb = 0; nb < 4; ++nb) {
+                    double bv = xr[nb * 8];
+                    if (jb.nsrc == 3) bv += xr[kc * XS + nb * 8] + xr[2 * kc * XS + nb * 8];
+                    if (jb.ystore >= 0 && k0 + g + tig < jb.K) Z[(size_t)(jb.ystore + k0 + g + tig) * L + t0 + nb * 8 + gid] = bv;
 #pragma unroll
-        for (int r = 0; r < MT; ++r) {
-            if (r < jb.nr) {
-                double s0 = acc[r][0], s1 = acc[r][TPT - 1];
-                if (jb.eptr >= 0) {
-                    const int a = __ldg(e0 + jb.eptr + r), b = __ldg(e1 + jb.eptr + r);
-                    if (a >= 0) {
-                        const double* za = Z + (size_t)a * ldb + t0;
-                        s0 += za[0];
-                        if (TPT == 2 && has1) s1 += za[32];
-                    }
-                    if (b >= 0) {
-                        const double* zb = Z + (size_t)b * ldb + t0;
-                        s0 += zb[0];
-                        if (TPT == 2 && has1) s1 += zb[32];
-                    }
+                    for (int rb = 0; rb < 4; ++rb)
+                        if (rb < nrb) dmma(acc[rb][nb], a[rb], bv);
                 }
-                double* zo = Z + (size_t)(jb.out0 + r) * ldb + t0;
-                zo[0] = s0;
-                if (TPT == 2 && has1) zo[32] = s1;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_empty + 8 * s);
+        }
+#pragma unroll
+        for (int rb = 0; rb < 4; ++rb) {
+            const int r = rb * 8 + gid;
+            if (rb < nrb && r < jb.nr) {
+                double* zo = Z + (size_t)(jb.out0 + r) * L + t0 + 2 * tig;
+#pragma unroll
+                for (int nb = 0; nb < 4; ++nb) *reinterpret_cast<double2*>(zo + nb * 8) = make_double2(acc[rb][nb][0], acc[rb][nb][1]);
             }
         }
-    }
-}
-
-// grid = (ceil(njobs / TG_WARPS), ceil(ldb / (32*TPT))), block = (32, TG_WARPS)
-constexpr int TG_WARPS = 4;
-
-template <int MAXMT, int TPT>
-__global__ void __launch_bounds__(32 * TG_WARPS) k_tile_gemm(const Job* __restrict__ jobs, int njobs,
-                                                             const int* __restrict__ i0, const int* __restrict__ i1,
-                                                             const int* __restrict__ i2, const int* __restrict__ e0,
-                                                             const int* __restrict__ e1,
-                                                             const double* __restrict__ vals, double* Z, int ldb) {
-    const int j = blockIdx.x * TG_WARPS + threadIdx.y;
-    if (j >= njobs) return;
-    const int t0 = blockIdx.y * 32 * TPT + threadIdx.x;
-    if (t0 >= ldb) return;
-    const bool has1 = (TPT == 2) && (t0 + 32 < ldb);
-    const Job jb = jobs[j];
-    switch (jb.MT) {  // warp-uniform
-        case 0: tg_run<0, TPT>(jb, i0, i1, i2, e0, e1, vals, Z, (size_t)ldb, t0, has1); break;
-        case 8: tg_run<8, TPT>(jb, i0, i1, i2, e0, e1, vals, Z, (size_t)ldb, t0, has1); break;
-        case 16: tg_run<16, TPT>(jb, i0, i1, i2, e0, e1, vals, Z, (size_t)ldb, t0, has1); break;
-        default:
-            if (MAXMT >= 32) tg_run<(MAXMT >= 32 ? 32 : 16), TPT>(jb, i0, i1, i2, e0, e1, vals, Z, (size_t)ldb, t0, has1);
-            break;
     }
 }
 
@@ -442,8 +484,8 @@ __global__ void k_log(int na, int ns, const double* __restrict__ dE, const doubl
 // host side
 // ----------------------------------------------------------------------------------------------
 struct DevPlan {
-    int n = 0, nU = 0, njobs = 0, nlaunch = 0, maxmt = 0;
-    Job* jobs = nullptr;
+    int n = 0, nU = 0, njobs = 0, nlaunch = 0;
+    SolveJob* jobs = nullptr;
     int *i0 = nullptr, *i1 = nullptr, *i2 = nullptr, *e0 = nullptr, *e1 = nullptr;
     double* vals = nullptr;
     std::vector<int> launch_ptr;
@@ -453,7 +495,7 @@ struct DevPlan {
 }  // namespace
 
 struct fcb_context {
-    int device = 0;
+    int device = 0, num_sms = 0;
     cudaStream_t stream = nullptr;
     std::string error;
     int B = 0, ldb = 0;
@@ -536,22 +578,26 @@ int upload_plan(fcb_context* h, DevPlan& d, const fcb_plan& p) {
     d.njobs = p.njobs;
     d.nlaunch = p.nlaunch;
     d.n_forward = p.n_forward_launches;
-    std::vector<Job> jobs(p.njobs);
+    std::vector<SolveJob> jobs(p.njobs);
     size_t nidx = 0, nvals = 0, nepi = 0;
-    d.maxmt = 0;
+    const int zrow = 2 * p.n + p.nU;
     for (int i = 0; i < p.njobs; ++i) {
-        Job& j = jobs[i];
-        j.K = p.job_K[i]; j.MT = p.job_MT[i]; j.nr = p.job_nr[i]; j.nsrc = p.job_nsrc[i];
+        SolveJob& j = jobs[i];
+        j.K = p.job_K[i]; j.nrb = p.job_nrb[i]; j.nr = p.job_nr[i]; j.nsrc = p.job_nsrc[i];
         j.out0 = p.job_out0[i]; j.ystore = p.job_ystore[i];
         j.iptr = p.job_iptr[i]; j.vptr = p.job_vptr[i]; j.eptr = p.job_eptr[i];
-        if (j.MT != 0 && j.MT != 8 && j.MT != 16 && j.MT != 32)
-            return fail(h, FCB_ERR_INVALID, "plan job %d: tile height %d not in {0,8,16,32}", i, j.MT);
-        if (j.nr > j.MT || j.K < 0 || (j.vptr & 1)) return fail(h, FCB_ERR_INVALID, "plan job %d is malformed", i);
-        if (j.MT > d.maxmt) d.maxmt = j.MT;
-        nidx = std::max(nidx, (size_t)(j.iptr + j.K));
-        nvals = std::max(nvals, (size_t)(j.vptr + (long long)j.K * j.MT));
+        if (j.nrb < 0 || j.nrb > 4) return fail(h, FCB_ERR_INVALID, "plan job %d: %d row blocks not in [0,4]", i, j.nrb);
+        if (j.nr > 8 * j.nrb || j.K < 0 || (j.vptr & 1) || (j.nsrc != 1 && j.nsrc != 3) || j.out0 + j.nr > zrow ||
+            (j.ystore >= 0 && j.ystore + j.K > zrow))
+            return fail(h, FCB_ERR_INVALID, "plan job %d is malformed", i);
+        const long long K4 = (j.K + 3) & ~3;
+        nidx = std::max(nidx, (size_t)(j.iptr + K4));
+        nvals = std::max(nvals, (size_t)(j.vptr + K4 * 8 * j.nrb));
         if (j.eptr >= 0) nepi = std::max(nepi, (size_t)(j.eptr + j.nr));
     }
+    for (size_t k = 0; k < nidx; ++k)
+        if (p.i0[k] < 0 || p.i0[k] > zrow || p.i1[k] < 0 || p.i1[k] > zrow || p.i2[k] < 0 || p.i2[k] > zrow)
+            return fail(h, FCB_ERR_INVALID, "plan gather index %zu out of range", k);
     TRY(upload(h, &d.jobs, jobs.data(), jobs.size()));
     CK(cudaStreamSynchronize(h->stream));  // jobs vector goes out of scope
     TRY(upload(h, &d.i0, p.i0, nidx));
@@ -642,21 +688,17 @@ int enqueue_measure(fcb_context* h, const double* up) {
 }
 
 int enqueue_solve(fcb_context* h, const DevPlan& pl, PhaseMark* pm) {
-    const bool tpt2 = (h->ldb % 64) == 0;
-    dim3 block(32, TG_WARPS);
+    const int nwarp_c = std::min(SV_MAXW, h->ldb / 32);
+    const int nslab = (h->ldb + 32 * SV_MAXW - 1) / (32 * SV_MAXW);
+    const int resident = std::max(1, 2 * h->num_sms / nslab);  // 2 CTAs per SM (shared memory + registers)
+    dim3 block(32, nwarp_c + 1);
     for (int l = 0; l < pl.nlaunch; ++l) {
         if (pm && l == pl.n_forward) pm->mark(FCB_PHASE_BACKWARD);
         const int j0 = pl.launch_ptr[l], nj = pl.launch_ptr[l + 1] - j0;
         if (nj <= 0) continue;
-        dim3 grid((nj + TG_WARPS - 1) / TG_WARPS, tpt2 ? h->ldb / 64 : h->ldb / 32);
-#define TG_LAUNCH(MAXMT, TPT) \
-    k_tile_gemm<MAXMT, TPT><<<grid, block, 0, h->stream>>>(pl.jobs + j0, nj, pl.i0, pl.i1, pl.i2, pl.e0, pl.e1, pl.vals, h->Z, h->ldb)
-        if (pl.maxmt >= 32) {
-            if (tpt2) TG_LAUNCH(32, 2); else TG_LAUNCH(32, 1);
-        } else {
-            if (tpt2) TG_LAUNCH(16, 2); else TG_LAUNCH(16, 1);
-        }
-#undef TG_LAUNCH
+        dim3 grid(std::min(nj, resident), nslab);
+        k_front_sweep<<<grid, block, SV_SMEM_BYTES, h->stream>>>(pl.jobs + j0, nj, pl.i0, pl.i1, pl.i2, pl.e0, pl.e1,
+                                                                 pl.vals, h->Z, h->ldb);
         h->launches += 1;
     }
     if (pm && pl.n_forward >= pl.nlaunch) pm->mark(FCB_PHASE_BACKWARD);
@@ -667,9 +709,7 @@ int enqueue_solve(fcb_context* h, const DevPlan& pl, PhaseMark* pm) {
 // one step with the current (order, parity); u_ctrl already in h->uctrl
 int enqueue_step(fcb_context* h, int order, int parity, PhaseMark* pm) {
     const DevPlan& pl = h->plan[order - 1];
-    double* cur = h->up[parity];
     double* nxt = h->up[1 - parity];
-    (void)cur;
     if (pm) pm->mark(FCB_PHASE_RHS);
     {
         dim3 grid((h->n + 7) / 8, h->ldb / 32), block(32, 8);
@@ -793,6 +833,8 @@ int create_impl(fcb_context* h, const fcb_problem* p, int B) {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, h->device));
     if (prop.major < 10) return fail(h, FCB_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", h->device, prop.major, prop.minor);
+    h->num_sms = prop.multiProcessorCount;
+    CK(cudaFuncSetAttribute(k_front_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, SV_SMEM_BYTES));
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     for (auto& e : h->ev) CK(cudaEventCreate(&e));
     h->B = B;
@@ -804,6 +846,7 @@ int create_impl(fcb_context* h, const fcb_problem* p, int B) {
     h->dt = p->dt; h->nonlinear = p->nonlinear;
     if (h->n + h->nbc != h->N) return fail(h, FCB_ERR_INVALID, "n_free (%d) + n_bc (%d) != N (%d)", h->n, h->nbc, h->N);
     if (p->plan[0].n != h->n || p->plan[1].n != h->n) return fail(h, FCB_ERR_INVALID, "plan size does not match n_free");
+    if (p->plan[0].nU != p->plan[1].nU) return fail(h, FCB_ERR_INVALID, "the two plans must share one symbolic structure (nU differs)");
     if (!(p->dt > 0)) return fail(h, FCB_ERR_INVALID, "dt must be positive");
     {
         double phi[7][6], dphi[7][6][2], w[7], mass[6][6];
@@ -876,7 +919,7 @@ int create_impl(fcb_context* h, const fcb_problem* p, int B) {
     }
     TRY(upload<double>(h, &h->avec, nullptr, (size_t)h->Nv * L));
     {
-        const size_t zrows = (size_t)2 * h->n + (size_t)std::max(p->plan[0].nU, p->plan[1].nU);
+        const size_t zrows = (size_t)2 * h->n + (size_t)p->plan[0].nU + 1;  // last row stays zero (padded gathers)
         TRY(upload<double>(h, &h->Z, nullptr, zrows * L));
     }
     TRY(upload<double>(h, &h->epart, nullptr, (size_t)h->nblk_total * L));

@@ -6,7 +6,7 @@ forward/backward substitutions per step (``solver.set_operator(A)`` at
 This module is the setup-time half of the replacement: it factorises the same
 matrix on the host along the nested-dissection tree of ordering.py and emits a
 *solve plan* whose per-step application is two sweeps of dense block-row
-products over the whole ensemble (csrc/fcb200.cu, kernel ``fcb_block_rows``).
+FP64 tensor-core tile products over the whole ensemble (csrc/fcb200.cu, kernel ``k_front_sweep``).
 
 Block form used (no triangular factors inside a supernode): for the front of
 supernode t with fully-summed block F11 (w x w) and subdomain-boundary rows
@@ -193,16 +193,18 @@ class BlockFactor:
 
 @dataclass
 class SolvePlan:
-    """Flat job arrays consumed by the CUDA kernel ``k_tile_gemm`` (csrc/fcb200.cu).
+    """Flat job arrays consumed by the CUDA kernel ``k_front_sweep`` (csrc/fcb200.cu).
 
     The kernel works on one buffer Z with rows
         [0, n)          b on entry, x on exit            (solver row order)
         [n, 2n)         y (forward-eliminated RHS)
         [2n, 2n + nU)   update vectors u_t of every supernode (its subdomain-boundary rows)
-    A *job* is a small dense GEMM  acc[MT x traj] = V[MT x K] . x[K x traj]  whose K input rows
-    are gathered as  x_k = Z[i0[k]] (+ Z[i1[k]] + Z[i2[k]] when nsrc == 3, -1 = absent) and whose
-    ``nr`` output rows are written to consecutive rows  Z[out0 + r] = acc[r] (+ Z[e0[r]] + Z[e1[r]]).
-    ``ystore >= 0`` additionally stores the gathered x_k rows to Z[ystore + k] (the job that owns y_t).
+        2n + nU         a row of zeros (``zrow``): the source of padded / absent gathers
+    A *job* is a small dense GEMM  acc[8*nrb x traj] = V[8*nrb x K4] . x[K4 x traj]  (K4 = K rounded up
+    to a multiple of 4, the k-depth of one FP64 tensor-core MMA) whose input rows are gathered as
+    x_k = Z[i0[k]] (+ Z[i1[k]] + Z[i2[k]] when nsrc == 3) and whose ``nr`` output rows are written to
+    consecutive rows  Z[out0 + r] = acc[r] (+ Z[e0[r]] + Z[e1[r]], -1 = absent).
+    ``ystore >= 0`` additionally stores the gathered x_k (k < K) to Z[ystore + k] (the job that owns y_t).
 
         forward  (per supernode t, tiles over its m boundary rows, launches by tree height):
             x_k = b_t[k] + sum_children u_c[..]            (= y_t)
@@ -210,18 +212,20 @@ class SolvePlan:
         backward (tiles over its w own rows, launches by tree depth):
             x_t[r] = (F11^-1 y_t)[r] - (G_t x_struct(t))[r]
 
+    ``vals`` holds every job's V in MMA A-fragment order: [K4/4][nrb][8 rows][4 k] doubles, so the 32
+    lanes of a warp read one 8x4 fragment as 256 contiguous bytes.
     Every output row is produced by exactly one job: no atomics, bit-reproducible."""
 
     n: int
     nU: int
-    job_K: np.ndarray  # int32 [njobs]
-    job_MT: np.ndarray  # int32 tile height of the value block (0 = store-only job, else 8/16/32)
-    job_nr: np.ndarray  # int32 valid output rows (<= MT)
+    job_K: np.ndarray  # int32 [njobs] gathered rows (index arrays are padded to K4 with zrow)
+    job_nrb: np.ndarray  # int32 8-row blocks of the value tile (0 = store-only job, else 1..4)
+    job_nr: np.ndarray  # int32 valid output rows (<= 8*nrb)
     job_nsrc: np.ndarray  # int32 1 or 3
     job_out0: np.ndarray  # int32
     job_ystore: np.ndarray  # int32 (-1 = none)
     job_iptr: np.ndarray  # int64 offsets into i0/i1/i2
-    job_vptr: np.ndarray  # int64 offsets into vals ([K][MT] per job)
+    job_vptr: np.ndarray  # int64 offsets into vals
     job_eptr: np.ndarray  # int64 offsets into e0/e1 (-1 = no epilogue gather)
     i0: np.ndarray
     i1: np.ndarray
@@ -237,37 +241,40 @@ class SolvePlan:
         return int(self.vals.size)
 
     @property
-    def z_rows(self) -> int:
+    def zrow(self) -> int:
         return 2 * self.n + self.nU
 
+    @property
+    def z_rows(self) -> int:
+        return 2 * self.n + self.nU + 1
 
-def _row_tiles(nrows: int, max_mt: int = 32) -> list[tuple[int, int, int]]:
-    """Split ``nrows`` into (r0, nr, MT) chunks with MT in {8,16,32} and little padding."""
+
+def _row_tiles(nrows: int, max_rb: int = 4) -> list[tuple[int, int, int]]:
+    """Split ``nrows`` into (r0, nr, nrb) tiles of at most ``max_rb`` 8-row blocks, evenly sized."""
+    nblk = (nrows + 7) // 8
+    ntile = (nblk + max_rb - 1) // max_rb
     out, r0 = [], 0
-    while nrows - r0 >= max_mt:
-        out.append((r0, max_mt, max_mt))
-        r0 += max_mt
-    rem = nrows - r0
-    while rem > 0:
-        if rem <= 8:
-            mt = 8
-        elif rem <= 16:
-            mt = 16
-        elif rem <= 24 and max_mt >= 16:
-            mt = 16
-        else:
-            mt = 32
-        mt = min(mt, max_mt)
-        nr = min(rem, mt)
-        out.append((r0, nr, mt))
+    for t in range(ntile):
+        nb = nblk // ntile + (1 if t < nblk % ntile else 0)
+        nr = min(8 * nb, nrows - r0)
+        out.append((r0, nr, nb))
         r0 += nr
-        rem -= nr
+    assert r0 == nrows
     return out
 
 
-def build_plan(fac: BlockFactor, max_mt: int = 32, target_jobs: int = 1200) -> SolvePlan:
-    """``max_mt``: largest tile height; levels with few rows use smaller tiles so that a launch
-    has at least ~``target_jobs`` independent warps' worth of work where possible."""
+def _pack_fragments(V: np.ndarray, nrb: int) -> np.ndarray:
+    """V [nr, K] -> A-fragment order [K4/4][nrb][8][4] (zero padded), flattened."""
+    nr, K = V.shape
+    K4 = (K + 3) // 4 * 4
+    P = np.zeros((8 * nrb, K4))
+    P[:nr, :K] = V
+    return P.reshape(nrb, 8, K4 // 4, 4).transpose(2, 0, 1, 3).ravel()
+
+
+def build_plan(fac: BlockFactor, max_rb: int = 4, target_jobs: int = 296) -> SolvePlan:
+    """``max_rb``: largest tile height in 8-row blocks; levels with few rows use shorter tiles so that
+    a launch has at least ~``target_jobs`` independent CTAs' worth of work where possible."""
     sym = fac.sym
     sns = sym.supernodes
     n = sym.n
@@ -277,10 +284,11 @@ def build_plan(fac: BlockFactor, max_mt: int = 32, target_jobs: int = 1200) -> S
         uoff[i + 1] = uoff[i] + len(s.struct)
     nU = int(uoff[-1])
     UB = 2 * n  # first row of the U region
+    ZROW = 2 * n + nU
 
-    def child_sources(i: int, rows: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+    def child_sources(i: int, rows: np.ndarray, absent: int) -> tuple[np.ndarray, np.ndarray]:
         """Z rows of the (at most two) children's update vectors that hit the given solver rows."""
-        srcs = [np.full(len(rows), -1, dtype=np.int64), np.full(len(rows), -1, dtype=np.int64)]
+        srcs = [np.full(len(rows), absent, dtype=np.int64), np.full(len(rows), absent, dtype=np.int64)]
         ch = sym.children[i]
         if len(ch) > 2:
             raise NotImplementedError("solve plan assumes a binary dissection tree")
@@ -297,37 +305,35 @@ def build_plan(fac: BlockFactor, max_mt: int = 32, target_jobs: int = 1200) -> S
     jobs: list[dict] = []
     launches: list[list[int]] = []
 
-    def tile_height_for(level_rows: int) -> int:
-        for mt in (32, 16, 8):
-            if mt <= max_mt and level_rows / mt * 4 >= target_jobs:  # x4 trajectory tiles at B=256
-                return mt
-        return 8
+    def tile_blocks_for(level_rows: list[int]) -> int:
+        for rb in range(max_rb, 1, -1):
+            if sum((r + 8 * rb - 1) // (8 * rb) for r in level_rows) >= target_jobs:
+                return rb
+        return 1
 
     max_h = max(s.height for s in sns)
     for h in range(max_h + 1):
         ids = [i for i, s in enumerate(sns) if s.height == h]
-        level_rows = sum(len(sns[i].struct) for i in ids)
-        mt_cap = tile_height_for(level_rows)
+        rb_cap = tile_blocks_for([len(sns[i].struct) for i in ids])
         cur: list[int] = []
         for i in ids:
             s = sns[i]
             w, m = s.c1 - s.c0, len(s.struct)
             own = np.arange(s.c0, s.c1, dtype=np.int64)
-            a1, a2 = child_sources(i, own)
+            a1, a2 = child_sources(i, own, ZROW)
             nsrc = 3 if sym.children[i] else 1
             E = fac.blocks[i][0]
             if m == 0:
                 if w:
-                    jobs.append(dict(K=w, MT=0, nr=0, nsrc=nsrc, out0=0, ystore=n + s.c0, i0=own, i1=a1, i2=a2,
+                    jobs.append(dict(K=w, nrb=0, nr=0, nsrc=nsrc, out0=0, ystore=n + s.c0, i0=own, i1=a1, i2=a2,
                                      vals=np.zeros(0), e0=None, e1=None))
                     cur.append(len(jobs) - 1)
                 continue
-            e0, e1 = child_sources(i, s.struct)
-            for t, (r0, nr, mt) in enumerate(_row_tiles(m, mt_cap)):
-                V = np.zeros((w, mt))
-                V[:, :nr] = -E[r0 : r0 + nr, :].T
-                jobs.append(dict(K=w, MT=mt, nr=nr, nsrc=nsrc, out0=UB + int(uoff[i]) + r0,
-                                 ystore=(n + s.c0) if t == 0 else -1, i0=own, i1=a1, i2=a2, vals=V.ravel(),
+            e0, e1 = child_sources(i, s.struct, -1)
+            for t, (r0, nr, nrb) in enumerate(_row_tiles(m, rb_cap)):
+                jobs.append(dict(K=w, nrb=nrb, nr=nr, nsrc=nsrc, out0=UB + int(uoff[i]) + r0,
+                                 ystore=(n + s.c0) if t == 0 else -1, i0=own, i1=a1, i2=a2,
+                                 vals=_pack_fragments(-E[r0 : r0 + nr, :], nrb),
                                  e0=e0[r0 : r0 + nr] if nsrc == 3 else None, e1=e1[r0 : r0 + nr] if nsrc == 3 else None))
                 cur.append(len(jobs) - 1)
         if cur:
@@ -336,8 +342,7 @@ def build_plan(fac: BlockFactor, max_mt: int = 32, target_jobs: int = 1200) -> S
     max_d = max(s.depth for s in sns)
     for dpt in range(max_d + 1):
         ids = [i for i, s in enumerate(sns) if s.depth == dpt]
-        level_rows = sum(sns[i].c1 - sns[i].c0 for i in ids)
-        mt_cap = tile_height_for(level_rows)
+        rb_cap = tile_blocks_for([sns[i].c1 - sns[i].c0 for i in ids])
         cur = []
         for i in ids:
             s = sns[i]
@@ -347,35 +352,34 @@ def build_plan(fac: BlockFactor, max_mt: int = 32, target_jobs: int = 1200) -> S
             _, Finv, G = fac.blocks[i]
             full = np.concatenate([Finv, -G], axis=1)  # [w, w+m]
             idx = np.concatenate([n + np.arange(s.c0, s.c1, dtype=np.int64), s.struct.astype(np.int64)])
-            for r0, nr, mt in _row_tiles(w, mt_cap):
-                V = np.zeros((full.shape[1], mt))
-                V[:, :nr] = full[r0 : r0 + nr, :].T
-                jobs.append(dict(K=full.shape[1], MT=mt, nr=nr, nsrc=1, out0=s.c0 + r0, ystore=-1, i0=idx, i1=None,
-                                 i2=None, vals=V.ravel(), e0=None, e1=None))
+            for r0, nr, nrb in _row_tiles(w, rb_cap):
+                jobs.append(dict(K=full.shape[1], nrb=nrb, nr=nr, nsrc=1, out0=s.c0 + r0, ystore=-1, i0=idx, i1=None,
+                                 i2=None, vals=_pack_fragments(full[r0 : r0 + nr, :], nrb), e0=None, e1=None))
                 cur.append(len(jobs) - 1)
         if cur:
             launches.append(cur)
-    # longest jobs first inside each launch (shorter tail), then flatten
+    # longest jobs first inside each launch (the kernel deals them round-robin to persistent CTAs)
     order: list[int] = []
     launch_ptr = [0]
     for cur in launches:
-        cur = sorted(cur, key=lambda j: -(jobs[j]["K"] * max(jobs[j]["MT"], 1)))
+        cur = sorted(cur, key=lambda j: -(jobs[j]["K"] * jobs[j]["nsrc"] + jobs[j]["K"] * jobs[j]["nrb"] + 8 * jobs[j]["nrb"]))
         order += cur
         launch_ptr.append(len(order))
     nj = len(order)
     K = np.array([jobs[j]["K"] for j in order], dtype=np.int32)
+    K4 = (K.astype(np.int64) + 3) // 4 * 4
     iptr = np.zeros(nj + 1, dtype=np.int64)
-    iptr[1:] = np.cumsum(K)
-    i0 = np.empty(int(iptr[-1]), dtype=np.int32)
-    i1 = np.full(int(iptr[-1]), -1, dtype=np.int32)
-    i2 = np.full(int(iptr[-1]), -1, dtype=np.int32)
+    iptr[1:] = np.cumsum(K4)
+    i0 = np.full(int(iptr[-1]), ZROW, dtype=np.int32)
+    i1 = np.full(int(iptr[-1]), ZROW, dtype=np.int32)
+    i2 = np.full(int(iptr[-1]), ZROW, dtype=np.int32)
     vptr = np.zeros(nj, dtype=np.int64)
     eptr = np.full(nj, -1, dtype=np.int64)
     vparts, e0p, e1p = [], [], []
     vpos = epos = 0
     for q, j in enumerate(order):
         jb = jobs[j]
-        sl = slice(iptr[q], iptr[q + 1])
+        sl = slice(iptr[q], iptr[q] + jb["K"])
         i0[sl] = jb["i0"]
         if jb["nsrc"] == 3:
             i1[sl], i2[sl] = jb["i1"], jb["i2"]
@@ -390,7 +394,7 @@ def build_plan(fac: BlockFactor, max_mt: int = 32, target_jobs: int = 1200) -> S
     cat = lambda xs, dt: np.concatenate(xs).astype(dt) if xs else np.zeros(0, dt)  # noqa: E731
     return SolvePlan(
         n=n, nU=nU, job_K=K,
-        job_MT=np.array([jobs[j]["MT"] for j in order], dtype=np.int32),
+        job_nrb=np.array([jobs[j]["nrb"] for j in order], dtype=np.int32),
         job_nr=np.array([jobs[j]["nr"] for j in order], dtype=np.int32),
         job_nsrc=np.array([jobs[j]["nsrc"] for j in order], dtype=np.int32),
         job_out0=np.array([jobs[j]["out0"] for j in order], dtype=np.int32),
@@ -402,7 +406,7 @@ def build_plan(fac: BlockFactor, max_mt: int = 32, target_jobs: int = 1200) -> S
 
 
 def apply_plan_host(plan: SolvePlan, b_perm: np.ndarray) -> np.ndarray:
-    """Numpy emulation of the CUDA sweeps, job by job (tests only)."""
+    """Numpy emulation of the CUDA sweeps, job by job, from the packed arrays (tests only)."""
     b = np.asarray(b_perm, dtype=np.float64)
     squeeze = b.ndim == 1
     if squeeze:
@@ -411,25 +415,25 @@ def apply_plan_host(plan: SolvePlan, b_perm: np.ndarray) -> np.ndarray:
     Z = np.zeros((plan.z_rows, b.shape[1]))
     Z[:n] = b
     for q in range(len(plan.job_K)):
-        K, MT, nr = int(plan.job_K[q]), int(plan.job_MT[q]), int(plan.job_nr[q])
-        sl = slice(plan.job_iptr[q], plan.job_iptr[q] + K)
+        K, nrb, nr = int(plan.job_K[q]), int(plan.job_nrb[q]), int(plan.job_nr[q])
+        K4 = (K + 3) // 4 * 4
+        sl = slice(plan.job_iptr[q], plan.job_iptr[q] + K4)
         x = Z[plan.i0[sl]]
         if plan.job_nsrc[q] == 3:
-            for extra in (plan.i1[sl], plan.i2[sl]):
-                has = extra >= 0
-                x = x.copy()
-                x[has] += Z[extra[has]]
+            x = x + Z[plan.i1[sl]] + Z[plan.i2[sl]]
         if plan.job_ystore[q] >= 0:
-            Z[plan.job_ystore[q] : plan.job_ystore[q] + K] = x
-        if MT == 0:
+            Z[plan.job_ystore[q] : plan.job_ystore[q] + K] = x[:K]
+        if nrb == 0:
             continue
-        V = plan.vals[plan.job_vptr[q] : plan.job_vptr[q] + K * MT].reshape(K, MT)
-        acc = V[:, :nr].T @ x
+        V = plan.vals[plan.job_vptr[q] : plan.job_vptr[q] + K4 * 8 * nrb]
+        V = V.reshape(K4 // 4, nrb, 8, 4).transpose(1, 2, 0, 3).reshape(8 * nrb, K4)
+        acc = V[:nr] @ x
         if plan.job_eptr[q] >= 0:
             es = slice(plan.job_eptr[q], plan.job_eptr[q] + nr)
             for extra in (plan.e0[es], plan.e1[es]):
                 has = extra >= 0
                 acc[has] += Z[extra[has]]
         Z[plan.job_out0[q] : plan.job_out0[q] + nr] = acc
+    assert not Z[plan.zrow].any()
     x = Z[:n]
     return x[:, 0] if squeeze else x

@@ -45,16 +45,16 @@ typedef enum fcb_status {
  * (src/flowcontrol/flowsolver.py:694-697, 812-814). */
 typedef struct fcb_plan {
     int32_t n;                /* free unknowns                                                    */
-    int32_t nU;               /* rows of the update-vector region (Z has 2n + nU rows)            */
+    int32_t nU;               /* rows of the update-vector region (Z has 2n + nU + 1 rows, last = 0) */
     int32_t njobs;
-    const int32_t* job_K;      /* [njobs] gathered input rows                                      */
-    const int32_t* job_MT;     /* [njobs] tile height of the value block: 0 (store only), 8, 16, 32 */
-    const int32_t* job_nr;     /* [njobs] valid output rows (<= MT)                                */
-    const int32_t* job_nsrc;   /* [njobs] 1: x_k = Z[i0[k]]; 3: + Z[i1[k]] + Z[i2[k]] (-1 = absent) */
+    const int32_t* job_K;      /* [njobs] gathered input rows (index lists padded to K4 = 4*ceil(K/4)) */
+    const int32_t* job_nrb;    /* [njobs] 8-row blocks of the value tile: 0 (store only) .. 4        */
+    const int32_t* job_nr;     /* [njobs] valid output rows (<= 8*nrb)                             */
+    const int32_t* job_nsrc;   /* [njobs] 1: x_k = Z[i0[k]]; 3: + Z[i1[k]] + Z[i2[k]] (2n+nU = zero row) */
     const int32_t* job_out0;   /* [njobs] first output row in Z                                    */
     const int32_t* job_ystore; /* [njobs] first row to store the gathered x_k to, or -1            */
     const int64_t* job_iptr;   /* [njobs] offsets into i0/i1/i2                                    */
-    const int64_t* job_vptr;   /* [njobs] offsets into vals ([K][MT] per job, even)                */
+    const int64_t* job_vptr;   /* [njobs] offsets into vals ([K4/4][nrb][8][4] per job: MMA A fragments) */
     const int64_t* job_eptr;   /* [njobs] offsets into e0/e1 (output-row gathers), or -1           */
     const int32_t *i0, *i1, *i2;
     const int32_t *e0, *e1;

@@ -133,10 +133,12 @@ def test_multifrontal_matches_superlu_and_plan_matches_factor(small):
     Aff = A[sym.perm][:, sym.perm].tocsc()
     xref = spla.splu(Aff).solve(b)
     assert np.linalg.norm(x - xref) / np.linalg.norm(xref) < 1e-11
-    for max_mt in (8, 16, 32):
-        plan = build_plan(fac, max_mt=max_mt, target_jobs=40)
+    for max_rb in (1, 2, 4):
+        plan = build_plan(fac, max_rb=max_rb, target_jobs=40)
         assert np.abs(apply_plan_host(plan, b) - x).max() < 1e-12 * np.abs(x).max()
-        assert set(np.unique(plan.job_MT).tolist()) <= {0, 8, 16, 32} and plan.job_MT.max() <= max_mt
+        assert plan.job_nrb.min() >= 0 and plan.job_nrb.max() <= max_rb
+        assert np.all(plan.job_nr <= 8 * plan.job_nrb) and np.all(plan.job_nr > 8 * (plan.job_nrb - 1))
+        assert np.all(plan.job_vptr % 2 == 0) and plan.i0.max() <= plan.zrow
         # every x row and every y row is produced exactly once; jobs of one launch never read rows
         # that the same launch writes
         n = sym.n
@@ -150,7 +152,7 @@ def test_multifrontal_matches_superlu_and_plan_matches_factor(small):
             written, read = set(), set()
             for q in range(plan.launch_ptr[l], plan.launch_ptr[l + 1]):
                 K, nr = int(plan.job_K[q]), int(plan.job_nr[q])
-                written |= set(range(plan.job_out0[q], plan.job_out0[q] + nr)) if plan.job_MT[q] else set()
+                written |= set(range(plan.job_out0[q], plan.job_out0[q] + nr)) if plan.job_nrb[q] else set()
                 if plan.job_ystore[q] >= 0:
                     written |= set(range(plan.job_ystore[q], plan.job_ystore[q] + K))
                 sl = slice(plan.job_iptr[q], plan.job_iptr[q] + K)
@@ -161,6 +163,7 @@ def test_multifrontal_matches_superlu_and_plan_matches_factor(small):
                     es = slice(plan.job_eptr[q], plan.job_eptr[q] + nr)
                     read |= set(plan.e0[es].tolist()) | set(plan.e1[es].tolist())
             read.discard(-1)
+            assert plan.zrow not in written
             assert not (written & read)
 
 
