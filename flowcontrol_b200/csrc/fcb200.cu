@@ -24,6 +24,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -196,17 +197,30 @@ __global__ void __launch_bounds__(256) k_rhs_build(int n, int Nv, const int* __r
 // conflict-free.  CTAs are persistent: CTA c runs jobs c, c+gridDim.x, ... of the launch and the
 // ring keeps filling across job boundaries.  Every Z row is written by exactly one job: no atomics.
 // ----------------------------------------------------------------------------------------------
-constexpr int SV_SLOTS = 12;   // gathered rows per stage (3 planes x 4 k for nsrc == 3, 12 k otherwise)
-constexpr int SV_STAGES = 4;
-constexpr int SV_MAXW = 8;     // consumer warps per CTA
-constexpr int SV_XS_MAX = 32 * SV_MAXW + 8;
-constexpr int SV_STAGE_BYTES = SV_SLOTS * SV_XS_MAX * 8 + SV_SLOTS * 32 * 8;  // rows + V slice (4 row blocks)
-constexpr int SV_SMEM_BYTES = SV_STAGES * SV_STAGE_BYTES + 2 * SV_STAGES * 8;
+constexpr int SV_SLOTS = 12;    // gathered rows per stage (3 planes x 4 k for nsrc == 3, 12 k otherwise)
+constexpr int SV_MAXSTAGES = 8;  // ring depth is chosen per launch from the shared memory one CTA may use
+constexpr int SV_PREFETCH = 4;   // stage records the producer keeps in flight
+constexpr int SV_JREC = 72;      // ints per job record
+constexpr int SV_SREC = 16;      // ints per stage record
 
-struct SolveJob {
-    int K, nrb, nr, nsrc, out0, ystore;
-    long long iptr, vptr, eptr;
+// Shared-memory geometry of one ring stage for NWC consumer warps (32*NWC trajectories per CTA).
+template <int NWC>
+struct SweepCfg {
+    static constexpr int NT = 32 * NWC;
+    static constexpr int XS = NT + 8;                      // row stride in doubles (== 8 mod 16)
+    static constexpr int VOFF = SV_SLOTS * XS * 8;         // V slice (up to 12 k x 32 rows)
+    static constexpr int JOFF = VOFF + SV_SLOTS * 32 * 8;  // job record (first stage of a job only)
+    static constexpr int STAGE_BYTES = JOFF + 384;
+    static constexpr int MIN_CTAS = NWC == 8 ? 2 : (NWC == 4 ? 3 : 4);
+    __host__ __device__ static constexpr int smem_bytes(int stages) { return stages * STAGE_BYTES + 2 * SV_MAXSTAGES * 8; }
 };
+
+// The host compiles every launch into one instruction stream per CTA (upload_plan):
+//   stage record (16 ints): rows[12] by shared-memory slot (-1 = unused), V offset / 32 doubles, V bytes,
+//                           job record index if this is the first stage of a job (else -1)
+//   job record   (72 ints): K, nrb, nr, nsrc, out0, ystore, has_seed, -, e0[32], e1[32]
+// The producer reads consecutive 64-byte stage records; the job record rides into shared memory with
+// the job's first stage, so nothing on the device chases a pointer.
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -239,23 +253,110 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
                  : "d"(a), "d"(b));
 }
 
-// grid = (persistent CTAs, slabs of 256 trajectories), block = (32, consumer warps + 1)
-__global__ void __launch_bounds__(32 * (SV_MAXW + 1), 2)
-    k_front_sweep(const SolveJob* __restrict__ jobs, int njobs, const int* __restrict__ i0, const int* __restrict__ i1,
-                  const int* __restrict__ i2, const int* __restrict__ e0, const int* __restrict__ e1,
-                  const double* __restrict__ vals, double* Z, int ldb) {
+struct RingPos {
+    int s;
+    uint32_t ph;
+    __device__ __forceinline__ void advance(int nstages) {
+        if (++s == nstages) { s = 0; ph ^= 1; }
+    }
+};
+
+// One job on one consumer warp: seeds, the stage loop (NRB row blocks x 4 trajectory blocks of 8), store.
+template <int NWC, int NRB, bool SRC3, bool YST>
+__device__ __forceinline__ void sweep_job(unsigned char* smem, uint32_t bar_full, uint32_t bar_empty, RingPos& rp, int nstages,
+                                          const int* jh, int K, int nr, int out0, int ystore, bool seed, double* Z, size_t L,
+                                          int t0, int wid, int lane) {
+    using C = SweepCfg<NWC>;
+    constexpr int XS = C::XS;
+    constexpr int KC = SRC3 ? SV_SLOTS / 3 : SV_SLOTS;
+    constexpr int NA = NRB > 0 ? NRB : 1;
+    const int gid = lane >> 2, tig = lane & 3;
+    double acc[NA][4][2];
+#pragma unroll
+    for (int rb = 0; rb < NA; ++rb)
+#pragma unroll
+        for (int nb = 0; nb < 4; ++nb) acc[rb][nb][0] = acc[rb][nb][1] = 0.0;
+    if (NRB > 0 && seed) {
+        // the children's update rows that land on these output rows seed the accumulators
+#pragma unroll
+        for (int rb = 0; rb < NRB; ++rb) {
+            const int ea = jh[8 + rb * 8 + gid], eb = jh[40 + rb * 8 + gid];
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb) {
+                const int col = t0 + nb * 8 + 2 * tig;
+                if (ea >= 0) {
+                    const double2 v = *reinterpret_cast<const double2*>(Z + (size_t)ea * L + col);
+                    acc[rb][nb][0] += v.x;
+                    acc[rb][nb][1] += v.y;
+                }
+                if (eb >= 0) {
+                    const double2 v = *reinterpret_cast<const double2*>(Z + (size_t)eb * L + col);
+                    acc[rb][nb][0] += v.x;
+                    acc[rb][nb][1] += v.y;
+                }
+            }
+        }
+    }
+    const int K4 = (K + 3) & ~3;
+    double* zy = YST ? Z + (size_t)(ystore + tig) * L + t0 + gid : nullptr;
+    int kleft = K - tig;  // rows of this lane's k index still inside the job
+    int k0 = 0;
+    do {
+        const int nk = min(KC, K4 - k0);
+        mbar_wait(bar_full + 8 * rp.s, rp.ph);
+        const unsigned char* st = smem + rp.s * C::STAGE_BYTES;
+        const double* xr = reinterpret_cast<const double*>(st) + tig * XS + wid * 32 + gid;
+        const double* vs = reinterpret_cast<const double*>(st + C::VOFF) + lane;
+        for (int g = 0; g < nk; g += 4) {
+            double a[NA];
+#pragma unroll
+            for (int rb = 0; rb < NRB; ++rb) a[rb] = vs[rb * 32];
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb) {
+                double bv = xr[nb * 8];
+                if (SRC3) bv += xr[KC * XS + nb * 8] + xr[2 * KC * XS + nb * 8];
+                if (YST && kleft > 0) zy[nb * 8] = bv;
+#pragma unroll
+                for (int rb = 0; rb < NRB; ++rb) dmma(acc[rb][nb], a[rb], bv);
+            }
+            vs += NRB * 32;
+            xr += 4 * XS;
+            if (YST) { zy += 4 * L; kleft -= 4; }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_empty + 8 * rp.s);
+        rp.advance(nstages);
+        k0 += KC;
+    } while (k0 < K4);
+    if (NRB > 0) {
+#pragma unroll
+        for (int rb = 0; rb < NRB; ++rb) {
+            const int r = rb * 8 + gid;
+            if (r < nr) {
+                double* zo = Z + (size_t)(out0 + r) * L + t0 + 2 * tig;
+#pragma unroll
+                for (int nb = 0; nb < 4; ++nb) *reinterpret_cast<double2*>(zo + nb * 8) = make_double2(acc[rb][nb][0], acc[rb][nb][1]);
+            }
+        }
+    }
+}
+
+// grid = (persistent CTAs, slabs of 32*NWC trajectories), block = (32, NWC + 1)
+template <int NWC>
+__global__ void __launch_bounds__(32 * (NWC + 1), SweepCfg<NWC>::MIN_CTAS)
+    k_front_sweep(const int* __restrict__ srec, const int* __restrict__ jrec, const int* __restrict__ cta_sptr,
+                  const int* __restrict__ cta_jptr, const double* __restrict__ vals, double* Z, int ldb, int nstages) {
+    using C = SweepCfg<NWC>;
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x, wid = threadIdx.y;
-    const int nwarp_c = blockDim.y - 1;  // consumer warps launched
-    const int slab0 = blockIdx.y * (32 * SV_MAXW);
-    const int NT = min(32 * nwarp_c, ldb - slab0);  // trajectories of this CTA (multiple of 32)
-    const int nact = NT >> 5;                       // active consumer warps
-    const int XS = NT + 8;                          // shared-memory row stride in doubles
+    const int slab0 = blockIdx.y * C::NT;
+    const int NT = min(C::NT, ldb - slab0);  // trajectories of this CTA (multiple of 32)
+    const int nact = NT >> 5;                // active consumer warps
     const uint32_t sbase = smem_u32(smem);
-    const uint32_t bar_full = sbase + SV_STAGES * SV_STAGE_BYTES;
-    const uint32_t bar_empty = bar_full + SV_STAGES * 8;
+    const uint32_t bar_full = sbase + nstages * C::STAGE_BYTES;
+    const uint32_t bar_empty = bar_full + SV_MAXSTAGES * 8;
     if (threadIdx.x == 0 && threadIdx.y == 0) {
-        for (int s = 0; s < SV_STAGES; ++s) {
+        for (int s = 0; s < nstages; ++s) {
             mbar_init(bar_full + 8 * s, 1);
             mbar_init(bar_empty + 8 * s, nact);
         }
@@ -264,111 +365,80 @@ __global__ void __launch_bounds__(32 * (SV_MAXW + 1), 2)
     __syncthreads();
     const size_t L = (size_t)ldb;
 
-    if (wid == nwarp_c) {
-        // ---------------- producer warp ----------------
-        uint32_t it = 0;
-        for (int j = blockIdx.x; j < njobs; j += gridDim.x) {
-            const SolveJob jb = jobs[j];
-            const int K4 = (jb.K + 3) & ~3;
-            const int kc = (jb.nsrc == 3) ? SV_SLOTS / 3 : SV_SLOTS;
-            for (int k0 = 0; k0 < K4; k0 += kc, ++it) {
-                const int nk = min(kc, K4 - k0);
-                const int nrows = nk * jb.nsrc;  // <= SV_SLOTS <= 32: one row per lane
-                int row = -1, slot = 0;
-                if (lane < nrows) {
-                    const int p = lane / nk, k = lane - p * nk;
-                    const int* ip = (p == 0) ? i0 : (p == 1 ? i1 : i2);
-                    row = __ldg(ip + jb.iptr + k0 + k);
-                    slot = p * kc + k;
+    if (wid == NWC) {
+        // ---------------- producer warp: stream the stage records, issue the bulk copies ----------------
+        const int sbeg = __ldg(cta_sptr + blockIdx.x), ns = __ldg(cta_sptr + blockIdx.x + 1) - sbeg;
+        const int* rec = srec + (size_t)sbeg * SV_SREC + lane;
+        int q[SV_PREFETCH];
+#pragma unroll
+        for (int u = 0; u < SV_PREFETCH; ++u) q[u] = (u < ns && lane < SV_SREC) ? __ldg(rec + u * SV_SREC) : -1;
+        RingPos rp{0, 1};  // parity 1: the first wait on a fresh "empty" barrier passes
+        for (int c0 = 0; c0 < ns; c0 += SV_PREFETCH) {
+            int qn[SV_PREFETCH];
+#pragma unroll
+            for (int u = 0; u < SV_PREFETCH; ++u)
+                qn[u] = (c0 + SV_PREFETCH + u < ns && lane < SV_SREC) ? __ldg(rec + (c0 + SV_PREFETCH + u) * SV_SREC) : -1;
+#pragma unroll
+            for (int u = 0; u < SV_PREFETCH; ++u) {
+                if (c0 + u < ns) {  // warp-uniform
+                    const int v = q[u];
+                    const bool is_row = lane < SV_SLOTS && v >= 0;
+                    const int nrows = __popc(__ballot_sync(0xffffffffu, is_row));
+                    const int voff = __shfl_sync(0xffffffffu, v, SV_SLOTS);
+                    const uint32_t vbytes = (uint32_t)__shfl_sync(0xffffffffu, v, SV_SLOTS + 1);
+                    const int jidx = __shfl_sync(0xffffffffu, v, SV_SLOTS + 2);
+                    const uint32_t full = bar_full + 8 * rp.s;
+                    const uint32_t sx = sbase + rp.s * C::STAGE_BYTES;
+                    mbar_wait(bar_empty + 8 * rp.s, rp.ph);
+                    if (lane == 0) {
+                        mbar_expect_tx(full, (uint32_t)nrows * (uint32_t)NT * 8u + vbytes + (jidx >= 0 ? SV_JREC * 4u : 0u));
+                        if (vbytes) bulk_g2s(sx + C::VOFF, vals + (size_t)voff * 32, vbytes, full);
+                        if (jidx >= 0) bulk_g2s(sx + C::JOFF, jrec + (size_t)jidx * SV_JREC, SV_JREC * 4u, full);
+                    }
+                    __syncwarp();
+                    if (is_row) bulk_g2s(sx + (uint32_t)(lane * C::XS) * 8u, Z + (size_t)v * L + slab0, (uint32_t)NT * 8u, full);
+                    rp.advance(nstages);
                 }
-                const int s = it % SV_STAGES;
-                const uint32_t full = bar_full + 8 * s;
-                mbar_wait(bar_empty + 8 * s, ((it / SV_STAGES) & 1) ^ 1);
-                const uint32_t sx = sbase + s * SV_STAGE_BYTES;
-                if (lane == 0) {
-                    const uint32_t vbytes = (uint32_t)nk * 64u * (uint32_t)jb.nrb;
-                    mbar_expect_tx(full, (uint32_t)nrows * (uint32_t)NT * 8u + vbytes);
-                    if (vbytes) bulk_g2s(sx + SV_SLOTS * SV_XS_MAX * 8, vals + jb.vptr + (size_t)k0 * 8 * jb.nrb, vbytes, full);
-                }
-                __syncwarp();
-                if (row >= 0) bulk_g2s(sx + (uint32_t)(slot * XS) * 8u, Z + (size_t)row * L + slab0, (uint32_t)NT * 8u, full);
             }
+#pragma unroll
+            for (int u = 0; u < SV_PREFETCH; ++u) q[u] = qn[u];
         }
         return;
     }
     if (wid >= nact) return;
 
     // ---------------- consumer warps ----------------
-    const int gid = lane >> 2, tig = lane & 3;
     const int t0 = slab0 + wid * 32;  // first trajectory of this warp
-    uint32_t it = 0;
-    for (int j = blockIdx.x; j < njobs; j += gridDim.x) {
-        const SolveJob jb = jobs[j];
-        const int K4 = (jb.K + 3) & ~3;
-        const int nrb = jb.nrb;
-        const int kc = (jb.nsrc == 3) ? SV_SLOTS / 3 : SV_SLOTS;
-        double acc[4][4][2];
-#pragma unroll
-        for (int rb = 0; rb < 4; ++rb)
-#pragma unroll
-            for (int nb = 0; nb < 4; ++nb) acc[rb][nb][0] = acc[rb][nb][1] = 0.0;
-        if (jb.eptr >= 0) {
-            // the children's update rows that land on these output rows seed the accumulators
-#pragma unroll
-            for (int rb = 0; rb < 4; ++rb) {
-                const int r = rb * 8 + gid;
-                if (rb < nrb && r < jb.nr) {
-                    const int ea = __ldg(e0 + jb.eptr + r), eb = __ldg(e1 + jb.eptr + r);
-#pragma unroll
-                    for (int nb = 0; nb < 4; ++nb) {
-                        const int col = t0 + nb * 8 + 2 * tig;
-                        if (ea >= 0) {
-                            const double2 v = *reinterpret_cast<const double2*>(Z + (size_t)ea * L + col);
-                            acc[rb][nb][0] += v.x;
-                            acc[rb][nb][1] += v.y;
-                        }
-                        if (eb >= 0) {
-                            const double2 v = *reinterpret_cast<const double2*>(Z + (size_t)eb * L + col);
-                            acc[rb][nb][0] += v.x;
-                            acc[rb][nb][1] += v.y;
-                        }
-                    }
-                }
-            }
+    const int nj = __ldg(cta_jptr + blockIdx.x + 1) - __ldg(cta_jptr + blockIdx.x);
+    RingPos rp{0, 0};
+    for (int j = 0; j < nj; ++j) {
+        mbar_wait(bar_full + 8 * rp.s, rp.ph);  // the job record arrives with the job's first stage
+        const int* jh = reinterpret_cast<const int*>(smem + rp.s * C::STAGE_BYTES + C::JOFF);
+        const int4 h0 = *reinterpret_cast<const int4*>(jh);
+        const int4 h1 = *reinterpret_cast<const int4*>(jh + 4);
+        const int K = h0.x, nrb = h0.y, nr = h0.z, out0 = h1.x, ystore = h1.y;
+        const bool src3 = h0.w == 3, seed = h1.z != 0;
+#define SWEEP_RUN(NRB, S3, YS) \
+    sweep_job<NWC, NRB, S3, YS>(smem, bar_full, bar_empty, rp, nstages, jh, K, nr, out0, ystore, seed, Z, L, t0, wid, lane)
+#define SWEEP_CASE(NRB)                                        \
+    case NRB:                                                  \
+        if (src3) {                                            \
+            if (ystore >= 0) SWEEP_RUN(NRB, true, true);       \
+            else SWEEP_RUN(NRB, true, false);                  \
+        } else {                                               \
+            if (ystore >= 0) SWEEP_RUN(NRB, false, true);      \
+            else SWEEP_RUN(NRB, false, false);                 \
+        }                                                      \
+        break;
+        switch (nrb) {
+            SWEEP_CASE(0)
+            SWEEP_CASE(1)
+            SWEEP_CASE(2)
+            SWEEP_CASE(3)
+            SWEEP_CASE(4)
         }
-        for (int k0 = 0; k0 < K4; k0 += kc, ++it) {
-            const int nk = min(kc, K4 - k0);
-            const int s = it % SV_STAGES;
-            mbar_wait(bar_full + 8 * s, (it / SV_STAGES) & 1);
-            const double* xs = reinterpret_cast<const double*>(smem + s * SV_STAGE_BYTES) + wid * 32 + gid;
-            const double* vs = reinterpret_cast<const double*>(smem + s * SV_STAGE_BYTES + SV_SLOTS * SV_XS_MAX * 8) + lane;
-            for (int g = 0; g < nk; g += 4) {
-                double a[4];
-#pragma unroll
-                for (int rb = 0; rb < 4; ++rb) a[rb] = (rb < nrb) ? vs[((g >> 2) * nrb + rb) * 32] : 0.0;
-                const double* xr = xs + (g + tig) * XS;
-#pragma unroll
-                for (int nb = 0; nb < 4; ++nb) {
-                    double bv = xr[nb * 8];
-                    if (jb.nsrc == 3) bv += xr[kc * XS + nb * 8] + xr[2 * kc * XS + nb * 8];
-                    if (jb.ystore >= 0 && k0 + g + tig < jb.K) Z[(size_t)(jb.ystore + k0 + g + tig) * L + t0 + nb * 8 + gid] = bv;
-#pragma unroll
-                    for (int rb = 0; rb < 4; ++rb)
-                        if (rb < nrb) dmma(acc[rb][nb], a[rb], bv);
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_empty + 8 * s);
-        }
-#pragma unroll
-        for (int rb = 0; rb < 4; ++rb) {
-            const int r = rb * 8 + gid;
-            if (rb < nrb && r < jb.nr) {
-                double* zo = Z + (size_t)(jb.out0 + r) * L + t0 + 2 * tig;
-#pragma unroll
-                for (int nb = 0; nb < 4; ++nb) *reinterpret_cast<double2*>(zo + nb * 8) = make_double2(acc[rb][nb][0], acc[rb][nb][1]);
-            }
-        }
+#undef SWEEP_CASE
+#undef SWEEP_RUN
     }
 }
 
@@ -485,17 +555,18 @@ __global__ void k_log(int na, int ns, const double* __restrict__ dE, const doubl
 // ----------------------------------------------------------------------------------------------
 struct DevPlan {
     int n = 0, nU = 0, njobs = 0, nlaunch = 0;
-    SolveJob* jobs = nullptr;
-    int *i0 = nullptr, *i1 = nullptr, *i2 = nullptr, *e0 = nullptr, *e1 = nullptr;
+    int *srec = nullptr, *jrec = nullptr, *cta_sptr = nullptr, *cta_jptr = nullptr;
     double* vals = nullptr;
-    std::vector<int> launch_ptr;
+    struct Launch { int grid, nwc, nslab, nstages, cta_off; };
+    std::vector<Launch> launches;
     int n_forward = 0;
+    long long nstages_total = 0;
 };
 
 }  // namespace
 
 struct fcb_context {
-    int device = 0, num_sms = 0;
+    int device = 0, num_sms = 0, smem_per_sm = 0, force_nwc = 0;
     cudaStream_t stream = nullptr;
     std::string error;
     int B = 0, ldb = 0;
@@ -572,41 +643,119 @@ int upload(fcb_context* h, T** dst, const T* src, size_t count) {
         if (rc_ != FCB_OK) return rc_; \
     } while (0)
 
+// Compile a SolvePlan into per-CTA instruction streams (see k_front_sweep) and upload it.
 int upload_plan(fcb_context* h, DevPlan& d, const fcb_plan& p) {
     d.n = p.n;
     d.nU = p.nU;
     d.njobs = p.njobs;
     d.nlaunch = p.nlaunch;
     d.n_forward = p.n_forward_launches;
-    std::vector<SolveJob> jobs(p.njobs);
-    size_t nidx = 0, nvals = 0, nepi = 0;
     const int zrow = 2 * p.n + p.nU;
+    size_t nvals = 0;
     for (int i = 0; i < p.njobs; ++i) {
-        SolveJob& j = jobs[i];
-        j.K = p.job_K[i]; j.nrb = p.job_nrb[i]; j.nr = p.job_nr[i]; j.nsrc = p.job_nsrc[i];
-        j.out0 = p.job_out0[i]; j.ystore = p.job_ystore[i];
-        j.iptr = p.job_iptr[i]; j.vptr = p.job_vptr[i]; j.eptr = p.job_eptr[i];
-        if (j.nrb < 0 || j.nrb > 4) return fail(h, FCB_ERR_INVALID, "plan job %d: %d row blocks not in [0,4]", i, j.nrb);
-        if (j.nr > 8 * j.nrb || j.K < 0 || (j.vptr & 1) || (j.nsrc != 1 && j.nsrc != 3) || j.out0 + j.nr > zrow ||
-            (j.ystore >= 0 && j.ystore + j.K > zrow))
+        const int K = p.job_K[i], nrb = p.job_nrb[i], nr = p.job_nr[i], nsrc = p.job_nsrc[i];
+        if (nrb < 0 || nrb > 4) return fail(h, FCB_ERR_INVALID, "plan job %d: %d row blocks not in [0,4]", i, nrb);
+        if (nr > 8 * nrb || nr < 0 || K < 0 || (p.job_vptr[i] & 31) || (nsrc != 1 && nsrc != 3) || p.job_out0[i] < 0 ||
+            p.job_out0[i] + nr > zrow || (p.job_ystore[i] >= 0 && p.job_ystore[i] + K > zrow) || p.job_iptr[i] < 0)
             return fail(h, FCB_ERR_INVALID, "plan job %d is malformed", i);
-        const long long K4 = (j.K + 3) & ~3;
-        nidx = std::max(nidx, (size_t)(j.iptr + K4));
-        nvals = std::max(nvals, (size_t)(j.vptr + K4 * 8 * j.nrb));
-        if (j.eptr >= 0) nepi = std::max(nepi, (size_t)(j.eptr + j.nr));
+        const long long K4 = (K + 3) & ~3;
+        for (long long k = p.job_iptr[i]; k < p.job_iptr[i] + K4; ++k)
+            if (p.i0[k] < 0 || p.i0[k] > zrow || (nsrc == 3 && (p.i1[k] < 0 || p.i1[k] > zrow || p.i2[k] < 0 || p.i2[k] > zrow)))
+                return fail(h, FCB_ERR_INVALID, "plan job %d: gather index out of range", i);
+        if (p.job_eptr[i] >= 0)
+            for (int r = 0; r < nr; ++r)
+                if (p.e0[p.job_eptr[i] + r] >= zrow || p.e1[p.job_eptr[i] + r] >= zrow)
+                    return fail(h, FCB_ERR_INVALID, "plan job %d: seed index out of range", i);
+        nvals = std::max(nvals, (size_t)(p.job_vptr[i] + K4 * 8 * nrb));
     }
-    for (size_t k = 0; k < nidx; ++k)
-        if (p.i0[k] < 0 || p.i0[k] > zrow || p.i1[k] < 0 || p.i1[k] > zrow || p.i2[k] < 0 || p.i2[k] > zrow)
-            return fail(h, FCB_ERR_INVALID, "plan gather index %zu out of range", k);
-    TRY(upload(h, &d.jobs, jobs.data(), jobs.size()));
-    CK(cudaStreamSynchronize(h->stream));  // jobs vector goes out of scope
-    TRY(upload(h, &d.i0, p.i0, nidx));
-    TRY(upload(h, &d.i1, p.i1, nidx));
-    TRY(upload(h, &d.i2, p.i2, nidx));
-    TRY(upload(h, &d.e0, p.e0, nepi ? nepi : 1));
-    TRY(upload(h, &d.e1, p.e1, nepi ? nepi : 1));
-    TRY(upload(h, &d.vals, p.vals, nvals ? nvals : 2));
-    d.launch_ptr.assign(p.launch_ptr, p.launch_ptr + p.nlaunch + 1);
+    std::vector<int> srec, jrec, cta_sptr, cta_jptr;
+    d.launches.clear();
+    const int nw_all = h->ldb / 32;  // 32-trajectory warps needed to cover the ensemble
+    for (int l = 0; l < p.nlaunch; ++l) {
+        const int j0 = p.launch_ptr[l], nj = p.launch_ptr[l + 1] - j0;
+        DevPlan::Launch L{0, 8, 1, 4, (int)cta_sptr.size()};
+        if (nj <= 0) { d.launches.push_back(L); continue; }
+        // CTA width: as wide as the ensemble allows (V and the row gathers are shared by the whole CTA),
+        // narrower when the launch has too few jobs to occupy the SMs
+        int nwc = nw_all >= 8 ? 8 : (nw_all >= 4 ? 4 : (nw_all >= 2 ? 2 : 1));
+        while (nwc > 2 && (long long)nj * ((nw_all + nwc - 1) / nwc) < h->num_sms) nwc >>= 1;
+        if (h->force_nwc > 0) nwc = h->force_nwc;
+        L.nwc = nwc;
+        L.nslab = (nw_all + nwc - 1) / nwc;
+        const int min_ctas = nwc == 8 ? 2 : (nwc == 4 ? 3 : 4);
+        const int stage_bytes = nwc == 8 ? SweepCfg<8>::STAGE_BYTES : nwc == 4 ? SweepCfg<4>::STAGE_BYTES : nwc == 2 ? SweepCfg<2>::STAGE_BYTES : SweepCfg<1>::STAGE_BYTES;
+        const int per_sm = ((long long)nj * L.nslab >= (long long)min_ctas * h->num_sms) ? min_ctas
+                           : std::max(1, (int)(((long long)nj * L.nslab + h->num_sms - 1) / h->num_sms));
+        L.grid = std::min(nj, std::max(1, per_sm * h->num_sms / L.nslab));
+        L.nstages = std::max(2, std::min(SV_MAXSTAGES, (h->smem_per_sm / per_sm - 1024 - 2 * SV_MAXSTAGES * 8) / stage_bytes));
+        // longest-processing-time assignment of jobs to CTAs (cost in rough SM cycles)
+        auto stages_of = [&](int j) {
+            const int K4 = (p.job_K[j] + 3) & ~3, kc = p.job_nsrc[j] == 3 ? SV_SLOTS / 3 : SV_SLOTS;
+            return std::max(1, (K4 + kc - 1) / kc);
+        };
+        std::vector<std::pair<long long, int>> order(nj);
+        for (int q = 0; q < nj; ++q) {
+            const int j = j0 + q, K4 = (p.job_K[j] + 3) & ~3;
+            order[q] = {-(600LL + 150LL * stages_of(j) + 8LL * K4 * std::max(1, p.job_nrb[j])), j};
+        }
+        std::sort(order.begin(), order.end());
+        std::vector<std::vector<int>> mine(L.grid);
+        std::vector<std::pair<long long, int>> heap(L.grid);  // (load, cta) min-heap
+        for (int c = 0; c < L.grid; ++c) heap[c] = {0, c};
+        auto cmp = [](const std::pair<long long, int>& a, const std::pair<long long, int>& b) { return a > b; };
+        std::make_heap(heap.begin(), heap.end(), cmp);
+        for (auto& [negcost, j] : order) {
+            std::pop_heap(heap.begin(), heap.end(), cmp);
+            heap.back().first += -negcost;
+            mine[heap.back().second].push_back(j);
+            std::push_heap(heap.begin(), heap.end(), cmp);
+        }
+        for (int c = 0; c < L.grid; ++c) {
+            cta_sptr.push_back((int)(srec.size() / SV_SREC));
+            cta_jptr.push_back((int)(jrec.size() / SV_JREC));
+            for (int j : mine[c]) {
+                const int K = p.job_K[j], nrb = p.job_nrb[j], nr = p.job_nr[j], nsrc = p.job_nsrc[j];
+                const int K4 = (K + 3) & ~3, kc = nsrc == 3 ? SV_SLOTS / 3 : SV_SLOTS;
+                const size_t jb = jrec.size();
+                jrec.resize(jb + SV_JREC, -1);
+                jrec[jb + 0] = K; jrec[jb + 1] = nrb; jrec[jb + 2] = nr; jrec[jb + 3] = nsrc;
+                jrec[jb + 4] = p.job_out0[j]; jrec[jb + 5] = p.job_ystore[j]; jrec[jb + 6] = p.job_eptr[j] >= 0 ? 1 : 0;
+                if (p.job_eptr[j] >= 0)
+                    for (int r = 0; r < nr; ++r) {
+                        jrec[jb + 8 + r] = p.e0[p.job_eptr[j] + r];
+                        jrec[jb + 40 + r] = p.e1[p.job_eptr[j] + r];
+                    }
+                int k0 = 0;
+                do {  // a job with K == 0 still gets one (empty) stage that carries its record
+                    const int nk = std::max(0, std::min(kc, K4 - k0));
+                    const size_t sb = srec.size();
+                    srec.resize(sb + SV_SREC, -1);
+                    for (int pl = 0; pl < nsrc; ++pl) {
+                        const int32_t* ip = pl == 0 ? p.i0 : (pl == 1 ? p.i1 : p.i2);
+                        for (int k = 0; k < nk; ++k) srec[sb + pl * kc + k] = ip[p.job_iptr[j] + k0 + k];
+                    }
+                    const long long voff = p.job_vptr[j] + (long long)k0 * 8 * nrb;
+                    srec[sb + SV_SLOTS] = (int)(voff / 32);
+                    srec[sb + SV_SLOTS + 1] = nk * 64 * nrb;
+                    srec[sb + SV_SLOTS + 2] = k0 == 0 ? (int)(jb / SV_JREC) : -1;
+                    k0 += kc;
+                } while (k0 < K4);
+            }
+        }
+        cta_sptr.push_back((int)(srec.size() / SV_SREC));  // one past the last CTA of this launch
+        cta_jptr.push_back((int)(jrec.size() / SV_JREC));
+        d.launches.push_back(L);
+    }
+    d.nstages_total = (long long)(srec.size() / SV_SREC);
+    if (srec.empty()) srec.resize(SV_SREC, -1);
+    if (jrec.empty()) jrec.resize(SV_JREC, -1);
+    if (cta_sptr.empty()) { cta_sptr.push_back(0); cta_jptr.push_back(0); }
+    TRY(upload(h, &d.srec, srec.data(), srec.size()));
+    TRY(upload(h, &d.jrec, jrec.data(), jrec.size()));
+    TRY(upload(h, &d.cta_sptr, cta_sptr.data(), cta_sptr.size()));
+    TRY(upload(h, &d.cta_jptr, cta_jptr.data(), cta_jptr.size()));
+    TRY(upload(h, &d.vals, p.vals, nvals ? nvals : 32));
+    CK(cudaStreamSynchronize(h->stream));  // host vectors go out of scope
     return FCB_OK;
 }
 
@@ -687,18 +836,24 @@ int enqueue_measure(fcb_context* h, const double* up) {
     return FCB_OK;
 }
 
+template <int NWC>
+void launch_sweep(fcb_context* h, const DevPlan& pl, const DevPlan::Launch& L) {
+    dim3 grid(L.grid, L.nslab), block(32, NWC + 1);
+    k_front_sweep<NWC><<<grid, block, SweepCfg<NWC>::smem_bytes(L.nstages), h->stream>>>(
+        pl.srec, pl.jrec, pl.cta_sptr + L.cta_off, pl.cta_jptr + L.cta_off, pl.vals, h->Z, h->ldb, L.nstages);
+}
+
 int enqueue_solve(fcb_context* h, const DevPlan& pl, PhaseMark* pm) {
-    const int nwarp_c = std::min(SV_MAXW, h->ldb / 32);
-    const int nslab = (h->ldb + 32 * SV_MAXW - 1) / (32 * SV_MAXW);
-    const int resident = std::max(1, 2 * h->num_sms / nslab);  // 2 CTAs per SM (shared memory + registers)
-    dim3 block(32, nwarp_c + 1);
     for (int l = 0; l < pl.nlaunch; ++l) {
         if (pm && l == pl.n_forward) pm->mark(FCB_PHASE_BACKWARD);
-        const int j0 = pl.launch_ptr[l], nj = pl.launch_ptr[l + 1] - j0;
-        if (nj <= 0) continue;
-        dim3 grid(std::min(nj, resident), nslab);
-        k_front_sweep<<<grid, block, SV_SMEM_BYTES, h->stream>>>(pl.jobs + j0, nj, pl.i0, pl.i1, pl.i2, pl.e0, pl.e1,
-                                                                 pl.vals, h->Z, h->ldb);
+        const DevPlan::Launch& L = pl.launches[l];
+        if (L.grid <= 0) continue;
+        switch (L.nwc) {
+            case 8: launch_sweep<8>(h, pl, L); break;
+            case 4: launch_sweep<4>(h, pl, L); break;
+            case 2: launch_sweep<2>(h, pl, L); break;
+            default: launch_sweep<1>(h, pl, L); break;
+        }
         h->launches += 1;
     }
     if (pm && pl.n_forward >= pl.nlaunch) pm->mark(FCB_PHASE_BACKWARD);
@@ -817,8 +972,7 @@ void destroy(fcb_context* h) {
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (int i = 0; i < 2; ++i) {
-        void* pp[] = {h->plan[i].jobs, h->plan[i].i0, h->plan[i].i1, h->plan[i].i2, h->plan[i].e0, h->plan[i].e1,
-                      h->plan[i].vals};
+        void* pp[] = {h->plan[i].srec, h->plan[i].jrec, h->plan[i].cta_sptr, h->plan[i].cta_jptr, h->plan[i].vals};
         for (void* q : pp)
             if (q) cudaFree(q);
     }
@@ -834,11 +988,22 @@ int create_impl(fcb_context* h, const fcb_problem* p, int B) {
     CK(cudaGetDeviceProperties(&prop, h->device));
     if (prop.major < 10) return fail(h, FCB_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", h->device, prop.major, prop.minor);
     h->num_sms = prop.multiProcessorCount;
-    CK(cudaFuncSetAttribute(k_front_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, SV_SMEM_BYTES));
-    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    for (auto& e : h->ev) CK(cudaEventCreate(&e));
     h->B = B;
     h->ldb = (B + 31) / 32 * 32;
+    h->smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
+    {
+        const int optin = (int)prop.sharedMemPerBlockOptin;
+        CK(cudaFuncSetAttribute(k_front_sweep<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::min(optin, SweepCfg<8>::smem_bytes(SV_MAXSTAGES))));
+        CK(cudaFuncSetAttribute(k_front_sweep<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::min(optin, SweepCfg<4>::smem_bytes(SV_MAXSTAGES))));
+        CK(cudaFuncSetAttribute(k_front_sweep<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::min(optin, SweepCfg<2>::smem_bytes(SV_MAXSTAGES))));
+        CK(cudaFuncSetAttribute(k_front_sweep<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::min(optin, SweepCfg<1>::smem_bytes(SV_MAXSTAGES))));
+        const char* env = getenv("FCB_SWEEP_WARPS");  // tuning knob: force the CTA width of every sweep launch
+        h->force_nwc = env ? atoi(env) : 0;
+        if (h->force_nwc != 0 && h->force_nwc != 1 && h->force_nwc != 2 && h->force_nwc != 4 && h->force_nwc != 8) h->force_nwc = 0;
+        if (h->force_nwc * 32 > h->ldb && h->force_nwc > 1) h->force_nwc = 0;
+    }
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (auto& e : h->ev) CK(cudaEventCreate(&e));
     h->nT = p->nT; h->nN = p->nN; h->nV = p->nV;
     h->Nv = 2 * p->nN;
     h->N = h->Nv + p->nV;

@@ -324,9 +324,12 @@ def build_plan(fac: BlockFactor, max_rb: int = 4, target_jobs: int = 296) -> Sol
             nsrc = 3 if sym.children[i] else 1
             E = fac.blocks[i][0]
             if m == 0:
-                if w:
-                    jobs.append(dict(K=w, nrb=0, nr=0, nsrc=nsrc, out0=0, ystore=n + s.c0, i0=own, i1=a1, i2=a2,
-                                     vals=np.zeros(0), e0=None, e1=None))
+                # root of the tree: nothing to update, only y_t = b_t + children; rows are independent,
+                # so the copy is cut into short store-only jobs that spread over the SMs
+                for r0 in range(0, w, 16):
+                    sl = slice(r0, min(w, r0 + 16))
+                    jobs.append(dict(K=sl.stop - r0, nrb=0, nr=0, nsrc=nsrc, out0=0, ystore=n + s.c0 + r0, i0=own[sl],
+                                     i1=a1[sl], i2=a2[sl], vals=np.zeros(0), e0=None, e1=None))
                     cur.append(len(jobs) - 1)
                 continue
             e0, e1 = child_sources(i, s.struct, -1)
