@@ -194,8 +194,8 @@ def run_ours(args):
     ldb = (B + 31) // 32 * 32
     # algorithmic bytes of one solve (all launches of both sweeps): factor values + gather indices read
     # once; b read, y written, update vectors written and read once (forward); y read, x written (backward)
-    solve_bytes = 8 * plan.nnz_padded + 4 * len(plan.i0) + 8 * (4 * n + 2 * plan.nU) * ldb
-    solve_flops = 2.0 * plan.nnz_padded * ldb
+    solve_bytes = 8 * plan.nnz + 4 * len(plan.i0) + 8 * (4 * n + 2 * plan.nU) * ldb
+    solve_flops = 2.0 * plan.nnz * ldb
     hbm_peak, peak_src = peaks()
     achieved = solve_bytes / (solve_ms * 1e-3) / 1e9
     roofline = {

@@ -560,13 +560,13 @@ struct DevPlan {
     struct Launch { int grid, nwc, nslab, nstages, cta_off; };
     std::vector<Launch> launches;
     int n_forward = 0;
-    long long nstages_total = 0;
+    long long nstages_total = 0, packed_doubles = 0;
 };
 
 }  // namespace
 
 struct fcb_context {
-    int device = 0, num_sms = 0, smem_per_sm = 0, force_nwc = 0;
+    int device = 0, num_sms = 0, smem_per_sm = 0, force_nwc = 0, force_nrb = 0;
     cudaStream_t stream = nullptr;
     std::string error;
     int B = 0, ldb = 0;
@@ -644,41 +644,67 @@ int upload(fcb_context* h, T** dst, const T* src, size_t count) {
     } while (0)
 
 // Compile a SolvePlan into per-CTA instruction streams (see k_front_sweep) and upload it.
+// Tiling policy per launch (the blocks of one elimination-tree level): tiles as tall as possible (up to
+// 4 row blocks of 8) while the launch still has ~4 warp-jobs per SM; CTAs as wide as possible (up to 8
+// warps x 32 trajectories, sharing one copy of V and of the gathered rows) while there is at least
+// one CTA per SM.
 int upload_plan(fcb_context* h, DevPlan& d, const fcb_plan& p) {
     d.n = p.n;
     d.nU = p.nU;
-    d.njobs = p.njobs;
     d.nlaunch = p.nlaunch;
     d.n_forward = p.n_forward_launches;
     const int zrow = 2 * p.n + p.nU;
-    size_t nvals = 0;
-    for (int i = 0; i < p.njobs; ++i) {
-        const int K = p.job_K[i], nrb = p.job_nrb[i], nr = p.job_nr[i], nsrc = p.job_nsrc[i];
-        if (nrb < 0 || nrb > 4) return fail(h, FCB_ERR_INVALID, "plan job %d: %d row blocks not in [0,4]", i, nrb);
-        if (nr > 8 * nrb || nr < 0 || K < 0 || (p.job_vptr[i] & 31) || (nsrc != 1 && nsrc != 3) || p.job_out0[i] < 0 ||
-            p.job_out0[i] + nr > zrow || (p.job_ystore[i] >= 0 && p.job_ystore[i] + K > zrow) || p.job_iptr[i] < 0)
-            return fail(h, FCB_ERR_INVALID, "plan job %d is malformed", i);
-        const long long K4 = (K + 3) & ~3;
-        for (long long k = p.job_iptr[i]; k < p.job_iptr[i] + K4; ++k)
+    for (int i = 0; i < p.nblocks; ++i) {
+        const int K = p.blk_K[i], M = p.blk_M[i], nsrc = p.blk_nsrc[i];
+        if (K < 0 || M < 0 || (nsrc != 1 && nsrc != 3) || p.blk_out0[i] < 0 || p.blk_out0[i] + M > zrow ||
+            (p.blk_ystore[i] >= 0 && p.blk_ystore[i] + K > zrow) || p.blk_iptr[i] < 0 || p.blk_vptr[i] < 0)
+            return fail(h, FCB_ERR_INVALID, "plan block %d is malformed", i);
+        for (long long k = p.blk_iptr[i]; k < p.blk_iptr[i] + K; ++k)
             if (p.i0[k] < 0 || p.i0[k] > zrow || (nsrc == 3 && (p.i1[k] < 0 || p.i1[k] > zrow || p.i2[k] < 0 || p.i2[k] > zrow)))
-                return fail(h, FCB_ERR_INVALID, "plan job %d: gather index out of range", i);
-        if (p.job_eptr[i] >= 0)
-            for (int r = 0; r < nr; ++r)
-                if (p.e0[p.job_eptr[i] + r] >= zrow || p.e1[p.job_eptr[i] + r] >= zrow)
-                    return fail(h, FCB_ERR_INVALID, "plan job %d: seed index out of range", i);
-        nvals = std::max(nvals, (size_t)(p.job_vptr[i] + K4 * 8 * nrb));
+                return fail(h, FCB_ERR_INVALID, "plan block %d: gather index out of range", i);
+        if (p.blk_eptr[i] >= 0)
+            for (int r = 0; r < M; ++r)
+                if (p.e0[p.blk_eptr[i] + r] >= zrow || p.e1[p.blk_eptr[i] + r] >= zrow)
+                    return fail(h, FCB_ERR_INVALID, "plan block %d: seed index out of range", i);
     }
+    struct Tile { int blk, r0, nr, nrb, k_lo, k_hi; bool ystore; };  // rows [r0, r0+nr) of a block; ystore rows [k_lo,k_hi)
     std::vector<int> srec, jrec, cta_sptr, cta_jptr;
+    std::vector<double> packed;
     d.launches.clear();
     const int nw_all = h->ldb / 32;  // 32-trajectory warps needed to cover the ensemble
     for (int l = 0; l < p.nlaunch; ++l) {
-        const int j0 = p.launch_ptr[l], nj = p.launch_ptr[l + 1] - j0;
+        const int b0 = p.launch_ptr[l], b1 = p.launch_ptr[l + 1];
         DevPlan::Launch L{0, 8, 1, 4, (int)cta_sptr.size()};
-        if (nj <= 0) { d.launches.push_back(L); continue; }
-        // CTA width: as wide as the ensemble allows (V and the row gathers are shared by the whole CTA),
-        // narrower when the launch has too few jobs to occupy the SMs
+        if (b1 <= b0) { d.launches.push_back(L); continue; }
+        // ---- tile height
+        auto njobs_for = [&](int nrb) {
+            long long c = 0;
+            for (int b = b0; b < b1; ++b) c += p.blk_M[b] > 0 ? (p.blk_M[b] + 8 * nrb - 1) / (8 * nrb) : (p.blk_K[b] + 15) / 16;
+            return c;
+        };
+        int nrb_cap = 4;
+        while (nrb_cap > 1 && njobs_for(nrb_cap) * nw_all < 4LL * h->num_sms) --nrb_cap;
+        if (h->force_nrb > 0) nrb_cap = h->force_nrb;
+        std::vector<Tile> tiles;
+        for (int b = b0; b < b1; ++b) {
+            const int M = p.blk_M[b], K = p.blk_K[b];
+            if (M == 0) {
+                // store-only block (the root of the tree): rows are independent, cut into short copy jobs
+                for (int k = 0; k < K; k += 16) tiles.push_back({b, 0, 0, 0, k, std::min(K, k + 16), true});
+                continue;
+            }
+            const int nblk = (M + 7) / 8, ntile = (nblk + nrb_cap - 1) / nrb_cap;
+            int r0 = 0;
+            for (int t = 0; t < ntile; ++t) {
+                const int nb = nblk / ntile + (t < nblk % ntile ? 1 : 0), nr = std::min(8 * nb, M - r0);
+                tiles.push_back({b, r0, nr, nb, 0, K, t == 0 && p.blk_ystore[b] >= 0});
+                r0 += nr;
+            }
+        }
+        const int nj = (int)tiles.size();
+        // ---- CTA width
         int nwc = nw_all >= 8 ? 8 : (nw_all >= 4 ? 4 : (nw_all >= 2 ? 2 : 1));
-        while (nwc > 2 && (long long)nj * ((nw_all + nwc - 1) / nwc) < h->num_sms) nwc >>= 1;
+        while (nwc > 1 && (long long)nj * ((nw_all + nwc - 1) / nwc) < (long long)h->num_sms * (nwc == 8 ? 2 : 1)) nwc >>= 1;
         if (h->force_nwc > 0) nwc = h->force_nwc;
         L.nwc = nwc;
         L.nslab = (nw_all + nwc - 1) / nwc;
@@ -688,55 +714,68 @@ int upload_plan(fcb_context* h, DevPlan& d, const fcb_plan& p) {
                            : std::max(1, (int)(((long long)nj * L.nslab + h->num_sms - 1) / h->num_sms));
         L.grid = std::min(nj, std::max(1, per_sm * h->num_sms / L.nslab));
         L.nstages = std::max(2, std::min(SV_MAXSTAGES, (h->smem_per_sm / per_sm - 1024 - 2 * SV_MAXSTAGES * 8) / stage_bytes));
-        // longest-processing-time assignment of jobs to CTAs (cost in rough SM cycles)
-        auto stages_of = [&](int j) {
-            const int K4 = (p.job_K[j] + 3) & ~3, kc = p.job_nsrc[j] == 3 ? SV_SLOTS / 3 : SV_SLOTS;
+        // ---- longest-processing-time assignment of tiles to CTAs (cost in rough SM cycles)
+        auto ktile = [&](const Tile& t) { return t.nrb > 0 ? p.blk_K[t.blk] : t.k_hi - t.k_lo; };
+        auto stages_of = [&](const Tile& t) {
+            const int K4 = (ktile(t) + 3) & ~3, kc = p.blk_nsrc[t.blk] == 3 ? SV_SLOTS / 3 : SV_SLOTS;
             return std::max(1, (K4 + kc - 1) / kc);
         };
         std::vector<std::pair<long long, int>> order(nj);
-        for (int q = 0; q < nj; ++q) {
-            const int j = j0 + q, K4 = (p.job_K[j] + 3) & ~3;
-            order[q] = {-(600LL + 150LL * stages_of(j) + 8LL * K4 * std::max(1, p.job_nrb[j])), j};
-        }
+        for (int q = 0; q < nj; ++q)
+            order[q] = {-(600LL + 150LL * stages_of(tiles[q]) + 8LL * ((ktile(tiles[q]) + 3) & ~3) * std::max(1, tiles[q].nrb)), q};
         std::sort(order.begin(), order.end());
         std::vector<std::vector<int>> mine(L.grid);
         std::vector<std::pair<long long, int>> heap(L.grid);  // (load, cta) min-heap
         for (int c = 0; c < L.grid; ++c) heap[c] = {0, c};
         auto cmp = [](const std::pair<long long, int>& a, const std::pair<long long, int>& b) { return a > b; };
         std::make_heap(heap.begin(), heap.end(), cmp);
-        for (auto& [negcost, j] : order) {
+        for (auto& [negcost, q] : order) {
             std::pop_heap(heap.begin(), heap.end(), cmp);
             heap.back().first += -negcost;
-            mine[heap.back().second].push_back(j);
+            mine[heap.back().second].push_back(q);
             std::push_heap(heap.begin(), heap.end(), cmp);
         }
+        // ---- emit the streams; V goes out in MMA A-fragment order [K4/4][nrb][8 rows][4 k]
         for (int c = 0; c < L.grid; ++c) {
             cta_sptr.push_back((int)(srec.size() / SV_SREC));
             cta_jptr.push_back((int)(jrec.size() / SV_JREC));
-            for (int j : mine[c]) {
-                const int K = p.job_K[j], nrb = p.job_nrb[j], nr = p.job_nr[j], nsrc = p.job_nsrc[j];
-                const int K4 = (K + 3) & ~3, kc = nsrc == 3 ? SV_SLOTS / 3 : SV_SLOTS;
+            for (int q : mine[c]) {
+                const Tile& t = tiles[q];
+                const int b = t.blk, Kb = p.blk_K[b], nsrc = p.blk_nsrc[b];
+                const int K = t.k_hi - t.k_lo, K4 = (K + 3) & ~3, kc = nsrc == 3 ? SV_SLOTS / 3 : SV_SLOTS;
                 const size_t jb = jrec.size();
                 jrec.resize(jb + SV_JREC, -1);
-                jrec[jb + 0] = K; jrec[jb + 1] = nrb; jrec[jb + 2] = nr; jrec[jb + 3] = nsrc;
-                jrec[jb + 4] = p.job_out0[j]; jrec[jb + 5] = p.job_ystore[j]; jrec[jb + 6] = p.job_eptr[j] >= 0 ? 1 : 0;
-                if (p.job_eptr[j] >= 0)
-                    for (int r = 0; r < nr; ++r) {
-                        jrec[jb + 8 + r] = p.e0[p.job_eptr[j] + r];
-                        jrec[jb + 40 + r] = p.e1[p.job_eptr[j] + r];
+                jrec[jb + 0] = K; jrec[jb + 1] = t.nrb; jrec[jb + 2] = t.nr; jrec[jb + 3] = nsrc;
+                jrec[jb + 4] = p.blk_out0[b] + t.r0;
+                jrec[jb + 5] = t.ystore ? p.blk_ystore[b] + t.k_lo : -1;
+                const bool seeded = t.nrb > 0 && p.blk_eptr[b] >= 0;
+                jrec[jb + 6] = seeded ? 1 : 0;
+                if (seeded)
+                    for (int r = 0; r < t.nr; ++r) {
+                        jrec[jb + 8 + r] = p.e0[p.blk_eptr[b] + t.r0 + r];
+                        jrec[jb + 40 + r] = p.e1[p.blk_eptr[b] + t.r0 + r];
                     }
+                const size_t v0 = packed.size();
+                if (t.nrb > 0) {
+                    packed.resize(v0 + (size_t)K4 * 8 * t.nrb, 0.0);
+                    const double* V = p.vals + p.blk_vptr[b];
+                    for (int r = 0; r < t.nr; ++r) {
+                        const double* vr = V + (size_t)(t.r0 + r) * Kb;
+                        double* dst = packed.data() + v0 + (size_t)(r >> 3) * 32 + (size_t)(r & 7) * 4;
+                        for (int k = 0; k < K; ++k) dst[(size_t)(k >> 2) * t.nrb * 32 + (k & 3)] = vr[k];
+                    }
+                }
                 int k0 = 0;
                 do {  // a job with K == 0 still gets one (empty) stage that carries its record
                     const int nk = std::max(0, std::min(kc, K4 - k0));
                     const size_t sb = srec.size();
                     srec.resize(sb + SV_SREC, -1);
                     for (int pl = 0; pl < nsrc; ++pl) {
-                        const int32_t* ip = pl == 0 ? p.i0 : (pl == 1 ? p.i1 : p.i2);
-                        for (int k = 0; k < nk; ++k) srec[sb + pl * kc + k] = ip[p.job_iptr[j] + k0 + k];
+                        const int32_t* ip = (pl == 0 ? p.i0 : (pl == 1 ? p.i1 : p.i2)) + p.blk_iptr[b] + t.k_lo;
+                        for (int k = 0; k < nk; ++k) srec[sb + pl * kc + k] = (k0 + k < K) ? ip[k0 + k] : zrow;
                     }
-                    const long long voff = p.job_vptr[j] + (long long)k0 * 8 * nrb;
-                    srec[sb + SV_SLOTS] = (int)(voff / 32);
-                    srec[sb + SV_SLOTS + 1] = nk * 64 * nrb;
+                    srec[sb + SV_SLOTS] = (int)((v0 + (size_t)k0 * 8 * t.nrb) / 32);
+                    srec[sb + SV_SLOTS + 1] = nk * 64 * t.nrb;
                     srec[sb + SV_SLOTS + 2] = k0 == 0 ? (int)(jb / SV_JREC) : -1;
                     k0 += kc;
                 } while (k0 < K4);
@@ -747,14 +786,18 @@ int upload_plan(fcb_context* h, DevPlan& d, const fcb_plan& p) {
         d.launches.push_back(L);
     }
     d.nstages_total = (long long)(srec.size() / SV_SREC);
+    d.njobs = (int)(jrec.size() / SV_JREC);
+    d.packed_doubles = (long long)packed.size();
+    if (packed.size() / 32 > 0x7fffffffULL) return fail(h, FCB_ERR_INVALID, "factor too large for 32-bit tile offsets");
     if (srec.empty()) srec.resize(SV_SREC, -1);
     if (jrec.empty()) jrec.resize(SV_JREC, -1);
+    if (packed.empty()) packed.resize(32, 0.0);
     if (cta_sptr.empty()) { cta_sptr.push_back(0); cta_jptr.push_back(0); }
     TRY(upload(h, &d.srec, srec.data(), srec.size()));
     TRY(upload(h, &d.jrec, jrec.data(), jrec.size()));
     TRY(upload(h, &d.cta_sptr, cta_sptr.data(), cta_sptr.size()));
     TRY(upload(h, &d.cta_jptr, cta_jptr.data(), cta_jptr.size()));
-    TRY(upload(h, &d.vals, p.vals, nvals ? nvals : 32));
+    TRY(upload(h, &d.vals, packed.data(), packed.size()));
     CK(cudaStreamSynchronize(h->stream));  // host vectors go out of scope
     return FCB_OK;
 }
@@ -1001,6 +1044,9 @@ int create_impl(fcb_context* h, const fcb_problem* p, int B) {
         h->force_nwc = env ? atoi(env) : 0;
         if (h->force_nwc != 0 && h->force_nwc != 1 && h->force_nwc != 2 && h->force_nwc != 4 && h->force_nwc != 8) h->force_nwc = 0;
         if (h->force_nwc * 32 > h->ldb && h->force_nwc > 1) h->force_nwc = 0;
+        env = getenv("FCB_SWEEP_ROWBLOCKS");  // tuning knob: force the tile height (8-row blocks) of every launch
+        h->force_nrb = env ? atoi(env) : 0;
+        if (h->force_nrb < 0 || h->force_nrb > 4) h->force_nrb = 0;
     }
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     for (auto& e : h->ev) CK(cudaEventCreate(&e));

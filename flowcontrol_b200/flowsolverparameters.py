@@ -88,4 +88,3 @@ class ParamEnsemble(ParamFlowSolver):
     batch: int = 1
     device: int = 0
     leaf_cells: int = 8  # nested-dissection leaf size (ordering.py)
-    rows_per_tile: int = 32  # largest solve-plan tile height: 8, 16, 24 or 32 (multifrontal.py)

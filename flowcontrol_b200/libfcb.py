@@ -25,10 +25,9 @@ PHASE_NAMES = ("rhs", "forward", "backward", "post", "element", "measure")
 
 class fcb_plan(C.Structure):
     _fields_ = [
-        ("n", C.c_int32), ("nU", C.c_int32), ("njobs", C.c_int32),
-        ("job_K", c_i32p), ("job_nrb", c_i32p), ("job_nr", c_i32p), ("job_nsrc", c_i32p),
-        ("job_out0", c_i32p), ("job_ystore", c_i32p),
-        ("job_iptr", c_i64p), ("job_vptr", c_i64p), ("job_eptr", c_i64p),
+        ("n", C.c_int32), ("nU", C.c_int32), ("nblocks", C.c_int32),
+        ("blk_K", c_i32p), ("blk_M", c_i32p), ("blk_nsrc", c_i32p), ("blk_out0", c_i32p), ("blk_ystore", c_i32p),
+        ("blk_iptr", c_i64p), ("blk_vptr", c_i64p), ("blk_eptr", c_i64p),
         ("i0", c_i32p), ("i1", c_i32p), ("i2", c_i32p), ("e0", c_i32p), ("e1", c_i32p), ("vals", c_f64p),
         ("nlaunch", C.c_int32), ("launch_ptr", c_i32p), ("n_forward_launches", C.c_int32),
     ]
@@ -146,10 +145,10 @@ class ProblemPack:
         for o in (1, 2):
             s.ctrl_rhs[o - 1] = _ptr(arr(prob.ctrl_rhs[o], np.float64), c_f64p)
             p, q = prob.plans[o], s.plan[o - 1]
-            q.n, q.nU, q.njobs = p.n, p.nU, len(p.job_K)
-            for name in ("job_K", "job_nrb", "job_nr", "job_nsrc", "job_out0", "job_ystore", "i0", "i1", "i2", "e0", "e1"):
+            q.n, q.nU, q.nblocks = p.n, p.nU, len(p.blk_K)
+            for name in ("blk_K", "blk_M", "blk_nsrc", "blk_out0", "blk_ystore", "i0", "i1", "i2", "e0", "e1"):
                 setattr(q, name, _ptr(arr(getattr(p, name), np.int32), c_i32p))
-            for name in ("job_iptr", "job_vptr", "job_eptr"):
+            for name in ("blk_iptr", "blk_vptr", "blk_eptr"):
                 setattr(q, name, _ptr(arr(getattr(p, name), np.int64), c_i64p))
             q.vals = _ptr(arr(p.vals, np.float64), c_f64p)
             q.n_forward_launches = p.n_forward_launches

@@ -193,51 +193,48 @@ class BlockFactor:
 
 @dataclass
 class SolvePlan:
-    """Flat job arrays consumed by the CUDA kernel ``k_front_sweep`` (csrc/fcb200.cu).
+    """Flat block arrays handed to the CUDA library (include/fcb200.h: fcb_plan); the library cuts every
+    block into tensor-core tiles for the actual ensemble width and SM count (csrc/fcb200.cu: upload_plan).
 
-    The kernel works on one buffer Z with rows
+    The device works on one buffer Z with rows
         [0, n)          b on entry, x on exit            (solver row order)
         [n, 2n)         y (forward-eliminated RHS)
         [2n, 2n + nU)   update vectors u_t of every supernode (its subdomain-boundary rows)
-        2n + nU         a row of zeros (``zrow``): the source of padded / absent gathers
-    A *job* is a small dense GEMM  acc[8*nrb x traj] = V[8*nrb x K4] . x[K4 x traj]  (K4 = K rounded up
-    to a multiple of 4, the k-depth of one FP64 tensor-core MMA) whose input rows are gathered as
-    x_k = Z[i0[k]] (+ Z[i1[k]] + Z[i2[k]] when nsrc == 3) and whose ``nr`` output rows are written to
-    consecutive rows  Z[out0 + r] = acc[r] (+ Z[e0[r]] + Z[e1[r]], -1 = absent).
-    ``ystore >= 0`` additionally stores the gathered x_k (k < K) to Z[ystore + k] (the job that owns y_t).
+        2n + nU         a row of zeros (``zrow``): the source of absent gathers
+    A *block* is a dense product  acc[M x traj] = V[M x K] . x[K x traj]  whose input rows are gathered as
+    x_k = Z[i0[k]] (+ Z[i1[k]] + Z[i2[k]] when nsrc == 3) and whose M output rows go to consecutive rows
+    Z[out0 + r] = acc[r] (+ Z[e0[r]] + Z[e1[r]], -1 = absent).  ``ystore >= 0`` additionally stores the
+    gathered x_k to Z[ystore + k] (the block that owns y_t; M may be 0 for a store-only block).
 
-        forward  (per supernode t, tiles over its m boundary rows, launches by tree height):
-            x_k = b_t[k] + sum_children u_c[..]            (= y_t)
+        forward  (one block per supernode t, launches by tree height):
+            x_k = b_t[k] + sum_children u_c[..]            (= y_t, stored)
             u_t[r] = sum_children u_c[..] - (E_t y_t)[r]
-        backward (tiles over its w own rows, launches by tree depth):
+        backward (launches by tree depth):
             x_t[r] = (F11^-1 y_t)[r] - (G_t x_struct(t))[r]
 
-    ``vals`` holds every job's V in MMA A-fragment order: [K4/4][nrb][8 rows][4 k] doubles, so the 32
-    lanes of a warp read one 8x4 fragment as 256 contiguous bytes.
-    Every output row is produced by exactly one job: no atomics, bit-reproducible."""
+    Every output row is produced by exactly one block: no atomics, bit-reproducible."""
 
     n: int
     nU: int
-    job_K: np.ndarray  # int32 [njobs] gathered rows (index arrays are padded to K4 with zrow)
-    job_nrb: np.ndarray  # int32 8-row blocks of the value tile (0 = store-only job, else 1..4)
-    job_nr: np.ndarray  # int32 valid output rows (<= 8*nrb)
-    job_nsrc: np.ndarray  # int32 1 or 3
-    job_out0: np.ndarray  # int32
-    job_ystore: np.ndarray  # int32 (-1 = none)
-    job_iptr: np.ndarray  # int64 offsets into i0/i1/i2
-    job_vptr: np.ndarray  # int64 offsets into vals
-    job_eptr: np.ndarray  # int64 offsets into e0/e1 (-1 = no epilogue gather)
+    blk_K: np.ndarray  # int32 [nblk] gathered rows
+    blk_M: np.ndarray  # int32 output rows (0 = store-only)
+    blk_nsrc: np.ndarray  # int32 1 or 3
+    blk_out0: np.ndarray  # int32
+    blk_ystore: np.ndarray  # int32 (-1 = none)
+    blk_iptr: np.ndarray  # int64 offsets into i0/i1/i2 (K entries per block)
+    blk_vptr: np.ndarray  # int64 offsets into vals (row-major [M, K] per block)
+    blk_eptr: np.ndarray  # int64 offsets into e0/e1 (M entries per block; -1 = no seed gather)
     i0: np.ndarray
     i1: np.ndarray
     i2: np.ndarray
     e0: np.ndarray
     e1: np.ndarray
     vals: np.ndarray
-    launch_ptr: np.ndarray  # int32 [nlaunch+1] job ranges, forward launches first
+    launch_ptr: np.ndarray  # int32 [nlaunch+1] block ranges, forward launches first
     n_forward_launches: int
 
     @property
-    def nnz_padded(self) -> int:
+    def nnz(self) -> int:
         return int(self.vals.size)
 
     @property
@@ -249,32 +246,7 @@ class SolvePlan:
         return 2 * self.n + self.nU + 1
 
 
-def _row_tiles(nrows: int, max_rb: int = 4) -> list[tuple[int, int, int]]:
-    """Split ``nrows`` into (r0, nr, nrb) tiles of at most ``max_rb`` 8-row blocks, evenly sized."""
-    nblk = (nrows + 7) // 8
-    ntile = (nblk + max_rb - 1) // max_rb
-    out, r0 = [], 0
-    for t in range(ntile):
-        nb = nblk // ntile + (1 if t < nblk % ntile else 0)
-        nr = min(8 * nb, nrows - r0)
-        out.append((r0, nr, nb))
-        r0 += nr
-    assert r0 == nrows
-    return out
-
-
-def _pack_fragments(V: np.ndarray, nrb: int) -> np.ndarray:
-    """V [nr, K] -> A-fragment order [K4/4][nrb][8][4] (zero padded), flattened."""
-    nr, K = V.shape
-    K4 = (K + 3) // 4 * 4
-    P = np.zeros((8 * nrb, K4))
-    P[:nr, :K] = V
-    return P.reshape(nrb, 8, K4 // 4, 4).transpose(2, 0, 1, 3).ravel()
-
-
-def build_plan(fac: BlockFactor, max_rb: int = 4, target_jobs: int = 296) -> SolvePlan:
-    """``max_rb``: largest tile height in 8-row blocks; levels with few rows use shorter tiles so that
-    a launch has at least ~``target_jobs`` independent CTAs' worth of work where possible."""
+def build_plan(fac: BlockFactor) -> SolvePlan:
     sym = fac.sym
     sns = sym.supernodes
     n = sym.n
@@ -302,52 +274,28 @@ def build_plan(fac: BlockFactor, max_rb: int = 4, target_jobs: int = 296) -> Sol
             srcs[slot][hit] = UB + uoff[c] + pos_c[hit]
         return srcs[0], srcs[1]
 
-    jobs: list[dict] = []
-    launches: list[list[int]] = []
-
-    def tile_blocks_for(level_rows: list[int]) -> int:
-        for rb in range(max_rb, 1, -1):
-            if sum((r + 8 * rb - 1) // (8 * rb) for r in level_rows) >= target_jobs:
-                return rb
-        return 1
-
+    blocks: list[dict] = []
+    launch_ptr = [0]
     max_h = max(s.height for s in sns)
     for h in range(max_h + 1):
-        ids = [i for i, s in enumerate(sns) if s.height == h]
-        rb_cap = tile_blocks_for([len(sns[i].struct) for i in ids])
-        cur: list[int] = []
-        for i in ids:
+        for i in (i for i, s in enumerate(sns) if s.height == h):
             s = sns[i]
             w, m = s.c1 - s.c0, len(s.struct)
+            if w == 0 and m == 0:
+                continue
             own = np.arange(s.c0, s.c1, dtype=np.int64)
             a1, a2 = child_sources(i, own, ZROW)
-            nsrc = 3 if sym.children[i] else 1
-            E = fac.blocks[i][0]
-            if m == 0:
-                # root of the tree: nothing to update, only y_t = b_t + children; rows are independent,
-                # so the copy is cut into short store-only jobs that spread over the SMs
-                for r0 in range(0, w, 16):
-                    sl = slice(r0, min(w, r0 + 16))
-                    jobs.append(dict(K=sl.stop - r0, nrb=0, nr=0, nsrc=nsrc, out0=0, ystore=n + s.c0 + r0, i0=own[sl],
-                                     i1=a1[sl], i2=a2[sl], vals=np.zeros(0), e0=None, e1=None))
-                    cur.append(len(jobs) - 1)
-                continue
+            has_children = bool(sym.children[i])
             e0, e1 = child_sources(i, s.struct, -1)
-            for t, (r0, nr, nrb) in enumerate(_row_tiles(m, rb_cap)):
-                jobs.append(dict(K=w, nrb=nrb, nr=nr, nsrc=nsrc, out0=UB + int(uoff[i]) + r0,
-                                 ystore=(n + s.c0) if t == 0 else -1, i0=own, i1=a1, i2=a2,
-                                 vals=_pack_fragments(-E[r0 : r0 + nr, :], nrb),
-                                 e0=e0[r0 : r0 + nr] if nsrc == 3 else None, e1=e1[r0 : r0 + nr] if nsrc == 3 else None))
-                cur.append(len(jobs) - 1)
-        if cur:
-            launches.append(cur)
-    n_fwd = len(launches)
+            blocks.append(dict(K=w, M=m, nsrc=3 if has_children else 1, out0=UB + int(uoff[i]), ystore=n + s.c0,
+                               i0=own, i1=a1, i2=a2, vals=-fac.blocks[i][0], e0=e0 if has_children else None,
+                               e1=e1 if has_children else None))
+        if len(blocks) > launch_ptr[-1]:
+            launch_ptr.append(len(blocks))
+    n_fwd = len(launch_ptr) - 1
     max_d = max(s.depth for s in sns)
     for dpt in range(max_d + 1):
-        ids = [i for i, s in enumerate(sns) if s.depth == dpt]
-        rb_cap = tile_blocks_for([sns[i].c1 - sns[i].c0 for i in ids])
-        cur = []
-        for i in ids:
+        for i in (i for i, s in enumerate(sns) if s.depth == dpt):
             s = sns[i]
             w = s.c1 - s.c0
             if w == 0:
@@ -355,61 +303,50 @@ def build_plan(fac: BlockFactor, max_rb: int = 4, target_jobs: int = 296) -> Sol
             _, Finv, G = fac.blocks[i]
             full = np.concatenate([Finv, -G], axis=1)  # [w, w+m]
             idx = np.concatenate([n + np.arange(s.c0, s.c1, dtype=np.int64), s.struct.astype(np.int64)])
-            for r0, nr, nrb in _row_tiles(w, rb_cap):
-                jobs.append(dict(K=full.shape[1], nrb=nrb, nr=nr, nsrc=1, out0=s.c0 + r0, ystore=-1, i0=idx, i1=None,
-                                 i2=None, vals=_pack_fragments(full[r0 : r0 + nr, :], nrb), e0=None, e1=None))
-                cur.append(len(jobs) - 1)
-        if cur:
-            launches.append(cur)
-    # longest jobs first inside each launch (the kernel deals them round-robin to persistent CTAs)
-    order: list[int] = []
-    launch_ptr = [0]
-    for cur in launches:
-        cur = sorted(cur, key=lambda j: -(jobs[j]["K"] * jobs[j]["nsrc"] + jobs[j]["K"] * jobs[j]["nrb"] + 8 * jobs[j]["nrb"]))
-        order += cur
-        launch_ptr.append(len(order))
-    nj = len(order)
-    K = np.array([jobs[j]["K"] for j in order], dtype=np.int32)
-    K4 = (K.astype(np.int64) + 3) // 4 * 4
-    iptr = np.zeros(nj + 1, dtype=np.int64)
-    iptr[1:] = np.cumsum(K4)
+            blocks.append(dict(K=full.shape[1], M=w, nsrc=1, out0=s.c0, ystore=-1, i0=idx, i1=None, i2=None, vals=full,
+                               e0=None, e1=None))
+        if len(blocks) > launch_ptr[-1]:
+            launch_ptr.append(len(blocks))
+    nb = len(blocks)
+    K = np.array([b["K"] for b in blocks], dtype=np.int32)
+    M = np.array([b["M"] for b in blocks], dtype=np.int32)
+    iptr = np.zeros(nb + 1, dtype=np.int64)
+    iptr[1:] = np.cumsum(K)
     i0 = np.full(int(iptr[-1]), ZROW, dtype=np.int32)
     i1 = np.full(int(iptr[-1]), ZROW, dtype=np.int32)
     i2 = np.full(int(iptr[-1]), ZROW, dtype=np.int32)
-    vptr = np.zeros(nj, dtype=np.int64)
-    eptr = np.full(nj, -1, dtype=np.int64)
+    vptr = np.zeros(nb, dtype=np.int64)
+    eptr = np.full(nb, -1, dtype=np.int64)
     vparts, e0p, e1p = [], [], []
     vpos = epos = 0
-    for q, j in enumerate(order):
-        jb = jobs[j]
-        sl = slice(iptr[q], iptr[q] + jb["K"])
-        i0[sl] = jb["i0"]
-        if jb["nsrc"] == 3:
-            i1[sl], i2[sl] = jb["i1"], jb["i2"]
+    for q, b in enumerate(blocks):
+        sl = slice(iptr[q], iptr[q + 1])
+        i0[sl] = b["i0"]
+        if b["nsrc"] == 3:
+            i1[sl], i2[sl] = b["i1"], b["i2"]
         vptr[q] = vpos
-        vparts.append(jb["vals"])
-        vpos += jb["vals"].size
-        if jb["e0"] is not None:
+        v = np.ascontiguousarray(b["vals"], dtype=np.float64).reshape(int(M[q]), int(K[q]))
+        vparts.append(v.ravel())
+        vpos += v.size
+        if b["e0"] is not None:
             eptr[q] = epos
-            e0p.append(jb["e0"])
-            e1p.append(jb["e1"])
-            epos += jb["nr"]
+            e0p.append(b["e0"])
+            e1p.append(b["e1"])
+            epos += int(M[q])
     cat = lambda xs, dt: np.concatenate(xs).astype(dt) if xs else np.zeros(0, dt)  # noqa: E731
     return SolvePlan(
-        n=n, nU=nU, job_K=K,
-        job_nrb=np.array([jobs[j]["nrb"] for j in order], dtype=np.int32),
-        job_nr=np.array([jobs[j]["nr"] for j in order], dtype=np.int32),
-        job_nsrc=np.array([jobs[j]["nsrc"] for j in order], dtype=np.int32),
-        job_out0=np.array([jobs[j]["out0"] for j in order], dtype=np.int32),
-        job_ystore=np.array([jobs[j]["ystore"] for j in order], dtype=np.int32),
-        job_iptr=iptr[:-1].copy(), job_vptr=vptr, job_eptr=eptr,
+        n=n, nU=nU, blk_K=K, blk_M=M,
+        blk_nsrc=np.array([b["nsrc"] for b in blocks], dtype=np.int32),
+        blk_out0=np.array([b["out0"] for b in blocks], dtype=np.int32),
+        blk_ystore=np.array([b["ystore"] for b in blocks], dtype=np.int32),
+        blk_iptr=iptr[:-1].copy(), blk_vptr=vptr, blk_eptr=eptr,
         i0=i0, i1=i1, i2=i2, e0=cat(e0p, np.int32), e1=cat(e1p, np.int32), vals=cat(vparts, np.float64),
         launch_ptr=np.array(launch_ptr, dtype=np.int32), n_forward_launches=n_fwd,
     )
 
 
 def apply_plan_host(plan: SolvePlan, b_perm: np.ndarray) -> np.ndarray:
-    """Numpy emulation of the CUDA sweeps, job by job, from the packed arrays (tests only)."""
+    """Numpy emulation of the device sweeps, block by block, from the flat arrays (tests only)."""
     b = np.asarray(b_perm, dtype=np.float64)
     squeeze = b.ndim == 1
     if squeeze:
@@ -417,26 +354,24 @@ def apply_plan_host(plan: SolvePlan, b_perm: np.ndarray) -> np.ndarray:
     n = plan.n
     Z = np.zeros((plan.z_rows, b.shape[1]))
     Z[:n] = b
-    for q in range(len(plan.job_K)):
-        K, nrb, nr = int(plan.job_K[q]), int(plan.job_nrb[q]), int(plan.job_nr[q])
-        K4 = (K + 3) // 4 * 4
-        sl = slice(plan.job_iptr[q], plan.job_iptr[q] + K4)
+    for q in range(len(plan.blk_K)):
+        K, M = int(plan.blk_K[q]), int(plan.blk_M[q])
+        sl = slice(plan.blk_iptr[q], plan.blk_iptr[q] + K)
         x = Z[plan.i0[sl]]
-        if plan.job_nsrc[q] == 3:
+        if plan.blk_nsrc[q] == 3:
             x = x + Z[plan.i1[sl]] + Z[plan.i2[sl]]
-        if plan.job_ystore[q] >= 0:
-            Z[plan.job_ystore[q] : plan.job_ystore[q] + K] = x[:K]
-        if nrb == 0:
+        if plan.blk_ystore[q] >= 0:
+            Z[plan.blk_ystore[q] : plan.blk_ystore[q] + K] = x
+        if M == 0:
             continue
-        V = plan.vals[plan.job_vptr[q] : plan.job_vptr[q] + K4 * 8 * nrb]
-        V = V.reshape(K4 // 4, nrb, 8, 4).transpose(1, 2, 0, 3).reshape(8 * nrb, K4)
-        acc = V[:nr] @ x
-        if plan.job_eptr[q] >= 0:
-            es = slice(plan.job_eptr[q], plan.job_eptr[q] + nr)
+        V = plan.vals[plan.blk_vptr[q] : plan.blk_vptr[q] + M * K].reshape(M, K)
+        acc = V @ x
+        if plan.blk_eptr[q] >= 0:
+            es = slice(plan.blk_eptr[q], plan.blk_eptr[q] + M)
             for extra in (plan.e0[es], plan.e1[es]):
                 has = extra >= 0
                 acc[has] += Z[extra[has]]
-        Z[plan.job_out0[q] : plan.job_out0[q] + nr] = acc
+        Z[plan.blk_out0[q] : plan.blk_out0[q] + M] = acc
     assert not Z[plan.zrow].any()
     x = Z[:n]
     return x[:, 0] if squeeze else x

@@ -114,7 +114,6 @@ class FlowProblem:
         shift: float = 0.0,
         pin_pressure: bool = False,
         leaf_cells: int = 8,
-        rows_per_tile: int = 32,
         symbolic: SymbolicFactor | None = None,
     ):
         self.tab, self.blocks = tab, blocks
@@ -147,7 +146,7 @@ class FlowProblem:
             self.A_raw[order] = A
             fac = BlockFactor(self.sym, A)
             self.factors[order] = fac
-            self.plans[order] = build_plan(fac, max_rb=max(1, min(4, rows_per_tile // 8)))
+            self.plans[order] = build_plan(fac)
             # rhs contribution per unit u_ctrl_k in solver row order: (F_k - A[:,Gamma] shape_k)[perm]
             lift = (A @ G.T).toarray().T if na else np.zeros((0, tab.N))
             self.ctrl_rhs[order] = np.ascontiguousarray((force - lift)[:, self.sym.perm])

@@ -40,27 +40,30 @@ typedef enum fcb_status {
     FCB_ERR_STATE = -4      /* call order violated (e.g. step before state)*/
 } fcb_status;
 
-/* Solve plan of one factorised LHS (flowcontrol_b200/multifrontal.py: SolvePlan).
- * Replaces the MUMPS factors held by dolfin.LUSolver after set_operator
- * (src/flowcontrol/flowsolver.py:694-697, 812-814). */
+/* Solve plan of one factorised LHS (flowcontrol_b200/multifrontal.py: SolvePlan): the dense blocks of a
+ * multifrontal factorisation in application order.  Replaces the MUMPS factors held by dolfin.LUSolver
+ * after set_operator (src/flowcontrol/flowsolver.py:694-697, 812-814).
+ * The device buffer Z has rows [0,n) b -> x, [n,2n) y, [2n,2n+nU) update vectors, row 2n+nU = zeros.
+ * Block q:  x_k = Z[i0[k]] (+ Z[i1[k]] + Z[i2[k]] if nsrc == 3), k < K;  if ystore >= 0: Z[ystore+k] = x_k;
+ *           Z[out0+r] = sum_k V[r][k] x_k (+ Z[e0[r]] + Z[e1[r]] if eptr >= 0, -1 = absent), r < M.
+ * Blocks of one launch are independent (no block reads a row another block of that launch writes). */
 typedef struct fcb_plan {
-    int32_t n;                /* free unknowns                                                    */
-    int32_t nU;               /* rows of the update-vector region (Z has 2n + nU + 1 rows, last = 0) */
-    int32_t njobs;
-    const int32_t* job_K;      /* [njobs] gathered input rows (index lists padded to K4 = 4*ceil(K/4)) */
-    const int32_t* job_nrb;    /* [njobs] 8-row blocks of the value tile: 0 (store only) .. 4        */
-    const int32_t* job_nr;     /* [njobs] valid output rows (<= 8*nrb)                             */
-    const int32_t* job_nsrc;   /* [njobs] 1: x_k = Z[i0[k]]; 3: + Z[i1[k]] + Z[i2[k]] (2n+nU = zero row) */
-    const int32_t* job_out0;   /* [njobs] first output row in Z                                    */
-    const int32_t* job_ystore; /* [njobs] first row to store the gathered x_k to, or -1            */
-    const int64_t* job_iptr;   /* [njobs] offsets into i0/i1/i2                                    */
-    const int64_t* job_vptr;   /* [njobs] offsets into vals ([K4/4][nrb][8][4] per job: MMA A fragments) */
-    const int64_t* job_eptr;   /* [njobs] offsets into e0/e1 (output-row gathers), or -1           */
+    int32_t n;                 /* free unknowns                                                    */
+    int32_t nU;                /* rows of the update-vector region                                 */
+    int32_t nblocks;
+    const int32_t* blk_K;      /* [nblocks] gathered input rows                                    */
+    const int32_t* blk_M;      /* [nblocks] output rows (0 = store-only block)                     */
+    const int32_t* blk_nsrc;   /* [nblocks] 1 or 3 gather lists                                    */
+    const int32_t* blk_out0;   /* [nblocks] first output row in Z                                  */
+    const int32_t* blk_ystore; /* [nblocks] first row to store the gathered x_k to, or -1          */
+    const int64_t* blk_iptr;   /* [nblocks] offsets into i0/i1/i2 (K entries per block)            */
+    const int64_t* blk_vptr;   /* [nblocks] offsets into vals (row-major M x K per block)          */
+    const int64_t* blk_eptr;   /* [nblocks] offsets into e0/e1 (M entries per block), or -1        */
     const int32_t *i0, *i1, *i2;
     const int32_t *e0, *e1;
     const double* vals;
     int32_t nlaunch;
-    const int32_t* launch_ptr; /* [nlaunch+1] job ranges; jobs of a launch are independent          */
+    const int32_t* launch_ptr; /* [nlaunch+1] block ranges; blocks of a launch are independent      */
     int32_t n_forward_launches;
 } fcb_plan;
 

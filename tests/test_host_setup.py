@@ -133,38 +133,35 @@ def test_multifrontal_matches_superlu_and_plan_matches_factor(small):
     Aff = A[sym.perm][:, sym.perm].tocsc()
     xref = spla.splu(Aff).solve(b)
     assert np.linalg.norm(x - xref) / np.linalg.norm(xref) < 1e-11
-    for max_rb in (1, 2, 4):
-        plan = build_plan(fac, max_rb=max_rb, target_jobs=40)
-        assert np.abs(apply_plan_host(plan, b) - x).max() < 1e-12 * np.abs(x).max()
-        assert plan.job_nrb.min() >= 0 and plan.job_nrb.max() <= max_rb
-        assert np.all(plan.job_nr <= 8 * plan.job_nrb) and np.all(plan.job_nr > 8 * (plan.job_nrb - 1))
-        assert np.all(plan.job_vptr % 2 == 0) and plan.i0.max() <= plan.zrow
-        # every x row and every y row is produced exactly once; jobs of one launch never read rows
-        # that the same launch writes
-        n = sym.n
-        bw = np.arange(len(plan.job_K)) >= plan.launch_ptr[plan.n_forward_launches]
-        rows_x = np.concatenate([np.arange(o, o + r) for o, r in zip(plan.job_out0[bw], plan.job_nr[bw])])
-        assert sorted(rows_x.tolist()) == list(range(n))
-        ys = plan.job_ystore >= 0
-        rows_y = np.concatenate([np.arange(o, o + k) for o, k in zip(plan.job_ystore[ys], plan.job_K[ys])])
-        assert sorted(rows_y.tolist()) == list(range(n, 2 * n))
-        for l in range(len(plan.launch_ptr) - 1):
-            written, read = set(), set()
-            for q in range(plan.launch_ptr[l], plan.launch_ptr[l + 1]):
-                K, nr = int(plan.job_K[q]), int(plan.job_nr[q])
-                written |= set(range(plan.job_out0[q], plan.job_out0[q] + nr)) if plan.job_nrb[q] else set()
-                if plan.job_ystore[q] >= 0:
-                    written |= set(range(plan.job_ystore[q], plan.job_ystore[q] + K))
-                sl = slice(plan.job_iptr[q], plan.job_iptr[q] + K)
-                read |= set(plan.i0[sl].tolist())
-                if plan.job_nsrc[q] == 3:
-                    read |= set(plan.i1[sl].tolist()) | set(plan.i2[sl].tolist())
-                if plan.job_eptr[q] >= 0:
-                    es = slice(plan.job_eptr[q], plan.job_eptr[q] + nr)
-                    read |= set(plan.e0[es].tolist()) | set(plan.e1[es].tolist())
-            read.discard(-1)
-            assert plan.zrow not in written
-            assert not (written & read)
+    plan = build_plan(fac)
+    assert np.abs(apply_plan_host(plan, b) - x).max() < 1e-12 * np.abs(x).max()
+    assert plan.i0.max() <= plan.zrow and plan.nnz == sym.factor_entries()
+    # every x row and every y row is produced exactly once; blocks of one launch never read rows
+    # that the same launch writes
+    n = sym.n
+    bw = np.arange(len(plan.blk_K)) >= plan.launch_ptr[plan.n_forward_launches]
+    rows_x = np.concatenate([np.arange(o, o + r) for o, r in zip(plan.blk_out0[bw], plan.blk_M[bw])])
+    assert sorted(rows_x.tolist()) == list(range(n))
+    ys = plan.blk_ystore >= 0
+    rows_y = np.concatenate([np.arange(o, o + k) for o, k in zip(plan.blk_ystore[ys], plan.blk_K[ys])])
+    assert sorted(rows_y.tolist()) == list(range(n, 2 * n))
+    for l in range(len(plan.launch_ptr) - 1):
+        written, read = set(), set()
+        for q in range(plan.launch_ptr[l], plan.launch_ptr[l + 1]):
+            K, M = int(plan.blk_K[q]), int(plan.blk_M[q])
+            written |= set(range(plan.blk_out0[q], plan.blk_out0[q] + M))
+            if plan.blk_ystore[q] >= 0:
+                written |= set(range(plan.blk_ystore[q], plan.blk_ystore[q] + K))
+            sl = slice(plan.blk_iptr[q], plan.blk_iptr[q] + K)
+            read |= set(plan.i0[sl].tolist())
+            if plan.blk_nsrc[q] == 3:
+                read |= set(plan.i1[sl].tolist()) | set(plan.i2[sl].tolist())
+            if plan.blk_eptr[q] >= 0:
+                es = slice(plan.blk_eptr[q], plan.blk_eptr[q] + M)
+                read |= set(plan.e0[es].tolist()) | set(plan.e1[es].tolist())
+        read.discard(-1)
+        assert plan.zrow not in written
+        assert not (written & read)
 
 
 def test_problem_rhs_and_lifting_match_oracle():
