@@ -18,6 +18,7 @@
 //   k_measure     sensors (sparse rows) + energy reduction (fixed order)
 // Closed loop adds k_controller before and k_log after, all inside one CUDA graph.
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -184,42 +185,54 @@ __global__ void __launch_bounds__(256) k_rhs_build(int n, int Nv, const int* __r
 // ----------------------------------------------------------------------------------------------
 // Multifrontal sweeps: dense tile products on the FP64 tensor cores, fed by bulk-async (TMA) copies.
 //
-// One job (multifrontal.py: SolvePlan) = 8*nrb output rows x all trajectories of the CTA's slab:
-//   x_k   = Z[i0[k]] (+ Z[i1[k]] + Z[i2[k]])          gathered input rows, k < K4
+// One job (a row tile of a SolvePlan block) = 8*nrb output rows x the W = 32*NWC trajectories of the CTA's slab:
+//   x_k   = Z[i0[k]] (+ Z[i1[k]] + Z[i2[k]])          gathered input rows
 //   acc   = sum_k V[:,k] x_k                           mma.sync m8n8k4 f64: M = rows, N = trajectories
 //   Z[out0 + r] = acc_r (+ Z[e0[r]] + Z[e1[r]])        r < nr
-// CTA = SV_MAXW consumer warps (32 trajectories each, up to 256 per slab) + 1 producer warp.  The
-// producer streams, per stage of a ring, up to SV_SLOTS gathered rows (one cp.async.bulk per row,
-// 8*NT bytes each) and the matching slice of V (one cp.async.bulk; the host packs V in A-fragment
-// order so a fragment is one conflict-free 256-byte shared-memory read) and signals an mbarrier;
-// consumers multiply out of shared memory and hand the stage back through a second mbarrier.
-// Row stride in shared memory is NT+8 doubles (== 8 mod 16), which makes the 4x8 B-fragment reads
-// conflict-free.  CTAs are persistent: CTA c runs jobs c, c+gridDim.x, ... of the launch and the
+// CTA = NWC consumer warps (32 trajectories each) + 1 producer warp.  Per stage of a ring the
+// producer copies up to SV_SLOTS gathered rows and the matching slice of V into shared memory and
+// signals an mbarrier; consumers multiply out of shared memory and hand the stage back through a
+// second mbarrier.  The gather lists of a multifrontal solve are almost entirely runs of consecutive
+// rows, and Z is described to the TMA unit as a 2-D tensor [rows][ldb]: a run of 1/2/4/8 rows x W
+// columns is ONE cp.async.bulk.tensor box copy (1 to 4 copies per stage instead of 12 row copies), it
+// lands densely in shared memory, and rows past the end of Z read as zeros (absent gathers).
+// V is packed on the host in A-fragment order (a fragment = one conflict-free 256-byte read).
+// B fragments are read as 16-byte pairs: lane (g = lane/4, t = lane%4) reads columns 2g, 2g+1 of row
+// k0+t in a 16-column group and feeds two MMAs (n-block "even columns", n-block "odd columns"); with
+// dense rows a warp's 512 bytes then spread over all 32 banks four times, the minimum.  The C
+// fragments of such a pair hold 4 consecutive trajectories per lane (32-byte stores).
+// CTAs are persistent: the host compiles each launch into one instruction stream per CTA, and the
 // ring keeps filling across job boundaries.  Every Z row is written by exactly one job: no atomics.
 // ----------------------------------------------------------------------------------------------
-constexpr int SV_SLOTS = 12;    // gathered rows per stage (3 planes x 4 k for nsrc == 3, 12 k otherwise)
+#ifndef SV_MINCTAS8
+#define SV_MINCTAS8 2  // CTAs per SM the 8-warp sweep kernel is compiled for (2 => 96 registers per thread)
+#endif
 constexpr int SV_MAXSTAGES = 8;  // ring depth is chosen per launch from the shared memory one CTA may use
 constexpr int SV_PREFETCH = 4;   // stage records the producer keeps in flight
 constexpr int SV_JREC = 72;      // ints per job record
-constexpr int SV_SREC = 16;      // ints per stage record
+constexpr int SV_SREC = 32;      // ints per stage record
+constexpr int SV_MAXRUNS = 13;   // box copies per stage record
+constexpr int SV_RED_BYTES = 3 * 32 * 32 * 8;  // k-split: partial accumulators of consumer warps 1..3
 
-// Shared-memory geometry of one ring stage for NWC consumer warps (32*NWC trajectories per CTA).
+// Shared-memory geometry of one ring stage for NWC consumer warps (W = 32*NWC trajectories) and `slots`
+// gathered rows per stage (a launch parameter: 3 planes x slots/3 k for nsrc == 3, slots k otherwise).
 template <int NWC>
 struct SweepCfg {
-    static constexpr int NT = 32 * NWC;
-    static constexpr int XS = NT + 8;                      // row stride in doubles (== 8 mod 16)
-    static constexpr int VOFF = SV_SLOTS * XS * 8;         // V slice (up to 12 k x 32 rows)
-    static constexpr int JOFF = VOFF + SV_SLOTS * 32 * 8;  // job record (first stage of a job only)
-    static constexpr int STAGE_BYTES = JOFF + 384;
-    static constexpr int MIN_CTAS = NWC == 8 ? 2 : (NWC == 4 ? 3 : 4);
-    __host__ __device__ static constexpr int smem_bytes(int stages) { return stages * STAGE_BYTES + 2 * SV_MAXSTAGES * 8; }
+    static constexpr int W = 32 * NWC;  // trajectories per CTA = shared-memory row length (dense)
+    static constexpr int MIN_CTAS = NWC == 8 ? SV_MINCTAS8 : (NWC == 4 ? 3 : 4);
+    __host__ __device__ static constexpr int voff(int slots) { return slots * W * 8; }             // V slice: slots k x 32 rows
+    __host__ __device__ static constexpr int joff(int slots) { return voff(slots) + slots * 256; }  // job record (first stage of a job)
+    __host__ __device__ static constexpr int hoff(int slots) { return joff(slots) + 384; }          // stage header (nk, ...)
+    __host__ __device__ static constexpr int stage_bytes(int slots) { return hoff(slots) + 128; }
+    __host__ __device__ static constexpr int smem_bytes(int stages, int slots) { return stages * stage_bytes(slots) + 2 * SV_MAXSTAGES * 8; }
 };
 
 // The host compiles every launch into one instruction stream per CTA (upload_plan):
-//   stage record (16 ints): rows[12] by shared-memory slot (-1 = unused), V offset / 32 doubles, V bytes,
-//                           job record index if this is the first stage of a job (else -1)
-//   job record   (72 ints): K, nrb, nr, nsrc, out0, ystore, has_seed, -, e0[32], e1[32]
-// The producer reads consecutive 64-byte stage records; the job record rides into shared memory with
+//   stage record (32 ints): nk, npieces, V offset / 32 doubles, V bytes, job record index if this is the first
+//                           stage of a job (else -1), total rows, then per piece (source row, slot << 8 | log2 rows);
+//                           its first 16 bytes also ride into shared memory as the stage header (consumers read nk)
+//   job record   (72 ints): K, nrb, nr, nsrc, out0, ystore, has_seed, stages, e0[32], e1[32]
+// The producer reads consecutive 128-byte stage records; the job record rides into shared memory with
 // the job's first stage, so nothing on the device chases a pointer.
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -247,11 +260,27 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
+// one box of the Z tensor: rows [row, row + box height) x columns [col, col + box width)
+__device__ __forceinline__ void tma_box_g2s(uint32_t dst, const void* tmap, int col, int row, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(tmap), "r"(col), "r"(row), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(c[0]), "+d"(c[1])
                  : "d"(a), "d"(b));
 }
+
+struct alignas(64) SweepMaps {
+    CUtensorMap m[6];  // boxes of 1, 2, 4, 8, 16, 32 rows x W columns of Z
+};
 
 struct RingPos {
     int s;
@@ -261,165 +290,221 @@ struct RingPos {
     }
 };
 
-// One job on one consumer warp: seeds, the stage loop (NRB row blocks x 4 trajectory blocks of 8), store.
-template <int NWC, int NRB, bool SRC3, bool YST>
+// One job on one consumer warp: seeds, the stage loop (NRB row blocks x 2 pairs of trajectory blocks), store.
+// acc[rb][p][0..3] = trajectories t0 + 16p + 4*(lane%4) + 0..3 of output row 8*rb + lane/4.
+// KS (k-split, narrow CTAs only): the 4 consumer warps share ONE 32-trajectory tile and take the job's stages
+// round-robin (warp kw owns stages kw, kw+4, ...); partial sums meet in shared memory and warp 0 stores.
+template <int NWC, bool KS, int NRB, bool SRC3, bool YST>
 __device__ __forceinline__ void sweep_job(unsigned char* smem, uint32_t bar_full, uint32_t bar_empty, RingPos& rp, int nstages,
-                                          const int* jh, int K, int nr, int out0, int ystore, bool seed, double* Z, size_t L,
-                                          int t0, int wid, int lane) {
+                                          int slots, const int* jh, int nst, int K, int nr, int out0, int ystore, bool seed,
+                                          double* Z, size_t L, int t0, int c0, int lane, int kw, double* red) {
+    // t0: first trajectory (global column) of this warp; c0: its first column inside the CTA's shared-memory rows
     using C = SweepCfg<NWC>;
-    constexpr int XS = C::XS;
-    constexpr int KC = SRC3 ? SV_SLOTS / 3 : SV_SLOTS;
+    constexpr int W = C::W;
     constexpr int NA = NRB > 0 ? NRB : 1;
     const int gid = lane >> 2, tig = lane & 3;
-    double acc[NA][4][2];
+    const int stage_bytes = C::stage_bytes(slots), voff = C::voff(slots), hoff = C::hoff(slots);
+    const int plane = SRC3 ? ((slots / 3) & ~3) * W : 0;  // doubles between the three source planes of a stage
+    double ce[NA][2][2], co[NA][2][2];  // even / odd column MMAs of each pair
 #pragma unroll
     for (int rb = 0; rb < NA; ++rb)
 #pragma unroll
-        for (int nb = 0; nb < 4; ++nb) acc[rb][nb][0] = acc[rb][nb][1] = 0.0;
-    if (NRB > 0 && seed) {
+        for (int p = 0; p < 2; ++p) ce[rb][p][0] = ce[rb][p][1] = co[rb][p][0] = co[rb][p][1] = 0.0;
+    if (NRB > 0 && seed && (!KS || kw == 0)) {
         // the children's update rows that land on these output rows seed the accumulators
 #pragma unroll
         for (int rb = 0; rb < NRB; ++rb) {
             const int ea = jh[8 + rb * 8 + gid], eb = jh[40 + rb * 8 + gid];
 #pragma unroll
-            for (int nb = 0; nb < 4; ++nb) {
-                const int col = t0 + nb * 8 + 2 * tig;
+            for (int p = 0; p < 2; ++p) {
+                const int col = t0 + 16 * p + 4 * tig;
                 if (ea >= 0) {
-                    const double2 v = *reinterpret_cast<const double2*>(Z + (size_t)ea * L + col);
-                    acc[rb][nb][0] += v.x;
-                    acc[rb][nb][1] += v.y;
+                    const double4 v = *reinterpret_cast<const double4*>(Z + (size_t)ea * L + col);
+                    ce[rb][p][0] += v.x; co[rb][p][0] += v.y; ce[rb][p][1] += v.z; co[rb][p][1] += v.w;
                 }
                 if (eb >= 0) {
-                    const double2 v = *reinterpret_cast<const double2*>(Z + (size_t)eb * L + col);
-                    acc[rb][nb][0] += v.x;
-                    acc[rb][nb][1] += v.y;
+                    const double4 v = *reinterpret_cast<const double4*>(Z + (size_t)eb * L + col);
+                    ce[rb][p][0] += v.x; co[rb][p][0] += v.y; ce[rb][p][1] += v.z; co[rb][p][1] += v.w;
                 }
             }
         }
     }
-    const int K4 = (K + 3) & ~3;
-    double* zy = YST ? Z + (size_t)(ystore + tig) * L + t0 + gid : nullptr;
+    double* zy = YST ? Z + (size_t)(ystore + tig) * L + t0 + 2 * gid : nullptr;
     int kleft = K - tig;  // rows of this lane's k index still inside the job
-    int k0 = 0;
-    do {
-        const int nk = min(KC, K4 - k0);
+    for (int si = 0; si < nst; ++si) {
         mbar_wait(bar_full + 8 * rp.s, rp.ph);
-        const unsigned char* st = smem + rp.s * C::STAGE_BYTES;
-        const double* xr = reinterpret_cast<const double*>(st) + tig * XS + wid * 32 + gid;
-        const double* vs = reinterpret_cast<const double*>(st + C::VOFF) + lane;
+        const unsigned char* st = smem + rp.s * stage_bytes;
+        const int nk = *reinterpret_cast<const int*>(st + hoff);
+        const double* xr = reinterpret_cast<const double*>(st) + tig * W + c0 + 2 * gid;
+        const double* vs = reinterpret_cast<const double*>(st + voff) + lane;
+        if (KS && (si & 3) != kw) {  // another warp's stage: only keep pace with the ring
+            if (YST) { zy += (size_t)nk * L; kleft -= nk; }
+        } else
         for (int g = 0; g < nk; g += 4) {
             double a[NA];
 #pragma unroll
             for (int rb = 0; rb < NRB; ++rb) a[rb] = vs[rb * 32];
 #pragma unroll
-            for (int nb = 0; nb < 4; ++nb) {
-                double bv = xr[nb * 8];
-                if (SRC3) bv += xr[KC * XS + nb * 8] + xr[2 * KC * XS + nb * 8];
-                if (YST && kleft > 0) zy[nb * 8] = bv;
+            for (int p = 0; p < 2; ++p) {
+                double2 bv = *reinterpret_cast<const double2*>(xr + 16 * p);
+                if (SRC3) {
+                    const double2 b1 = *reinterpret_cast<const double2*>(xr + plane + 16 * p);
+                    const double2 b2 = *reinterpret_cast<const double2*>(xr + 2 * plane + 16 * p);
+                    bv.x += b1.x + b2.x;
+                    bv.y += b1.y + b2.y;
+                }
+                if (YST && kleft > 0) *reinterpret_cast<double2*>(zy + 16 * p) = bv;
 #pragma unroll
-                for (int rb = 0; rb < NRB; ++rb) dmma(acc[rb][nb], a[rb], bv);
+                for (int rb = 0; rb < NRB; ++rb) {
+                    dmma(ce[rb][p], a[rb], bv.x);
+                    dmma(co[rb][p], a[rb], bv.y);
+                }
             }
             vs += NRB * 32;
-            xr += 4 * XS;
+            xr += 4 * W;
             if (YST) { zy += 4 * L; kleft -= 4; }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_empty + 8 * rp.s);
         rp.advance(nstages);
-        k0 += KC;
-    } while (k0 < K4);
+    }
+    if (KS && NRB > 0) {
+        // k-split: warps 1..3 park their partial sums in shared memory, warp 0 adds them up
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // warp 0 is done reading the previous job's partials
+        if (kw > 0) {
+            double* r = red + (size_t)(kw - 1) * (NRB * 8 * 32) + lane;
+#pragma unroll
+            for (int rb = 0; rb < NRB; ++rb)
+#pragma unroll
+                for (int p = 0; p < 2; ++p) {
+                    r[((rb * 2 + p) * 4 + 0) * 32] = ce[rb][p][0];
+                    r[((rb * 2 + p) * 4 + 1) * 32] = ce[rb][p][1];
+                    r[((rb * 2 + p) * 4 + 2) * 32] = co[rb][p][0];
+                    r[((rb * 2 + p) * 4 + 3) * 32] = co[rb][p][1];
+                }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (kw > 0) return;
+#pragma unroll
+        for (int w = 0; w < 3; ++w) {
+            const double* r = red + (size_t)w * (NRB * 8 * 32) + lane;
+#pragma unroll
+            for (int rb = 0; rb < NRB; ++rb)
+#pragma unroll
+                for (int p = 0; p < 2; ++p) {
+                    ce[rb][p][0] += r[((rb * 2 + p) * 4 + 0) * 32];
+                    ce[rb][p][1] += r[((rb * 2 + p) * 4 + 1) * 32];
+                    co[rb][p][0] += r[((rb * 2 + p) * 4 + 2) * 32];
+                    co[rb][p][1] += r[((rb * 2 + p) * 4 + 3) * 32];
+                }
+        }
+    }
     if (NRB > 0) {
 #pragma unroll
         for (int rb = 0; rb < NRB; ++rb) {
             const int r = rb * 8 + gid;
             if (r < nr) {
-                double* zo = Z + (size_t)(out0 + r) * L + t0 + 2 * tig;
+                double* zo = Z + (size_t)(out0 + r) * L + t0 + 4 * tig;
 #pragma unroll
-                for (int nb = 0; nb < 4; ++nb) *reinterpret_cast<double2*>(zo + nb * 8) = make_double2(acc[rb][nb][0], acc[rb][nb][1]);
+                for (int p = 0; p < 2; ++p)
+                    *reinterpret_cast<double4*>(zo + 16 * p) = make_double4(ce[rb][p][0], co[rb][p][0], ce[rb][p][1], co[rb][p][1]);
             }
         }
     }
 }
 
-// grid = (persistent CTAs, slabs of 32*NWC trajectories), block = (32, NWC + 1)
-template <int NWC>
-__global__ void __launch_bounds__(32 * (NWC + 1), SweepCfg<NWC>::MIN_CTAS)
-    k_front_sweep(const int* __restrict__ srec, const int* __restrict__ jrec, const int* __restrict__ cta_sptr,
-                  const int* __restrict__ cta_jptr, const double* __restrict__ vals, double* Z, int ldb, int nstages) {
+// grid = (persistent CTAs, slabs of 32*NWC trajectories); ldb is a multiple of 32*NWC.
+// block = (32, NWC + 1), or (32, 5) for the k-split variant (NWC == 1, four consumer warps on one tile)
+template <int NWC, bool KS>
+__global__ void __launch_bounds__(32 * (KS ? 5 : NWC + 1), KS ? 3 : SweepCfg<NWC>::MIN_CTAS)
+    k_front_sweep(const __grid_constant__ SweepMaps maps, const int* __restrict__ srec, const int* __restrict__ jrec,
+                  const int* __restrict__ cta_sptr, const int* __restrict__ cta_jptr, const double* __restrict__ vals,
+                  double* Z, int ldb, int nstages, int slots, unsigned long long* dbg) {
     using C = SweepCfg<NWC>;
     extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int NCW = KS ? 4 : NWC;  // consumer warps
     const int lane = threadIdx.x, wid = threadIdx.y;
-    const int slab0 = blockIdx.y * C::NT;
-    const int NT = min(C::NT, ldb - slab0);  // trajectories of this CTA (multiple of 32)
-    const int nact = NT >> 5;                // active consumer warps
+    const int slab0 = blockIdx.y * C::W;
+    if (dbg) {  // FCB_SWEEP_DEBUG timeline: 8 slots per CTA (see fcb_profile_step)
+        dbg += (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8;
+        if (lane == 0 && wid == 0) dbg[0] = globaltimer_ns();
+    }
     const uint32_t sbase = smem_u32(smem);
-    const uint32_t bar_full = sbase + nstages * C::STAGE_BYTES;
+    const int stage_bytes = C::stage_bytes(slots);
+    const uint32_t bar_full = sbase + nstages * stage_bytes;
     const uint32_t bar_empty = bar_full + SV_MAXSTAGES * 8;
     if (threadIdx.x == 0 && threadIdx.y == 0) {
         for (int s = 0; s < nstages; ++s) {
             mbar_init(bar_full + 8 * s, 1);
-            mbar_init(bar_empty + 8 * s, nact);
+            mbar_init(bar_empty + 8 * s, NCW);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    const size_t L = (size_t)ldb;
 
-    if (wid == NWC) {
+    if (wid == NCW) {
         // ---------------- producer warp: stream the stage records, issue the bulk copies ----------------
         const int sbeg = __ldg(cta_sptr + blockIdx.x), ns = __ldg(cta_sptr + blockIdx.x + 1) - sbeg;
         const int* rec = srec + (size_t)sbeg * SV_SREC + lane;
         int q[SV_PREFETCH];
 #pragma unroll
-        for (int u = 0; u < SV_PREFETCH; ++u) q[u] = (u < ns && lane < SV_SREC) ? __ldg(rec + u * SV_SREC) : -1;
+        for (int u = 0; u < SV_PREFETCH; ++u) q[u] = (u < ns) ? __ldg(rec + u * SV_SREC) : 0;
         RingPos rp{0, 1};  // parity 1: the first wait on a fresh "empty" barrier passes
         for (int c0 = 0; c0 < ns; c0 += SV_PREFETCH) {
             int qn[SV_PREFETCH];
 #pragma unroll
             for (int u = 0; u < SV_PREFETCH; ++u)
-                qn[u] = (c0 + SV_PREFETCH + u < ns && lane < SV_SREC) ? __ldg(rec + (c0 + SV_PREFETCH + u) * SV_SREC) : -1;
+                qn[u] = (c0 + SV_PREFETCH + u < ns) ? __ldg(rec + (c0 + SV_PREFETCH + u) * SV_SREC) : 0;
 #pragma unroll
             for (int u = 0; u < SV_PREFETCH; ++u) {
                 if (c0 + u < ns) {  // warp-uniform
                     const int v = q[u];
-                    const bool is_row = lane < SV_SLOTS && v >= 0;
-                    const int nrows = __popc(__ballot_sync(0xffffffffu, is_row));
-                    const int voff = __shfl_sync(0xffffffffu, v, SV_SLOTS);
-                    const uint32_t vbytes = (uint32_t)__shfl_sync(0xffffffffu, v, SV_SLOTS + 1);
-                    const int jidx = __shfl_sync(0xffffffffu, v, SV_SLOTS + 2);
+                    const int npieces = __shfl_sync(0xffffffffu, v, 1);
+                    const int voff = __shfl_sync(0xffffffffu, v, 2);
+                    const uint32_t vbytes = (uint32_t)__shfl_sync(0xffffffffu, v, 3);
+                    const int jidx = __shfl_sync(0xffffffffu, v, 4);
+                    const uint32_t nrows = (uint32_t)__shfl_sync(0xffffffffu, v, 5);
+                    const int src = __shfl_sync(0xffffffffu, v, 6 + 2 * (lane < SV_MAXRUNS ? lane : 0));
+                    const int dsc = __shfl_sync(0xffffffffu, v, 7 + 2 * (lane < SV_MAXRUNS ? lane : 0));
                     const uint32_t full = bar_full + 8 * rp.s;
-                    const uint32_t sx = sbase + rp.s * C::STAGE_BYTES;
+                    const uint32_t sx = sbase + rp.s * stage_bytes;
                     mbar_wait(bar_empty + 8 * rp.s, rp.ph);
                     if (lane == 0) {
-                        mbar_expect_tx(full, (uint32_t)nrows * (uint32_t)NT * 8u + vbytes + (jidx >= 0 ? SV_JREC * 4u : 0u));
-                        if (vbytes) bulk_g2s(sx + C::VOFF, vals + (size_t)voff * 32, vbytes, full);
-                        if (jidx >= 0) bulk_g2s(sx + C::JOFF, jrec + (size_t)jidx * SV_JREC, SV_JREC * 4u, full);
+                        mbar_expect_tx(full, nrows * (uint32_t)(C::W * 8) + vbytes + 16u + (jidx >= 0 ? SV_JREC * 4u : 0u));
+                        bulk_g2s(sx + C::hoff(slots), srec + (size_t)(sbeg + c0 + u) * SV_SREC, 16u, full);
+                        if (vbytes) bulk_g2s(sx + C::voff(slots), vals + (size_t)voff * 32, vbytes, full);
+                        if (jidx >= 0) bulk_g2s(sx + C::joff(slots), jrec + (size_t)jidx * SV_JREC, SV_JREC * 4u, full);
                     }
                     __syncwarp();
-                    if (is_row) bulk_g2s(sx + (uint32_t)(lane * C::XS) * 8u, Z + (size_t)v * L + slab0, (uint32_t)NT * 8u, full);
+                    if (lane < npieces)  // one box copy per run of 1..32 consecutive rows
+                        tma_box_g2s(sx + (uint32_t)((dsc >> 8) * C::W * 8), &maps.m[dsc & 7], slab0, src, full);
+                    if (dbg && lane == 0 && c0 + u == 0) dbg[1] = globaltimer_ns();
                     rp.advance(nstages);
                 }
             }
 #pragma unroll
             for (int u = 0; u < SV_PREFETCH; ++u) q[u] = qn[u];
         }
+        if (dbg && lane == 0) { dbg[5] = globaltimer_ns(); dbg[7] = (unsigned long long)ns; }
         return;
     }
-    if (wid >= nact) return;
 
     // ---------------- consumer warps ----------------
-    const int t0 = slab0 + wid * 32;  // first trajectory of this warp
+    const int c0 = KS ? 0 : wid * 32, t0 = slab0 + c0;  // first column / trajectory of this warp
+    double* red = reinterpret_cast<double*>(smem + nstages * stage_bytes + 2 * SV_MAXSTAGES * 8);  // k-split partial sums
+    const size_t L = (size_t)ldb;
     const int nj = __ldg(cta_jptr + blockIdx.x + 1) - __ldg(cta_jptr + blockIdx.x);
     RingPos rp{0, 0};
     for (int j = 0; j < nj; ++j) {
         mbar_wait(bar_full + 8 * rp.s, rp.ph);  // the job record arrives with the job's first stage
-        const int* jh = reinterpret_cast<const int*>(smem + rp.s * C::STAGE_BYTES + C::JOFF);
+        if (dbg && j == 0 && lane == 0 && wid == 0) dbg[2] = globaltimer_ns();
+        const int* jh = reinterpret_cast<const int*>(smem + rp.s * stage_bytes + C::joff(slots));
         const int4 h0 = *reinterpret_cast<const int4*>(jh);
         const int4 h1 = *reinterpret_cast<const int4*>(jh + 4);
-        const int K = h0.x, nrb = h0.y, nr = h0.z, out0 = h1.x, ystore = h1.y;
+        const int K = h0.x, nrb = h0.y, nr = h0.z, out0 = h1.x, ystore = h1.y, nst = h1.w;
         const bool src3 = h0.w == 3, seed = h1.z != 0;
 #define SWEEP_RUN(NRB, S3, YS) \
-    sweep_job<NWC, NRB, S3, YS>(smem, bar_full, bar_empty, rp, nstages, jh, K, nr, out0, ystore, seed, Z, L, t0, wid, lane)
+    sweep_job<NWC, KS, NRB, S3, YS>(smem, bar_full, bar_empty, rp, nstages, slots, jh, nst, K, nr, out0, ystore, seed, Z, L, t0, c0, lane, wid, red)
 #define SWEEP_CASE(NRB)                                        \
     case NRB:                                                  \
         if (src3) {                                            \
@@ -439,7 +524,9 @@ __global__ void __launch_bounds__(32 * (NWC + 1), SweepCfg<NWC>::MIN_CTAS)
         }
 #undef SWEEP_CASE
 #undef SWEEP_RUN
+        if (dbg && j == 0 && lane == 0 && wid == 0) dbg[3] = globaltimer_ns();
     }
+    if (dbg && lane == 0 && wid == 0) { dbg[4] = globaltimer_ns(); dbg[6] = (unsigned long long)nj; }
 }
 
 // un-permute the solution into canonical numbering, apply Dirichlet values, flag non-finite velocity.
@@ -557,7 +644,7 @@ struct DevPlan {
     int n = 0, nU = 0, njobs = 0, nlaunch = 0;
     int *srec = nullptr, *jrec = nullptr, *cta_sptr = nullptr, *cta_jptr = nullptr;
     double* vals = nullptr;
-    struct Launch { int grid, nwc, nslab, nstages, cta_off; };
+    struct Launch { int grid, nwc, nslab, nstages, slots, cta_off, ksplit; };
     std::vector<Launch> launches;
     int n_forward = 0;
     long long nstages_total = 0, packed_doubles = 0;
@@ -566,7 +653,11 @@ struct DevPlan {
 }  // namespace
 
 struct fcb_context {
-    int device = 0, num_sms = 0, smem_per_sm = 0, force_nwc = 0, force_nrb = 0;
+    int device = 0, num_sms = 0, smem_per_sm = 0, force_nrb = 0, force_nwc = 0, max_nwc = 4, allow_ksplit = 1;
+    SweepMaps zmaps[4];  // TMA descriptors of Z for CTA widths of 32, 64, 128, 256 trajectories
+    int kslots = 12;                        // ... and for k-split CTAs, whose 4 warps each need stages in flight (FCB_SWEEP_KSLOTS)
+    int force_slots[4] = {48, 36, 24, 12};  // gathered rows per ring stage for those widths (FCB_SWEEP_SLOTS=a,b,c,d)
+    unsigned long long* sweep_dbg = nullptr;  // FCB_SWEEP_DEBUG=<file>: per-CTA timeline of the sweeps of a profiled step
     cudaStream_t stream = nullptr;
     std::string error;
     int B = 0, ldb = 0;
@@ -674,17 +765,26 @@ int upload_plan(fcb_context* h, DevPlan& d, const fcb_plan& p) {
     const int nw_all = h->ldb / 32;  // 32-trajectory warps needed to cover the ensemble
     for (int l = 0; l < p.nlaunch; ++l) {
         const int b0 = p.launch_ptr[l], b1 = p.launch_ptr[l + 1];
-        DevPlan::Launch L{0, 8, 1, 4, (int)cta_sptr.size()};
+        DevPlan::Launch L{0, 4, 1, 4, 12, (int)cta_sptr.size(), 0};
         if (b1 <= b0) { d.launches.push_back(L); continue; }
-        // ---- tile height
+        // ---- tile height and CTA width: tall tiles (V reuse, fewer re-reads of the gathered rows) and wide
+        // CTAs (one copy of V per CTA) as long as the launch still fills the machine; narrow first, then shorten
         auto njobs_for = [&](int nrb) {
             long long c = 0;
             for (int b = b0; b < b1; ++b) c += p.blk_M[b] > 0 ? (p.blk_M[b] + 8 * nrb - 1) / (8 * nrb) : (p.blk_K[b] + 15) / 16;
             return c;
         };
-        int nrb_cap = 4;
-        while (nrb_cap > 1 && njobs_for(nrb_cap) * nw_all < 4LL * h->num_sms) --nrb_cap;
+        int nrb_cap = 4, nwc = std::min(h->max_nwc, nw_all);
+        while (nw_all % nwc) nwc >>= 1;
+        const long long want = 2LL * h->num_sms;
+        while (nwc > 1 && njobs_for(nrb_cap) * (nw_all / nwc) < want) nwc >>= 1;
+        // a launch that is still too small at one 32-trajectory tile per CTA splits K over the CTA's four consumer warps
+        L.ksplit = (nwc == 1 && h->allow_ksplit) ? 1 : 0;
+        while (nrb_cap > 1 && njobs_for(nrb_cap) * (nw_all / nwc) < want) --nrb_cap;
         if (h->force_nrb > 0) nrb_cap = h->force_nrb;
+        if (h->force_nwc > 0 && nw_all % h->force_nwc == 0) nwc = h->force_nwc;
+        L.nwc = nwc;
+        L.nslab = nw_all / nwc;
         std::vector<Tile> tiles;
         for (int b = b0; b < b1; ++b) {
             const int M = p.blk_M[b], K = p.blk_K[b];
@@ -702,22 +802,20 @@ int upload_plan(fcb_context* h, DevPlan& d, const fcb_plan& p) {
             }
         }
         const int nj = (int)tiles.size();
-        // ---- CTA width
-        int nwc = nw_all >= 8 ? 8 : (nw_all >= 4 ? 4 : (nw_all >= 2 ? 2 : 1));
-        while (nwc > 1 && (long long)nj * ((nw_all + nwc - 1) / nwc) < (long long)h->num_sms * (nwc == 8 ? 2 : 1)) nwc >>= 1;
-        if (h->force_nwc > 0) nwc = h->force_nwc;
-        L.nwc = nwc;
-        L.nslab = (nw_all + nwc - 1) / nwc;
-        const int min_ctas = nwc == 8 ? 2 : (nwc == 4 ? 3 : 4);
-        const int stage_bytes = nwc == 8 ? SweepCfg<8>::STAGE_BYTES : nwc == 4 ? SweepCfg<4>::STAGE_BYTES : nwc == 2 ? SweepCfg<2>::STAGE_BYTES : SweepCfg<1>::STAGE_BYTES;
-        const int per_sm = ((long long)nj * L.nslab >= (long long)min_ctas * h->num_sms) ? min_ctas
-                           : std::max(1, (int)(((long long)nj * L.nslab + h->num_sms - 1) / h->num_sms));
+        const int min_ctas = nwc == 8 ? SV_MINCTAS8 : ((nwc == 4 || L.ksplit) ? 3 : 4);
+        // rows per stage: ~24 KB of gathered rows for the wide CTAs, less for narrow ones (their V slice is as large)
+        L.slots = L.ksplit ? h->kslots : h->force_slots[nwc == 8 ? 3 : nwc == 4 ? 2 : nwc == 2 ? 1 : 0];
+        const int stage_bytes = nwc == 8 ? SweepCfg<8>::stage_bytes(L.slots) : nwc == 4 ? SweepCfg<4>::stage_bytes(L.slots)
+                                : nwc == 2 ? SweepCfg<2>::stage_bytes(L.slots) : SweepCfg<1>::stage_bytes(L.slots);
+        const long long nctas = (long long)nj * L.nslab;
+        const int per_sm = (nctas >= (long long)min_ctas * h->num_sms) ? min_ctas : std::max(1, (int)((nctas + h->num_sms - 1) / h->num_sms));
         L.grid = std::min(nj, std::max(1, per_sm * h->num_sms / L.nslab));
-        L.nstages = std::max(2, std::min(SV_MAXSTAGES, (h->smem_per_sm / per_sm - 1024 - 2 * SV_MAXSTAGES * 8) / stage_bytes));
+        L.nstages = std::max(2, std::min(SV_MAXSTAGES, (h->smem_per_sm / per_sm - 1024 - 2 * SV_MAXSTAGES * 8 - (L.ksplit ? SV_RED_BYTES : 0)) / stage_bytes));
+        const int kc1 = L.slots & ~3, kc3 = (L.slots / 3) & ~3;
         // ---- longest-processing-time assignment of tiles to CTAs (cost in rough SM cycles)
         auto ktile = [&](const Tile& t) { return t.nrb > 0 ? p.blk_K[t.blk] : t.k_hi - t.k_lo; };
         auto stages_of = [&](const Tile& t) {
-            const int K4 = (ktile(t) + 3) & ~3, kc = p.blk_nsrc[t.blk] == 3 ? SV_SLOTS / 3 : SV_SLOTS;
+            const int K4 = (ktile(t) + 3) & ~3, kc = p.blk_nsrc[t.blk] == 3 ? kc3 : kc1;
             return std::max(1, (K4 + kc - 1) / kc);
         };
         std::vector<std::pair<long long, int>> order(nj);
@@ -742,7 +840,7 @@ int upload_plan(fcb_context* h, DevPlan& d, const fcb_plan& p) {
             for (int q : mine[c]) {
                 const Tile& t = tiles[q];
                 const int b = t.blk, Kb = p.blk_K[b], nsrc = p.blk_nsrc[b];
-                const int K = t.k_hi - t.k_lo, K4 = (K + 3) & ~3, kc = nsrc == 3 ? SV_SLOTS / 3 : SV_SLOTS;
+                const int K = t.k_hi - t.k_lo, K4 = (K + 3) & ~3, kc = nsrc == 3 ? kc3 : kc1;
                 const size_t jb = jrec.size();
                 jrec.resize(jb + SV_JREC, -1);
                 jrec[jb + 0] = K; jrec[jb + 1] = t.nrb; jrec[jb + 2] = t.nr; jrec[jb + 3] = nsrc;
@@ -765,20 +863,53 @@ int upload_plan(fcb_context* h, DevPlan& d, const fcb_plan& p) {
                         for (int k = 0; k < K; ++k) dst[(size_t)(k >> 2) * t.nrb * 32 + (k & 3)] = vr[k];
                     }
                 }
-                int k0 = 0;
+                int k0 = 0, nst = 0;
                 do {  // a job with K == 0 still gets one (empty) stage that carries its record
-                    const int nk = std::max(0, std::min(kc, K4 - k0));
+                    int nk = std::max(0, std::min(kc, K4 - k0));
                     const size_t sb = srec.size();
-                    srec.resize(sb + SV_SREC, -1);
-                    for (int pl = 0; pl < nsrc; ++pl) {
-                        const int32_t* ip = (pl == 0 ? p.i0 : (pl == 1 ? p.i1 : p.i2)) + p.blk_iptr[b] + t.k_lo;
-                        for (int k = 0; k < nk; ++k) srec[sb + pl * kc + k] = (k0 + k < K) ? ip[k0 + k] : zrow;
+                    srec.resize(sb + SV_SREC, 0);
+                    int npieces = 0, nrows = 0;
+                    for (;;) {  // shrink the stage until its box copies fit the record
+                        npieces = nrows = 0;
+                        bool too_many = false;
+                        for (int pl = 0; pl < nsrc && !too_many; ++pl) {
+                            const int32_t* ip = (pl == 0 ? p.i0 : (pl == 1 ? p.i1 : p.i2)) + p.blk_iptr[b] + t.k_lo;
+                            int run_src = -1, run_slot = 0, run_len = 0, zpos = 0;
+                            auto flush = [&]() {
+                                // a run of consecutive rows goes out as box copies of 32, 16, 8, 4, 2, 1 rows
+                                for (int lg = 5; lg >= 0; --lg)
+                                    while (run_len >= (1 << lg)) {
+                                        if (npieces >= SV_MAXRUNS) { too_many = true; return; }
+                                        srec[sb + 6 + 2 * npieces] = run_src;
+                                        srec[sb + 7 + 2 * npieces] = (run_slot << 8) | lg;
+                                        ++npieces;
+                                        nrows += 1 << lg;
+                                        run_src += 1 << lg; run_slot += 1 << lg; run_len -= 1 << lg;
+                                    }
+                            };
+                            for (int k = 0; k < nk && !too_many; ++k) {
+                                int row = (k0 + k < K) ? ip[k0 + k] : zrow;
+                                if (row == zrow) row = zrow + zpos++;  // absent / padded rows lie past the end of the tensor: zeros
+                                if (run_len > 0 && row == run_src + run_len) { ++run_len; continue; }
+                                flush();
+                                run_src = row; run_slot = pl * kc + k; run_len = 1;
+                            }
+                            if (!too_many) flush();
+                        }
+                        if (!too_many) break;
+                        if (nk <= 4) return fail(h, FCB_ERR_INVALID, "internal: a 4-row stage needs more than %d box copies", SV_MAXRUNS);
+                        nk -= 4;
                     }
-                    srec[sb + SV_SLOTS] = (int)((v0 + (size_t)k0 * 8 * t.nrb) / 32);
-                    srec[sb + SV_SLOTS + 1] = nk * 64 * t.nrb;
-                    srec[sb + SV_SLOTS + 2] = k0 == 0 ? (int)(jb / SV_JREC) : -1;
-                    k0 += kc;
+                    srec[sb + 0] = nk;
+                    srec[sb + 1] = npieces;
+                    srec[sb + 2] = (int)((v0 + (size_t)k0 * 8 * t.nrb) / 32);
+                    srec[sb + 3] = nk * 64 * t.nrb;
+                    srec[sb + 4] = k0 == 0 ? (int)(jb / SV_JREC) : -1;
+                    srec[sb + 5] = nrows;
+                    k0 += std::max(nk, 4);
+                    ++nst;
                 } while (k0 < K4);
+                jrec[jb + 7] = nst;
             }
         }
         cta_sptr.push_back((int)(srec.size() / SV_SREC));  // one past the last CTA of this launch
@@ -789,7 +920,7 @@ int upload_plan(fcb_context* h, DevPlan& d, const fcb_plan& p) {
     d.njobs = (int)(jrec.size() / SV_JREC);
     d.packed_doubles = (long long)packed.size();
     if (packed.size() / 32 > 0x7fffffffULL) return fail(h, FCB_ERR_INVALID, "factor too large for 32-bit tile offsets");
-    if (srec.empty()) srec.resize(SV_SREC, -1);
+    if (srec.empty()) srec.resize(SV_SREC, 0);
     if (jrec.empty()) jrec.resize(SV_JREC, -1);
     if (packed.empty()) packed.resize(32, 0.0);
     if (cta_sptr.empty()) { cta_sptr.push_back(0); cta_jptr.push_back(0); }
@@ -879,11 +1010,13 @@ int enqueue_measure(fcb_context* h, const double* up) {
     return FCB_OK;
 }
 
-template <int NWC>
-void launch_sweep(fcb_context* h, const DevPlan& pl, const DevPlan::Launch& L) {
-    dim3 grid(L.grid, L.nslab), block(32, NWC + 1);
-    k_front_sweep<NWC><<<grid, block, SweepCfg<NWC>::smem_bytes(L.nstages), h->stream>>>(
-        pl.srec, pl.jrec, pl.cta_sptr + L.cta_off, pl.cta_jptr + L.cta_off, pl.vals, h->Z, h->ldb, L.nstages);
+constexpr size_t DBG_PER_LAUNCH = 8 * 8192;  // 8 timeline slots for up to 8192 CTAs
+
+template <int NWC, bool KS>
+void launch_sweep(fcb_context* h, const DevPlan& pl, const DevPlan::Launch& L, int mapset, unsigned long long* dbg) {
+    k_front_sweep<NWC, KS><<<dim3(L.grid, L.nslab), dim3(32, KS ? 5 : NWC + 1), SweepCfg<NWC>::smem_bytes(L.nstages, L.slots) + (KS ? SV_RED_BYTES : 0), h->stream>>>(
+        h->zmaps[mapset], pl.srec, pl.jrec, pl.cta_sptr + L.cta_off, pl.cta_jptr + L.cta_off, pl.vals, h->Z, h->ldb,
+        L.nstages, L.slots, dbg);
 }
 
 int enqueue_solve(fcb_context* h, const DevPlan& pl, PhaseMark* pm) {
@@ -891,11 +1024,15 @@ int enqueue_solve(fcb_context* h, const DevPlan& pl, PhaseMark* pm) {
         if (pm && l == pl.n_forward) pm->mark(FCB_PHASE_BACKWARD);
         const DevPlan::Launch& L = pl.launches[l];
         if (L.grid <= 0) continue;
+        unsigned long long* dbg = (pm && h->sweep_dbg) ? h->sweep_dbg + (size_t)l * DBG_PER_LAUNCH : nullptr;
         switch (L.nwc) {
-            case 8: launch_sweep<8>(h, pl, L); break;
-            case 4: launch_sweep<4>(h, pl, L); break;
-            case 2: launch_sweep<2>(h, pl, L); break;
-            default: launch_sweep<1>(h, pl, L); break;
+            case 8: launch_sweep<8, false>(h, pl, L, 3, dbg); break;
+            case 4: launch_sweep<4, false>(h, pl, L, 2, dbg); break;
+            case 2: launch_sweep<2, false>(h, pl, L, 1, dbg); break;
+            default:
+                if (L.ksplit) launch_sweep<1, true>(h, pl, L, 0, dbg);
+                else launch_sweep<1, false>(h, pl, L, 0, dbg);
+                break;
         }
         h->launches += 1;
     }
@@ -1011,7 +1148,7 @@ void destroy(fcb_context* h) {
     void* ptrs[] = {h->first_mask, h->cell_nodes, h->colour_cells, h->perm, h->iperm, h->Jinv, h->detJ, h->bc_shape, h->ctrl_rhs[0],
                     h->ctrl_rhs[1], h->sensor_ptr, h->sensor_idx, h->sensor_val, h->up[0], h->up[1], h->avec,
                     h->bvec[0], h->bvec[1], h->Z, h->epart, h->uctrl, h->y, h->dE, h->diverged, h->Ad, h->Bd, h->Cd,
-                    h->Dd, h->Ky, h->Fu, h->xk[0], h->xk[1], h->series, h->counter};
+                    h->Dd, h->Ky, h->Fu, h->xk[0], h->xk[1], h->series, h->counter, h->sweep_dbg};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (int i = 0; i < 2; ++i) {
@@ -1032,18 +1169,36 @@ int create_impl(fcb_context* h, const fcb_problem* p, int B) {
     if (prop.major < 10) return fail(h, FCB_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", h->device, prop.major, prop.minor);
     h->num_sms = prop.multiProcessorCount;
     h->B = B;
-    h->ldb = (B + 31) / 32 * 32;
+    h->ldb = B <= 32 ? 32 : (B <= 64 ? 64 : (B + 127) / 128 * 128);  // a multiple of every sweep CTA width in use
     h->smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
     {
         const int optin = (int)prop.sharedMemPerBlockOptin;
-        CK(cudaFuncSetAttribute(k_front_sweep<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::min(optin, SweepCfg<8>::smem_bytes(SV_MAXSTAGES))));
-        CK(cudaFuncSetAttribute(k_front_sweep<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::min(optin, SweepCfg<4>::smem_bytes(SV_MAXSTAGES))));
-        CK(cudaFuncSetAttribute(k_front_sweep<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::min(optin, SweepCfg<2>::smem_bytes(SV_MAXSTAGES))));
-        CK(cudaFuncSetAttribute(k_front_sweep<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::min(optin, SweepCfg<1>::smem_bytes(SV_MAXSTAGES))));
-        const char* env = getenv("FCB_SWEEP_WARPS");  // tuning knob: force the CTA width of every sweep launch
+        CK(cudaFuncSetAttribute(k_front_sweep<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+        CK(cudaFuncSetAttribute(k_front_sweep<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+        CK(cudaFuncSetAttribute(k_front_sweep<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+        CK(cudaFuncSetAttribute(k_front_sweep<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+        CK(cudaFuncSetAttribute(k_front_sweep<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+        const char* env = getenv("FCB_SWEEP_WARPS");  // tuning knobs: force / cap the CTA width of the sweep launches
         h->force_nwc = env ? atoi(env) : 0;
-        if (h->force_nwc != 0 && h->force_nwc != 1 && h->force_nwc != 2 && h->force_nwc != 4 && h->force_nwc != 8) h->force_nwc = 0;
-        if (h->force_nwc * 32 > h->ldb && h->force_nwc > 1) h->force_nwc = 0;
+        if (h->force_nwc != 1 && h->force_nwc != 2 && h->force_nwc != 4 && h->force_nwc != 8) h->force_nwc = 0;
+        env = getenv("FCB_SWEEP_KSPLIT");
+        if (env) h->allow_ksplit = atoi(env) != 0;
+        env = getenv("FCB_SWEEP_SLOTS");
+        if (env) {
+            int v[4];
+            if (sscanf(env, "%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3]) == 4)
+                for (int i = 0; i < 4; ++i)
+                    if (v[i] >= 12 && v[i] <= 96 && v[i] % 12 == 0) h->force_slots[i] = v[i];
+        }
+        env = getenv("FCB_SWEEP_KSLOTS");
+        if (env && atoi(env) >= 12 && atoi(env) <= 96 && atoi(env) % 12 == 0) h->kslots = atoi(env);
+        env = getenv("FCB_SWEEP_MAXWARPS");
+        if (env && (atoi(env) == 1 || atoi(env) == 2 || atoi(env) == 4 || atoi(env) == 8)) h->max_nwc = atoi(env);
+        if (getenv("FCB_SWEEP_DEBUG")) {
+            size_t nl = (size_t)std::max(p->plan[0].nlaunch, p->plan[1].nlaunch);
+            CK(cudaMalloc((void**)&h->sweep_dbg, nl * DBG_PER_LAUNCH * sizeof(unsigned long long)));
+            CK(cudaMemset(h->sweep_dbg, 0, nl * DBG_PER_LAUNCH * sizeof(unsigned long long)));
+        }
         env = getenv("FCB_SWEEP_ROWBLOCKS");  // tuning knob: force the tile height (8-row blocks) of every launch
         h->force_nrb = env ? atoi(env) : 0;
         if (h->force_nrb < 0 || h->force_nrb > 4) h->force_nrb = 0;
@@ -1130,8 +1285,30 @@ int create_impl(fcb_context* h, const fcb_problem* p, int B) {
     }
     TRY(upload<double>(h, &h->avec, nullptr, (size_t)h->Nv * L));
     {
-        const size_t zrows = (size_t)2 * h->n + (size_t)p->plan[0].nU + 1;  // last row stays zero (padded gathers)
-        TRY(upload<double>(h, &h->Z, nullptr, zrows * L));
+        const size_t zrows = (size_t)2 * h->n + (size_t)p->plan[0].nU;
+        TRY(upload<double>(h, &h->Z, nullptr, (zrows + 1) * L));
+        // TMA view of Z: [zrows][ldb] doubles; boxes of 1/2/4/8 rows x 32/64/128/256 columns.  Rows >= zrows are
+        // outside the tensor and read as zeros, which is what the plan's "absent" gather index (2n + nU) needs.
+        typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) return fail(h, FCB_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+        for (int wi = 0; wi < 4; ++wi)
+            for (int hi = 0; hi < 6; ++hi) {
+                const cuuint32_t width = 32u << wi;
+                if ((int)width > h->ldb) { memset(&h->zmaps[wi].m[hi], 0, sizeof(CUtensorMap)); continue; }
+                const cuuint64_t gdim[2] = {(cuuint64_t)h->ldb, (cuuint64_t)zrows};
+                const cuuint64_t gstride[1] = {(cuuint64_t)h->ldb * sizeof(double)};
+                const cuuint32_t box[2] = {width, 1u << hi};
+                const cuuint32_t estride[2] = {1, 1};
+                const CUresult r = ((EncodeTiled)fn)(&h->zmaps[wi].m[hi], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, h->Z, gdim, gstride, box,
+                                                     estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r != CUDA_SUCCESS) return fail(h, FCB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for a %ux%u box", (int)r, width, 1u << hi);
+            }
     }
     TRY(upload<double>(h, &h->epart, nullptr, (size_t)h->nblk_total * L));
     TRY(upload<double>(h, &h->uctrl, nullptr, (size_t)(h->na > 0 ? h->na : 1) * L));
@@ -1322,6 +1499,22 @@ int fcb_profile_step(fcb_handle h, const double* u_ctrl, float* ms, int32_t* lau
     h->parity ^= 1;
     h->order = 2;
     for (int i = 0; i < FCB_NPHASES; ++i) CK(cudaEventElapsedTime(&ms[i], h->ev[i], h->ev[i + 1]));
+    if (h->sweep_dbg) {
+        const char* path = getenv("FCB_SWEEP_DEBUG");
+        std::vector<unsigned long long> host((size_t)pl.nlaunch * DBG_PER_LAUNCH);
+        CK(cudaMemcpy(host.data(), h->sweep_dbg, host.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        if (FILE* f = fopen(path, "wb")) {
+            const int hdr[2] = {pl.nlaunch, pl.n_forward};
+            fwrite(hdr, sizeof(int), 2, f);
+            for (int l = 0; l < pl.nlaunch; ++l) {
+                const DevPlan::Launch& L = pl.launches[l];
+                const int meta[4] = {L.grid, L.nslab, L.nwc, L.nstages};
+                fwrite(meta, sizeof(int), 4, f);
+                fwrite(host.data() + (size_t)l * DBG_PER_LAUNCH, sizeof(unsigned long long), (size_t)L.grid * L.nslab * 8, f);
+            }
+            fclose(f);
+        }
+    }
     if (launches) {
         launches[FCB_PHASE_RHS] = 1;
         launches[FCB_PHASE_FORWARD] = pl.n_forward;
