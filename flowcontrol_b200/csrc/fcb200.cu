@@ -204,6 +204,9 @@ __global__ void __launch_bounds__(256) k_rhs_build(int n, int Nv, const int* __r
 // CTAs are persistent: the host compiles each launch into one instruction stream per CTA, and the
 // ring keeps filling across job boundaries.  Every Z row is written by exactly one job: no atomics.
 // ----------------------------------------------------------------------------------------------
+#ifndef SV_MINCTAS4
+#define SV_MINCTAS4 3  // CTAs per SM the 4-warp sweep kernels are compiled for (3 => 128 registers per thread)
+#endif
 #ifndef SV_MINCTAS8
 #define SV_MINCTAS8 2  // CTAs per SM the 8-warp sweep kernel is compiled for (2 => 96 registers per thread)
 #endif
@@ -219,7 +222,7 @@ constexpr int SV_RED_BYTES = 3 * 32 * 32 * 8;  // k-split: partial accumulators 
 template <int NWC>
 struct SweepCfg {
     static constexpr int W = 32 * NWC;  // trajectories per CTA = shared-memory row length (dense)
-    static constexpr int MIN_CTAS = NWC == 8 ? SV_MINCTAS8 : (NWC == 4 ? 3 : 4);
+    static constexpr int MIN_CTAS = NWC == 8 ? SV_MINCTAS8 : (NWC == 4 ? SV_MINCTAS4 : 4);
     __host__ __device__ static constexpr int voff(int slots) { return slots * W * 8; }             // V slice: slots k x 32 rows
     __host__ __device__ static constexpr int joff(int slots) { return voff(slots) + slots * 256; }  // job record (first stage of a job)
     __host__ __device__ static constexpr int hoff(int slots) { return joff(slots) + 384; }          // stage header (nk, ...)
@@ -416,7 +419,7 @@ __device__ __forceinline__ void sweep_job(unsigned char* smem, uint32_t bar_full
 // grid = (persistent CTAs, slabs of 32*NWC trajectories); ldb is a multiple of 32*NWC.
 // block = (32, NWC + 1), or (32, 5) for the k-split variant (NWC == 1, four consumer warps on one tile)
 template <int NWC, bool KS>
-__global__ void __launch_bounds__(32 * (KS ? 5 : NWC + 1), KS ? 3 : SweepCfg<NWC>::MIN_CTAS)
+__global__ void __launch_bounds__(32 * (KS ? 5 : NWC + 1), KS ? SV_MINCTAS4 : SweepCfg<NWC>::MIN_CTAS)
     k_front_sweep(const __grid_constant__ SweepMaps maps, const int* __restrict__ srec, const int* __restrict__ jrec,
                   const int* __restrict__ cta_sptr, const int* __restrict__ cta_jptr, const double* __restrict__ vals,
                   double* Z, int ldb, int nstages, int slots, unsigned long long* dbg) {
@@ -655,7 +658,7 @@ struct DevPlan {
 struct fcb_context {
     int device = 0, num_sms = 0, smem_per_sm = 0, force_nrb = 0, force_nwc = 0, max_nwc = 4, allow_ksplit = 1;
     SweepMaps zmaps[4];  // TMA descriptors of Z for CTA widths of 32, 64, 128, 256 trajectories
-    int kslots = 12;                        // ... and for k-split CTAs, whose 4 warps each need stages in flight (FCB_SWEEP_KSLOTS)
+    int kslots = 24;                        // ... and for k-split CTAs, whose 4 warps each need stages in flight (FCB_SWEEP_KSLOTS)
     int force_slots[4] = {48, 36, 24, 12};  // gathered rows per ring stage for those widths (FCB_SWEEP_SLOTS=a,b,c,d)
     unsigned long long* sweep_dbg = nullptr;  // FCB_SWEEP_DEBUG=<file>: per-CTA timeline of the sweeps of a profiled step
     cudaStream_t stream = nullptr;
@@ -802,7 +805,7 @@ int upload_plan(fcb_context* h, DevPlan& d, const fcb_plan& p) {
             }
         }
         const int nj = (int)tiles.size();
-        const int min_ctas = nwc == 8 ? SV_MINCTAS8 : ((nwc == 4 || L.ksplit) ? 3 : 4);
+        const int min_ctas = nwc == 8 ? SV_MINCTAS8 : ((nwc == 4 || L.ksplit) ? SV_MINCTAS4 : 4);
         // rows per stage: ~24 KB of gathered rows for the wide CTAs, less for narrow ones (their V slice is as large)
         L.slots = L.ksplit ? h->kslots : h->force_slots[nwc == 8 ? 3 : nwc == 4 ? 2 : nwc == 2 ? 1 : 0];
         const int stage_bytes = nwc == 8 ? SweepCfg<8>::stage_bytes(L.slots) : nwc == 4 ? SweepCfg<4>::stage_bytes(L.slots)
