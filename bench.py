@@ -29,7 +29,7 @@ B_PER_GPU = 256
 METRIC = "trajectory-steps/s (cylinder Re=100 closed-loop ensemble)"
 UNIT = "trajectory-steps/s"
 WORKLOAD = "cylinder O1 Re=100 dt=0.005, closed loop, 256 gain-swept 13-state LTI controllers per GPU (BASELINE configs[1])"
-FP64_PEAK_TFLOPS = 33.6  # measured on this pool's B200 with tools/bench_src/fp64_peak.cu (DFMA pipe)
+FP64_PEAK_TFLOPS = 37.1  # measured on this pool's B200 with tools/bench_src/fp64_peak.cu (DMMA m8n8k4; DFMA: 33.6)
 
 
 def peaks():
@@ -199,14 +199,14 @@ def run_ours(args):
     hbm_peak, peak_src = peaks()
     achieved = solve_bytes / (solve_ms * 1e-3) / 1e9
     roofline = {
-        "kernel": "k_tile_gemm (multifrontal forward+backward sweeps, all launches of one solve)",
+        "kernel": "k_front_sweep (multifrontal forward+backward sweeps on FP64 tensor cores, all launches of one solve)",
         "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
         "peak_source": peak_src, "traffic": None,
         "launches_per_step": solve_launches, "ms_per_launch": solve_ms / solve_launches, "ms_per_step": solve_ms,
         "algorithmic_bytes_per_step": solve_bytes,
         "fp64": {"achieved_tflops": solve_flops / (solve_ms * 1e-3) / 1e12, "peak_tflops": FP64_PEAK_TFLOPS,
                  "frac": solve_flops / (solve_ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS,
-                 "note": "the solve is FP64-FMA bound at B=256, not HBM bound (DESIGN.md); peak = measured DFMA rate"},
+                 "note": "the sweeps run on the FP64 tensor pipe (mma.sync m8n8k4); peak = measured DMMA rate (profiles/r01_fp64_peak.log)"},
         "phase_ms": phase_ms,
     }
 
