@@ -26,6 +26,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <climits>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -159,6 +160,171 @@ __global__ void __launch_bounds__(32 * ELEM_WARPS, 3) k_element(const ElemArgs p
         for (int w = 1; w < ELEM_WARPS; ++w) s += se[w][threadIdx.x];
         p.epart[(size_t)(p.blk_offset + blockIdx.x) * ldb + b] = s;
     }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Patch form of the element kernel: one CTA = one patch of ~32 neighbouring cells x 32 trajectories.
+// The patch's node rows of a and b are accumulated in shared memory (4 rows per node: a_x, a_y, b_x, b_y),
+// so a node shared by 6 cells costs ONE global write instead of 6 read-modify-writes.  Cells are processed
+// in rounds of EP_WARPS cells that share no node (one cell per warp, __syncthreads between rounds): no
+// atomics, fixed summation order.  Nodes interior to the patch are written straight to a/b; nodes shared
+// with other patches go to a scratch slot and k_patch_merge sums the (2-4) partials per node, again in a
+// fixed order.  The next round's gathers are issued before the current round's arithmetic.
+// ----------------------------------------------------------------------------------------------
+constexpr int EP_WARPS = 4;
+
+struct PatchArgs {
+    const int* pcell_ptr;          // [npatch+1] into pcells, multiples of EP_WARPS
+    const int* pcells;             // cell id or -1, grouped in rounds of EP_WARPS
+    const unsigned char* plnode;   // [len(pcells)*6] patch-local index of the cell's nodes
+    const int* pnode_ptr;          // [npatch+1] into pnode_dst
+    const int* pnode_dst;          // >= 0: node id (interior to the patch), < 0: -(scratch slot + 1)
+    const int* cell_nodes;
+    const double* Jinv;
+    const double* detJ;
+    const double* u;               // [2nN, ldb]
+    double* a;
+    double* b;
+    double* scratch;               // [nslots, 4, ldb]
+    double* epart;                 // [npatch, ldb]
+    int nN, ldb;
+    double ca, cb;
+};
+
+struct CellIn {
+    int cell;
+    int ln[6];
+    double g00, g01, g10, g11, det;
+    double ux[6], uy[6];
+};
+
+__device__ __forceinline__ void patch_load_cell(const PatchArgs& p, int slot, int b, CellIn& c) {
+    c.cell = __ldg(p.pcells + slot);
+    if (c.cell < 0) return;  // warp-uniform
+    const size_t ldb = (size_t)p.ldb;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        c.ln[i] = __ldg(p.plnode + (size_t)slot * 6 + i);
+        const int nd = __ldg(p.cell_nodes + c.cell * 6 + i);
+        c.ux[i] = p.u[(size_t)nd * ldb + b];
+        c.uy[i] = p.u[(size_t)(nd + p.nN) * ldb + b];
+    }
+    c.g00 = __ldg(p.Jinv + c.cell * 4 + 0); c.g01 = __ldg(p.Jinv + c.cell * 4 + 1);
+    c.g10 = __ldg(p.Jinv + c.cell * 4 + 2); c.g11 = __ldg(p.Jinv + c.cell * 4 + 3);
+    c.det = __ldg(p.detJ + c.cell);
+}
+
+// grid = (npatch, ldb/32), block = (32, EP_WARPS), dynamic smem = max patch nodes * 4 * 32 doubles
+template <bool NONLINEAR>
+__global__ void __launch_bounds__(32 * EP_WARPS) k_element_patch(const PatchArgs p) {
+    extern __shared__ __align__(16) double acc[];  // [node][4][32]
+    const int lane = threadIdx.x, w = threadIdx.y;
+    const int b = blockIdx.y * 32 + lane;
+    const int c0 = __ldg(p.pcell_ptr + blockIdx.x), c1 = __ldg(p.pcell_ptr + blockIdx.x + 1);
+    const int n0 = __ldg(p.pnode_ptr + blockIdx.x), nn = __ldg(p.pnode_ptr + blockIdx.x + 1) - n0;
+    for (int i = w; i < nn * 4; i += EP_WARPS) acc[i * 32 + lane] = 0.0;
+    CellIn cur, nxt;
+    patch_load_cell(p, c0 + w, b, cur);
+    __syncthreads();
+    double e_acc = 0.0;
+    for (int r = c0; r < c1; r += EP_WARPS) {
+        nxt.cell = -1;
+        if (r + EP_WARPS < c1) patch_load_cell(p, r + EP_WARPS + w, b, nxt);
+        if (cur.cell >= 0) {
+            double rx[6], ry[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) { rx[i] = 0.0; ry[i] = 0.0; }
+            if (NONLINEAR) {
+#pragma unroll
+                for (int q = 0; q < 7; ++q) {
+                    double vx = 0.0, vy = 0.0, ax0 = 0.0, ax1 = 0.0, ay0 = 0.0, ay1 = 0.0;
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) {
+                        vx = fma(c_phi[q][i], cur.ux[i], vx);
+                        vy = fma(c_phi[q][i], cur.uy[i], vy);
+                        ax0 = fma(c_dphi[q][i][0], cur.ux[i], ax0);
+                        ax1 = fma(c_dphi[q][i][1], cur.ux[i], ax1);
+                        ay0 = fma(c_dphi[q][i][0], cur.uy[i], ay0);
+                        ay1 = fma(c_dphi[q][i][1], cur.uy[i], ay1);
+                    }
+                    const double dux_dx = ax0 * cur.g00 + ax1 * cur.g10, dux_dy = ax0 * cur.g01 + ax1 * cur.g11;
+                    const double duy_dx = ay0 * cur.g00 + ay1 * cur.g10, duy_dy = ay0 * cur.g01 + ay1 * cur.g11;
+                    const double wq = c_w[q] * cur.det;
+                    const double cx = wq * (vx * dux_dx + vy * dux_dy);
+                    const double cy = wq * (vx * duy_dx + vy * duy_dy);
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) {
+                        rx[i] = fma(c_phi[q][i], cx, rx[i]);
+                        ry[i] = fma(c_phi[q][i], cy, ry[i]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                double mx = 0.0, my = 0.0;
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    mx = fma(c_mass[i][j], cur.ux[j], mx);
+                    my = fma(c_mass[i][j], cur.uy[j], my);
+                }
+                mx *= cur.det;
+                my *= cur.det;
+                e_acc = fma(cur.ux[i], mx, e_acc);
+                e_acc = fma(cur.uy[i], my, e_acc);
+                double* s = acc + (size_t)cur.ln[i] * 128 + lane;  // cells of one round share no node
+                s[0] += p.ca * mx - 2.0 * rx[i];
+                s[32] += p.ca * my - 2.0 * ry[i];
+                s[64] += p.cb * mx + rx[i];
+                s[96] += p.cb * my + ry[i];
+            }
+        }
+        __syncthreads();
+        cur = nxt;
+    }
+    const size_t ldb = (size_t)p.ldb;
+    for (int j = w; j < nn; j += EP_WARPS) {
+        const int dst = __ldg(p.pnode_dst + n0 + j);
+        const double* s = acc + (size_t)j * 128 + lane;
+        if (dst >= 0) {
+            p.a[(size_t)dst * ldb + b] = s[0];
+            p.a[(size_t)(dst + p.nN) * ldb + b] = s[32];
+            p.b[(size_t)dst * ldb + b] = s[64];
+            p.b[(size_t)(dst + p.nN) * ldb + b] = s[96];
+        } else {
+            double* z = p.scratch + (size_t)(-1 - dst) * 4 * ldb + b;
+            z[0] = s[0]; z[ldb] = s[32]; z[2 * ldb] = s[64]; z[3 * ldb] = s[96];
+        }
+    }
+    __shared__ double se[EP_WARPS][32];
+    se[w][lane] = e_acc;
+    __syncthreads();
+    if (w == 0) {
+        double t = se[0][lane];
+#pragma unroll
+        for (int k = 1; k < EP_WARPS; ++k) t += se[k][lane];
+        p.epart[(size_t)blockIdx.x * ldb + b] = t;
+    }
+}
+
+// nodes shared between patches: a/b rows = sum of the patches' partials (fixed order).
+// grid = (ceil(nshared/8), ldb/32), block = (32, 8)
+__global__ void __launch_bounds__(256) k_patch_merge(int nshared, const int* __restrict__ mptr, const int* __restrict__ msrc,
+                                                    const int* __restrict__ mnode, const double* __restrict__ scratch,
+                                                    double* __restrict__ a, double* __restrict__ bvec, int nN, int ldb) {
+    const int i = blockIdx.x * blockDim.y + threadIdx.y;
+    const int b = blockIdx.y * 32 + threadIdx.x;
+    if (i >= nshared) return;
+    const size_t L = (size_t)ldb;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    for (int k = __ldg(mptr + i); k < __ldg(mptr + i + 1); ++k) {
+        const double* z = scratch + (size_t)__ldg(msrc + k) * 4 * L + b;
+        s0 += z[0]; s1 += z[L]; s2 += z[2 * L]; s3 += z[3 * L];
+    }
+    const int nd = __ldg(mnode + i);
+    a[(size_t)nd * L + b] = s0;
+    a[(size_t)(nd + nN) * L + b] = s1;
+    bvec[(size_t)nd * L + b] = s2;
+    bvec[(size_t)(nd + nN) * L + b] = s3;
 }
 
 // rhs in solver row order.  grid = (ceil(n/8), ldb/32), block = (32, 8)
@@ -675,6 +841,13 @@ struct fcb_context {
     double* sensor_val = nullptr;
     std::vector<int> colour_ptr, colour_blk_offset;
     int nblk_total = 0;
+    // patch form of the element kernel
+    int use_patches = 1, npatch = 0, nshared = 0, patch_smem = 0;
+    int *pcell_ptr = nullptr, *pcells = nullptr, *pnode_ptr = nullptr, *pnode_dst = nullptr, *mptr = nullptr, *msrc = nullptr,
+        *mnode = nullptr;
+    unsigned char* plnode = nullptr;
+    double* pscratch = nullptr;
+    int patch_stats[4] = {0, 0, 0, 0};  // patches, max nodes per patch, scratch slots, rounds
     DevPlan plan[2];
     // state
     double *up[2] = {nullptr, nullptr}, *avec = nullptr, *bvec[2] = {nullptr, nullptr}, *Z = nullptr;
@@ -976,6 +1149,26 @@ struct PhaseMark {
 };
 
 int enqueue_element(fcb_context* h, const double* u, double* a, double* b) {
+    if (h->use_patches) {
+        PatchArgs p;
+        p.pcell_ptr = h->pcell_ptr; p.pcells = h->pcells; p.plnode = h->plnode;
+        p.pnode_ptr = h->pnode_ptr; p.pnode_dst = h->pnode_dst;
+        p.cell_nodes = h->cell_nodes; p.Jinv = h->Jinv; p.detJ = h->detJ;
+        p.u = u; p.a = a; p.b = b; p.scratch = h->pscratch; p.epart = h->epart;
+        p.nN = h->nN; p.ldb = h->ldb;
+        p.ca = 2.0 / h->dt; p.cb = -0.5 / h->dt;
+        dim3 grid(h->npatch, h->ldb / 32), block(32, EP_WARPS);
+        if (h->nonlinear) k_element_patch<true><<<grid, block, h->patch_smem, h->stream>>>(p);
+        else k_element_patch<false><<<grid, block, h->patch_smem, h->stream>>>(p);
+        h->launches += 1;
+        if (h->nshared > 0) {
+            dim3 g2((h->nshared + 7) / 8, h->ldb / 32), b2(32, 8);
+            k_patch_merge<<<g2, b2, 0, h->stream>>>(h->nshared, h->mptr, h->msrc, h->mnode, h->pscratch, a, b, h->nN, h->ldb);
+            h->launches += 1;
+        }
+        CK(cudaGetLastError());
+        return FCB_OK;
+    }
     for (int c = 0; c < h->ncolours; ++c) {
         ElemArgs p;
         p.cells = h->colour_cells + h->colour_ptr[c];
@@ -1151,7 +1344,8 @@ void destroy(fcb_context* h) {
     void* ptrs[] = {h->first_mask, h->cell_nodes, h->colour_cells, h->perm, h->iperm, h->Jinv, h->detJ, h->bc_shape, h->ctrl_rhs[0],
                     h->ctrl_rhs[1], h->sensor_ptr, h->sensor_idx, h->sensor_val, h->up[0], h->up[1], h->avec,
                     h->bvec[0], h->bvec[1], h->Z, h->epart, h->uctrl, h->y, h->dE, h->diverged, h->Ad, h->Bd, h->Cd,
-                    h->Dd, h->Ky, h->Fu, h->xk[0], h->xk[1], h->series, h->counter, h->sweep_dbg};
+                    h->Dd, h->Ky, h->Fu, h->xk[0], h->xk[1], h->series, h->counter, h->sweep_dbg,
+                    h->pcell_ptr, h->pcells, h->pnode_ptr, h->pnode_dst, h->mptr, h->msrc, h->mnode, h->plnode, h->pscratch};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (int i = 0; i < 2; ++i) {
@@ -1163,6 +1357,109 @@ void destroy(fcb_context* h) {
         if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
+}
+
+// Group the cells into patches for k_element_patch.  The nested-dissection numbering of the solver is a
+// space-filling order of the mesh, so sorting cells by the lowest solver row among their nodes and cutting
+// the list into chunks gives compact patches without needing coordinates.
+int build_patches(fcb_context* h, const fcb_problem* p, const std::vector<int>& iperm) {
+    const int nT = p->nT, nN = p->nN;
+    const char* env = getenv("FCB_ELEMENT");  // "colour": the coloured global-scatter kernel (A/B measurements)
+    if (env && std::string(env) == "colour") { h->use_patches = 0; return FCB_OK; }
+    int pc = 32;
+    env = getenv("FCB_PATCH_CELLS");
+    if (env && atoi(env) >= EP_WARPS && atoi(env) <= 40) pc = atoi(env);
+    std::vector<std::pair<int, int>> key(nT);
+    for (int e = 0; e < nT; ++e) {
+        int k = INT_MAX;
+        for (int i = 0; i < 6; ++i) {
+            const int nd = p->cell_nodes[e * 6 + i];
+            for (int c = 0; c < 2; ++c) {
+                const int r = iperm[nd + c * nN];
+                if (r >= 0) k = std::min(k, r);
+            }
+        }
+        key[e] = {k, e};
+    }
+    std::sort(key.begin(), key.end());
+    const int npatch = (nT + pc - 1) / pc;
+    std::vector<int> pcell_ptr(1, 0), pcells, pnode_ptr(1, 0), pnode_dst, node_npatch(nN, 0);
+    std::vector<unsigned char> plnode;
+    std::vector<std::vector<int>> patch_nodes(npatch);
+    std::vector<int> local(nN, -1);
+    int max_nodes = 0;
+    for (int q = 0; q < npatch; ++q) {
+        const int e0 = q * pc, e1 = std::min(nT, e0 + pc);
+        std::vector<int>& nodes = patch_nodes[q];
+        for (int k = e0; k < e1; ++k)
+            for (int i = 0; i < 6; ++i) {
+                const int nd = p->cell_nodes[key[k].second * 6 + i];
+                if (local[nd] < 0) { local[nd] = (int)nodes.size(); nodes.push_back(nd); }
+            }
+        if (nodes.size() > 255) return fail(h, FCB_ERR_INVALID, "element patch with %zu nodes (limit 255)", nodes.size());
+        max_nodes = std::max(max_nodes, (int)nodes.size());
+        // rounds of up to EP_WARPS cells that share no node (greedy)
+        std::vector<std::vector<int>> rounds;
+        std::vector<std::vector<char>> used;  // per round: node taken
+        for (int k = e0; k < e1; ++k) {
+            const int e = key[k].second;
+            size_t r = 0;
+            for (;; ++r) {
+                if (r == rounds.size()) { rounds.emplace_back(); used.emplace_back(nodes.size(), 0); }
+                if ((int)rounds[r].size() >= EP_WARPS) continue;
+                bool ok = true;
+                for (int i = 0; i < 6 && ok; ++i) ok = !used[r][local[p->cell_nodes[e * 6 + i]]];
+                if (ok) break;
+            }
+            rounds[r].push_back(e);
+            for (int i = 0; i < 6; ++i) used[r][local[p->cell_nodes[e * 6 + i]]] = 1;
+        }
+        for (auto& rd : rounds)
+            for (int wv = 0; wv < EP_WARPS; ++wv) {
+                const int e = wv < (int)rd.size() ? rd[wv] : -1;
+                pcells.push_back(e);
+                for (int i = 0; i < 6; ++i) plnode.push_back(e >= 0 ? (unsigned char)local[p->cell_nodes[e * 6 + i]] : 0);
+            }
+        pcell_ptr.push_back((int)pcells.size());
+        for (int nd : nodes) { ++node_npatch[nd]; local[nd] = -1; }
+    }
+    // interior nodes are written directly; shared ones get a scratch slot per (patch, node)
+    std::vector<std::vector<int>> slots_of(nN);
+    int nslots = 0;
+    for (int q = 0; q < npatch; ++q) {
+        for (int nd : patch_nodes[q]) {
+            if (node_npatch[nd] == 1) pnode_dst.push_back(nd);
+            else { pnode_dst.push_back(-1 - nslots); slots_of[nd].push_back(nslots); ++nslots; }
+        }
+        pnode_ptr.push_back((int)pnode_dst.size());
+    }
+    std::vector<int> mptr(1, 0), msrc, mnode;
+    for (int nd = 0; nd < nN; ++nd)
+        if (node_npatch[nd] > 1) {
+            for (int sl : slots_of[nd]) msrc.push_back(sl);
+            mptr.push_back((int)msrc.size());
+            mnode.push_back(nd);
+        } else if (node_npatch[nd] == 0)
+            return fail(h, FCB_ERR_INVALID, "P2 node %d belongs to no cell", nd);
+    h->npatch = npatch;
+    h->nshared = (int)mnode.size();
+    h->patch_smem = max_nodes * 4 * 32 * (int)sizeof(double);
+    h->nblk_total = npatch;
+    if (h->patch_smem > 200 * 1024) return fail(h, FCB_ERR_INVALID, "element patches too large for shared memory");
+    CK(cudaFuncSetAttribute(k_element_patch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->patch_smem));
+    CK(cudaFuncSetAttribute(k_element_patch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->patch_smem));
+    TRY(upload(h, &h->pcell_ptr, pcell_ptr.data(), pcell_ptr.size()));
+    TRY(upload(h, &h->pcells, pcells.data(), pcells.size()));
+    TRY(upload(h, &h->plnode, plnode.data(), plnode.size()));
+    TRY(upload(h, &h->pnode_ptr, pnode_ptr.data(), pnode_ptr.size()));
+    TRY(upload(h, &h->pnode_dst, pnode_dst.data(), pnode_dst.size()));
+    TRY(upload(h, &h->mptr, mptr.data(), mptr.size()));
+    TRY(upload(h, &h->msrc, msrc.data(), std::max<size_t>(msrc.size(), 1)));
+    TRY(upload(h, &h->mnode, mnode.data(), std::max<size_t>(mnode.size(), 1)));
+    TRY(upload<double>(h, &h->pscratch, nullptr, (size_t)std::max(nslots, 1) * 4 * h->ldb));
+    CK(cudaStreamSynchronize(h->stream));  // host vectors go out of scope
+    h->patch_stats[0] = npatch; h->patch_stats[1] = max_nodes; h->patch_stats[2] = nslots; h->patch_stats[3] = (int)(pcells.size() / EP_WARPS);
+    return FCB_OK;
 }
 
 int create_impl(fcb_context* h, const fcb_problem* p, int B) {
@@ -1273,6 +1570,7 @@ int create_impl(fcb_context* h, const fcb_problem* p, int B) {
         }
         TRY(upload(h, &h->iperm, iperm.data(), iperm.size()));
         CK(cudaStreamSynchronize(h->stream));
+        TRY(build_patches(h, p, iperm));
     }
     TRY(upload(h, &h->bc_shape, p->bc_shape, (size_t)p->na * p->n_bc));
     for (int o = 0; o < 2; ++o) TRY(upload(h, &h->ctrl_rhs[o], p->ctrl_rhs[o], (size_t)p->na * p->n_free));
