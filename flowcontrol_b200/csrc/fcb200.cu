@@ -13,7 +13,7 @@
 //   k_front_sweep forward sweep  (one launch per elimination-tree height): y_t, u_t = sum_children u_c - E_t y_t
 //   k_front_sweep backward sweep (one launch per elimination-tree depth):  x_t = F11^-1 y_t - G_t x_struct(t)
 //   k_post        un-permute, Dirichlet values, non-finite flag
-//   k_element     per cell: convection N(u) (7-point Radon rule) + mass M u, coloured scatter into
+//   k_element_patch per patch of cells: convection N(u) (7-point Radon rule) + mass M u, accumulated in shared memory into
 //                 a = (2/dt) M u - 2 N(u),  b = -(1/2dt) M u + N(u);  energy partials u.(M u)
 //   k_measure     sensors (sparse rows) + energy reduction (fixed order)
 // Closed loop adds k_controller before and k_log after, all inside one CUDA graph.
@@ -22,6 +22,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -48,49 +49,131 @@ __constant__ double c_mass[6][6];     // reference mass matrix (int phi_a phi_b 
 // ----------------------------------------------------------------------------------------------
 // kernels
 // ----------------------------------------------------------------------------------------------
-constexpr int ELEM_WARPS = 4;  // warps (cells in flight) per CTA
-constexpr int ELEM_CPW = 4;    // cells per warp (sequential)
+// ----------------------------------------------------------------------------------------------
+// Element kernel, patch form: one CTA = one patch of ~28 neighbouring cells x 32 trajectories; each of its
+// EP_WARPS warps owns a compact sub-patch (a quarter of the cells) and integrates its cells one after the
+// other with NO synchronisation: the node rows (a_x, a_y, b_x, b_y) of a sub-patch are accumulated in the
+// warp's own rows of shared memory, so a node shared by 6 cells costs one global write instead of 6
+// read-modify-writes and no atomics or colouring are needed.  After one __syncthreads the rows of a node that
+// several sub-patches touched are summed in a fixed order; nodes interior to the patch go straight to global
+// memory, nodes shared with other patches go to a scratch slot and k_patch_merge sums the (2-4) partials.
+// The gathers of a warp's next cell are issued before the arithmetic of the current one.
+// Fused output (bprev != NULL): instead of a the kernel writes the NEXT step's right-hand side rows
+// Z[row(dof)] = a + b_{n-1} (solver order), so no separate rhs pass reads a and b again.
+// ----------------------------------------------------------------------------------------------
+constexpr int EP_WARPS = 4;
 
-struct ElemArgs {
-    const int* cells;       // cells of this colour
-    int ncells;
-    const int* cell_nodes;  // [nT*6]
-    const unsigned char* first;  // [nT] bit i set: this cell is the first (lowest colour) to touch local node i
-    const double* Jinv;     // [nT*4]
-    const double* detJ;     // [nT]
-    const double* u;        // [2nN, ldb]
-    double* a;              // [2nN, ldb] written by the first colour touching a node, accumulated afterwards
-    double* b;              // [2nN, ldb] likewise
-    double* epart;          // [nblk_total, ldb]
-    int blk_offset;
-    int nN;
-    int ldb;
-    double ca, cb;          // mass coefficients: a += ca*Mu - 2 N ; b += cb*Mu + N
+struct PatchArgs {
+    const int* pcell_ptr;          // [npatch*EP_WARPS+1] cell ranges of every warp
+    const int* pcells;             // cell ids
+    const unsigned char* plnode;   // [len(pcells)*6] accumulator row (inside the CTA) of the cell's nodes
+    const int* pnode_ptr;          // [npatch+1] into the per-node arrays below (unique nodes of the patch)
+    const int* pnode_dst;          // >= 0: node id (interior to the patch), < 0: -(scratch slot + 1)
+    const unsigned char* psrc;     // [4 per node] accumulator rows to sum (255 = none), first entry always valid
+    const int* prow;               // [3 per node] solver rows of its ux, uy, p dofs (< 0: none / Dirichlet)
+    const int* pacc_rows;          // [npatch] accumulator rows the patch uses
+    const int* cell_nodes;
+    const double* Jinv;
+    const double* detJ;
+    const double* u;               // [2nN, ldb]
+    double* a;
+    double* b;
+    double* scratch;               // [nslots, 4, ldb]
+    double* epart;                 // [npatch, ldb]
+    const double* bprev;           // b of the previous state (fused rhs), or NULL: store a instead
+    double* Zb;
+    int nN, nV, ldb;
+    double ca, cb;
 };
 
-template <bool NONLINEAR>
-__global__ void __launch_bounds__(32 * ELEM_WARPS, 3) k_element(const ElemArgs p) {
-    const int b = blockIdx.y * 32 + threadIdx.x;
+// a/b rows of one node go out: either as a and b, or (fused) as next-step rhs rows and b
+template <bool ADD_BPREV>  // false: the caller's ax, ay already contain b_{n-1}
+__device__ __forceinline__ void emit_node(const double* bprev, double* Zb, int rx, int ry, int rp, double* a, double* bout, int nN,
+                                          size_t ldb, int nd, int b, double ax, double ay, double bx, double by) {
+    const size_t ox = (size_t)nd * ldb + b, oy = (size_t)(nd + nN) * ldb + b;
+    if (bprev) {
+        if (rx >= 0) Zb[(size_t)rx * ldb + b] = ADD_BPREV ? ax + bprev[ox] : ax;
+        if (ry >= 0) Zb[(size_t)ry * ldb + b] = ADD_BPREV ? ay + bprev[oy] : ay;
+        if (rp >= 0) Zb[(size_t)rp * ldb + b] = 0.0;  // continuity rows of the rhs are zero (the solve left the pressure there)
+    } else {
+        a[ox] = ax;
+        a[oy] = ay;
+    }
+    bout[ox] = bx;
+    bout[oy] = by;
+}
+
+struct CellIn {
+    int ln[6];
+    double g00, g01, g10, g11, det;
+    double ux[6], uy[6];
+};
+
+__device__ __forceinline__ void patch_load_cell(const PatchArgs& p, int slot, int b, CellIn& c) {
+    const int cell = __ldg(p.pcells + slot);
     const size_t ldb = (size_t)p.ldb;
-    double e_acc = 0.0;
-#pragma unroll 1
-    for (int c = 0; c < ELEM_CPW; ++c) {
-        const int ci = (blockIdx.x * ELEM_WARPS + threadIdx.y) * ELEM_CPW + c;
-        if (ci >= p.ncells) break;  // warp-uniform
-        const int cell = __ldg(p.cells + ci);
-        int nd[6];
 #pragma unroll
-        for (int i = 0; i < 6; ++i) nd[i] = __ldg(p.cell_nodes + cell * 6 + i);
-        const double g00 = __ldg(p.Jinv + cell * 4 + 0), g01 = __ldg(p.Jinv + cell * 4 + 1);
-        const double g10 = __ldg(p.Jinv + cell * 4 + 2), g11 = __ldg(p.Jinv + cell * 4 + 3);
-        const double det = __ldg(p.detJ + cell);
-        const unsigned first = __ldg(p.first + cell);
-        double ux[6], uy[6];
+    for (int i = 0; i < 6; ++i) {
+        c.ln[i] = __ldg(p.plnode + (size_t)slot * 6 + i);
+        const int nd = __ldg(p.cell_nodes + cell * 6 + i);
+        c.ux[i] = p.u[(size_t)nd * ldb + b];
+        c.uy[i] = p.u[(size_t)(nd + p.nN) * ldb + b];
+    }
+    c.g00 = __ldg(p.Jinv + cell * 4 + 0); c.g01 = __ldg(p.Jinv + cell * 4 + 1);
+    c.g10 = __ldg(p.Jinv + cell * 4 + 2); c.g11 = __ldg(p.Jinv + cell * 4 + 3);
+    c.det = __ldg(p.detJ + cell);
+}
+
+// grid = (npatch, ldb/32), block = (32, EP_WARPS), dynamic smem = max accumulator rows * 4 * 32 doubles
+template <bool NONLINEAR>
+__global__ void __launch_bounds__(32 * EP_WARPS, 2) k_element_patch(const PatchArgs p) {
+    extern __shared__ __align__(16) double acc[];  // [row][4][32]
+    const int lane = threadIdx.x, w = threadIdx.y;
+    const int b = blockIdx.y * 32 + lane;
+    const int c0 = __ldg(p.pcell_ptr + blockIdx.x * EP_WARPS + w), c1 = __ldg(p.pcell_ptr + blockIdx.x * EP_WARPS + w + 1);
+    const int n0 = __ldg(p.pnode_ptr + blockIdx.x), nn = __ldg(p.pnode_ptr + blockIdx.x + 1) - n0;
+    const int nrows = __ldg(p.pacc_rows + blockIdx.x);
+    CellIn cur, nxt;
+    if (c0 < c1) patch_load_cell(p, c0, b, cur);
+    // accumulators start at zero, except (fused right-hand side) the a rows of the patch's own nodes, which start from
+    // b_{n-1}: those loads are all in flight together with the first cell's gathers
+    if (p.bprev) {
+        const size_t ldb = (size_t)p.ldb;
+        const int chunk = (nn + EP_WARPS - 1) / EP_WARPS;
+        for (int j0 = w * chunk; j0 < min(nn, (w + 1) * chunk); j0 += 32) {
+            const int cnt = min(32, min(nn, (w + 1) * chunk) - j0);
+            int l_dst = -1;
+            unsigned l_src = 0xffffffffu;
+            if (lane < cnt) {
+                l_dst = __ldg(p.pnode_dst + n0 + j0 + lane);
+                l_src = __ldg(reinterpret_cast<const unsigned*>(p.psrc) + n0 + j0 + lane);
+            }
+#pragma unroll 8
+            for (int i = 0; i < cnt; ++i) {
+                const int dst = __shfl_sync(0xffffffffu, l_dst, i);
+                const unsigned src = __shfl_sync(0xffffffffu, l_src, i);
+                double v0 = 0.0, v1 = 0.0;
+                if (dst >= 0) {  // warp-uniform
+                    v0 = p.bprev[(size_t)dst * ldb + b];
+                    v1 = p.bprev[(size_t)(dst + p.nN) * ldb + b];
+                }
 #pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            ux[i] = p.u[(size_t)nd[i] * ldb + b];
-            uy[i] = p.u[(size_t)(nd[i] + p.nN) * ldb + b];
+                for (int k = 0; k < 4; ++k) {
+                    const unsigned rk = (src >> (8 * k)) & 255u;
+                    if (rk != 255u) {
+                        double* t = acc + (size_t)rk * 128 + lane;
+                        t[0] = k == 0 ? v0 : 0.0; t[32] = k == 0 ? v1 : 0.0; t[64] = 0.0; t[96] = 0.0;
+                    }
+                }
+            }
         }
+    } else {
+        for (int i = w; i < nrows * 4; i += EP_WARPS) acc[i * 32 + lane] = 0.0;
+    }
+    __syncthreads();
+    double e_acc = 0.0;
+    for (int r = c0; r < c1; ++r) {
+        if (r + 1 < c1) patch_load_cell(p, r + 1, b, nxt);
         double rx[6], ry[6];
 #pragma unroll
         for (int i = 0; i < 6; ++i) { rx[i] = 0.0; ry[i] = 0.0; }
@@ -100,17 +183,17 @@ __global__ void __launch_bounds__(32 * ELEM_WARPS, 3) k_element(const ElemArgs p
                 double vx = 0.0, vy = 0.0, ax0 = 0.0, ax1 = 0.0, ay0 = 0.0, ay1 = 0.0;
 #pragma unroll
                 for (int i = 0; i < 6; ++i) {
-                    vx = fma(c_phi[q][i], ux[i], vx);
-                    vy = fma(c_phi[q][i], uy[i], vy);
-                    ax0 = fma(c_dphi[q][i][0], ux[i], ax0);
-                    ax1 = fma(c_dphi[q][i][1], ux[i], ax1);
-                    ay0 = fma(c_dphi[q][i][0], uy[i], ay0);
-                    ay1 = fma(c_dphi[q][i][1], uy[i], ay1);
+                    vx = fma(c_phi[q][i], cur.ux[i], vx);
+                    vy = fma(c_phi[q][i], cur.uy[i], vy);
+                    ax0 = fma(c_dphi[q][i][0], cur.ux[i], ax0);
+                    ax1 = fma(c_dphi[q][i][1], cur.ux[i], ax1);
+                    ay0 = fma(c_dphi[q][i][0], cur.uy[i], ay0);
+                    ay1 = fma(c_dphi[q][i][1], cur.uy[i], ay1);
                 }
                 // physical gradients: d_j u = sum_k (d_ref_k u) Jinv[k][j]
-                const double dux_dx = ax0 * g00 + ax1 * g10, dux_dy = ax0 * g01 + ax1 * g11;
-                const double duy_dx = ay0 * g00 + ay1 * g10, duy_dy = ay0 * g01 + ay1 * g11;
-                const double wq = c_w[q] * det;
+                const double dux_dx = ax0 * cur.g00 + ax1 * cur.g10, dux_dy = ax0 * cur.g01 + ax1 * cur.g11;
+                const double duy_dx = ay0 * cur.g00 + ay1 * cur.g10, duy_dy = ay0 * cur.g01 + ay1 * cur.g11;
+                const double wq = c_w[q] * cur.det;
                 const double cx = wq * (vx * dux_dx + vy * dux_dy);
                 const double cy = wq * (vx * duy_dx + vy * duy_dy);
 #pragma unroll
@@ -120,179 +203,66 @@ __global__ void __launch_bounds__(32 * ELEM_WARPS, 3) k_element(const ElemArgs p
                 }
             }
         }
-        // mass product and energy
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
             double mx = 0.0, my = 0.0;
 #pragma unroll
             for (int j = 0; j < 6; ++j) {
-                mx = fma(c_mass[i][j], ux[j], mx);
-                my = fma(c_mass[i][j], uy[j], my);
+                mx = fma(c_mass[i][j], cur.ux[j], mx);
+                my = fma(c_mass[i][j], cur.uy[j], my);
             }
-            mx *= det;
-            my *= det;
-            e_acc = fma(ux[i], mx, e_acc);
-            e_acc = fma(uy[i], my, e_acc);
-            const size_t ox = (size_t)nd[i] * ldb + b;
-            const size_t oy = (size_t)(nd[i] + p.nN) * ldb + b;
-            // same-colour cells share no node: plain (read-modify-)write, no atomics.  The lowest colour
-            // touching a node overwrites, so the vectors need no zero fill between steps.
-            double vax = p.ca * mx - 2.0 * rx[i], vay = p.ca * my - 2.0 * ry[i];
-            double vbx = p.cb * mx + rx[i], vby = p.cb * my + ry[i];
-            if (!((first >> i) & 1u)) {  // warp-uniform
-                vax += p.a[ox];
-                vay += p.a[oy];
-                vbx += p.b[ox];
-                vby += p.b[oy];
-            }
-            p.a[ox] = vax;
-            p.a[oy] = vay;
-            p.b[ox] = vbx;
-            p.b[oy] = vby;
+            mx *= cur.det;
+            my *= cur.det;
+            e_acc = fma(cur.ux[i], mx, e_acc);
+            e_acc = fma(cur.uy[i], my, e_acc);
+            double* s = acc + (size_t)cur.ln[i] * 128 + lane;  // rows of this warp's sub-patch: nobody else touches them
+            s[0] += p.ca * mx - 2.0 * rx[i];
+            s[32] += p.ca * my - 2.0 * ry[i];
+            s[64] += p.cb * mx + rx[i];
+            s[96] += p.cb * my + ry[i];
         }
-    }
-    __shared__ double se[ELEM_WARPS][32];
-    se[threadIdx.y][threadIdx.x] = e_acc;
-    __syncthreads();
-    if (threadIdx.y == 0) {
-        double s = se[0][threadIdx.x];
-#pragma unroll
-        for (int w = 1; w < ELEM_WARPS; ++w) s += se[w][threadIdx.x];
-        p.epart[(size_t)(p.blk_offset + blockIdx.x) * ldb + b] = s;
-    }
-}
-
-// ----------------------------------------------------------------------------------------------
-// Patch form of the element kernel: one CTA = one patch of ~32 neighbouring cells x 32 trajectories.
-// The patch's node rows of a and b are accumulated in shared memory (4 rows per node: a_x, a_y, b_x, b_y),
-// so a node shared by 6 cells costs ONE global write instead of 6 read-modify-writes.  Cells are processed
-// in rounds of EP_WARPS cells that share no node (one cell per warp, __syncthreads between rounds): no
-// atomics, fixed summation order.  Nodes interior to the patch are written straight to a/b; nodes shared
-// with other patches go to a scratch slot and k_patch_merge sums the (2-4) partials per node, again in a
-// fixed order.  The next round's gathers are issued before the current round's arithmetic.
-// ----------------------------------------------------------------------------------------------
-constexpr int EP_WARPS = 4;
-
-struct PatchArgs {
-    const int* pcell_ptr;          // [npatch+1] into pcells, multiples of EP_WARPS
-    const int* pcells;             // cell id or -1, grouped in rounds of EP_WARPS
-    const unsigned char* plnode;   // [len(pcells)*6] patch-local index of the cell's nodes
-    const int* pnode_ptr;          // [npatch+1] into pnode_dst
-    const int* pnode_dst;          // >= 0: node id (interior to the patch), < 0: -(scratch slot + 1)
-    const int* cell_nodes;
-    const double* Jinv;
-    const double* detJ;
-    const double* u;               // [2nN, ldb]
-    double* a;
-    double* b;
-    double* scratch;               // [nslots, 4, ldb]
-    double* epart;                 // [npatch, ldb]
-    int nN, ldb;
-    double ca, cb;
-};
-
-struct CellIn {
-    int cell;
-    int ln[6];
-    double g00, g01, g10, g11, det;
-    double ux[6], uy[6];
-};
-
-__device__ __forceinline__ void patch_load_cell(const PatchArgs& p, int slot, int b, CellIn& c) {
-    c.cell = __ldg(p.pcells + slot);
-    if (c.cell < 0) return;  // warp-uniform
-    const size_t ldb = (size_t)p.ldb;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-        c.ln[i] = __ldg(p.plnode + (size_t)slot * 6 + i);
-        const int nd = __ldg(p.cell_nodes + c.cell * 6 + i);
-        c.ux[i] = p.u[(size_t)nd * ldb + b];
-        c.uy[i] = p.u[(size_t)(nd + p.nN) * ldb + b];
-    }
-    c.g00 = __ldg(p.Jinv + c.cell * 4 + 0); c.g01 = __ldg(p.Jinv + c.cell * 4 + 1);
-    c.g10 = __ldg(p.Jinv + c.cell * 4 + 2); c.g11 = __ldg(p.Jinv + c.cell * 4 + 3);
-    c.det = __ldg(p.detJ + c.cell);
-}
-
-// grid = (npatch, ldb/32), block = (32, EP_WARPS), dynamic smem = max patch nodes * 4 * 32 doubles
-template <bool NONLINEAR>
-__global__ void __launch_bounds__(32 * EP_WARPS) k_element_patch(const PatchArgs p) {
-    extern __shared__ __align__(16) double acc[];  // [node][4][32]
-    const int lane = threadIdx.x, w = threadIdx.y;
-    const int b = blockIdx.y * 32 + lane;
-    const int c0 = __ldg(p.pcell_ptr + blockIdx.x), c1 = __ldg(p.pcell_ptr + blockIdx.x + 1);
-    const int n0 = __ldg(p.pnode_ptr + blockIdx.x), nn = __ldg(p.pnode_ptr + blockIdx.x + 1) - n0;
-    for (int i = w; i < nn * 4; i += EP_WARPS) acc[i * 32 + lane] = 0.0;
-    CellIn cur, nxt;
-    patch_load_cell(p, c0 + w, b, cur);
-    __syncthreads();
-    double e_acc = 0.0;
-    for (int r = c0; r < c1; r += EP_WARPS) {
-        nxt.cell = -1;
-        if (r + EP_WARPS < c1) patch_load_cell(p, r + EP_WARPS + w, b, nxt);
-        if (cur.cell >= 0) {
-            double rx[6], ry[6];
-#pragma unroll
-            for (int i = 0; i < 6; ++i) { rx[i] = 0.0; ry[i] = 0.0; }
-            if (NONLINEAR) {
-#pragma unroll
-                for (int q = 0; q < 7; ++q) {
-                    double vx = 0.0, vy = 0.0, ax0 = 0.0, ax1 = 0.0, ay0 = 0.0, ay1 = 0.0;
-#pragma unroll
-                    for (int i = 0; i < 6; ++i) {
-                        vx = fma(c_phi[q][i], cur.ux[i], vx);
-                        vy = fma(c_phi[q][i], cur.uy[i], vy);
-                        ax0 = fma(c_dphi[q][i][0], cur.ux[i], ax0);
-                        ax1 = fma(c_dphi[q][i][1], cur.ux[i], ax1);
-                        ay0 = fma(c_dphi[q][i][0], cur.uy[i], ay0);
-                        ay1 = fma(c_dphi[q][i][1], cur.uy[i], ay1);
-                    }
-                    const double dux_dx = ax0 * cur.g00 + ax1 * cur.g10, dux_dy = ax0 * cur.g01 + ax1 * cur.g11;
-                    const double duy_dx = ay0 * cur.g00 + ay1 * cur.g10, duy_dy = ay0 * cur.g01 + ay1 * cur.g11;
-                    const double wq = c_w[q] * cur.det;
-                    const double cx = wq * (vx * dux_dx + vy * dux_dy);
-                    const double cy = wq * (vx * duy_dx + vy * duy_dy);
-#pragma unroll
-                    for (int i = 0; i < 6; ++i) {
-                        rx[i] = fma(c_phi[q][i], cx, rx[i]);
-                        ry[i] = fma(c_phi[q][i], cy, ry[i]);
-                    }
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 6; ++i) {
-                double mx = 0.0, my = 0.0;
-#pragma unroll
-                for (int j = 0; j < 6; ++j) {
-                    mx = fma(c_mass[i][j], cur.ux[j], mx);
-                    my = fma(c_mass[i][j], cur.uy[j], my);
-                }
-                mx *= cur.det;
-                my *= cur.det;
-                e_acc = fma(cur.ux[i], mx, e_acc);
-                e_acc = fma(cur.uy[i], my, e_acc);
-                double* s = acc + (size_t)cur.ln[i] * 128 + lane;  // cells of one round share no node
-                s[0] += p.ca * mx - 2.0 * rx[i];
-                s[32] += p.ca * my - 2.0 * ry[i];
-                s[64] += p.cb * mx + rx[i];
-                s[96] += p.cb * my + ry[i];
-            }
-        }
-        __syncthreads();
         cur = nxt;
     }
+    __syncthreads();
+    // write-out: every warp takes a contiguous chunk of the patch's nodes; the lanes fetch the chunk's destinations
+    // with one coalesced load each, then the rows go out four nodes at a time (independent loads in flight)
     const size_t ldb = (size_t)p.ldb;
-    for (int j = w; j < nn; j += EP_WARPS) {
-        const int dst = __ldg(p.pnode_dst + n0 + j);
-        const double* s = acc + (size_t)j * 128 + lane;
-        if (dst >= 0) {
-            p.a[(size_t)dst * ldb + b] = s[0];
-            p.a[(size_t)(dst + p.nN) * ldb + b] = s[32];
-            p.b[(size_t)dst * ldb + b] = s[64];
-            p.b[(size_t)(dst + p.nN) * ldb + b] = s[96];
-        } else {
-            double* z = p.scratch + (size_t)(-1 - dst) * 4 * ldb + b;
-            z[0] = s[0]; z[ldb] = s[32]; z[2 * ldb] = s[64]; z[3 * ldb] = s[96];
+    const int chunk = (nn + EP_WARPS - 1) / EP_WARPS;
+    for (int j0 = w * chunk; j0 < min(nn, (w + 1) * chunk); j0 += 32) {
+        const int cnt = min(32, min(nn, (w + 1) * chunk) - j0);
+        int l_dst = 0, l_rx = -1, l_ry = -1, l_rp = -1;
+        unsigned l_src = 0xffffffffu;
+        if (lane < cnt) {
+            l_dst = __ldg(p.pnode_dst + n0 + j0 + lane);
+            l_src = __ldg(reinterpret_cast<const unsigned*>(p.psrc) + n0 + j0 + lane);
+            if (p.bprev) {
+                l_rx = __ldg(p.prow + (size_t)(n0 + j0 + lane) * 3 + 0);
+                l_ry = __ldg(p.prow + (size_t)(n0 + j0 + lane) * 3 + 1);
+                l_rp = __ldg(p.prow + (size_t)(n0 + j0 + lane) * 3 + 2);
+            }
+        }
+#pragma unroll 4
+        for (int i = 0; i < cnt; ++i) {
+            const int dst = __shfl_sync(0xffffffffu, l_dst, i);
+            const unsigned src = __shfl_sync(0xffffffffu, l_src, i);
+            const int rx = __shfl_sync(0xffffffffu, l_rx, i), ry = __shfl_sync(0xffffffffu, l_ry, i);
+            const int rp = __shfl_sync(0xffffffffu, l_rp, i);
+            const double* s = acc + (size_t)(src & 255u) * 128 + lane;
+            double v0 = s[0], v1 = s[32], v2 = s[64], v3 = s[96];
+#pragma unroll
+            for (int k = 1; k < 4; ++k) {
+                const unsigned rk = (src >> (8 * k)) & 255u;
+                if (rk != 255u) {  // warp-uniform
+                    const double* t = acc + (size_t)rk * 128 + lane;
+                    v0 += t[0]; v1 += t[32]; v2 += t[64]; v3 += t[96];
+                }
+            }
+            if (dst >= 0) {
+                emit_node<false>(p.bprev, p.Zb, rx, ry, rp, p.a, p.b, p.nN, ldb, dst, b, v0, v1, v2, v3);
+            } else {
+                double* z = p.scratch + (size_t)(-1 - dst) * 4 * ldb + b;
+                z[0] = v0; z[ldb] = v1; z[2 * ldb] = v2; z[3 * ldb] = v3;
+            }
         }
     }
     __shared__ double se[EP_WARPS][32];
@@ -309,22 +279,47 @@ __global__ void __launch_bounds__(32 * EP_WARPS) k_element_patch(const PatchArgs
 // nodes shared between patches: a/b rows = sum of the patches' partials (fixed order).
 // grid = (ceil(nshared/8), ldb/32), block = (32, 8)
 __global__ void __launch_bounds__(256) k_patch_merge(int nshared, const int* __restrict__ mptr, const int* __restrict__ msrc,
-                                                    const int* __restrict__ mnode, const double* __restrict__ scratch,
-                                                    double* __restrict__ a, double* __restrict__ bvec, int nN, int ldb) {
+                                                    const int* __restrict__ mnode, const int* __restrict__ mrow,
+                                                    const double* __restrict__ scratch, double* a, double* bvec,
+                                                    const double* bprev, double* Zb, int nN, int ldb) {
     const int i = blockIdx.x * blockDim.y + threadIdx.y;
     const int b = blockIdx.y * 32 + threadIdx.x;
     if (i >= nshared) return;
     const size_t L = (size_t)ldb;
+    const int k0 = __ldg(mptr + i), k1 = __ldg(mptr + i + 1), nd = __ldg(mnode + i);
+    const int rx = __ldg(mrow + 3 * i), ry = __ldg(mrow + 3 * i + 1), rp = __ldg(mrow + 3 * i + 2);
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    for (int k = __ldg(mptr + i); k < __ldg(mptr + i + 1); ++k) {
+    for (int k = k0; k < k1; ++k) {
         const double* z = scratch + (size_t)__ldg(msrc + k) * 4 * L + b;
         s0 += z[0]; s1 += z[L]; s2 += z[2 * L]; s3 += z[3 * L];
     }
-    const int nd = __ldg(mnode + i);
-    a[(size_t)nd * L + b] = s0;
-    a[(size_t)(nd + nN) * L + b] = s1;
-    bvec[(size_t)nd * L + b] = s2;
-    bvec[(size_t)(nd + nN) * L + b] = s3;
+    emit_node<true>(bprev, Zb, rx, ry, rp, a, bvec, nN, L, nd, b, s0, s1, s2, s3);
+}
+
+// control terms of the fused right-hand side: Z[row] += sum_k coef[k][i] * u_ctrl[k] on the (few) rows where the lifting /
+// force vectors are non-zero.  grid = (ceil(nrows/8), ldb/32), block = (32, 8)
+__global__ void __launch_bounds__(256) k_ctrl_add(int nrows, const int* __restrict__ rows, const double* __restrict__ coef, int na,
+                                                 const double* __restrict__ uctrl, double* __restrict__ Z, int ldb) {
+    const int i = blockIdx.x * blockDim.y + threadIdx.y;
+    const int b = blockIdx.y * 32 + threadIdx.x;
+    if (i >= nrows) return;
+    double v = Z[(size_t)__ldg(rows + i) * ldb + b];
+    for (int k = 0; k < na; ++k) v = fma(__ldg(coef + (size_t)k * nrows + i), uctrl[(size_t)k * ldb + b], v);
+    Z[(size_t)__ldg(rows + i) * ldb + b] = v;
+}
+
+// Dirichlet rows of the new state: value = sum_k shape[k][j] * u_ctrl[k].  grid = (ceil(nbc/8), ldb/32), block = (32, 8)
+__global__ void __launch_bounds__(256) k_bc_fill(int nbc, const int* __restrict__ bc_dofs, int na, const double* __restrict__ bc_shape,
+                                                const double* __restrict__ uctrl, double* __restrict__ up, int ldb) {
+    const int j = blockIdx.x * blockDim.y + threadIdx.y;
+    const int b = blockIdx.y * 32 + threadIdx.x;
+    if (j >= nbc) return;
+    double v = 0.0;
+    for (int k = 0; k < na; ++k) {
+        const double sh = __ldg(bc_shape + (size_t)k * nbc + j);
+        if (sh != 0.0) v = fma(sh, uctrl[(size_t)k * ldb + b], v);
+    }
+    up[(size_t)__ldg(bc_dofs + j) * ldb + b] = v;
 }
 
 // rhs in solver row order.  grid = (ceil(n/8), ldb/32), block = (32, 8)
@@ -400,7 +395,8 @@ struct SweepCfg {
 //   stage record (32 ints): nk, npieces, V offset / 32 doubles, V bytes, job record index if this is the first
 //                           stage of a job (else -1), total rows, then per piece (source row, slot << 8 | log2 rows);
 //                           its first 16 bytes also ride into shared memory as the stage header (consumers read nk)
-//   job record   (72 ints): K, nrb, nr, nsrc, out0, ystore, has_seed, stages, e0[32], e1[32]
+//   job record   (72 ints): K, nrb, nr, nsrc, out0, ystore, seed mode, stages, e0[32], e1[32]
+//                           (seed mode 1: e0/e1 = update rows to start from; 2: e0 = canonical dof of each output row)
 // The producer reads consecutive 128-byte stage records; the job record rides into shared memory with
 // the job's first stage, so nothing on the device chases a pointer.
 
@@ -465,8 +461,9 @@ struct RingPos {
 // round-robin (warp kw owns stages kw, kw+4, ...); partial sums meet in shared memory and warp 0 stores.
 template <int NWC, bool KS, int NRB, bool SRC3, bool YST>
 __device__ __forceinline__ void sweep_job(unsigned char* smem, uint32_t bar_full, uint32_t bar_empty, RingPos& rp, int nstages,
-                                          int slots, const int* jh, int nst, int K, int nr, int out0, int ystore, bool seed,
-                                          double* Z, size_t L, int t0, int c0, int lane, int kw, double* red) {
+                                          int slots, const int* jh, int nst, int K, int nr, int out0, int ystore, int seed,
+                                          double* Z, size_t L, int t0, int c0, int lane, int kw, double* red, double* xout,
+                                          int* diverged, int Nv) {
     // t0: first trajectory (global column) of this warp; c0: its first column inside the CTA's shared-memory rows
     using C = SweepCfg<NWC>;
     constexpr int W = C::W;
@@ -479,7 +476,10 @@ __device__ __forceinline__ void sweep_job(unsigned char* smem, uint32_t bar_full
     for (int rb = 0; rb < NA; ++rb)
 #pragma unroll
         for (int p = 0; p < 2; ++p) ce[rb][p][0] = ce[rb][p][1] = co[rb][p][0] = co[rb][p][1] = 0.0;
-    if (NRB > 0 && seed && (!KS || kw == 0)) {
+    int xdof[NA];  // seed mode 2: canonical dof of this lane's output rows (read now: the record's stage slot is recycled later)
+#pragma unroll
+    for (int rb = 0; rb < NA; ++rb) xdof[rb] = (NRB > 0 && seed == 2) ? jh[8 + rb * 8 + gid] : 0;
+    if (NRB > 0 && seed == 1 && (!KS || kw == 0)) {
         // the children's update rows that land on these output rows seed the accumulators
 #pragma unroll
         for (int rb = 0; rb < NRB; ++rb) {
@@ -577,6 +577,23 @@ __device__ __forceinline__ void sweep_job(unsigned char* smem, uint32_t bar_full
 #pragma unroll
                 for (int p = 0; p < 2; ++p)
                     *reinterpret_cast<double4*>(zo + 16 * p) = make_double4(ce[rb][p][0], co[rb][p][0], ce[rb][p][1], co[rb][p][1]);
+                if (seed == 2) {
+                    // backward sweep: x_t also goes out in canonical numbering (the new state), with the divergence check
+                    const int dof = xdof[rb];
+                    double* xo = xout + (size_t)dof * L + t0 + 4 * tig;
+#pragma unroll
+                    for (int p = 0; p < 2; ++p) {
+                        const double4 v = make_double4(ce[rb][p][0], co[rb][p][0], ce[rb][p][1], co[rb][p][1]);
+                        *reinterpret_cast<double4*>(xo + 16 * p) = v;
+                        if (dof < Nv) {
+                            int* dv = diverged + t0 + 16 * p + 4 * tig;
+                            if (!isfinite(v.x)) dv[0] = 1;
+                            if (!isfinite(v.y)) dv[1] = 1;
+                            if (!isfinite(v.z)) dv[2] = 1;
+                            if (!isfinite(v.w)) dv[3] = 1;
+                        }
+                    }
+                }
             }
         }
     }
@@ -588,7 +605,7 @@ template <int NWC, bool KS>
 __global__ void __launch_bounds__(32 * (KS ? 5 : NWC + 1), KS ? SV_MINCTAS4 : SweepCfg<NWC>::MIN_CTAS)
     k_front_sweep(const __grid_constant__ SweepMaps maps, const int* __restrict__ srec, const int* __restrict__ jrec,
                   const int* __restrict__ cta_sptr, const int* __restrict__ cta_jptr, const double* __restrict__ vals,
-                  double* Z, int ldb, int nstages, int slots, unsigned long long* dbg) {
+                  double* Z, int ldb, int nstages, int slots, double* xout, int* diverged, int Nv, unsigned long long* dbg) {
     using C = SweepCfg<NWC>;
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int NCW = KS ? 4 : NWC;  // consumer warps
@@ -610,6 +627,7 @@ __global__ void __launch_bounds__(32 * (KS ? 5 : NWC + 1), KS ? SV_MINCTAS4 : Sw
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the next level may start its prologue
 
     if (wid == NCW) {
         // ---------------- producer warp: stream the stage records, issue the bulk copies ----------------
@@ -619,6 +637,7 @@ __global__ void __launch_bounds__(32 * (KS ? 5 : NWC + 1), KS ? SV_MINCTAS4 : Sw
 #pragma unroll
         for (int u = 0; u < SV_PREFETCH; ++u) q[u] = (u < ns) ? __ldg(rec + u * SV_SREC) : 0;
         RingPos rp{0, 1};  // parity 1: the first wait on a fresh "empty" barrier passes
+        asm volatile("griddepcontrol.wait;" ::: "memory");  // Z rows of the previous level are complete and visible
         for (int c0 = 0; c0 < ns; c0 += SV_PREFETCH) {
             int qn[SV_PREFETCH];
 #pragma unroll
@@ -664,6 +683,7 @@ __global__ void __launch_bounds__(32 * (KS ? 5 : NWC + 1), KS ? SV_MINCTAS4 : Sw
     const size_t L = (size_t)ldb;
     const int nj = __ldg(cta_jptr + blockIdx.x + 1) - __ldg(cta_jptr + blockIdx.x);
     RingPos rp{0, 0};
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     for (int j = 0; j < nj; ++j) {
         mbar_wait(bar_full + 8 * rp.s, rp.ph);  // the job record arrives with the job's first stage
         if (dbg && j == 0 && lane == 0 && wid == 0) dbg[2] = globaltimer_ns();
@@ -671,9 +691,10 @@ __global__ void __launch_bounds__(32 * (KS ? 5 : NWC + 1), KS ? SV_MINCTAS4 : Sw
         const int4 h0 = *reinterpret_cast<const int4*>(jh);
         const int4 h1 = *reinterpret_cast<const int4*>(jh + 4);
         const int K = h0.x, nrb = h0.y, nr = h0.z, out0 = h1.x, ystore = h1.y, nst = h1.w;
-        const bool src3 = h0.w == 3, seed = h1.z != 0;
+        const bool src3 = h0.w == 3;
+        const int seed = h1.z;  // 0: none, 1: accumulators start from the children's update rows, 2: outputs also go to xout
 #define SWEEP_RUN(NRB, S3, YS) \
-    sweep_job<NWC, KS, NRB, S3, YS>(smem, bar_full, bar_empty, rp, nstages, slots, jh, nst, K, nr, out0, ystore, seed, Z, L, t0, c0, lane, wid, red)
+    sweep_job<NWC, KS, NRB, S3, YS>(smem, bar_full, bar_empty, rp, nstages, slots, jh, nst, K, nr, out0, ystore, seed, Z, L, t0, c0, lane, wid, red, xout, diverged, Nv)
 #define SWEEP_CASE(NRB)                                        \
     case NRB:                                                  \
         if (src3) {                                            \
@@ -696,31 +717,6 @@ __global__ void __launch_bounds__(32 * (KS ? 5 : NWC + 1), KS ? SV_MINCTAS4 : Sw
         if (dbg && j == 0 && lane == 0 && wid == 0) dbg[3] = globaltimer_ns();
     }
     if (dbg && lane == 0 && wid == 0) { dbg[4] = globaltimer_ns(); dbg[6] = (unsigned long long)nj; }
-}
-
-// un-permute the solution into canonical numbering, apply Dirichlet values, flag non-finite velocity.
-// grid = (ceil(N/8), ldb/32), block = (32, 8)
-__global__ void __launch_bounds__(256) k_post(int N, int Nv, int n, const int* __restrict__ iperm,
-                                             const double* __restrict__ Z, int na, int nbc,
-                                             const double* __restrict__ bc_shape, const double* __restrict__ uctrl,
-                                             double* __restrict__ up, int* __restrict__ diverged, int ldb) {
-    const int i = blockIdx.x * blockDim.y + threadIdx.y;
-    const int b = blockIdx.y * 32 + threadIdx.x;
-    if (i >= N) return;
-    const int r = __ldg(iperm + i);
-    double v;
-    if (r >= 0) {
-        v = Z[(size_t)r * ldb + b];
-    } else {
-        const int j = -1 - r;
-        v = 0.0;
-        for (int k = 0; k < na; ++k) {
-            const double s = __ldg(bc_shape + (size_t)k * nbc + j);
-            if (s != 0.0) v = fma(s, uctrl[(size_t)k * ldb + b], v);
-        }
-    }
-    up[(size_t)i * ldb + b] = v;
-    if (i < Nv && !isfinite(v)) diverged[b] = 1;
 }
 
 // sensors + energy.  grid = ldb/32, block = (32, 8)
@@ -830,30 +826,33 @@ struct fcb_context {
     cudaStream_t stream = nullptr;
     std::string error;
     int B = 0, ldb = 0;
-    int nT = 0, nN = 0, nV = 0, Nv = 0, N = 0, n = 0, nbc = 0, na = 0, ns = 0, ncolours = 0;
+    int nT = 0, nN = 0, nV = 0, Nv = 0, N = 0, n = 0, nbc = 0, na = 0, ns = 0;
     double dt = 0.0;
     int nonlinear = 1;
     // constant device data
-    int *cell_nodes = nullptr, *colour_cells = nullptr, *perm = nullptr, *iperm = nullptr;
-    unsigned char* first_mask = nullptr;
+    int *cell_nodes = nullptr, *perm = nullptr, *iperm = nullptr;
     double *Jinv = nullptr, *detJ = nullptr, *bc_shape = nullptr, *ctrl_rhs[2] = {nullptr, nullptr};
     int *sensor_ptr = nullptr, *sensor_idx = nullptr;
     double* sensor_val = nullptr;
-    std::vector<int> colour_ptr, colour_blk_offset;
-    int nblk_total = 0;
+    int nblk_total = 0;  // rows of the energy partial sums (one per element patch)
     // patch form of the element kernel
-    int use_patches = 1, npatch = 0, nshared = 0, patch_smem = 0;
+    int use_pdl = 1;
+    int npatch = 0, nshared = 0, patch_smem = 0;
     int *pcell_ptr = nullptr, *pcells = nullptr, *pnode_ptr = nullptr, *pnode_dst = nullptr, *mptr = nullptr, *msrc = nullptr,
-        *mnode = nullptr;
-    unsigned char* plnode = nullptr;
+        *mnode = nullptr, *prow = nullptr, *mrow = nullptr, *pacc_rows = nullptr;
+    unsigned char *plnode = nullptr, *psrc = nullptr;
     double* pscratch = nullptr;
-    int patch_stats[4] = {0, 0, 0, 0};  // patches, max nodes per patch, scratch slots, rounds
     DevPlan plan[2];
     // state
     double *up[2] = {nullptr, nullptr}, *avec = nullptr, *bvec[2] = {nullptr, nullptr}, *Z = nullptr;
     double *epart = nullptr, *uctrl = nullptr, *y = nullptr, *dE = nullptr;
     int* diverged = nullptr;
     int parity = 0, order = 1;
+    bool rhs_ready = false;  // Z[0,n) holds the fused right-hand side of the next step
+    int ncrow = 0;           // solver rows with a non-zero control coefficient (BDF2), their coefficients [na, ncrow]
+    int* crow = nullptr;
+    double* ccoef = nullptr;
+    int* bc_dofs = nullptr;
     bool have_state = false;
     // controllers
     bool have_ctrl = false;
@@ -915,7 +914,7 @@ int upload(fcb_context* h, T** dst, const T* src, size_t count) {
 // 4 row blocks of 8) while the launch still has ~4 warp-jobs per SM; CTAs as wide as possible (up to 8
 // warps x 32 trajectories, sharing one copy of V and of the gathered rows) while there is at least
 // one CTA per SM.
-int upload_plan(fcb_context* h, DevPlan& d, const fcb_plan& p) {
+int upload_plan(fcb_context* h, DevPlan& d, const fcb_plan& p, const int32_t* perm) {
     d.n = p.n;
     d.nU = p.nU;
     d.nlaunch = p.nlaunch;
@@ -1023,12 +1022,16 @@ int upload_plan(fcb_context* h, DevPlan& d, const fcb_plan& p) {
                 jrec[jb + 4] = p.blk_out0[b] + t.r0;
                 jrec[jb + 5] = t.ystore ? p.blk_ystore[b] + t.k_lo : -1;
                 const bool seeded = t.nrb > 0 && p.blk_eptr[b] >= 0;
-                jrec[jb + 6] = seeded ? 1 : 0;
+                const bool is_x = t.nrb > 0 && l >= p.n_forward_launches && p.blk_out0[b] + p.blk_M[b] <= p.n;  // rows of the solution
+                if (seeded && is_x) return fail(h, FCB_ERR_INVALID, "plan block %d: a backward block cannot carry seed rows", b);
+                jrec[jb + 6] = seeded ? 1 : (is_x ? 2 : 0);
                 if (seeded)
                     for (int r = 0; r < t.nr; ++r) {
                         jrec[jb + 8 + r] = p.e0[p.blk_eptr[b] + t.r0 + r];
                         jrec[jb + 40 + r] = p.e1[p.blk_eptr[b] + t.r0 + r];
                     }
+                if (is_x)
+                    for (int r = 0; r < t.nr; ++r) jrec[jb + 8 + r] = perm[p.blk_out0[b] + t.r0 + r];
                 const size_t v0 = packed.size();
                 if (t.nrb > 0) {
                     packed.resize(v0 + (size_t)K4 * 8 * t.nrb, 0.0);
@@ -1148,49 +1151,25 @@ struct PhaseMark {
     }
 };
 
-int enqueue_element(fcb_context* h, const double* u, double* a, double* b) {
-    if (h->use_patches) {
-        PatchArgs p;
-        p.pcell_ptr = h->pcell_ptr; p.pcells = h->pcells; p.plnode = h->plnode;
-        p.pnode_ptr = h->pnode_ptr; p.pnode_dst = h->pnode_dst;
-        p.cell_nodes = h->cell_nodes; p.Jinv = h->Jinv; p.detJ = h->detJ;
-        p.u = u; p.a = a; p.b = b; p.scratch = h->pscratch; p.epart = h->epart;
-        p.nN = h->nN; p.ldb = h->ldb;
-        p.ca = 2.0 / h->dt; p.cb = -0.5 / h->dt;
-        dim3 grid(h->npatch, h->ldb / 32), block(32, EP_WARPS);
-        if (h->nonlinear) k_element_patch<true><<<grid, block, h->patch_smem, h->stream>>>(p);
-        else k_element_patch<false><<<grid, block, h->patch_smem, h->stream>>>(p);
-        h->launches += 1;
-        if (h->nshared > 0) {
-            dim3 g2((h->nshared + 7) / 8, h->ldb / 32), b2(32, 8);
-            k_patch_merge<<<g2, b2, 0, h->stream>>>(h->nshared, h->mptr, h->msrc, h->mnode, h->pscratch, a, b, h->nN, h->ldb);
-            h->launches += 1;
-        }
-        CK(cudaGetLastError());
-        return FCB_OK;
-    }
-    for (int c = 0; c < h->ncolours; ++c) {
-        ElemArgs p;
-        p.cells = h->colour_cells + h->colour_ptr[c];
-        p.ncells = h->colour_ptr[c + 1] - h->colour_ptr[c];
-        if (p.ncells == 0) continue;
-        p.cell_nodes = h->cell_nodes;
-        p.first = h->first_mask;
-        p.Jinv = h->Jinv;
-        p.detJ = h->detJ;
-        p.u = u;
-        p.a = a;
-        p.b = b;
-        p.epart = h->epart;
-        p.blk_offset = h->colour_blk_offset[c];
-        p.nN = h->nN;
-        p.ldb = h->ldb;
-        p.ca = 2.0 / h->dt;
-        p.cb = -0.5 / h->dt;
-        const int per_blk = ELEM_WARPS * ELEM_CPW;
-        dim3 grid((p.ncells + per_blk - 1) / per_blk, h->ldb / 32), block(32, ELEM_WARPS);
-        if (h->nonlinear) k_element<true><<<grid, block, 0, h->stream>>>(p);
-        else k_element<false><<<grid, block, 0, h->stream>>>(p);
+// element pass on the state u: b <- b(u) and either a <- a(u) (bprev == nullptr) or, fused, the next step's
+// right-hand side rows Z[0,n) <- a(u) + bprev
+int enqueue_element(fcb_context* h, const double* u, double* a, double* b, const double* bprev) {
+    PatchArgs p;
+    p.pcell_ptr = h->pcell_ptr; p.pcells = h->pcells; p.plnode = h->plnode;
+    p.pnode_ptr = h->pnode_ptr; p.pnode_dst = h->pnode_dst; p.psrc = h->psrc; p.pacc_rows = h->pacc_rows;
+    p.cell_nodes = h->cell_nodes; p.Jinv = h->Jinv; p.detJ = h->detJ;
+    p.u = u; p.a = a; p.b = b; p.scratch = h->pscratch; p.epart = h->epart;
+    p.bprev = bprev; p.Zb = h->Z; p.prow = h->prow;
+    p.nN = h->nN; p.nV = h->nV; p.ldb = h->ldb;
+    p.ca = 2.0 / h->dt; p.cb = -0.5 / h->dt;
+    dim3 grid(h->npatch, h->ldb / 32), block(32, EP_WARPS);
+    if (h->nonlinear) k_element_patch<true><<<grid, block, h->patch_smem, h->stream>>>(p);
+    else k_element_patch<false><<<grid, block, h->patch_smem, h->stream>>>(p);
+    h->launches += 1;
+    if (h->nshared > 0) {
+        dim3 g2((h->nshared + 7) / 8, h->ldb / 32), b2(32, 8);
+        k_patch_merge<<<g2, b2, 0, h->stream>>>(h->nshared, h->mptr, h->msrc, h->mnode, h->mrow, h->pscratch, a, b, bprev, h->Z,
+                                                h->nN, h->ldb);
         h->launches += 1;
     }
     CK(cudaGetLastError());
@@ -1209,25 +1188,37 @@ int enqueue_measure(fcb_context* h, const double* up) {
 constexpr size_t DBG_PER_LAUNCH = 8 * 8192;  // 8 timeline slots for up to 8192 CTAs
 
 template <int NWC, bool KS>
-void launch_sweep(fcb_context* h, const DevPlan& pl, const DevPlan::Launch& L, int mapset, unsigned long long* dbg) {
-    k_front_sweep<NWC, KS><<<dim3(L.grid, L.nslab), dim3(32, KS ? 5 : NWC + 1), SweepCfg<NWC>::smem_bytes(L.nstages, L.slots) + (KS ? SV_RED_BYTES : 0), h->stream>>>(
-        h->zmaps[mapset], pl.srec, pl.jrec, pl.cta_sptr + L.cta_off, pl.cta_jptr + L.cta_off, pl.vals, h->Z, h->ldb,
-        L.nstages, L.slots, dbg);
+void launch_sweep(fcb_context* h, const DevPlan& pl, const DevPlan::Launch& L, int mapset, double* xout, unsigned long long* dbg) {
+    // programmatic dependent launch: the CTAs of level l+1 may start (barrier init, stream-record prefetch) while
+    // level l drains; they wait on griddepcontrol before touching Z
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(L.grid, L.nslab);
+    cfg.blockDim = dim3(32, KS ? 5 : NWC + 1);
+    cfg.dynamicSmemBytes = SweepCfg<NWC>::smem_bytes(L.nstages, L.slots) + (KS ? SV_RED_BYTES : 0);
+    cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = h->use_pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, k_front_sweep<NWC, KS>, h->zmaps[mapset], (const int*)pl.srec, (const int*)pl.jrec,
+                       (const int*)(pl.cta_sptr + L.cta_off), (const int*)(pl.cta_jptr + L.cta_off), (const double*)pl.vals, h->Z,
+                       h->ldb, L.nstages, L.slots, xout, h->diverged, h->Nv, dbg);
 }
 
-int enqueue_solve(fcb_context* h, const DevPlan& pl, PhaseMark* pm) {
+int enqueue_solve(fcb_context* h, const DevPlan& pl, double* xout, PhaseMark* pm) {
     for (int l = 0; l < pl.nlaunch; ++l) {
         if (pm && l == pl.n_forward) pm->mark(FCB_PHASE_BACKWARD);
         const DevPlan::Launch& L = pl.launches[l];
         if (L.grid <= 0) continue;
         unsigned long long* dbg = (pm && h->sweep_dbg) ? h->sweep_dbg + (size_t)l * DBG_PER_LAUNCH : nullptr;
         switch (L.nwc) {
-            case 8: launch_sweep<8, false>(h, pl, L, 3, dbg); break;
-            case 4: launch_sweep<4, false>(h, pl, L, 2, dbg); break;
-            case 2: launch_sweep<2, false>(h, pl, L, 1, dbg); break;
+            case 8: launch_sweep<8, false>(h, pl, L, 3, xout, dbg); break;
+            case 4: launch_sweep<4, false>(h, pl, L, 2, xout, dbg); break;
+            case 2: launch_sweep<2, false>(h, pl, L, 1, xout, dbg); break;
             default:
-                if (L.ksplit) launch_sweep<1, true>(h, pl, L, 0, dbg);
-                else launch_sweep<1, false>(h, pl, L, 0, dbg);
+                if (L.ksplit) launch_sweep<1, true>(h, pl, L, 0, xout, dbg);
+                else launch_sweep<1, false>(h, pl, L, 0, xout, dbg);
                 break;
         }
         h->launches += 1;
@@ -1238,27 +1229,35 @@ int enqueue_solve(fcb_context* h, const DevPlan& pl, PhaseMark* pm) {
 }
 
 // one step with the current (order, parity); u_ctrl already in h->uctrl
-int enqueue_step(fcb_context* h, int order, int parity, PhaseMark* pm) {
+// One step.  rhs_ready: Z[0,n) already holds a_n + b_{n-1} from the previous step's fused element pass and only the
+// control terms are missing; otherwise (first step after fcb_set_state) the right-hand side is built from a and b.
+int enqueue_step(fcb_context* h, int order, int parity, bool rhs_ready, PhaseMark* pm) {
     const DevPlan& pl = h->plan[order - 1];
     double* nxt = h->up[1 - parity];
     if (pm) pm->mark(FCB_PHASE_RHS);
-    {
+    if (rhs_ready && order == 2) {
+        if (h->ncrow > 0 && h->na > 0) {
+            dim3 grid((h->ncrow + 7) / 8, h->ldb / 32), block(32, 8);
+            k_ctrl_add<<<grid, block, 0, h->stream>>>(h->ncrow, h->crow, h->ccoef, h->na, h->uctrl, h->Z, h->ldb);
+            h->launches += 1;
+        }
+    } else {
         dim3 grid((h->n + 7) / 8, h->ldb / 32), block(32, 8);
         k_rhs_build<<<grid, block, 0, h->stream>>>(h->n, h->Nv, h->perm, h->avec, h->bvec[1 - parity], order, h->na,
                                                    h->ctrl_rhs[order - 1], h->uctrl, h->Z, h->ldb);
         h->launches += 1;
     }
     if (pm) pm->mark(FCB_PHASE_FORWARD);
-    TRY(enqueue_solve(h, pl, pm));
+    TRY(enqueue_solve(h, pl, nxt, pm));
     if (pm) pm->mark(FCB_PHASE_POST);
-    {
-        dim3 grid((h->N + 7) / 8, h->ldb / 32), block(32, 8);
-        k_post<<<grid, block, 0, h->stream>>>(h->N, h->Nv, h->n, h->iperm, h->Z, h->na, h->nbc, h->bc_shape, h->uctrl, nxt,
-                                              h->diverged, h->ldb);
+    if (h->nbc > 0) {
+        dim3 grid((h->nbc + 7) / 8, h->ldb / 32), block(32, 8);
+        k_bc_fill<<<grid, block, 0, h->stream>>>(h->nbc, h->bc_dofs, h->na, h->bc_shape, h->uctrl, nxt, h->ldb);
         h->launches += 1;
     }
     if (pm) pm->mark(FCB_PHASE_ELEMENT);
-    TRY(enqueue_element(h, nxt, h->avec, h->bvec[1 - parity]));
+    // b(u_new) replaces b_{n-1}; the rhs of the next step = a(u_new) + b_n, with b_n = bvec[parity]
+    TRY(enqueue_element(h, nxt, h->avec, h->bvec[1 - parity], h->bvec[parity]));
     if (pm) pm->mark(FCB_PHASE_MEASURE);
     TRY(enqueue_measure(h, nxt));
     if (pm) pm->mark(FCB_NPHASES);
@@ -1288,7 +1287,7 @@ int capture(fcb_context* h, cudaGraphExec_t* exec, int* nodes, bool loop, int pa
     CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
     int rc = FCB_OK;
     if (loop) rc = enqueue_controller(h, xparity);
-    if (rc == FCB_OK) rc = enqueue_step(h, 2, parity, nullptr);
+    if (rc == FCB_OK) rc = enqueue_step(h, 2, parity, true, nullptr);
     if (rc == FCB_OK && loop) rc = enqueue_log(h);
     cudaGraph_t graph = nullptr;
     cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
@@ -1315,7 +1314,7 @@ int copy_out(fcb_context* h, T* dst, const T* src, int rows) {
 }
 
 int run_one_step(fcb_context* h, bool loop) {
-    if (h->order == 2) {
+    if (h->order == 2 && h->rhs_ready) {
         cudaGraphExec_t* exec = loop ? &h->g_loop[h->parity][h->xparity] : &h->g_step[h->parity];
         int* nodes = loop ? &h->g_loop_nodes[h->parity][h->xparity] : &h->g_step_nodes[h->parity];
         if (!*exec) TRY(capture(h, exec, nodes, loop, h->parity, h->xparity));
@@ -1323,12 +1322,13 @@ int run_one_step(fcb_context* h, bool loop) {
         h->launches += *nodes;
     } else {
         if (loop) TRY(enqueue_controller(h, h->xparity));
-        TRY(enqueue_step(h, h->order, h->parity, nullptr));
+        TRY(enqueue_step(h, h->order, h->parity, h->rhs_ready, nullptr));
         if (loop) TRY(enqueue_log(h));
     }
     h->parity ^= 1;
     if (loop) h->xparity ^= 1;
     h->order = 2;
+    h->rhs_ready = true;
     return FCB_OK;
 }
 
@@ -1341,11 +1341,11 @@ void destroy(fcb_context* h) {
         for (int j = 0; j < 2; ++j)
             if (h->g_loop[i][j]) cudaGraphExecDestroy(h->g_loop[i][j]);
     }
-    void* ptrs[] = {h->first_mask, h->cell_nodes, h->colour_cells, h->perm, h->iperm, h->Jinv, h->detJ, h->bc_shape, h->ctrl_rhs[0],
+    void* ptrs[] = {h->crow, h->ccoef, h->bc_dofs, h->cell_nodes, h->perm, h->iperm, h->Jinv, h->detJ, h->bc_shape, h->ctrl_rhs[0],
                     h->ctrl_rhs[1], h->sensor_ptr, h->sensor_idx, h->sensor_val, h->up[0], h->up[1], h->avec,
                     h->bvec[0], h->bvec[1], h->Z, h->epart, h->uctrl, h->y, h->dE, h->diverged, h->Ad, h->Bd, h->Cd,
                     h->Dd, h->Ky, h->Fu, h->xk[0], h->xk[1], h->series, h->counter, h->sweep_dbg,
-                    h->pcell_ptr, h->pcells, h->pnode_ptr, h->pnode_dst, h->mptr, h->msrc, h->mnode, h->plnode, h->pscratch};
+                    h->pcell_ptr, h->pcells, h->pnode_ptr, h->pnode_dst, h->mptr, h->msrc, h->mnode, h->plnode, h->pscratch, h->prow, h->mrow, h->psrc, h->pacc_rows};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (int i = 0; i < 2; ++i) {
@@ -1364,10 +1364,8 @@ void destroy(fcb_context* h) {
 // the list into chunks gives compact patches without needing coordinates.
 int build_patches(fcb_context* h, const fcb_problem* p, const std::vector<int>& iperm) {
     const int nT = p->nT, nN = p->nN;
-    const char* env = getenv("FCB_ELEMENT");  // "colour": the coloured global-scatter kernel (A/B measurements)
-    if (env && std::string(env) == "colour") { h->use_patches = 0; return FCB_OK; }
-    int pc = 32;
-    env = getenv("FCB_PATCH_CELLS");
+    int pc = 28;  // 4 sub-patches of 7 cells: ~100 accumulator rows x 1 KB of shared memory, two CTAs per SM
+    const char* env = getenv("FCB_PATCH_CELLS");
     if (env && atoi(env) >= EP_WARPS && atoi(env) <= 40) pc = atoi(env);
     std::vector<std::pair<int, int>> key(nT);
     for (int e = 0; e < nT; ++e) {
@@ -1383,46 +1381,49 @@ int build_patches(fcb_context* h, const fcb_problem* p, const std::vector<int>& 
     }
     std::sort(key.begin(), key.end());
     const int npatch = (nT + pc - 1) / pc;
-    std::vector<int> pcell_ptr(1, 0), pcells, pnode_ptr(1, 0), pnode_dst, node_npatch(nN, 0);
-    std::vector<unsigned char> plnode;
+    std::vector<int> pcell_ptr(1, 0), pcells, pnode_ptr(1, 0), pnode_dst, node_npatch(nN, 0), pacc_rows;
+    std::vector<unsigned char> plnode, psrc;
     std::vector<std::vector<int>> patch_nodes(npatch);
-    std::vector<int> local(nN, -1);
-    int max_nodes = 0;
+    std::vector<int> local(nN, -1), uniq(nN, -1);
+    int max_rows = 0;
     for (int q = 0; q < npatch; ++q) {
-        const int e0 = q * pc, e1 = std::min(nT, e0 + pc);
+        const int e0 = q * pc, e1 = std::min(nT, e0 + pc), cpw = (e1 - e0 + EP_WARPS - 1) / EP_WARPS;
         std::vector<int>& nodes = patch_nodes[q];
-        for (int k = e0; k < e1; ++k)
-            for (int i = 0; i < 6; ++i) {
-                const int nd = p->cell_nodes[key[k].second * 6 + i];
-                if (local[nd] < 0) { local[nd] = (int)nodes.size(); nodes.push_back(nd); }
-            }
-        if (nodes.size() > 255) return fail(h, FCB_ERR_INVALID, "element patch with %zu nodes (limit 255)", nodes.size());
-        max_nodes = std::max(max_nodes, (int)nodes.size());
-        // rounds of up to EP_WARPS cells that share no node (greedy)
-        std::vector<std::vector<int>> rounds;
-        std::vector<std::vector<char>> used;  // per round: node taken
-        for (int k = e0; k < e1; ++k) {
-            const int e = key[k].second;
-            size_t r = 0;
-            for (;; ++r) {
-                if (r == rounds.size()) { rounds.emplace_back(); used.emplace_back(nodes.size(), 0); }
-                if ((int)rounds[r].size() >= EP_WARPS) continue;
-                bool ok = true;
-                for (int i = 0; i < 6 && ok; ++i) ok = !used[r][local[p->cell_nodes[e * 6 + i]]];
-                if (ok) break;
-            }
-            rounds[r].push_back(e);
-            for (int i = 0; i < 6; ++i) used[r][local[p->cell_nodes[e * 6 + i]]] = 1;
-        }
-        for (auto& rd : rounds)
-            for (int wv = 0; wv < EP_WARPS; ++wv) {
-                const int e = wv < (int)rd.size() ? rd[wv] : -1;
+        std::vector<std::array<unsigned char, 4>> src;  // per unique node: its accumulator rows
+        int rows = 0;
+        for (int g = 0; g < EP_WARPS; ++g) {
+            // sub-patch of warp g: a contiguous run of the (space-filling) cell order, with its own accumulator rows
+            std::vector<int> touched;
+            for (int k = std::min(e1, e0 + g * cpw); k < std::min(e1, e0 + (g + 1) * cpw); ++k) {
+                const int e = key[k].second;
                 pcells.push_back(e);
-                for (int i = 0; i < 6; ++i) plnode.push_back(e >= 0 ? (unsigned char)local[p->cell_nodes[e * 6 + i]] : 0);
+                for (int i = 0; i < 6; ++i) {
+                    const int nd = p->cell_nodes[e * 6 + i];
+                    if (local[nd] < 0) {
+                        local[nd] = rows++;
+                        touched.push_back(nd);
+                        if (uniq[nd] < 0) { uniq[nd] = (int)nodes.size(); nodes.push_back(nd); src.push_back({255, 255, 255, 255}); }
+                        auto& sl = src[uniq[nd]];
+                        int kk = 0;
+                        while (sl[kk] != 255) ++kk;  // at most one row per warp: kk < EP_WARPS
+                        sl[kk] = (unsigned char)local[nd];
+                    }
+                    plnode.push_back((unsigned char)local[nd]);
+                }
             }
-        pcell_ptr.push_back((int)pcells.size());
-        for (int nd : nodes) { ++node_npatch[nd]; local[nd] = -1; }
+            pcell_ptr.push_back((int)pcells.size());
+            for (int nd : touched) local[nd] = -1;
+        }
+        if (rows > 254) return fail(h, FCB_ERR_INVALID, "element patch with %d accumulator rows (limit 254)", rows);
+        max_rows = std::max(max_rows, rows);
+        pacc_rows.push_back(rows);
+        for (size_t j = 0; j < nodes.size(); ++j) {
+            for (int kk = 0; kk < 4; ++kk) psrc.push_back(src[j][kk]);
+            ++node_npatch[nodes[j]];
+            uniq[nodes[j]] = -1;
+        }
     }
+    const int max_nodes = max_rows;
     // interior nodes are written directly; shared ones get a scratch slot per (patch, node)
     std::vector<std::vector<int>> slots_of(nN);
     int nslots = 0;
@@ -1433,19 +1434,28 @@ int build_patches(fcb_context* h, const fcb_problem* p, const std::vector<int>& 
         }
         pnode_ptr.push_back((int)pnode_dst.size());
     }
+    auto rows_of = [&](int nd, std::vector<int>& out) {  // solver rows of the node's ux, uy and (vertex nodes) p dofs
+        out.push_back(iperm[nd]);
+        out.push_back(iperm[nd + nN]);
+        out.push_back(nd < p->nV ? iperm[2 * nN + nd] : -1);
+    };
+    std::vector<int> prow, mrow;
+    for (int q = 0; q < npatch; ++q)
+        for (int nd : patch_nodes[q]) rows_of(nd, prow);
     std::vector<int> mptr(1, 0), msrc, mnode;
     for (int nd = 0; nd < nN; ++nd)
         if (node_npatch[nd] > 1) {
             for (int sl : slots_of[nd]) msrc.push_back(sl);
             mptr.push_back((int)msrc.size());
             mnode.push_back(nd);
+            rows_of(nd, mrow);
         } else if (node_npatch[nd] == 0)
             return fail(h, FCB_ERR_INVALID, "P2 node %d belongs to no cell", nd);
     h->npatch = npatch;
     h->nshared = (int)mnode.size();
     h->patch_smem = max_nodes * 4 * 32 * (int)sizeof(double);
     h->nblk_total = npatch;
-    if (h->patch_smem > 200 * 1024) return fail(h, FCB_ERR_INVALID, "element patches too large for shared memory");
+    if (h->patch_smem > 220 * 1024) return fail(h, FCB_ERR_INVALID, "element patches too large for shared memory");
     CK(cudaFuncSetAttribute(k_element_patch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->patch_smem));
     CK(cudaFuncSetAttribute(k_element_patch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->patch_smem));
     TRY(upload(h, &h->pcell_ptr, pcell_ptr.data(), pcell_ptr.size()));
@@ -1456,9 +1466,15 @@ int build_patches(fcb_context* h, const fcb_problem* p, const std::vector<int>& 
     TRY(upload(h, &h->mptr, mptr.data(), mptr.size()));
     TRY(upload(h, &h->msrc, msrc.data(), std::max<size_t>(msrc.size(), 1)));
     TRY(upload(h, &h->mnode, mnode.data(), std::max<size_t>(mnode.size(), 1)));
+    TRY(upload(h, &h->prow, prow.data(), std::max<size_t>(prow.size(), 1)));
+    TRY(upload(h, &h->psrc, psrc.data(), std::max<size_t>(psrc.size(), 4)));
+    TRY(upload(h, &h->pacc_rows, pacc_rows.data(), pacc_rows.size()));
+    TRY(upload(h, &h->mrow, mrow.data(), std::max<size_t>(mrow.size(), 3)));
     TRY(upload<double>(h, &h->pscratch, nullptr, (size_t)std::max(nslots, 1) * 4 * h->ldb));
     CK(cudaStreamSynchronize(h->stream));  // host vectors go out of scope
-    h->patch_stats[0] = npatch; h->patch_stats[1] = max_nodes; h->patch_stats[2] = nslots; h->patch_stats[3] = (int)(pcells.size() / EP_WARPS);
+    if (getenv("FCB_VERBOSE"))
+        fprintf(stderr, "[fcb200] element patches: %d of <=%d cells, max %d accumulator rows (%d B smem), %d shared nodes in %d scratch slots\n",
+                npatch, pc, max_rows, h->patch_smem, h->nshared, nslots);
     return FCB_OK;
 }
 
@@ -1481,6 +1497,8 @@ int create_impl(fcb_context* h, const fcb_problem* p, int B) {
         const char* env = getenv("FCB_SWEEP_WARPS");  // tuning knobs: force / cap the CTA width of the sweep launches
         h->force_nwc = env ? atoi(env) : 0;
         if (h->force_nwc != 1 && h->force_nwc != 2 && h->force_nwc != 4 && h->force_nwc != 8) h->force_nwc = 0;
+        env = getenv("FCB_SWEEP_PDL");
+        if (env) h->use_pdl = atoi(env) != 0;
         env = getenv("FCB_SWEEP_KSPLIT");
         if (env) h->allow_ksplit = atoi(env) != 0;
         env = getenv("FCB_SWEEP_SLOTS");
@@ -1508,7 +1526,7 @@ int create_impl(fcb_context* h, const fcb_problem* p, int B) {
     h->nT = p->nT; h->nN = p->nN; h->nV = p->nV;
     h->Nv = 2 * p->nN;
     h->N = h->Nv + p->nV;
-    h->n = p->n_free; h->nbc = p->n_bc; h->na = p->na; h->ns = p->ns; h->ncolours = p->ncolours;
+    h->n = p->n_free; h->nbc = p->n_bc; h->na = p->na; h->ns = p->ns;
     h->dt = p->dt; h->nonlinear = p->nonlinear;
     if (h->n + h->nbc != h->N) return fail(h, FCB_ERR_INVALID, "n_free (%d) + n_bc (%d) != N (%d)", h->n, h->nbc, h->N);
     if (p->plan[0].n != h->n || p->plan[1].n != h->n) return fail(h, FCB_ERR_INVALID, "plan size does not match n_free");
@@ -1525,33 +1543,8 @@ int create_impl(fcb_context* h, const fcb_problem* p, int B) {
     TRY(upload(h, &h->cell_nodes, p->cell_nodes, (size_t)p->nT * 6));
     TRY(upload(h, &h->Jinv, p->Jinv, (size_t)p->nT * 4));
     TRY(upload(h, &h->detJ, p->detJ, (size_t)p->nT));
-    TRY(upload(h, &h->colour_cells, p->colour_cells, (size_t)p->nT));
-    h->colour_ptr.assign(p->colour_ptr, p->colour_ptr + p->ncolours + 1);
-    h->colour_blk_offset.resize(p->ncolours);
-    h->nblk_total = 0;
-    for (int c = 0; c < p->ncolours; ++c) {
-        h->colour_blk_offset[c] = h->nblk_total;
-        const int nc = h->colour_ptr[c + 1] - h->colour_ptr[c];
-        h->nblk_total += (nc + ELEM_WARPS * ELEM_CPW - 1) / (ELEM_WARPS * ELEM_CPW);
-    }
-    {
-        // first-writer mask: for every P2 node the lowest colour among the cells that contain it
-        std::vector<int> colour_of(p->nT, 0), min_colour(p->nN, p->ncolours);
-        for (int c = 0; c < p->ncolours; ++c)
-            for (int k = p->colour_ptr[c]; k < p->colour_ptr[c + 1]; ++k) colour_of[p->colour_cells[k]] = c;
-        for (int e = 0; e < p->nT; ++e)
-            for (int i = 0; i < 6; ++i) {
-                const int nd = p->cell_nodes[e * 6 + i];
-                if (nd < 0 || nd >= p->nN) return fail(h, FCB_ERR_INVALID, "cell_nodes out of range");
-                min_colour[nd] = std::min(min_colour[nd], colour_of[e]);
-            }
-        std::vector<unsigned char> mask(p->nT, 0);
-        for (int e = 0; e < p->nT; ++e)
-            for (int i = 0; i < 6; ++i)
-                if (min_colour[p->cell_nodes[e * 6 + i]] == colour_of[e]) mask[e] |= (unsigned char)(1u << i);
-        TRY(upload(h, &h->first_mask, mask.data(), mask.size()));
-        CK(cudaStreamSynchronize(h->stream));
-    }
+    for (size_t k = 0; k < (size_t)p->nT * 6; ++k)
+        if (p->cell_nodes[k] < 0 || p->cell_nodes[k] >= p->nN) return fail(h, FCB_ERR_INVALID, "cell_nodes out of range");
     TRY(upload(h, &h->perm, p->perm, (size_t)h->n));
     {
         std::vector<int> iperm(h->N, 0);
@@ -1574,11 +1567,26 @@ int create_impl(fcb_context* h, const fcb_problem* p, int B) {
     }
     TRY(upload(h, &h->bc_shape, p->bc_shape, (size_t)p->na * p->n_bc));
     for (int o = 0; o < 2; ++o) TRY(upload(h, &h->ctrl_rhs[o], p->ctrl_rhs[o], (size_t)p->na * p->n_free));
+    TRY(upload(h, &h->bc_dofs, p->bc_dofs, (size_t)p->n_bc));
+    {
+        // the control terms of the BDF2 right-hand side touch only the rows next to the actuated boundaries / force support
+        std::vector<int> rows;
+        for (int r = 0; r < p->n_free; ++r)
+            for (int k = 0; k < p->na; ++k)
+                if (p->ctrl_rhs[1][(size_t)k * p->n_free + r] != 0.0) { rows.push_back(r); break; }
+        std::vector<double> coef((size_t)p->na * rows.size());
+        for (int k = 0; k < p->na; ++k)
+            for (size_t i = 0; i < rows.size(); ++i) coef[(size_t)k * rows.size() + i] = p->ctrl_rhs[1][(size_t)k * p->n_free + rows[i]];
+        h->ncrow = (int)rows.size();
+        TRY(upload(h, &h->crow, rows.data(), std::max<size_t>(rows.size(), 1)));
+        TRY(upload(h, &h->ccoef, coef.data(), std::max<size_t>(coef.size(), 1)));
+        CK(cudaStreamSynchronize(h->stream));
+    }
     TRY(upload(h, &h->sensor_ptr, p->sensor_ptr, (size_t)p->ns + 1));
     const size_t snnz = p->ns ? (size_t)p->sensor_ptr[p->ns] : 0;
     TRY(upload(h, &h->sensor_idx, p->sensor_idx, snnz));
     TRY(upload(h, &h->sensor_val, p->sensor_val, snnz));
-    for (int o = 0; o < 2; ++o) TRY(upload_plan(h, h->plan[o], p->plan[o]));
+    for (int o = 0; o < 2; ++o) TRY(upload_plan(h, h->plan[o], p->plan[o], p->perm));
     const size_t L = (size_t)h->ldb;
     for (int i = 0; i < 2; ++i) {
         TRY(upload<double>(h, &h->up[i], nullptr, (size_t)h->N * L));
@@ -1668,8 +1676,11 @@ int fcb_set_state(fcb_handle h, const double* u_n, const double* u_nn, const dou
     TRY(copy_in(h, h->up[1], u_nn ? u_nn : u_n, h->Nv));
     if (p_n) TRY(copy_in(h, h->up[0] + (size_t)h->Nv * L, p_n, h->nV));
     // b_{n-1} from u_nn, then (a_n, b_n) and the energy partials from u_n
-    TRY(enqueue_element(h, h->up[1], h->avec, h->bvec[1]));
-    TRY(enqueue_element(h, h->up[0], h->avec, h->bvec[0]));
+    TRY(enqueue_element(h, h->up[1], h->avec, h->bvec[1], nullptr));
+    // a BDF2 (re)start goes through the same fused arithmetic as a running simulation, so that it continues a run
+    // bit for bit; a BDF1 start needs a(u_n) itself (rhs = a/2)
+    TRY(enqueue_element(h, h->up[0], h->avec, h->bvec[0], order == 2 ? h->bvec[1] : nullptr));
+    h->rhs_ready = (order == 2);
     TRY(enqueue_measure(h, h->up[0]));
     CK(cudaStreamSynchronize(h->stream));
     h->order = order;
@@ -1793,12 +1804,12 @@ int fcb_profile_step(fcb_handle h, const double* u_ctrl, float* ms, int32_t* lau
     CK(cudaSetDevice(h->device));
     if (h->na > 0 && u_ctrl) TRY(copy_in(h, h->uctrl, u_ctrl, h->na));
     PhaseMark pm{h, true};
-    const long long l0 = h->launches;
     const DevPlan& pl = h->plan[h->order - 1];
-    TRY(enqueue_step(h, h->order, h->parity, &pm));
+    TRY(enqueue_step(h, h->order, h->parity, h->rhs_ready, &pm));
     CK(cudaStreamSynchronize(h->stream));
     h->parity ^= 1;
     h->order = 2;
+    h->rhs_ready = true;
     for (int i = 0; i < FCB_NPHASES; ++i) CK(cudaEventElapsedTime(&ms[i], h->ev[i], h->ev[i + 1]));
     if (h->sweep_dbg) {
         const char* path = getenv("FCB_SWEEP_DEBUG");
@@ -1820,8 +1831,8 @@ int fcb_profile_step(fcb_handle h, const double* u_ctrl, float* ms, int32_t* lau
         launches[FCB_PHASE_RHS] = 1;
         launches[FCB_PHASE_FORWARD] = pl.n_forward;
         launches[FCB_PHASE_BACKWARD] = pl.nlaunch - pl.n_forward;
-        launches[FCB_PHASE_POST] = 1;
-        launches[FCB_PHASE_ELEMENT] = (int)(h->launches - l0) - 3 - (int)pl.nlaunch;
+        launches[FCB_PHASE_POST] = h->nbc > 0 ? 1 : 0;
+        launches[FCB_PHASE_ELEMENT] = 1 + (h->nshared > 0 ? 1 : 0);
         launches[FCB_PHASE_MEASURE] = 1;
     }
     return FCB_OK;

@@ -37,7 +37,6 @@ class fcb_problem(C.Structure):
     _fields_ = [
         ("nT", C.c_int32), ("nN", C.c_int32), ("nV", C.c_int32),
         ("cell_nodes", c_i32p), ("Jinv", c_f64p), ("detJ", c_f64p),
-        ("ncolours", C.c_int32), ("colour_ptr", c_i32p), ("colour_cells", c_i32p),
         ("n_free", C.c_int32), ("perm", c_i32p),
         ("n_bc", C.c_int32), ("bc_dofs", c_i32p),
         ("na", C.c_int32), ("bc_shape", c_f64p), ("ctrl_rhs", c_f64p * 2),
@@ -133,9 +132,6 @@ class ProblemPack:
         s.cell_nodes = _ptr(arr(tab.cell_nodes, np.int32), c_i32p)
         s.Jinv = _ptr(arr(tab.Jinv.reshape(-1, 4), np.float64), c_f64p)
         s.detJ = _ptr(arr(tab.detJ, np.float64), c_f64p)
-        s.ncolours = len(prob.colour_ptr) - 1
-        s.colour_ptr = _ptr(arr(prob.colour_ptr, np.int32), c_i32p)
-        s.colour_cells = _ptr(arr(prob.colour_cells, np.int32), c_i32p)
         s.n_free = prob.sym.n
         s.perm = _ptr(arr(prob.sym.perm, np.int32), c_i32p)
         s.n_bc = len(prob.dirichlet.dofs)

@@ -151,7 +151,6 @@ class FlowProblem:
             lift = (A @ G.T).toarray().T if na else np.zeros((0, tab.N))
             self.ctrl_rhs[order] = np.ascontiguousarray((force - lift)[:, self.sym.perm])
         self.sensor_ptr, self.sensor_idx, self.sensor_val = sensor_matrix(tab, self.sensors)
-        self.colour_ptr, self.colour_cells = tab.element_colouring()
 
     @property
     def na(self) -> int:

@@ -77,10 +77,6 @@ typedef struct fcb_problem {
     const int32_t* cell_nodes; /* [nT*6] P2 node ids, local order v0 v1 v2 m12 m02 m01 */
     const double* Jinv;        /* [nT*4] row-major d(ref)/d(phys)                      */
     const double* detJ;        /* [nT] |det J|                                         */
-    /* atomic-free scatter schedule */
-    int32_t ncolours;
-    const int32_t* colour_ptr;   /* [ncolours+1] */
-    const int32_t* colour_cells; /* [nT] cells grouped by colour */
     /* unknown numbering */
     int32_t n_free;
     const int32_t* perm;    /* [n_free] solver row -> canonical dof in [0, 2nN+nV) */
