@@ -288,6 +288,42 @@ def test_lidcavity_actuated_and_linear_superposition(root, built_lib):
     e.close()
 
 
+@pytest.mark.parametrize("B", [1, 40, 100, 300, 512])
+def test_ensemble_widths_match_oracle(root, built_lib, B):
+    """Every ensemble width (padding to 32/64/128-multiples, 1/2/4-warp and k-split sweep CTAs, several
+    128-trajectory slabs) gives the oracle's trajectory, for trajectory-dependent lid actuation."""
+    from flowcontrol_b200.ensemble import Ensemble
+    from flowcontrol_b200.examples import lidcavity as ex
+
+    UP0 = np.load(root / "tests/golden/lidcavity_baseflow.npz")["UP0"]
+    prob = ex.make_problem(Re=1000.0, UP0=UP0)
+    tab = prob.tab
+    case = cases.lidcavity(1000.0)
+    xy, tri = cases.load_mesh(case.mesh_file)
+    probe = sorted({0, B // 2, B - 1})
+    amp = 0.02 + 0.1 * np.arange(B) / max(B - 1, 1)  # lid speed of trajectory b
+    oracles = []
+    for b in probe:
+        orc = FlowOracle(case, xy, tri)
+        orc.set_base_flow(UP0)
+        orc.init_time_stepping()
+        oracles.append(orc)
+    ens = Ensemble(prob, B)
+    ens.set_state(oracles[0].ic[: tab.Nv], None, oracles[0].ic[tab.Nv :], order=1)
+    for k in range(4):
+        uc = (amp * np.cos(0.9 * k))[None, :]
+        ens.step(uc)
+        for orc, b in zip(oracles, probe):
+            orc.step([uc[0, b]])
+            assert np.allclose(ens.y_meas[:, b], orc.y_meas, rtol=SERIES_TOL, atol=0)
+            assert np.isclose(ens.dE[b], orc.dE, rtol=SERIES_TOL)
+    up = ens.fields(0)
+    for orc, b in zip(oracles, probe):
+        assert rel(up[: tab.Nv, b], orc.up[: tab.Nv]) < FIELD_TOL
+    assert not ens.diverged.any()
+    ens.close()
+
+
 def test_cavity_force_actuator_golden_trajectory(root, built_lib):
     """Open cavity Re=7500 (235 k dofs, body-force actuator, wall-shear sensor): the reference's
     10-step regression scenario (test_cavity.py:58-90) through the CUDA path."""
