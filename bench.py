@@ -163,6 +163,8 @@ def run_ours(args):
     # ---- device-resident closed loop (value) -------------------------------------------------
     ens.run_closed_loop(max(W, 3), log=False)  # warm-up: BDF1 start-up step + graph capture + steady BDF2
     series_dev = torch.empty((K, ncol, B), dtype=torch.float64, device="cuda")
+    if world > 1:
+        gather_series(torch.zeros_like(series_dev), total)  # warm-up: NCCL communicator + buffers exist before the timed region
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:

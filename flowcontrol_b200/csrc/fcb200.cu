@@ -1364,37 +1364,78 @@ void destroy(fcb_context* h) {
 // the list into chunks gives compact patches without needing coordinates.
 int build_patches(fcb_context* h, const fcb_problem* p, const std::vector<int>& iperm) {
     const int nT = p->nT, nN = p->nN;
-    int pc = 28;  // 4 sub-patches of 7 cells: ~100 accumulator rows x 1 KB of shared memory, two CTAs per SM
+    int pc = 26;  // cells per patch (upper bound): 4 sub-patches of <= 7 cells, ~100 accumulator rows x 1 KB: two CTAs per SM
     const char* env = getenv("FCB_PATCH_CELLS");
     if (env && atoi(env) >= EP_WARPS && atoi(env) <= 40) pc = atoi(env);
-    std::vector<std::pair<int, int>> key(nT);
-    for (int e = 0; e < nT; ++e) {
-        int k = INT_MAX;
-        for (int i = 0; i < 6; ++i) {
-            const int nd = p->cell_nodes[e * 6 + i];
-            for (int c = 0; c < 2; ++c) {
-                const int r = iperm[nd + c * nN];
-                if (r >= 0) k = std::min(k, r);
+    // Cell order: recursive coordinate bisection of the cell centroids (longer extent, median split) when node
+    // coordinates are given, so that consecutive runs of cells are compact blobs at every scale; without
+    // coordinates, the solver's nested-dissection numbering (a space-filling order of the mesh) is used instead.
+    std::vector<std::pair<int, int>> key(nT), patch_range;  // patch_range: [lo, hi) in the cell order
+    if (p->node_xy) {
+        std::vector<double> cx(nT), cy(nT);
+        for (int e = 0; e < nT; ++e) {
+            double sx = 0, sy = 0;
+            for (int i = 0; i < 3; ++i) { sx += p->node_xy[2 * p->cell_nodes[e * 6 + i]]; sy += p->node_xy[2 * p->cell_nodes[e * 6 + i] + 1]; }
+            cx[e] = sx / 3; cy[e] = sy / 3;
+        }
+        std::vector<int> order(nT);
+        for (int e = 0; e < nT; ++e) order[e] = e;
+        struct Range { int lo, hi, below; };  // below: bisection levels below the patch level (-1: still above it)
+        std::vector<Range> stack{{0, nT, nT <= pc ? 0 : -1}};
+        if (nT <= pc) patch_range.push_back({0, nT});
+        while (!stack.empty()) {
+            const Range r = stack.back();
+            stack.pop_back();
+            if (r.hi - r.lo <= 1 || r.below >= 2) continue;  // two more levels order the cells of a patch into its 4 sub-patches
+            double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
+            for (int k = r.lo; k < r.hi; ++k) {
+                x0 = std::min(x0, cx[order[k]]); x1 = std::max(x1, cx[order[k]]);
+                y0 = std::min(y0, cy[order[k]]); y1 = std::max(y1, cy[order[k]]);
+            }
+            const std::vector<double>& c = (x1 - x0 >= y1 - y0) ? cx : cy;
+            const int mid = r.lo + (r.hi - r.lo) / 2;
+            std::nth_element(order.begin() + r.lo, order.begin() + mid, order.begin() + r.hi,
+                             [&](int a, int b) { return c[a] < c[b] || (c[a] == c[b] && a < b); });
+            for (const auto& half : {std::pair<int, int>{r.lo, mid}, std::pair<int, int>{mid, r.hi}}) {
+                int below = r.below >= 0 ? r.below + 1 : -1;
+                if (r.below < 0 && half.second - half.first <= pc) { below = 0; patch_range.push_back(half); }
+                stack.push_back({half.first, half.second, below});
             }
         }
-        key[e] = {k, e};
+        std::sort(patch_range.begin(), patch_range.end());
+        for (int k = 0; k < nT; ++k) key[k] = {k, order[k]};
+    } else {
+        for (int e = 0; e < nT; ++e) {
+            int k = INT_MAX;
+            for (int i = 0; i < 6; ++i) {
+                const int nd = p->cell_nodes[e * 6 + i];
+                for (int c = 0; c < 2; ++c) {
+                    const int r = iperm[nd + c * nN];
+                    if (r >= 0) k = std::min(k, r);
+                }
+            }
+            key[e] = {k, e};
+        }
+        std::sort(key.begin(), key.end());
+        for (int lo = 0; lo < nT; lo += pc) patch_range.push_back({lo, std::min(nT, lo + pc)});
     }
-    std::sort(key.begin(), key.end());
-    const int npatch = (nT + pc - 1) / pc;
+    const int npatch = (int)patch_range.size();
     std::vector<int> pcell_ptr(1, 0), pcells, pnode_ptr(1, 0), pnode_dst, node_npatch(nN, 0), pacc_rows;
     std::vector<unsigned char> plnode, psrc;
     std::vector<std::vector<int>> patch_nodes(npatch);
     std::vector<int> local(nN, -1), uniq(nN, -1);
     int max_rows = 0;
     for (int q = 0; q < npatch; ++q) {
-        const int e0 = q * pc, e1 = std::min(nT, e0 + pc), cpw = (e1 - e0 + EP_WARPS - 1) / EP_WARPS;
+        const int e0 = patch_range[q].first, e1 = patch_range[q].second;
+        const int em = e0 + (e1 - e0) / 2;
+        const int cut[EP_WARPS + 1] = {e0, e0 + (em - e0) / 2, em, em + (e1 - em) / 2, e1};  // the quarters of the bisection
         std::vector<int>& nodes = patch_nodes[q];
         std::vector<std::array<unsigned char, 4>> src;  // per unique node: its accumulator rows
         int rows = 0;
         for (int g = 0; g < EP_WARPS; ++g) {
             // sub-patch of warp g: a contiguous run of the (space-filling) cell order, with its own accumulator rows
             std::vector<int> touched;
-            for (int k = std::min(e1, e0 + g * cpw); k < std::min(e1, e0 + (g + 1) * cpw); ++k) {
+            for (int k = cut[g]; k < cut[g + 1]; ++k) {
                 const int e = key[k].second;
                 pcells.push_back(e);
                 for (int i = 0; i < 6; ++i) {

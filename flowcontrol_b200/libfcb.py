@@ -36,7 +36,7 @@ class fcb_plan(C.Structure):
 class fcb_problem(C.Structure):
     _fields_ = [
         ("nT", C.c_int32), ("nN", C.c_int32), ("nV", C.c_int32),
-        ("cell_nodes", c_i32p), ("Jinv", c_f64p), ("detJ", c_f64p),
+        ("cell_nodes", c_i32p), ("Jinv", c_f64p), ("detJ", c_f64p), ("node_xy", c_f64p),
         ("n_free", C.c_int32), ("perm", c_i32p),
         ("n_bc", C.c_int32), ("bc_dofs", c_i32p),
         ("na", C.c_int32), ("bc_shape", c_f64p), ("ctrl_rhs", c_f64p * 2),
@@ -132,6 +132,7 @@ class ProblemPack:
         s.cell_nodes = _ptr(arr(tab.cell_nodes, np.int32), c_i32p)
         s.Jinv = _ptr(arr(tab.Jinv.reshape(-1, 4), np.float64), c_f64p)
         s.detJ = _ptr(arr(tab.detJ, np.float64), c_f64p)
+        s.node_xy = _ptr(arr(tab.node_xy, np.float64), c_f64p)
         s.n_free = prob.sym.n
         s.perm = _ptr(arr(prob.sym.perm, np.int32), c_i32p)
         s.n_bc = len(prob.dirichlet.dofs)

@@ -113,7 +113,7 @@ class FlowProblem:
         nonlinear: bool = True,
         shift: float = 0.0,
         pin_pressure: bool = False,
-        leaf_cells: int = 8,
+        leaf_cells: int = 16,
         symbolic: SymbolicFactor | None = None,
     ):
         self.tab, self.blocks = tab, blocks

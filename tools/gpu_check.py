@@ -28,7 +28,7 @@ def near(a, b, tol=3e-16):
     return np.abs(a - b) <= tol
 
 
-def build_cylinder_problem(leaf_cells=8):
+def build_cylinder_problem(leaf_cells=16):
     tab = TaylorHoodTables.from_file(ROOT / "data/meshes/cylinder_O1.npz")
     blocks = ScalarBlocks(tab)
     r = 0.5
@@ -65,7 +65,7 @@ if __name__ == "__main__":
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
     nsteps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
     import os
-    prob, UP0 = build_cylinder_problem(leaf_cells=int(os.environ.get("FCB_LEAF", "8")))
+    prob, UP0 = build_cylinder_problem(leaf_cells=int(os.environ.get("FCB_LEAF", "16")))
     tab = prob.tab
     ic = default_ic(tab, UP0)
     ens = Ensemble(prob, B)
