@@ -359,8 +359,7 @@ __global__ void __launch_bounds__(256) k_rhs_build(int n, int Nv, const int* __r
 // lands densely in shared memory, and rows past the end of Z read as zeros (absent gathers).
 // V is packed on the host in A-fragment order (a fragment = one conflict-free 256-byte read).
 // B fragments are read as 16-byte pairs: lane (g = lane/4, t = lane%4) reads columns 2g, 2g+1 of row
-// k0+t in a 16-column group and feeds two MMAs (n-block "even columns", n-block "odd columns"); with
-// dense rows a warp's 512 bytes then spread over all 32 banks four times, the minimum.  The C
+// k0+t in a 16-column group and feeds two MMAs (n-block "even columns", n-block "odd columns").  The C
 // fragments of such a pair hold 4 consecutive trajectories per lane (32-byte stores).
 // CTAs are persistent: the host compiles each launch into one instruction stream per CTA, and the
 // ring keeps filling across job boundaries.  Every Z row is written by exactly one job: no atomics.
@@ -382,9 +381,10 @@ constexpr int SV_RED_BYTES = 3 * 32 * 32 * 8;  // k-split: partial accumulators 
 // gathered rows per stage (a launch parameter: 3 planes x slots/3 k for nsrc == 3, slots k otherwise).
 template <int NWC>
 struct SweepCfg {
-    static constexpr int W = 32 * NWC;  // trajectories per CTA = shared-memory row length (dense)
+    static constexpr int W = 32 * NWC;  // trajectories per CTA
+    static constexpr int XS = W + 4;    // shared-memory row stride in doubles (== 4 mod 16: conflict-free B fragments)
     static constexpr int MIN_CTAS = NWC == 8 ? SV_MINCTAS8 : (NWC == 4 ? SV_MINCTAS4 : 4);
-    __host__ __device__ static constexpr int voff(int slots) { return slots * W * 8; }             // V slice: slots k x 32 rows
+    __host__ __device__ static constexpr int voff(int slots) { return slots * XS * 8; }            // V slice: slots k x 32 rows
     __host__ __device__ static constexpr int joff(int slots) { return voff(slots) + slots * 256; }  // job record (first stage of a job)
     __host__ __device__ static constexpr int hoff(int slots) { return joff(slots) + 384; }          // stage header (nk, ...)
     __host__ __device__ static constexpr int stage_bytes(int slots) { return hoff(slots) + 128; }
@@ -466,11 +466,11 @@ __device__ __forceinline__ void sweep_job(unsigned char* smem, uint32_t bar_full
                                           int* diverged, int Nv) {
     // t0: first trajectory (global column) of this warp; c0: its first column inside the CTA's shared-memory rows
     using C = SweepCfg<NWC>;
-    constexpr int W = C::W;
+    constexpr int XS = C::XS;
     constexpr int NA = NRB > 0 ? NRB : 1;
     const int gid = lane >> 2, tig = lane & 3;
     const int stage_bytes = C::stage_bytes(slots), voff = C::voff(slots), hoff = C::hoff(slots);
-    const int plane = SRC3 ? ((slots / 3) & ~3) * W : 0;  // doubles between the three source planes of a stage
+    const int plane = SRC3 ? ((slots / 3) & ~3) * XS : 0;  // doubles between the three source planes of a stage
     double ce[NA][2][2], co[NA][2][2];  // even / odd column MMAs of each pair
 #pragma unroll
     for (int rb = 0; rb < NA; ++rb)
@@ -504,7 +504,7 @@ __device__ __forceinline__ void sweep_job(unsigned char* smem, uint32_t bar_full
         mbar_wait(bar_full + 8 * rp.s, rp.ph);
         const unsigned char* st = smem + rp.s * stage_bytes;
         const int nk = *reinterpret_cast<const int*>(st + hoff);
-        const double* xr = reinterpret_cast<const double*>(st) + tig * W + c0 + 2 * gid;
+        const double* xr = reinterpret_cast<const double*>(st) + tig * XS + c0 + 2 * gid;
         const double* vs = reinterpret_cast<const double*>(st + voff) + lane;
         if (KS && (si & 3) != kw) {  // another warp's stage: only keep pace with the ring
             if (YST) { zy += (size_t)nk * L; kleft -= nk; }
@@ -530,7 +530,7 @@ __device__ __forceinline__ void sweep_job(unsigned char* smem, uint32_t bar_full
                 }
             }
             vs += NRB * 32;
-            xr += 4 * W;
+            xr += 4 * XS;
             if (YST) { zy += 4 * L; kleft -= 4; }
         }
         __syncwarp();
@@ -651,21 +651,26 @@ __global__ void __launch_bounds__(32 * (KS ? 5 : NWC + 1), KS ? SV_MINCTAS4 : Sw
                     const int voff = __shfl_sync(0xffffffffu, v, 2);
                     const uint32_t vbytes = (uint32_t)__shfl_sync(0xffffffffu, v, 3);
                     const int jidx = __shfl_sync(0xffffffffu, v, 4);
-                    const uint32_t nrows = (uint32_t)__shfl_sync(0xffffffffu, v, 5);
+                    const uint32_t xbytes = (uint32_t)__shfl_sync(0xffffffffu, v, 5);
                     const int src = __shfl_sync(0xffffffffu, v, 6 + 2 * (lane < SV_MAXRUNS ? lane : 0));
                     const int dsc = __shfl_sync(0xffffffffu, v, 7 + 2 * (lane < SV_MAXRUNS ? lane : 0));
                     const uint32_t full = bar_full + 8 * rp.s;
                     const uint32_t sx = sbase + rp.s * stage_bytes;
                     mbar_wait(bar_empty + 8 * rp.s, rp.ph);
                     if (lane == 0) {
-                        mbar_expect_tx(full, nrows * (uint32_t)(C::W * 8) + vbytes + 16u + (jidx >= 0 ? SV_JREC * 4u : 0u));
+                        mbar_expect_tx(full, xbytes + vbytes + 16u + (jidx >= 0 ? SV_JREC * 4u : 0u));
                         bulk_g2s(sx + C::hoff(slots), srec + (size_t)(sbeg + c0 + u) * SV_SREC, 16u, full);
                         if (vbytes) bulk_g2s(sx + C::voff(slots), vals + (size_t)voff * 32, vbytes, full);
                         if (jidx >= 0) bulk_g2s(sx + C::joff(slots), jrec + (size_t)jidx * SV_JREC, SV_JREC * 4u, full);
                     }
                     __syncwarp();
-                    if (lane < npieces)  // one box copy per run of 1..32 consecutive rows
-                        tma_box_g2s(sx + (uint32_t)((dsc >> 8) * C::W * 8), &maps.m[dsc & 7], slab0, src, full);
+                    if (lane < npieces) {
+                        const uint32_t dst = sx + (uint32_t)((dsc >> 8) * C::XS * 8);
+                        if (dsc & 128)  // a single row (its 4-row group is not a run of consecutive rows)
+                            bulk_g2s(dst, Z + (size_t)src * ldb + slab0, (uint32_t)(C::W * 8), full);
+                        else  // a run of 4..32 consecutive rows, starting on a 4-row boundary: one box copy
+                            tma_box_g2s(dst, &maps.m[dsc & 7], slab0, src, full);
+                    }
                     if (dbg && lane == 0 && c0 + u == 0) dbg[1] = globaltimer_ns();
                     rp.advance(nstages);
                 }
@@ -821,7 +826,7 @@ struct fcb_context {
     int device = 0, num_sms = 0, smem_per_sm = 0, force_nrb = 0, force_nwc = 0, max_nwc = 4, allow_ksplit = 1;
     SweepMaps zmaps[4];  // TMA descriptors of Z for CTA widths of 32, 64, 128, 256 trajectories
     int kslots = 24;                        // ... and for k-split CTAs, whose 4 warps each need stages in flight (FCB_SWEEP_KSLOTS)
-    int force_slots[4] = {48, 36, 24, 12};  // gathered rows per ring stage for those widths (FCB_SWEEP_SLOTS=a,b,c,d)
+    int force_slots[4] = {48, 36, 12, 12};  // gathered rows per ring stage for those widths (FCB_SWEEP_SLOTS=a,b,c,d)
     unsigned long long* sweep_dbg = nullptr;  // FCB_SWEEP_DEBUG=<file>: per-CTA timeline of the sweeps of a profiled step
     cudaStream_t stream = nullptr;
     std::string error;
@@ -987,6 +992,7 @@ int upload_plan(fcb_context* h, DevPlan& d, const fcb_plan& p, const int32_t* pe
         L.grid = std::min(nj, std::max(1, per_sm * h->num_sms / L.nslab));
         L.nstages = std::max(2, std::min(SV_MAXSTAGES, (h->smem_per_sm / per_sm - 1024 - 2 * SV_MAXSTAGES * 8 - (L.ksplit ? SV_RED_BYTES : 0)) / stage_bytes));
         const int kc1 = L.slots & ~3, kc3 = (L.slots / 3) & ~3;
+        const int stride_w = 32 * nwc;  // trajectories per CTA
         // ---- longest-processing-time assignment of tiles to CTAs (cost in rough SM cycles)
         auto ktile = [&](const Tile& t) { return t.nrb > 0 ? p.blk_K[t.blk] : t.k_hi - t.k_lo; };
         auto stages_of = [&](const Tile& t) {
@@ -1047,36 +1053,55 @@ int upload_plan(fcb_context* h, DevPlan& d, const fcb_plan& p, const int32_t* pe
                     int nk = std::max(0, std::min(kc, K4 - k0));
                     const size_t sb = srec.size();
                     srec.resize(sb + SV_SREC, 0);
-                    int npieces = 0, nrows = 0;
-                    for (;;) {  // shrink the stage until its box copies fit the record
-                        npieces = nrows = 0;
+                    int npieces = 0;
+                    int xbytes = 0;
+                    for (;;) {  // shrink the stage until its copies fit the record
+                        npieces = xbytes = 0;
                         bool too_many = false;
+                        auto add_piece = [&](int src, int slot, int code, int bytes) {
+                            if (npieces >= SV_MAXRUNS) { too_many = true; return; }
+                            srec[sb + 6 + 2 * npieces] = src;
+                            srec[sb + 7 + 2 * npieces] = (slot << 8) | code;
+                            ++npieces;
+                            xbytes += bytes;
+                        };
                         for (int pl = 0; pl < nsrc && !too_many; ++pl) {
                             const int32_t* ip = (pl == 0 ? p.i0 : (pl == 1 ? p.i1 : p.i2)) + p.blk_iptr[b] + t.k_lo;
-                            int run_src = -1, run_slot = 0, run_len = 0, zpos = 0;
+                            auto row_of = [&](int k) { return (k0 + k < K) ? ip[k0 + k] : zrow; };
+                            int run_src = -1, run_slot = 0, run_groups = 0;  // run of whole 4-row groups of consecutive rows
                             auto flush = [&]() {
-                                // a run of consecutive rows goes out as box copies of 32, 16, 8, 4, 2, 1 rows
-                                for (int lg = 5; lg >= 0; --lg)
-                                    while (run_len >= (1 << lg)) {
-                                        if (npieces >= SV_MAXRUNS) { too_many = true; return; }
-                                        srec[sb + 6 + 2 * npieces] = run_src;
-                                        srec[sb + 7 + 2 * npieces] = (run_slot << 8) | lg;
-                                        ++npieces;
-                                        nrows += 1 << lg;
-                                        run_src += 1 << lg; run_slot += 1 << lg; run_len -= 1 << lg;
+                                for (int lg = 3; lg >= 0 && !too_many; --lg)  // boxes of 32, 16, 8, 4 rows
+                                    while (run_groups >= (1 << lg) && !too_many) {
+                                        add_piece(run_src, run_slot, lg + 2, (4 << lg) * (stride_w + 4) * 8);
+                                        run_src += 4 << lg; run_slot += 4 << lg; run_groups -= 1 << lg;
                                     }
+                                run_groups = 0;
                             };
-                            for (int k = 0; k < nk && !too_many; ++k) {
-                                int row = (k0 + k < K) ? ip[k0 + k] : zrow;
-                                if (row == zrow) row = zrow + zpos++;  // absent / padded rows lie past the end of the tensor: zeros
-                                if (run_len > 0 && row == run_src + run_len) { ++run_len; continue; }
-                                flush();
-                                run_src = row; run_slot = pl * kc + k; run_len = 1;
+                            for (int g = 0; g < nk && !too_many; g += 4) {
+                                // absent / padded rows (index zrow) lie past the end of the tensor and read as zeros; a group
+                                // of them is "consecutive" from any OOB row, a mixed group is not
+                                int r0 = row_of(g);
+                                bool consecutive = true, all_absent = (r0 == zrow);
+                                for (int k = 1; k < 4; ++k) {
+                                    const int rk = row_of(g + k);
+                                    all_absent = all_absent && rk == zrow;
+                                    consecutive = consecutive && rk == r0 + k && rk != zrow && r0 != zrow;
+                                }
+                                if (all_absent) { consecutive = true; r0 = (run_groups > 0 && run_src + 4 * run_groups >= zrow) ? run_src + 4 * run_groups : zrow; }
+                                if (consecutive) {
+                                    if (run_groups > 0 && r0 == run_src + 4 * run_groups) { ++run_groups; continue; }
+                                    flush();
+                                    run_src = r0; run_slot = pl * kc + g; run_groups = 1;
+                                } else {
+                                    flush();
+                                    for (int k = 0; k < 4 && !too_many; ++k)
+                                        add_piece(row_of(g + k), pl * kc + g + k, 128, stride_w * 8);
+                                }
                             }
                             if (!too_many) flush();
                         }
                         if (!too_many) break;
-                        if (nk <= 4) return fail(h, FCB_ERR_INVALID, "internal: a 4-row stage needs more than %d box copies", SV_MAXRUNS);
+                        if (nk <= 4) return fail(h, FCB_ERR_INVALID, "internal: a 4-row stage needs more than %d copies", SV_MAXRUNS);
                         nk -= 4;
                     }
                     srec[sb + 0] = nk;
@@ -1084,7 +1109,7 @@ int upload_plan(fcb_context* h, DevPlan& d, const fcb_plan& p, const int32_t* pe
                     srec[sb + 2] = (int)((v0 + (size_t)k0 * 8 * t.nrb) / 32);
                     srec[sb + 3] = nk * 64 * t.nrb;
                     srec[sb + 4] = k0 == 0 ? (int)(jb / SV_JREC) : -1;
-                    srec[sb + 5] = nrows;
+                    srec[sb + 5] = xbytes;
                     k0 += std::max(nk, 4);
                     ++nst;
                 } while (k0 < K4);
@@ -1537,7 +1562,7 @@ int create_impl(fcb_context* h, const fcb_problem* p, int B) {
         CK(cudaFuncSetAttribute(k_front_sweep<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
         const char* env = getenv("FCB_SWEEP_WARPS");  // tuning knobs: force / cap the CTA width of the sweep launches
         h->force_nwc = env ? atoi(env) : 0;
-        if (h->force_nwc != 1 && h->force_nwc != 2 && h->force_nwc != 4 && h->force_nwc != 8) h->force_nwc = 0;
+        if (h->force_nwc != 1 && h->force_nwc != 2 && h->force_nwc != 4) h->force_nwc = 0;
         env = getenv("FCB_SWEEP_PDL");
         if (env) h->use_pdl = atoi(env) != 0;
         env = getenv("FCB_SWEEP_KSPLIT");
@@ -1552,7 +1577,7 @@ int create_impl(fcb_context* h, const fcb_problem* p, int B) {
         env = getenv("FCB_SWEEP_KSLOTS");
         if (env && atoi(env) >= 12 && atoi(env) <= 96 && atoi(env) % 12 == 0) h->kslots = atoi(env);
         env = getenv("FCB_SWEEP_MAXWARPS");
-        if (env && (atoi(env) == 1 || atoi(env) == 2 || atoi(env) == 4 || atoi(env) == 8)) h->max_nwc = atoi(env);
+        if (env && (atoi(env) == 1 || atoi(env) == 2 || atoi(env) == 4)) h->max_nwc = atoi(env);  // 8 would need a 260-column box
         if (getenv("FCB_SWEEP_DEBUG")) {
             size_t nl = (size_t)std::max(p->plan[0].nlaunch, p->plan[1].nlaunch);
             CK(cudaMalloc((void**)&h->sweep_dbg, nl * DBG_PER_LAUNCH * sizeof(unsigned long long)));
@@ -1649,10 +1674,10 @@ int create_impl(fcb_context* h, const fcb_problem* p, int B) {
         for (int wi = 0; wi < 4; ++wi)
             for (int hi = 0; hi < 6; ++hi) {
                 const cuuint32_t width = 32u << wi;
-                if ((int)width > h->ldb) { memset(&h->zmaps[wi].m[hi], 0, sizeof(CUtensorMap)); continue; }
+                if ((int)width > h->ldb || width + 4 > 256) { memset(&h->zmaps[wi].m[hi], 0, sizeof(CUtensorMap)); continue; }
                 const cuuint64_t gdim[2] = {(cuuint64_t)h->ldb, (cuuint64_t)zrows};
                 const cuuint64_t gstride[1] = {(cuuint64_t)h->ldb * sizeof(double)};
-                const cuuint32_t box[2] = {width, 1u << hi};
+                const cuuint32_t box[2] = {width + 4, 1u << hi};  // 4 spare columns: shared-memory row stride W+4 (see k_front_sweep)
                 const cuuint32_t estride[2] = {1, 1};
                 const CUresult r = ((EncodeTiled)fn)(&h->zmaps[wi].m[hi], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, h->Z, gdim, gstride, box,
                                                      estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
