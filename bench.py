@@ -51,7 +51,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -200,10 +200,27 @@ def run_ours(args):
     solve_flops = 2.0 * plan.nnz * ldb
     hbm_peak, peak_src = peaks()
     achieved = solve_bytes / (solve_ms * 1e-3) / 1e9
+    # measured DRAM traffic of the same launches (ncu, profiles/r01_kernel_summary.json written by tools/kernel_summary.py)
+    traffic = None
+    ks = ROOT / "profiles" / "r01_kernel_summary.json"
+    if ks.exists():
+        try:
+            traffic = float(json.loads(ks.read_text())["kernels"]["k_front_sweep"]["dram_bytes"])
+        except Exception:
+            traffic = None
+    # element kernel (second largest): reads u and b_{n-1}, writes the next rhs rows and b_n; ~600 FP64 FMA per cell
+    elem_bytes = 8 * (3 * tab.Nv + n) * ldb
+    elem_flops = 2.0 * 600 * tab.nT * ldb
     roofline = {
         "kernel": "k_front_sweep (multifrontal forward+backward sweeps on FP64 tensor cores, all launches of one solve)",
         "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-        "peak_source": peak_src, "traffic": None,
+        "peak_source": peak_src, "traffic": traffic,
+        "traffic_note": "dram__bytes_read+write summed over the sweep launches of one step (ncu); algorithmic bytes assume the factor is read once",
+        "element_kernel": {"ms_per_step": phase_ms["element"], "achieved_gbs": elem_bytes / (phase_ms["element"] * 1e-3) / 1e9,
+                           "hbm_frac": elem_bytes / (phase_ms["element"] * 1e-3) / 1e9 / hbm_peak,
+                           "fp64_tflops": elem_flops / (phase_ms["element"] * 1e-3) / 1e12,
+                           "fp64_frac_of_dfma_peak": elem_flops / (phase_ms["element"] * 1e-3) / 1e12 / 33.6,
+                           "algorithmic_bytes_per_step": elem_bytes},
         "launches_per_step": solve_launches, "ms_per_launch": solve_ms / solve_launches, "ms_per_step": solve_ms,
         "algorithmic_bytes_per_step": solve_bytes,
         "fp64": {"achieved_tflops": solve_flops / (solve_ms * 1e-3) / 1e12, "peak_tflops": FP64_PEAK_TFLOPS,
@@ -242,7 +259,7 @@ def run_ours(args):
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic (shipped mesh O1, cached base flow, gain-swept controllers, default ParamIC perturbation)",
             "config": {"workload": WORKLOAD, "trajectories_per_gpu": B_PER_GPU, "trajectories_total": total,
-                       "dofs_per_trajectory": int(tab.N), "l2": "working set >> L2 (Z 225 MB + factors 110 MB + state 400 MB per GPU); no flush needed",
+                       "dofs_per_trajectory": int(tab.N), "l2": "working set >> L2 (solve buffer 560 MB + packed factors 130 MB + state 430 MB per GPU vs 126 MB L2); no flush needed",
                        "parallelism": f"ensemble-sharded x{world}, time-series all-gather only"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches * world), "roofline": roofline,
             "all_finite": finite,
@@ -279,7 +296,7 @@ def run_reference(args):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -724,64 +724,79 @@ __global__ void __launch_bounds__(32 * (KS ? 5 : NWC + 1), KS ? SV_MINCTAS4 : Sw
     if (dbg && lane == 0 && wid == 0) { dbg[4] = globaltimer_ns(); dbg[6] = (unsigned long long)nj; }
 }
 
-// sensors + energy.  grid = ldb/32, block = (32, 8)
-__global__ void __launch_bounds__(256) k_measure(int ns, const int* __restrict__ sptr, const int* __restrict__ sidx,
-                                                const double* __restrict__ sval, const double* __restrict__ up,
-                                                double* __restrict__ y, const double* __restrict__ epart, int nblk,
-                                                double* __restrict__ dE, int ldb) {
+// sensors + energy.  grid = ldb/32, block = (32, MEAS_WARPS)
+constexpr int MEAS_WARPS = 32;
+__global__ void __launch_bounds__(32 * MEAS_WARPS) k_measure(int ns, const int* __restrict__ sptr, const int* __restrict__ sidx,
+                                                           const double* __restrict__ sval, const double* __restrict__ up,
+                                                           double* __restrict__ y, const double* __restrict__ epart, int nblk,
+                                                           double* __restrict__ dE, int ldb) {
     const int b = blockIdx.x * 32 + threadIdx.x;
     const int ty = threadIdx.y;
-    for (int s = ty; s < ns; s += blockDim.y) {
+    for (int s = ty; s < ns; s += MEAS_WARPS) {
         double acc = 0.0;
         for (int j = __ldg(sptr + s); j < __ldg(sptr + s + 1); ++j)
             acc = fma(__ldg(sval + j), up[(size_t)__ldg(sidx + j) * ldb + b], acc);
         y[(size_t)s * ldb + b] = acc;
     }
-    // energy: strided partial sums, then a fixed-order combine (deterministic)
-    double e = 0.0;
-    for (int k = ty; k < nblk; k += blockDim.y) e += epart[(size_t)k * ldb + b];
-    __shared__ double se[8][32];
-    se[ty][threadIdx.x] = e;
+    // energy: every warp sums a contiguous chunk of the patch partials (loads independent of each other), then the
+    // warps' sums are combined in a fixed order (deterministic)
+    const int chunk = (nblk + MEAS_WARPS - 1) / MEAS_WARPS;
+    const int k0 = ty * chunk, k1 = min(nblk, k0 + chunk);
+    double e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0;
+    int k = k0;
+    for (; k + 3 < k1; k += 4) {
+        e0 += epart[(size_t)k * ldb + b];
+        e1 += epart[(size_t)(k + 1) * ldb + b];
+        e2 += epart[(size_t)(k + 2) * ldb + b];
+        e3 += epart[(size_t)(k + 3) * ldb + b];
+    }
+    for (; k < k1; ++k) e0 += epart[(size_t)k * ldb + b];
+    __shared__ double se[MEAS_WARPS][32];
+    se[ty][threadIdx.x] = (e0 + e1) + (e2 + e3);
     __syncthreads();
     if (ty == 0) {
         double s = 0.0;
-        for (int w = 0; w < 8; ++w) s += se[w][threadIdx.x];
+        for (int w = 0; w < MEAS_WARPS; ++w) s += se[w][threadIdx.x];
         dE[b] = 0.5 * s;
     }
 }
 
 // One LTI controller per trajectory (controller.py:157-158): uses the PRE-update state for the output.
-// grid = ldb/32... one thread per trajectory.
-__global__ void k_controller(int nx, int ny, int nu, int ns, int na, const double* __restrict__ Ad,
-                             const double* __restrict__ Bd, const double* __restrict__ Cd,
-                             const double* __restrict__ Dd, const double* __restrict__ Ky,
-                             const double* __restrict__ Fu, const double* __restrict__ y,
-                             const double* __restrict__ xin, double* __restrict__ xout, double* __restrict__ uctrl,
-                             int ldb) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= ldb) return;
+// grid = ldb/32, block = (32, CTRL_ROWS): thread (b, i) owns row i of the state update of trajectory b, rows < nu also an
+// output; the rows of one trajectory meet in shared memory for the actuator fan-out.
+constexpr int CTRL_ROWS = 16;
+__global__ void __launch_bounds__(32 * CTRL_ROWS) k_controller(int nx, int ny, int nu, int ns, int na, const double* __restrict__ Ad,
+                                                              const double* __restrict__ Bd, const double* __restrict__ Cd,
+                                                              const double* __restrict__ Dd, const double* __restrict__ Ky,
+                                                              const double* __restrict__ Fu, const double* __restrict__ y,
+                                                              const double* __restrict__ xin, double* __restrict__ xout,
+                                                              double* __restrict__ uctrl, int ldb) {
+    const int b = blockIdx.x * 32 + threadIdx.x;
+    const int r = threadIdx.y;
     const size_t L = (size_t)ldb;
-    double v[8], uo[8];
+    double v[8];
     for (int i = 0; i < ny; ++i) {
         double s = 0.0;
         for (int j = 0; j < ns; ++j) s = fma(__ldg(Ky + i * ns + j), y[j * L + b], s);
         v[i] = s;
     }
-    for (int o = 0; o < nu; ++o) {
+    __shared__ double uo[8][32];
+    for (int o = r; o < nu; o += CTRL_ROWS) {
         double s = 0.0;
         for (int j = 0; j < nx; ++j) s = fma(Cd[(size_t)(o * nx + j) * L + b], xin[j * L + b], s);
         for (int j = 0; j < ny; ++j) s = fma(Dd[(size_t)(o * ny + j) * L + b], v[j], s);
-        uo[o] = s;
+        uo[o][threadIdx.x] = s;
     }
-    for (int i = 0; i < nx; ++i) {
+    for (int i = r; i < nx; i += CTRL_ROWS) {
         double s = 0.0;
         for (int j = 0; j < nx; ++j) s = fma(Ad[(size_t)(i * nx + j) * L + b], xin[j * L + b], s);
         for (int j = 0; j < ny; ++j) s = fma(Bd[(size_t)(i * ny + j) * L + b], v[j], s);
         xout[i * L + b] = s;
     }
-    for (int a = 0; a < na; ++a) {
+    __syncthreads();
+    for (int a = r; a < na; a += CTRL_ROWS) {
         double s = 0.0;
-        for (int o = 0; o < nu; ++o) s = fma(__ldg(Fu + a * nu + o), uo[o], s);
+        for (int o = 0; o < nu; ++o) s = fma(__ldg(Fu + a * nu + o), uo[o][threadIdx.x], s);
         uctrl[a * L + b] = s;
     }
 }
@@ -825,6 +840,7 @@ struct DevPlan {
 struct fcb_context {
     int device = 0, num_sms = 0, smem_per_sm = 0, force_nrb = 0, force_nwc = 0, max_nwc = 4, allow_ksplit = 1;
     SweepMaps zmaps[4];  // TMA descriptors of Z for CTA widths of 32, 64, 128, 256 trajectories
+    double want_ctas_per_sm = 2.0;          // a launch narrows its CTAs / shortens its tiles until it has this many CTAs per SM
     int kslots = 24;                        // ... and for k-split CTAs, whose 4 warps each need stages in flight (FCB_SWEEP_KSLOTS)
     int force_slots[4] = {48, 36, 12, 12};  // gathered rows per ring stage for those widths (FCB_SWEEP_SLOTS=a,b,c,d)
     unsigned long long* sweep_dbg = nullptr;  // FCB_SWEEP_DEBUG=<file>: per-CTA timeline of the sweeps of a profiled step
@@ -956,7 +972,7 @@ int upload_plan(fcb_context* h, DevPlan& d, const fcb_plan& p, const int32_t* pe
         };
         int nrb_cap = 4, nwc = std::min(h->max_nwc, nw_all);
         while (nw_all % nwc) nwc >>= 1;
-        const long long want = 2LL * h->num_sms;
+        const long long want = (long long)(h->want_ctas_per_sm * h->num_sms);
         while (nwc > 1 && njobs_for(nrb_cap) * (nw_all / nwc) < want) nwc >>= 1;
         // a launch that is still too small at one 32-trajectory tile per CTA splits K over the CTA's four consumer warps
         L.ksplit = (nwc == 1 && h->allow_ksplit) ? 1 : 0;
@@ -1202,7 +1218,7 @@ int enqueue_element(fcb_context* h, const double* u, double* a, double* b, const
 }
 
 int enqueue_measure(fcb_context* h, const double* up) {
-    dim3 grid(h->ldb / 32), block(32, 8);
+    dim3 grid(h->ldb / 32), block(32, MEAS_WARPS);
     k_measure<<<grid, block, 0, h->stream>>>(h->ns, h->sensor_ptr, h->sensor_idx, h->sensor_val, up, h->y, h->epart,
                                              h->nblk_total, h->dE, h->ldb);
     h->launches += 1;
@@ -1291,8 +1307,7 @@ int enqueue_step(fcb_context* h, int order, int parity, bool rhs_ready, PhaseMar
 }
 
 int enqueue_controller(fcb_context* h, int xparity) {
-    const int threads = 64;
-    k_controller<<<(h->ldb + threads - 1) / threads, threads, 0, h->stream>>>(
+    k_controller<<<h->ldb / 32, dim3(32, CTRL_ROWS), 0, h->stream>>>(
         h->nx, h->ny, h->nu, h->ns, h->na, h->Ad, h->Bd, h->Cd, h->Dd, h->Ky, h->Fu, h->y, h->xk[xparity],
         h->xk[1 - xparity], h->uctrl, h->ldb);
     h->launches += 1;
@@ -1574,6 +1589,8 @@ int create_impl(fcb_context* h, const fcb_problem* p, int B) {
                 for (int i = 0; i < 4; ++i)
                     if (v[i] >= 12 && v[i] <= 96 && v[i] % 12 == 0) h->force_slots[i] = v[i];
         }
+        env = getenv("FCB_SWEEP_WANT");
+        if (env && atof(env) > 0.0) h->want_ctas_per_sm = atof(env);
         env = getenv("FCB_SWEEP_KSLOTS");
         if (env && atoi(env) >= 12 && atoi(env) <= 96 && atoi(env) % 12 == 0) h->kslots = atoi(env);
         env = getenv("FCB_SWEEP_MAXWARPS");
