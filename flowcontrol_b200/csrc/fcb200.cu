@@ -296,6 +296,18 @@ __global__ void __launch_bounds__(256) k_patch_merge(int nshared, const int* __r
     emit_node<true>(bprev, Zb, rx, ry, rp, a, bvec, nN, L, nd, b, s0, s1, s2, s3);
 }
 
+// Z[dst[i]] = sum of Z[src[j]] (fixed order): right-hand side of the merged top of the elimination tree.
+// grid = (ceil(n/8), ldb/32), block = (32, 8)
+__global__ void __launch_bounds__(256) k_gather_sum(int nrows, const int* __restrict__ ptr, const int* __restrict__ src,
+                                                   const int* __restrict__ dst, double* Z, int ldb) {
+    const int i = blockIdx.x * blockDim.y + threadIdx.y;
+    const int b = blockIdx.y * 32 + threadIdx.x;
+    if (i >= nrows) return;
+    double s = 0.0;
+    for (int k = __ldg(ptr + i); k < __ldg(ptr + i + 1); ++k) s += Z[(size_t)__ldg(src + k) * ldb + b];
+    Z[(size_t)__ldg(dst + i) * ldb + b] = s;
+}
+
 // control terms of the fused right-hand side: Z[row] += sum_k coef[k][i] * u_ctrl[k] on the (few) rows where the lifting /
 // force vectors are non-zero.  grid = (ceil(nrows/8), ldb/32), block = (32, 8)
 __global__ void __launch_bounds__(256) k_ctrl_add(int nrows, const int* __restrict__ rows, const double* __restrict__ coef, int na,
@@ -828,6 +840,7 @@ __global__ void k_log(int na, int ns, const double* __restrict__ dE, const doubl
 struct DevPlan {
     int n = 0, nU = 0, njobs = 0, nlaunch = 0;
     int *srec = nullptr, *jrec = nullptr, *cta_sptr = nullptr, *cta_jptr = nullptr;
+    int asm_n = 0, *asm_ptr = nullptr, *asm_src = nullptr, *asm_dst = nullptr;
     double* vals = nullptr;
     struct Launch { int grid, nwc, nslab, nstages, slots, cta_off, ksplit; };
     std::vector<Launch> launches;
@@ -1149,6 +1162,18 @@ int upload_plan(fcb_context* h, DevPlan& d, const fcb_plan& p, const int32_t* pe
     TRY(upload(h, &d.cta_sptr, cta_sptr.data(), cta_sptr.size()));
     TRY(upload(h, &d.cta_jptr, cta_jptr.data(), cta_jptr.size()));
     TRY(upload(h, &d.vals, packed.data(), packed.size()));
+    d.asm_n = p.asm_n;
+    if (p.asm_n > 0) {
+        for (int i = 0; i < p.asm_n; ++i) {
+            if (p.asm_dst[i] < 0 || p.asm_dst[i] >= zrow || p.asm_ptr[i + 1] < p.asm_ptr[i])
+                return fail(h, FCB_ERR_INVALID, "plan gather-sum row %d is malformed", i);
+            for (int k = p.asm_ptr[i]; k < p.asm_ptr[i + 1]; ++k)
+                if (p.asm_src[k] < 0 || p.asm_src[k] >= zrow) return fail(h, FCB_ERR_INVALID, "plan gather-sum source out of range");
+        }
+        TRY(upload(h, &d.asm_ptr, p.asm_ptr, (size_t)p.asm_n + 1));
+        TRY(upload(h, &d.asm_src, p.asm_src, (size_t)std::max(1, p.asm_ptr[p.asm_n])));
+        TRY(upload(h, &d.asm_dst, p.asm_dst, (size_t)p.asm_n));
+    }
     CK(cudaStreamSynchronize(h->stream));  // host vectors go out of scope
     return FCB_OK;
 }
@@ -1250,6 +1275,11 @@ void launch_sweep(fcb_context* h, const DevPlan& pl, const DevPlan::Launch& L, i
 int enqueue_solve(fcb_context* h, const DevPlan& pl, double* xout, PhaseMark* pm) {
     for (int l = 0; l < pl.nlaunch; ++l) {
         if (pm && l == pl.n_forward) pm->mark(FCB_PHASE_BACKWARD);
+        if (l == pl.n_forward && pl.asm_n > 0) {
+            dim3 grid((pl.asm_n + 7) / 8, h->ldb / 32), block(32, 8);
+            k_gather_sum<<<grid, block, 0, h->stream>>>(pl.asm_n, pl.asm_ptr, pl.asm_src, pl.asm_dst, h->Z, h->ldb);
+            h->launches += 1;
+        }
         const DevPlan::Launch& L = pl.launches[l];
         if (L.grid <= 0) continue;
         unsigned long long* dbg = (pm && h->sweep_dbg) ? h->sweep_dbg + (size_t)l * DBG_PER_LAUNCH : nullptr;
@@ -1389,7 +1419,8 @@ void destroy(fcb_context* h) {
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (int i = 0; i < 2; ++i) {
-        void* pp[] = {h->plan[i].srec, h->plan[i].jrec, h->plan[i].cta_sptr, h->plan[i].cta_jptr, h->plan[i].vals};
+        void* pp[] = {h->plan[i].srec, h->plan[i].jrec, h->plan[i].cta_sptr, h->plan[i].cta_jptr, h->plan[i].vals,
+                      h->plan[i].asm_ptr, h->plan[i].asm_src, h->plan[i].asm_dst};
         for (void* q : pp)
             if (q) cudaFree(q);
     }
@@ -1913,7 +1944,7 @@ int fcb_profile_step(fcb_handle h, const double* u_ctrl, float* ms, int32_t* lau
     if (launches) {
         launches[FCB_PHASE_RHS] = 1;
         launches[FCB_PHASE_FORWARD] = pl.n_forward;
-        launches[FCB_PHASE_BACKWARD] = pl.nlaunch - pl.n_forward;
+        launches[FCB_PHASE_BACKWARD] = pl.nlaunch - pl.n_forward + (pl.asm_n > 0 ? 1 : 0);
         launches[FCB_PHASE_POST] = h->nbc > 0 ? 1 : 0;
         launches[FCB_PHASE_ELEMENT] = 1 + (h->nshared > 0 ? 1 : 0);
         launches[FCB_PHASE_MEASURE] = 1;

@@ -93,4 +93,4 @@ def make_problem(Re: float = 1000.0, UP0=None, **kw):
 
     pe = fs.params_ensemble
     return FlowProblem(tab, fs.blocks, Re, fs.params_time.dt, fs.bc.bcu, fs.params_control.actuator_list,
-                       fs.params_control.sensor_list, UP0, pin_pressure=True, leaf_cells=pe.leaf_cells)
+                       fs.params_control.sensor_list, UP0, pin_pressure=True, leaf_cells=pe.leaf_cells, top_levels=pe.top_levels)

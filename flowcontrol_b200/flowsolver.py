@@ -251,7 +251,7 @@ class FlowSolver(ABC):
             self.tables, self.blocks, self.params_flow.Re, self.params_time.dt, self.bc.bcu,
             self.params_control.actuator_list, self.params_control.sensor_list, self.fields.UP0.array,
             nonlinear=self.params_solver.is_eq_nonlinear, shift=self.params_solver.shift,
-            pin_pressure=self._pin_pressure(), leaf_cells=pe.leaf_cells,
+            pin_pressure=self._pin_pressure(), leaf_cells=pe.leaf_cells, top_levels=pe.top_levels,
         )
         if self.ensemble is not None:
             self.ensemble.close()

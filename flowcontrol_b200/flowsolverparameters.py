@@ -87,4 +87,5 @@ class ParamEnsemble(ParamFlowSolver):
 
     batch: int = 1
     device: int = 0
+    top_levels: int = 2  # levels at the top of the elimination tree merged into one dense inverse (multifrontal.py)
     leaf_cells: int = 16  # nested-dissection leaf size (ordering.py); 16 measured best on B200 (fewer, fatter bottom levels)

@@ -30,6 +30,7 @@ class fcb_plan(C.Structure):
         ("blk_iptr", c_i64p), ("blk_vptr", c_i64p), ("blk_eptr", c_i64p),
         ("i0", c_i32p), ("i1", c_i32p), ("i2", c_i32p), ("e0", c_i32p), ("e1", c_i32p), ("vals", c_f64p),
         ("nlaunch", C.c_int32), ("launch_ptr", c_i32p), ("n_forward_launches", C.c_int32),
+        ("asm_n", C.c_int32), ("asm_ptr", c_i32p), ("asm_src", c_i32p), ("asm_dst", c_i32p),
     ]
 
 
@@ -151,6 +152,10 @@ class ProblemPack:
             q.n_forward_launches = p.n_forward_launches
             q.nlaunch = len(p.launch_ptr) - 1
             q.launch_ptr = _ptr(arr(p.launch_ptr, np.int32), c_i32p)
+            q.asm_n = len(p.asm_dst)
+            q.asm_ptr = _ptr(arr(p.asm_ptr, np.int32), c_i32p)
+            q.asm_src = _ptr(arr(p.asm_src if len(p.asm_src) else np.zeros(1), np.int32), c_i32p)
+            q.asm_dst = _ptr(arr(p.asm_dst if len(p.asm_dst) else np.zeros(1), np.int32), c_i32p)
         s.ns = prob.ns
         s.sensor_ptr = _ptr(arr(prob.sensor_ptr, np.int32), c_i32p)
         s.sensor_idx = _ptr(arr(prob.sensor_idx, np.int32), c_i32p)

@@ -212,6 +212,11 @@ class SolvePlan:
         backward (launches by tree depth):
             x_t[r] = (F11^-1 y_t)[r] - (G_t x_struct(t))[r]
 
+    The top ``top_levels`` levels of the tree (a handful of large separators, whose level-by-level sweeps have too
+    little parallelism for a GPU) are merged: their right-hand side r_T = b_T + (updates of the supernodes just below)
+    is assembled by a gather-sum, and x_T = S^-1 r_T is ONE launch of dense blocks with the explicit inverse of the
+    top Schur complement (the "partitioned inverse" of the top separators).
+
     Every output row is produced by exactly one block: no atomics, bit-reproducible."""
 
     n: int
@@ -232,6 +237,11 @@ class SolvePlan:
     vals: np.ndarray
     launch_ptr: np.ndarray  # int32 [nlaunch+1] block ranges, forward launches first
     n_forward_launches: int
+    # gather-sum executed between the forward and the remaining launches: Z[asm_dst[i]] = sum_j Z[asm_src[j]],
+    # j in [asm_ptr[i], asm_ptr[i+1]) -- assembles the right-hand side of the merged top of the tree
+    asm_ptr: np.ndarray = None
+    asm_src: np.ndarray = None
+    asm_dst: np.ndarray = None
 
     @property
     def nnz(self) -> int:
@@ -246,7 +256,28 @@ class SolvePlan:
         return 2 * self.n + self.nU + 1
 
 
-def build_plan(fac: BlockFactor) -> SolvePlan:
+def top_inverse(fac: BlockFactor, top: list[int]) -> tuple[np.ndarray, np.ndarray]:
+    """Explicit inverse of the Schur complement of the supernodes ``top`` (closed under taking ancestors):
+    returns (solver rows of the top unknowns, S^-1) with x_T = S^-1 r_T."""
+    sns = fac.sym.supernodes
+    trows = np.concatenate([np.arange(sns[t].c0, sns[t].c1) for t in top]) if top else np.zeros(0, dtype=np.int64)
+    pos = {int(r): j for j, r in enumerate(trows)}
+    nT = len(trows)
+    Y = np.eye(nT)
+    own = {t: np.array([pos[r] for r in range(sns[t].c0, sns[t].c1)], dtype=np.int64) for t in top}
+    st = {t: np.array([pos[int(r)] for r in sns[t].struct], dtype=np.int64) for t in top}
+    for t in top:  # post-order: children first
+        E = fac.blocks[t][0]
+        if len(st[t]):
+            Y[st[t]] -= E @ Y[own[t]]
+    X = np.zeros((nT, nT))
+    for t in reversed(top):
+        _, Finv, G = fac.blocks[t]
+        X[own[t]] = Finv @ Y[own[t]] - (G @ X[st[t]] if len(st[t]) else 0.0)
+    return trows, X
+
+
+def build_plan(fac: BlockFactor, top_levels: int = 2) -> SolvePlan:
     sym = fac.sym
     sns = sym.supernodes
     n = sym.n
@@ -257,6 +288,9 @@ def build_plan(fac: BlockFactor) -> SolvePlan:
     nU = int(uoff[-1])
     UB = 2 * n  # first row of the U region
     ZROW = 2 * n + nU
+    top = [i for i, s in enumerate(sns) if s.depth < top_levels]  # post-order, closed under ancestors
+    in_top = np.zeros(nS, dtype=bool)
+    in_top[top] = True
 
     def child_sources(i: int, rows: np.ndarray, absent: int) -> tuple[np.ndarray, np.ndarray]:
         """Z rows of the (at most two) children's update vectors that hit the given solver rows."""
@@ -278,7 +312,7 @@ def build_plan(fac: BlockFactor) -> SolvePlan:
     launch_ptr = [0]
     max_h = max(s.height for s in sns)
     for h in range(max_h + 1):
-        for i in (i for i, s in enumerate(sns) if s.height == h):
+        for i in (i for i, s in enumerate(sns) if s.height == h and not in_top[i]):
             s = sns[i]
             w, m = s.c1 - s.c0, len(s.struct)
             if w == 0 and m == 0:
@@ -293,9 +327,41 @@ def build_plan(fac: BlockFactor) -> SolvePlan:
         if len(blocks) > launch_ptr[-1]:
             launch_ptr.append(len(blocks))
     n_fwd = len(launch_ptr) - 1
+    # merged top: assemble r_T into the y rows of the top unknowns, then x_T = S^-1 r_T
+    asm_ptr, asm_src, asm_dst = [0], [], []
+    if top:
+        trows, Sinv = top_inverse(fac, top)
+        frontier = [c for t in top for c in sym.children[t] if not in_top[c]]
+        for t in top:
+            s = sns[t]
+            rows = np.arange(s.c0, s.c1, dtype=np.int64)
+            srcs = [rows.copy()]  # b
+            for c in frontier:
+                st = sns[c].struct
+                if len(st) == 0:
+                    continue
+                pos = np.searchsorted(st, rows)
+                pos_c = np.minimum(pos, len(st) - 1)
+                srcs.append(np.where(st[pos_c] == rows, UB + uoff[c] + pos_c, -1))
+            S = np.stack(srcs, axis=1)
+            for k, r in enumerate(rows):
+                valid = S[k][S[k] >= 0]
+                asm_src.extend(valid.tolist())
+                asm_ptr.append(len(asm_src))
+                asm_dst.append(n + int(r))
+        pos = 0
+        for t in top:
+            s = sns[t]
+            w = s.c1 - s.c0
+            if w:
+                blocks.append(dict(K=len(trows), M=w, nsrc=1, out0=s.c0, ystore=-1, i0=n + trows, i1=None, i2=None,
+                                   vals=Sinv[pos : pos + w], e0=None, e1=None))
+            pos += w
+        if len(blocks) > launch_ptr[-1]:
+            launch_ptr.append(len(blocks))
     max_d = max(s.depth for s in sns)
     for dpt in range(max_d + 1):
-        for i in (i for i, s in enumerate(sns) if s.depth == dpt):
+        for i in (i for i, s in enumerate(sns) if s.depth == dpt and not in_top[i]):
             s = sns[i]
             w = s.c1 - s.c0
             if w == 0:
@@ -342,6 +408,8 @@ def build_plan(fac: BlockFactor) -> SolvePlan:
         blk_iptr=iptr[:-1].copy(), blk_vptr=vptr, blk_eptr=eptr,
         i0=i0, i1=i1, i2=i2, e0=cat(e0p, np.int32), e1=cat(e1p, np.int32), vals=cat(vparts, np.float64),
         launch_ptr=np.array(launch_ptr, dtype=np.int32), n_forward_launches=n_fwd,
+        asm_ptr=np.array(asm_ptr, dtype=np.int32), asm_src=np.array(asm_src, dtype=np.int32),
+        asm_dst=np.array(asm_dst, dtype=np.int32),
     )
 
 
@@ -354,7 +422,13 @@ def apply_plan_host(plan: SolvePlan, b_perm: np.ndarray) -> np.ndarray:
     n = plan.n
     Z = np.zeros((plan.z_rows, b.shape[1]))
     Z[:n] = b
-    for q in range(len(plan.blk_K)):
+    q_asm = int(plan.launch_ptr[plan.n_forward_launches])  # first block after the forward launches
+    for q in range(len(plan.blk_K) + 1):
+        if q == q_asm:
+            for i, dst in enumerate(plan.asm_dst):
+                Z[dst] = Z[plan.asm_src[plan.asm_ptr[i] : plan.asm_ptr[i + 1]]].sum(axis=0)
+        if q == len(plan.blk_K):
+            break
         K, M = int(plan.blk_K[q]), int(plan.blk_M[q])
         sl = slice(plan.blk_iptr[q], plan.blk_iptr[q] + K)
         x = Z[plan.i0[sl]]

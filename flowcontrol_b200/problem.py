@@ -114,6 +114,7 @@ class FlowProblem:
         shift: float = 0.0,
         pin_pressure: bool = False,
         leaf_cells: int = 16,
+        top_levels: int = 2,
         symbolic: SymbolicFactor | None = None,
     ):
         self.tab, self.blocks = tab, blocks
@@ -146,7 +147,7 @@ class FlowProblem:
             self.A_raw[order] = A
             fac = BlockFactor(self.sym, A)
             self.factors[order] = fac
-            self.plans[order] = build_plan(fac)
+            self.plans[order] = build_plan(fac, top_levels=top_levels)
             # rhs contribution per unit u_ctrl_k in solver row order: (F_k - A[:,Gamma] shape_k)[perm]
             lift = (A @ G.T).toarray().T if na else np.zeros((0, tab.N))
             self.ctrl_rhs[order] = np.ascontiguousarray((force - lift)[:, self.sym.perm])

@@ -65,6 +65,12 @@ typedef struct fcb_plan {
     int32_t nlaunch;
     const int32_t* launch_ptr; /* [nlaunch+1] block ranges; blocks of a launch are independent      */
     int32_t n_forward_launches;
+    /* gather-sum executed after the forward launches: Z[asm_dst[i]] = sum of Z[asm_src[j]], asm_ptr[i] <= j < asm_ptr[i+1]
+     * (right-hand side of the merged top of the elimination tree); asm_n may be 0 */
+    int32_t asm_n;
+    const int32_t* asm_ptr; /* [asm_n+1] */
+    const int32_t* asm_src;
+    const int32_t* asm_dst; /* [asm_n] */
 } fcb_plan;
 
 /* Everything that is constant over a run and shared by the whole ensemble.

@@ -133,9 +133,12 @@ def test_multifrontal_matches_superlu_and_plan_matches_factor(small):
     Aff = A[sym.perm][:, sym.perm].tocsc()
     xref = spla.splu(Aff).solve(b)
     assert np.linalg.norm(x - xref) / np.linalg.norm(xref) < 1e-11
-    plan = build_plan(fac)
-    assert np.abs(apply_plan_host(plan, b) - x).max() < 1e-12 * np.abs(x).max()
-    assert plan.i0.max() <= plan.zrow and plan.nnz == sym.factor_entries()
+    plan0 = build_plan(fac, top_levels=0)
+    assert np.abs(apply_plan_host(plan0, b) - x).max() < 1e-12 * np.abs(x).max()
+    assert plan0.i0.max() <= plan0.zrow and plan0.nnz == sym.factor_entries() and len(plan0.asm_dst) == 0
+    for tl in (1, 2, 4, 99):  # merged top of the tree (explicit inverse of the top Schur complement)
+        assert np.abs(apply_plan_host(build_plan(fac, top_levels=tl), b) - x).max() < 1e-12 * np.abs(x).max()
+    plan = build_plan(fac, top_levels=2)
     # every x row and every y row is produced exactly once; blocks of one launch never read rows
     # that the same launch writes
     n = sym.n
@@ -143,8 +146,8 @@ def test_multifrontal_matches_superlu_and_plan_matches_factor(small):
     rows_x = np.concatenate([np.arange(o, o + r) for o, r in zip(plan.blk_out0[bw], plan.blk_M[bw])])
     assert sorted(rows_x.tolist()) == list(range(n))
     ys = plan.blk_ystore >= 0
-    rows_y = np.concatenate([np.arange(o, o + k) for o, k in zip(plan.blk_ystore[ys], plan.blk_K[ys])])
-    assert sorted(rows_y.tolist()) == list(range(n, 2 * n))
+    rows_y = np.concatenate([np.arange(o, o + k) for o, k in zip(plan.blk_ystore[ys], plan.blk_K[ys])] + [plan.asm_dst])
+    assert sorted(rows_y.tolist()) == list(range(n, 2 * n))  # y rows: stored by a forward block or assembled for the top
     for l in range(len(plan.launch_ptr) - 1):
         written, read = set(), set()
         for q in range(plan.launch_ptr[l], plan.launch_ptr[l + 1]):

@@ -28,7 +28,7 @@ def near(a, b, tol=3e-16):
     return np.abs(a - b) <= tol
 
 
-def build_cylinder_problem(leaf_cells=16):
+def build_cylinder_problem(leaf_cells=16, top_levels=2):
     tab = TaylorHoodTables.from_file(ROOT / "data/meshes/cylinder_O1.npz")
     blocks = ScalarBlocks(tab)
     r = 0.5
@@ -45,7 +45,7 @@ def build_cylinder_problem(leaf_cells=16):
     sensors = [SensorPoint(sensor_type=SENSOR_TYPE.V, position=np.array(p)) for p in ((3.0, 0.0), (3.1, 1.0), (3.1, -1.0))]
     UP0 = np.load(ROOT / "tests/golden/cylinder_baseflow.npz")["UP0"]
     t0 = time.time()
-    prob = FlowProblem(tab, blocks, 100.0, 0.005, bcs, acts, sensors, UP0, leaf_cells=leaf_cells)
+    prob = FlowProblem(tab, blocks, 100.0, 0.005, bcs, acts, sensors, UP0, leaf_cells=leaf_cells, top_levels=top_levels)
     print(f"problem setup {time.time() - t0:.1f}s  n_free={prob.sym.n} factor entries={prob.sym.factor_entries() / 1e6:.2f}M "
           f"launches={len(prob.plans[2].launch_ptr) - 1}", flush=True)
     return prob, UP0
@@ -65,7 +65,7 @@ if __name__ == "__main__":
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
     nsteps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
     import os
-    prob, UP0 = build_cylinder_problem(leaf_cells=int(os.environ.get("FCB_LEAF", "16")))
+    prob, UP0 = build_cylinder_problem(leaf_cells=int(os.environ.get("FCB_LEAF", "16")), top_levels=int(os.environ.get("FCB_TOP", "2")))
     tab = prob.tab
     ic = default_ic(tab, UP0)
     ens = Ensemble(prob, B)
