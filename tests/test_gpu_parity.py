@@ -360,3 +360,60 @@ def test_cavity_force_actuator_golden_trajectory(root, built_lib):
     y_forced = ens.y_meas[:, 0].copy()
     assert np.all(np.isfinite(y_forced)) and not ens.diverged.any()
     ens.close()
+
+
+def test_pinball_golden_trajectory_and_rotation_actuators(root, built_lib):
+    """Fluidic pinball (302 k dofs): (a) the reference's regression scenario (test_pinball.py:69-110: Re=30, suction
+    mode, 10 steps) through the CUDA path against the oracle trajectory; (b) rotation mode (BASELINE configs[2]):
+    the three cylinder surfaces carry exactly the rotation profile x u_ctrl of each trajectory (actuator.py:241-251)."""
+    import tempfile
+    from pathlib import Path
+
+    from flowcontrol_b200.actuator import CYLINDER_ACTUATION_MODE
+    from flowcontrol_b200.ensemble import Ensemble
+    from flowcontrol_b200.examples.pinball import PinballFlowSolver
+    from flowcontrol_b200.flowfield import Field
+    from flowcontrol_b200.problem import FlowProblem
+
+    UP0 = np.load(root / "tests/golden/pinball_baseflow.npz")["UP0"]
+    gold = np.load(root / "tests/golden/pinball_traj.npz")
+    fs = PinballFlowSolver.make_default(Re=30.0, mode_actuation=CYLINDER_ACTUATION_MODE.SUCTION, path_out=Path(tempfile.mkdtemp()))
+    tab = fs.tables
+    fs._assign_steady_state(Field(UP0[: tab.Nv]), Field(UP0[tab.Nv :]))
+    prob = FlowProblem(tab, fs.blocks, 30.0, 0.005, fs.bc.bcu, fs.params_control.actuator_list,
+                       fs.params_control.sensor_list, UP0)
+    ic = fs._default_initial_perturbation()
+    B = 32
+    ens = Ensemble(prob, B)
+    y0 = ens.set_state(ic[: tab.Nv], None, ic[tab.Nv :], order=1)
+    assert np.allclose(y0[:, 0], gold["y_meas"][0], rtol=1e-9)
+    for i in range(10):
+        ens.step(np.repeat(gold["u_ctrl"][i][:, None], B, axis=1))
+        assert np.allclose(ens.y_meas[:, 0], gold["y_meas"][i + 1], rtol=SERIES_TOL, atol=0)
+        assert np.isclose(ens.dE[0], gold["dE"][i + 1], rtol=SERIES_TOL)
+    assert np.isclose(np.linalg.norm(ens.fields(0)[:, 0]), float(gold["up_norm"]), rtol=1e-9)
+    ens.close()
+    # (b) rotation mode on the same mesh (the suction base flow is only a linearisation point here)
+    fr = PinballFlowSolver.make_default(Re=30.0, mode_actuation=CYLINDER_ACTUATION_MODE.ROTATION, path_out=Path(tempfile.mkdtemp()))
+    fr._assign_steady_state(Field(UP0[: tab.Nv]), Field(UP0[tab.Nv :]))
+    acts = fr.params_control.actuator_list
+    pr = FlowProblem(fr.tables, fr.blocks, 30.0, 0.005, fr.bc.bcu, acts, fr.params_control.sensor_list, UP0)
+    er = Ensemble(pr, B)
+    er.set_state(ic[: tab.Nv], None, ic[tab.Nv :], order=1)
+    rng = np.random.default_rng(3)
+    uc = rng.uniform(-2, 2, size=(3, B))
+    for _ in range(2):
+        er.step(uc)
+    up = er.fields(0)
+    d = pr.dirichlet
+    assert np.abs(up[d.dofs] - (d.const[:, None] + d.shape.T @ uc)).max() == 0.0  # Dirichlet rows are imposed exactly
+    xy = fr.tables.node_xy
+    for k, a in enumerate(acts):  # the surface of cylinder k rotates with u_ctrl[k] * d/2
+        sx, sy = a.shape(xy[:, 0], xy[:, 1])
+        on = np.flatnonzero(np.abs(np.hypot(xy[:, 0] - a.position_x, xy[:, 1] - a.position_y) - 0.5) < 1e-6)
+        on = on[np.isin(on, d.dofs)]
+        assert len(on) > 50
+        assert np.allclose(up[on], np.outer(sx[on], uc[k]), atol=1e-14)
+        assert np.allclose(np.hypot(sx[on], sy[on]), 0.5, atol=1e-12)
+    assert np.isfinite(up).all() and not er.diverged.any()
+    er.close()
