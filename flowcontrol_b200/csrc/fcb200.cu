@@ -65,16 +65,14 @@ constexpr int EP_WARPS = 4;
 
 struct PatchArgs {
     const int* pcell_ptr;          // [npatch*EP_WARPS+1] cell ranges of every warp
-    const int* pcells;             // cell ids
-    const unsigned char* plnode;   // [len(pcells)*6] accumulator row (inside the CTA) of the cell's nodes
+    const int* pcnode;             // [nslots*6] P2 node ids of every cell slot (cells listed warp by warp)
+    const double* pgeo;            // [nslots*5] Jinv (4) and |det J| of every cell slot
+    const unsigned char* plnode;   // [nslots*6] accumulator row (inside the CTA) of the cell's nodes
     const int* pnode_ptr;          // [npatch+1] into the per-node arrays below (unique nodes of the patch)
     const int* pnode_dst;          // >= 0: node id (interior to the patch), < 0: -(scratch slot + 1)
     const unsigned char* psrc;     // [4 per node] accumulator rows to sum (255 = none), first entry always valid
     const int* prow;               // [3 per node] solver rows of its ux, uy, p dofs (< 0: none / Dirichlet)
     const int* pacc_rows;          // [npatch] accumulator rows the patch uses
-    const int* cell_nodes;
-    const double* Jinv;
-    const double* detJ;
     const double* u;               // [2nN, ldb]
     double* a;
     double* b;
@@ -109,19 +107,23 @@ struct CellIn {
     double ux[6], uy[6];
 };
 
-__device__ __forceinline__ void patch_load_cell(const PatchArgs& p, int slot, int b, CellIn& c) {
-    const int cell = __ldg(p.pcells + slot);
+// Two-deep software pipeline per warp: the node ids of cell r+2 are fetched while the node values of cell r+1 are in
+// flight and cell r is being integrated; every per-cell table is stored slot by slot, so no load depends on another
+// index load.
+__device__ __forceinline__ void patch_load_ids(const PatchArgs& p, int slot, int (&nd)[6]) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) nd[i] = __ldg(p.pcnode + (size_t)slot * 6 + i);
+}
+__device__ __forceinline__ void patch_load_cell(const PatchArgs& p, int slot, const int (&nd)[6], int b, CellIn& c) {
     const size_t ldb = (size_t)p.ldb;
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
         c.ln[i] = __ldg(p.plnode + (size_t)slot * 6 + i);
-        const int nd = __ldg(p.cell_nodes + cell * 6 + i);
-        c.ux[i] = p.u[(size_t)nd * ldb + b];
-        c.uy[i] = p.u[(size_t)(nd + p.nN) * ldb + b];
+        c.ux[i] = p.u[(size_t)nd[i] * ldb + b];
+        c.uy[i] = p.u[(size_t)(nd[i] + p.nN) * ldb + b];
     }
-    c.g00 = __ldg(p.Jinv + cell * 4 + 0); c.g01 = __ldg(p.Jinv + cell * 4 + 1);
-    c.g10 = __ldg(p.Jinv + cell * 4 + 2); c.g11 = __ldg(p.Jinv + cell * 4 + 3);
-    c.det = __ldg(p.detJ + cell);
+    const double* g = p.pgeo + (size_t)slot * 5;
+    c.g00 = __ldg(g); c.g01 = __ldg(g + 1); c.g10 = __ldg(g + 2); c.g11 = __ldg(g + 3); c.det = __ldg(g + 4);
 }
 
 // grid = (npatch, ldb/32), block = (32, EP_WARPS), dynamic smem = max accumulator rows * 4 * 32 doubles
@@ -134,7 +136,9 @@ __global__ void __launch_bounds__(32 * EP_WARPS, 2) k_element_patch(const PatchA
     const int n0 = __ldg(p.pnode_ptr + blockIdx.x), nn = __ldg(p.pnode_ptr + blockIdx.x + 1) - n0;
     const int nrows = __ldg(p.pacc_rows + blockIdx.x);
     CellIn cur, nxt;
-    if (c0 < c1) patch_load_cell(p, c0, b, cur);
+    int ids[6];
+    if (c0 < c1) { patch_load_ids(p, c0, ids); patch_load_cell(p, c0, ids, b, cur); }
+    if (c0 + 1 < c1) patch_load_ids(p, c0 + 1, ids);
     // accumulators start at zero, except (fused right-hand side) the a rows of the patch's own nodes, which start from
     // b_{n-1}: those loads are all in flight together with the first cell's gathers
     if (p.bprev) {
@@ -173,7 +177,8 @@ __global__ void __launch_bounds__(32 * EP_WARPS, 2) k_element_patch(const PatchA
     __syncthreads();
     double e_acc = 0.0;
     for (int r = c0; r < c1; ++r) {
-        if (r + 1 < c1) patch_load_cell(p, r + 1, b, nxt);
+        if (r + 1 < c1) patch_load_cell(p, r + 1, ids, b, nxt);
+        if (r + 2 < c1) patch_load_ids(p, r + 2, ids);
         double rx[6], ry[6];
 #pragma unroll
         for (int i = 0; i < 6; ++i) { rx[i] = 0.0; ry[i] = 0.0; }
@@ -872,7 +877,9 @@ struct fcb_context {
     // patch form of the element kernel
     int use_pdl = 1;
     int npatch = 0, nshared = 0, patch_smem = 0;
-    int *pcell_ptr = nullptr, *pcells = nullptr, *pnode_ptr = nullptr, *pnode_dst = nullptr, *mptr = nullptr, *msrc = nullptr,
+    int *pcell_ptr = nullptr, *pcnode = nullptr;
+    double* pgeo = nullptr;
+    int *pnode_ptr = nullptr, *pnode_dst = nullptr, *mptr = nullptr, *msrc = nullptr,
         *mnode = nullptr, *prow = nullptr, *mrow = nullptr, *pacc_rows = nullptr;
     unsigned char *plnode = nullptr, *psrc = nullptr;
     double* pscratch = nullptr;
@@ -1221,9 +1228,8 @@ struct PhaseMark {
 // right-hand side rows Z[0,n) <- a(u) + bprev
 int enqueue_element(fcb_context* h, const double* u, double* a, double* b, const double* bprev) {
     PatchArgs p;
-    p.pcell_ptr = h->pcell_ptr; p.pcells = h->pcells; p.plnode = h->plnode;
+    p.pcell_ptr = h->pcell_ptr; p.pcnode = h->pcnode; p.pgeo = h->pgeo; p.plnode = h->plnode;
     p.pnode_ptr = h->pnode_ptr; p.pnode_dst = h->pnode_dst; p.psrc = h->psrc; p.pacc_rows = h->pacc_rows;
-    p.cell_nodes = h->cell_nodes; p.Jinv = h->Jinv; p.detJ = h->detJ;
     p.u = u; p.a = a; p.b = b; p.scratch = h->pscratch; p.epart = h->epart;
     p.bprev = bprev; p.Zb = h->Z; p.prow = h->prow;
     p.nN = h->nN; p.nV = h->nV; p.ldb = h->ldb;
@@ -1415,7 +1421,7 @@ void destroy(fcb_context* h) {
                     h->ctrl_rhs[1], h->sensor_ptr, h->sensor_idx, h->sensor_val, h->up[0], h->up[1], h->avec,
                     h->bvec[0], h->bvec[1], h->Z, h->epart, h->uctrl, h->y, h->dE, h->diverged, h->Ad, h->Bd, h->Cd,
                     h->Dd, h->Ky, h->Fu, h->xk[0], h->xk[1], h->series, h->counter, h->sweep_dbg,
-                    h->pcell_ptr, h->pcells, h->pnode_ptr, h->pnode_dst, h->mptr, h->msrc, h->mnode, h->plnode, h->pscratch, h->prow, h->mrow, h->psrc, h->pacc_rows};
+                    h->pcell_ptr, h->pcnode, h->pgeo, h->pnode_ptr, h->pnode_dst, h->mptr, h->msrc, h->mnode, h->plnode, h->pscratch, h->prow, h->mrow, h->psrc, h->pacc_rows};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (int i = 0; i < 2; ++i) {
@@ -1491,7 +1497,8 @@ int build_patches(fcb_context* h, const fcb_problem* p, const std::vector<int>& 
         for (int lo = 0; lo < nT; lo += pc) patch_range.push_back({lo, std::min(nT, lo + pc)});
     }
     const int npatch = (int)patch_range.size();
-    std::vector<int> pcell_ptr(1, 0), pcells, pnode_ptr(1, 0), pnode_dst, node_npatch(nN, 0), pacc_rows;
+    std::vector<int> pcell_ptr(1, 0), pcells, pcnode, pnode_ptr(1, 0), pnode_dst, node_npatch(nN, 0), pacc_rows;
+    std::vector<double> pgeo;
     std::vector<unsigned char> plnode, psrc;
     std::vector<std::vector<int>> patch_nodes(npatch);
     std::vector<int> local(nN, -1), uniq(nN, -1);
@@ -1509,8 +1516,11 @@ int build_patches(fcb_context* h, const fcb_problem* p, const std::vector<int>& 
             for (int k = cut[g]; k < cut[g + 1]; ++k) {
                 const int e = key[k].second;
                 pcells.push_back(e);
+                for (int i = 0; i < 4; ++i) pgeo.push_back(p->Jinv[(size_t)e * 4 + i]);
+                pgeo.push_back(p->detJ[e]);
                 for (int i = 0; i < 6; ++i) {
                     const int nd = p->cell_nodes[e * 6 + i];
+                    pcnode.push_back(nd);
                     if (local[nd] < 0) {
                         local[nd] = rows++;
                         touched.push_back(nd);
@@ -1571,7 +1581,8 @@ int build_patches(fcb_context* h, const fcb_problem* p, const std::vector<int>& 
     CK(cudaFuncSetAttribute(k_element_patch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->patch_smem));
     CK(cudaFuncSetAttribute(k_element_patch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->patch_smem));
     TRY(upload(h, &h->pcell_ptr, pcell_ptr.data(), pcell_ptr.size()));
-    TRY(upload(h, &h->pcells, pcells.data(), pcells.size()));
+    TRY(upload(h, &h->pcnode, pcnode.data(), pcnode.size()));
+    TRY(upload(h, &h->pgeo, pgeo.data(), pgeo.size()));
     TRY(upload(h, &h->plnode, plnode.data(), plnode.size()));
     TRY(upload(h, &h->pnode_ptr, pnode_ptr.data(), pnode_ptr.size()));
     TRY(upload(h, &h->pnode_dst, pnode_dst.data(), pnode_dst.size()));
