@@ -16,7 +16,7 @@ from ..actuator import ActuatorBCParabolicV
 from ..flowfield import BoundaryConditions
 from ..flowsolver import FlowSolver, SubDomain, between, near
 from ..problem import DirichletBC
-from ..sensor import SENSOR_TYPE, SensorPoint
+from ..sensor import SENSOR_TYPE, SensorForceCoefficient, SensorPoint
 
 DATA = Path(__file__).resolve().parents[2] / "data" / "meshes"
 
@@ -54,6 +54,29 @@ class CylinderFlowSolver(FlowSolver):
             ],
             bcp=[],
         )
+
+    def force_sensors(self) -> list:
+        """[lift, drag] measurement rows of the cylinder (surfaces cylinder + actuator_up + actuator_lo,
+        cylinderflowsolver.py:115-126); append them to ``params_control.sensor_list`` to log cl, cd every step."""
+        subs = [self.get_subdomain(n).inside for n in ("cylinder", "actuator_up", "actuator_lo")]
+        D = self.params_flow.user_data["D"]
+        nu = self.params_flow.uinf * D / self.params_flow.Re
+
+        def body(x, y):
+            return subs[0](x, y) | subs[1](x, y) | subs[2](x, y)
+
+        return [SensorForceCoefficient(sensor_type=SENSOR_TYPE.OTHER, inside=body, component=c, nu=nu,
+                                       uinf=self.params_flow.uinf, D=D) for c in (1, 0)]
+
+    def compute_force_coefficients(self, u, p) -> tuple[float, float]:
+        """(cl, cd) of the fields (u, p) (numpy arrays or Field objects), cylinderflowsolver.py:115-126."""
+        vec = np.concatenate([np.asarray(u.vector().get_local() if hasattr(u, "vector") else u),
+                              np.asarray(p.vector().get_local() if hasattr(p, "vector") else p)])
+        out = []
+        for s in self.force_sensors():
+            idx, val = s.row(self.tables)
+            out.append(float(val @ vec[idx]))
+        return out[0], out[1]
 
     @classmethod
     def make_default(cls, Re: float = 100, path_out=None, num_steps: int = 10, save_every: int = 0,

@@ -15,7 +15,7 @@ from ..actuator import CYLINDER_ACTUATION_MODE, ActuatorBCParabolicV, ActuatorBC
 from ..flowfield import BoundaryConditions
 from ..flowsolver import FlowSolver, SubDomain, between, near
 from ..problem import DirichletBC
-from ..sensor import SENSOR_TYPE, SensorPoint
+from ..sensor import SENSOR_TYPE, SensorForceCoefficient, SensorPoint
 
 DATA = Path(__file__).resolve().parents[2] / "data" / "meshes"
 C30 = 1.5 * np.cos(np.pi / 6)
@@ -78,6 +78,26 @@ class PinballFlowSolver(FlowSolver):
         return BoundaryConditions(
             bcu=[DirichletBC(sub("inlet"), (0, 1), uni), DirichletBC(sub("walls"), (0, 1), uni)] + self._tail_bcs(), bcp=[]
         )
+
+    def compute_force_coefficients(self, u, p) -> dict:
+        """{surface: (cl, cd)} for each cylinder surface (pinballflowsolver.py:202-232)."""
+        vec = np.concatenate([np.asarray(u.vector().get_local() if hasattr(u, "vector") else u),
+                              np.asarray(p.vector().get_local() if hasattr(p, "vector") else p)])
+        D = self.params_flow.user_data["D"]
+        nu = self.params_flow.uinf * D / self.params_flow.Re
+        if self.params_control.user_data["mode_actuation"] == CYLINDER_ACTUATION_MODE.SUCTION:
+            names = ["cylinder_mid", "actuator_mid", "cylinder_top", "actuator_top", "cylinder_bot", "actuator_bot"]
+        else:
+            names = ["actuator_mid", "actuator_top", "actuator_bot"]
+        out = {}
+        for name in names:
+            vals = []
+            for c in (1, 0):
+                idx, val = SensorForceCoefficient(sensor_type=SENSOR_TYPE.OTHER, inside=self.get_subdomain(name).inside,
+                                                  component=c, nu=nu, uinf=self.params_flow.uinf, D=D).row(self.tables)
+                vals.append(float(val @ vec[idx]))
+            out[name] = (vals[0], vals[1])
+        return out
 
     @classmethod
     def make_default(cls, Re: float = 50, mode_actuation=None, path_out=None, num_steps: int = 10, save_every: int = 0,

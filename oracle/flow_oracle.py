@@ -425,6 +425,41 @@ def sensor_row(mesh: TaylorHoodMesh, s: SensorSpec):
     raise ValueError(s.kind)
 
 
+def force_coefficients(mesh: TaylorHoodMesh, inside, up: np.ndarray, nu: float, uinf: float = 1.0, D: float = 1.0):
+    """(cl, cd) of the body whose boundary facets satisfy ``inside``: int -(2 nu sym(grad u) - p I).n ds / (U^2 D / 2)
+    with n = FacetNormal (out of the fluid), evaluated on the mixed vector ``up`` by 2-point Gauss quadrature on every
+    facet (examples/cylinder/cylinderflowsolver.py:115-126, utils/physics.py:17-19)."""
+    edges = mesh.mark_facets(inside)
+    ecell = dict(zip(mesh.bnd_edges.tolist(), mesh.bnd_edge_cell.tolist()))
+    gp = 0.5 + np.array([-0.5, 0.5]) / np.sqrt(3.0)
+    F = np.zeros(2)
+    ux, uy, pr = up[: mesh.nN], up[mesh.nN : mesh.Nv], up[mesh.Nv :]
+    for e in edges:
+        c = ecell[int(e)]
+        a, b = mesh.edges[e]
+        xa, xb = mesh.xy[a], mesh.xy[b]
+        t = xb - xa
+        length = float(np.hypot(*t))
+        n = np.array([t[1], -t[0]]) / length
+        centroid = mesh.xy[mesh.tri[c]].mean(axis=0)
+        if n @ (centroid - xa) > 0:
+            n = -n
+        nodes = mesh.cell_nodes[c]
+        for s_ in gp:
+            x = xa + s_ * t
+            ref = mesh.Jinv[c] @ (x - mesh.xy[mesh.tri[c, 0]])
+            _, dref = p2_basis(np.array([ref[0]]), np.array([ref[1]]))
+            psi = p1_basis(np.array([ref[0]]), np.array([ref[1]]))[0]
+            dphys = dref[0] @ mesh.Jinv[c]  # [6, 2]
+            gu = np.array([ux[nodes] @ dphys, uy[nodes] @ dphys])  # gu[i, j] = d_j u_i
+            pq = psi @ pr[mesh.tri[c]]
+            sigma = nu * (gu + gu.T) - pq * np.eye(2)
+            F += 0.5 * length * (-(sigma @ n))
+    drag, lift = F
+    q = 0.5 * uinf**2 * D
+    return lift / q, drag / q
+
+
 # --------------------------------------------------------------------------- #
 # LTI controller (controller.py:121-159)
 # --------------------------------------------------------------------------- #

@@ -417,3 +417,49 @@ def test_pinball_golden_trajectory_and_rotation_actuators(root, built_lib):
         assert np.allclose(np.hypot(sx[on], sy[on]), 0.5, atol=1e-12)
     assert np.isfinite(up).all() and not er.diverged.any()
     er.close()
+
+
+def test_lift_drag_time_series_200_steps(root, cyl):
+    """Lift/drag coefficient rows (examples/cylinder/cylinderflowsolver.py:115-126 made a per-step measurement)
+    logged on the device over 200 closed-loop steps vs the oracle: sensor and lift series within 1e-6
+    (BASELINE.json north_star tolerance for the time series)."""
+    from flowcontrol_b200.controller import Controller, ControllerBank
+    from flowcontrol_b200.ensemble import Ensemble
+    from flowcontrol_b200.problem import FlowProblem
+    from oracle.flow_oracle import force_coefficients
+
+    fs, prob0, orc, UP0 = cyl
+    tab = prob0.tab
+    sensors = list(fs.params_control.sensor_list) + fs.force_sensors()
+    prob = FlowProblem(tab, fs.blocks, 100.0, 0.005, fs.bc.bcu, fs.params_control.actuator_list, sensors, UP0,
+                       symbolic=prob0.sym)
+    ic = fs._default_initial_perturbation()
+    B, nsteps = 32, 200
+    k = np.load(root / "tests/golden/Kopt_reduced13.npz")
+    ctrls = [Controller(k["A"], k["B"], k["C"], k["D"]) for _ in range(B)]
+    Ky, Fu = np.array([[-1.0, 0.0, 0.0, 0.0, 0.0]]), np.array([[1.0], [1.0]])
+    ens = Ensemble(prob, B)
+    ens.set_state(ic[: tab.Nv], None, ic[tab.Nv :], order=1)
+    ens.set_controllers(ControllerBank(ctrls, prob.dt, Ky, Fu))
+    series = ens.run_closed_loop(nsteps)  # columns: dE, u1, u2, y1..y3, cl, cd
+    assert series.shape == (nsteps, 8, B)
+    orc.case.ic = (0.0, 0.0, 1.0, 1.0)
+    orc.init_time_stepping()
+    K = ZOHController(k["A"], k["B"], k["C"], k["D"])
+    body = lambda x, y: np.hypot(x, y) < 0.6  # noqa: E731  every boundary facet of the cylinder
+    ref = np.zeros((nsteps, 5))
+    for s_ in range(nsteps):
+        u = K.step(-orc.y_meas[0], prob.dt)
+        orc.step([u[0], u[0]])
+        ref[s_, :3] = orc.y_meas
+        ref[s_, 3:] = force_coefficients(orc.mesh, body, orc.up, 0.01, 1.0, 1.0)
+    got = series[:, 3:, 0]
+    scale = np.abs(ref).max(axis=0)
+    assert (np.abs(got - ref).max(axis=0) / scale).max() < SERIES_TOL
+    assert np.abs(series - series[:, :, :1]).max() == 0.0  # identical controllers -> identical trajectories
+    # host-side evaluation on the full field agrees with base-flow value + logged perturbation part
+    cl0, cd0 = fs.compute_force_coefficients(UP0[: tab.Nv], UP0[tab.Nv :])
+    up = ens.fields(0)[:, 0]
+    cl, cd = fs.compute_force_coefficients(UP0[: tab.Nv] + up[: tab.Nv], UP0[tab.Nv :] + up[tab.Nv :])
+    assert np.isclose(cl, cl0 + series[-1, 6, 0], rtol=1e-9, atol=1e-12) and np.isclose(cd, cd0 + series[-1, 7, 0], rtol=1e-9)
+    ens.close()

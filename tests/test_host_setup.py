@@ -223,3 +223,39 @@ def test_force_actuator_unit_norm(small):
 
 def test_parabolic_width_helper():
     assert np.isclose(ActuatorBCParabolicV.angular_size_deg_to_width(10, 0.5), 0.5 * np.sin(np.deg2rad(5)))
+
+
+def test_force_coefficient_rows_match_oracle_and_closed_surface_identity():
+    """SensorForceCoefficient rows (product) vs the oracle's quadrature evaluation on random fields, and the exact
+    identity  oint p n ds = -Area * grad p  for a linear pressure on a closed polygonal hole (u = 0)."""
+    from flowcontrol_b200.sensor import SensorForceCoefficient
+
+    # square [0,1]^2 with a square hole [0.25,0.75]^2 removed (structured 8x8 grid)
+    xy, tri = unit_square_mesh(8)
+    cent = xy[tri].mean(axis=1)
+    keep = ~((cent[:, 0] > 0.25) & (cent[:, 0] < 0.75) & (cent[:, 1] > 0.25) & (cent[:, 1] < 0.75))
+    tri = tri[keep]
+    used = np.unique(tri)
+    remap = -np.ones(len(xy), dtype=np.int64)
+    remap[used] = np.arange(len(used))
+    xy, tri = xy[used], remap[tri].astype(np.int32)
+    tab = TaylorHoodTables.from_arrays(xy, tri)
+    om = fo.TaylorHoodMesh(xy, tri)
+
+    def hole(x, y):
+        return (x > 0.2) & (x < 0.8) & (y > 0.2) & (y < 0.8)
+
+    nu, uinf, D = 0.013, 1.3, 0.5
+    rows = [SensorForceCoefficient(sensor_type=SENSOR_TYPE.OTHER, inside=hole, component=c, nu=nu, uinf=uinf, D=D).row(tab)
+            for c in (1, 0)]  # lift, drag
+    rng = np.random.default_rng(4)
+    up = rng.standard_normal(tab.N)
+    cl, cd = fo.force_coefficients(om, hole, up, nu, uinf, D)
+    assert np.isclose(rows[0][1] @ up[rows[0][0]], cl, rtol=1e-12)
+    assert np.isclose(rows[1][1] @ up[rows[1][0]], cd, rtol=1e-12)
+    # u = 0, p = 2x - 3y: force on the hole = -Area * grad p (n points into the hole)
+    up = np.zeros(tab.N)
+    up[tab.Nv :] = 2.0 * tab.xy[:, 0] - 3.0 * tab.xy[:, 1]
+    q = 0.5 * uinf**2 * D
+    assert np.isclose(rows[1][1] @ up[rows[1][0]], -0.25 * 2.0 / q, rtol=1e-12)   # drag
+    assert np.isclose(rows[0][1] @ up[rows[0][0]], -0.25 * -3.0 / q, rtol=1e-12)  # lift
