@@ -78,18 +78,26 @@ struct PatchArgs {
     double* b;
     double* scratch;               // [nslots, 4, ldb]
     double* epart;                 // [npatch, ldb]
-    const double* bprev;           // b of the previous state (fused rhs), or NULL: store a instead
+    const double* bprev;           // b of the previous state (fused BDF rhs), else NULL
     double* Zb;
+    int mode;                      // 0: store a and b; 1: Zb rows = a + bprev, store b (BDF); 2: Zb rows += a (Crank-Nicolson)
     int nN, nV, ldb;
-    double ca, cb;
+    double ca, cb, na, nb;         // a = ca M u + na N(u), b = cb M u + nb N(u)
 };
 
 // a/b rows of one node go out: either as a and b, or (fused) as next-step rhs rows and b
-template <bool ADD_BPREV>  // false: the caller's ax, ay already contain b_{n-1}
-__device__ __forceinline__ void emit_node(const double* bprev, double* Zb, int rx, int ry, int rp, double* a, double* bout, int nN,
-                                          size_t ldb, int nd, int b, double ax, double ay, double bx, double by) {
+// rows of one node go out.  mode 0: a and b; mode 1 (fused BDF): next-step rhs rows Zb = a (+ bprev if ADD_BPREV, else the
+// caller's a already contains it) and b; mode 2 (Crank-Nicolson): Zb rows += a (k_spmm wrote E u_n there before)
+template <bool ADD_BPREV>
+__device__ __forceinline__ void emit_node(int mode, const double* bprev, double* Zb, int rx, int ry, int rp, double* a, double* bout,
+                                          int nN, size_t ldb, int nd, int b, double ax, double ay, double bx, double by) {
     const size_t ox = (size_t)nd * ldb + b, oy = (size_t)(nd + nN) * ldb + b;
-    if (bprev) {
+    if (mode == 2) {
+        if (rx >= 0) Zb[(size_t)rx * ldb + b] += ax;
+        if (ry >= 0) Zb[(size_t)ry * ldb + b] += ay;
+        return;
+    }
+    if (mode == 1) {
         if (rx >= 0) Zb[(size_t)rx * ldb + b] = ADD_BPREV ? ax + bprev[ox] : ax;
         if (ry >= 0) Zb[(size_t)ry * ldb + b] = ADD_BPREV ? ay + bprev[oy] : ay;
         if (rp >= 0) Zb[(size_t)rp * ldb + b] = 0.0;  // continuity rows of the rhs are zero (the solve left the pressure there)
@@ -141,7 +149,7 @@ __global__ void __launch_bounds__(32 * EP_WARPS, 2) k_element_patch(const PatchA
     if (c0 + 1 < c1) patch_load_ids(p, c0 + 1, ids);
     // accumulators start at zero, except (fused right-hand side) the a rows of the patch's own nodes, which start from
     // b_{n-1}: those loads are all in flight together with the first cell's gathers
-    if (p.bprev) {
+    if (p.mode == 1) {
         const size_t ldb = (size_t)p.ldb;
         const int chunk = (nn + EP_WARPS - 1) / EP_WARPS;
         for (int j0 = w * chunk; j0 < min(nn, (w + 1) * chunk); j0 += 32) {
@@ -221,10 +229,10 @@ __global__ void __launch_bounds__(32 * EP_WARPS, 2) k_element_patch(const PatchA
             e_acc = fma(cur.ux[i], mx, e_acc);
             e_acc = fma(cur.uy[i], my, e_acc);
             double* s = acc + (size_t)cur.ln[i] * 128 + lane;  // rows of this warp's sub-patch: nobody else touches them
-            s[0] += p.ca * mx - 2.0 * rx[i];
-            s[32] += p.ca * my - 2.0 * ry[i];
-            s[64] += p.cb * mx + rx[i];
-            s[96] += p.cb * my + ry[i];
+            s[0] += p.ca * mx + p.na * rx[i];
+            s[32] += p.ca * my + p.na * ry[i];
+            s[64] += p.cb * mx + p.nb * rx[i];
+            s[96] += p.cb * my + p.nb * ry[i];
         }
         cur = nxt;
     }
@@ -240,7 +248,7 @@ __global__ void __launch_bounds__(32 * EP_WARPS, 2) k_element_patch(const PatchA
         if (lane < cnt) {
             l_dst = __ldg(p.pnode_dst + n0 + j0 + lane);
             l_src = __ldg(reinterpret_cast<const unsigned*>(p.psrc) + n0 + j0 + lane);
-            if (p.bprev) {
+            if (p.mode != 0) {
                 l_rx = __ldg(p.prow + (size_t)(n0 + j0 + lane) * 3 + 0);
                 l_ry = __ldg(p.prow + (size_t)(n0 + j0 + lane) * 3 + 1);
                 l_rp = __ldg(p.prow + (size_t)(n0 + j0 + lane) * 3 + 2);
@@ -263,7 +271,7 @@ __global__ void __launch_bounds__(32 * EP_WARPS, 2) k_element_patch(const PatchA
                 }
             }
             if (dst >= 0) {
-                emit_node<false>(p.bprev, p.Zb, rx, ry, rp, p.a, p.b, p.nN, ldb, dst, b, v0, v1, v2, v3);
+                emit_node<false>(p.mode, p.bprev, p.Zb, rx, ry, rp, p.a, p.b, p.nN, ldb, dst, b, v0, v1, v2, v3);
             } else {
                 double* z = p.scratch + (size_t)(-1 - dst) * 4 * ldb + b;
                 z[0] = v0; z[ldb] = v1; z[2 * ldb] = v2; z[3 * ldb] = v3;
@@ -286,7 +294,7 @@ __global__ void __launch_bounds__(32 * EP_WARPS, 2) k_element_patch(const PatchA
 __global__ void __launch_bounds__(256) k_patch_merge(int nshared, const int* __restrict__ mptr, const int* __restrict__ msrc,
                                                     const int* __restrict__ mnode, const int* __restrict__ mrow,
                                                     const double* __restrict__ scratch, double* a, double* bvec,
-                                                    const double* bprev, double* Zb, int nN, int ldb) {
+                                                    const double* bprev, double* Zb, int mode, int nN, int ldb) {
     const int i = blockIdx.x * blockDim.y + threadIdx.y;
     const int b = blockIdx.y * 32 + threadIdx.x;
     if (i >= nshared) return;
@@ -298,7 +306,28 @@ __global__ void __launch_bounds__(256) k_patch_merge(int nshared, const int* __r
         const double* z = scratch + (size_t)__ldg(msrc + k) * 4 * L + b;
         s0 += z[0]; s1 += z[L]; s2 += z[2 * L]; s3 += z[3 * L];
     }
-    emit_node<true>(bprev, Zb, rx, ry, rp, a, bvec, nN, L, nd, b, s0, s1, s2, s3);
+    emit_node<true>(mode, bprev, Zb, rx, ry, rp, a, bvec, nN, L, nd, b, s0, s1, s2, s3);
+}
+
+// CSR SpMM over the ensemble's multi-RHS block: Z[r] = sum_j val[j] * X[idx[j]] for the n solver rows (Crank-Nicolson explicit
+// operator E = M/dt - (C + D + K/Re)/2 applied to u_n).  One warp = one row x 32 trajectories: column indices and values
+// are warp-uniform (broadcast), every X access is a coalesced 256-byte row segment, consecutive rows are neighbours in
+// the mesh (nested-dissection order) and share most of their columns through L1.  grid = (ceil(n/8), ldb/32), block = (32, 8)
+__global__ void __launch_bounds__(256) k_spmm(int n, const int* __restrict__ ptr, const int* __restrict__ idx,
+                                             const double* __restrict__ val, const double* __restrict__ X, double* __restrict__ Z,
+                                             int ldb) {
+    const int r = blockIdx.x * blockDim.y + threadIdx.y;
+    const int b = blockIdx.y * 32 + threadIdx.x;
+    if (r >= n) return;
+    const int j0 = __ldg(ptr + r), j1 = __ldg(ptr + r + 1);
+    double s0 = 0.0, s1 = 0.0;
+    int j = j0;
+    for (; j + 1 < j1; j += 2) {
+        s0 = fma(__ldg(val + j), X[(size_t)__ldg(idx + j) * ldb + b], s0);
+        s1 = fma(__ldg(val + j + 1), X[(size_t)__ldg(idx + j + 1) * ldb + b], s1);
+    }
+    if (j < j1) s0 = fma(__ldg(val + j), X[(size_t)__ldg(idx + j) * ldb + b], s0);
+    Z[(size_t)r * ldb + b] = s0 + s1;
 }
 
 // Z[dst[i]] = sum of Z[src[j]] (fixed order): right-hand side of the merged top of the elimination tree.
@@ -890,6 +919,11 @@ struct fcb_context {
     int* diverged = nullptr;
     int parity = 0, order = 1;
     bool rhs_ready = false;  // Z[0,n) holds the fused right-hand side of the next step
+    int scheme = 0;          // 0 = BDF1 -> BDF2, 1 = Crank-Nicolson
+    int *cn_ptr = nullptr, *cn_idx = nullptr;
+    double *cn_val = nullptr, *uctrl_prev = nullptr, *ccoef_prev = nullptr;
+    int ncrow_prev = 0;
+    int* crow_prev = nullptr;
     int ncrow = 0;           // solver rows with a non-zero control coefficient (BDF2), their coefficients [na, ncrow]
     int* crow = nullptr;
     double* ccoef = nullptr;
@@ -1228,12 +1262,20 @@ struct PhaseMark {
 // right-hand side rows Z[0,n) <- a(u) + bprev
 int enqueue_element(fcb_context* h, const double* u, double* a, double* b, const double* bprev) {
     PatchArgs p;
+    p.mode = h->scheme == 1 ? 2 : (bprev ? 1 : 0);
+    if (h->scheme == 1) {
+        // Crank-Nicolson: the rhs rows first receive E u (k_spmm), the element pass then adds -N(u) (nsforms.py:219-229)
+        dim3 grid((h->n + 7) / 8, h->ldb / 32), block(32, 8);
+        k_spmm<<<grid, block, 0, h->stream>>>(h->n, h->cn_ptr, h->cn_idx, h->cn_val, u, h->Z, h->ldb);
+        h->launches += 1;
+    }
     p.pcell_ptr = h->pcell_ptr; p.pcnode = h->pcnode; p.pgeo = h->pgeo; p.plnode = h->plnode;
     p.pnode_ptr = h->pnode_ptr; p.pnode_dst = h->pnode_dst; p.psrc = h->psrc; p.pacc_rows = h->pacc_rows;
     p.u = u; p.a = a; p.b = b; p.scratch = h->pscratch; p.epart = h->epart;
     p.bprev = bprev; p.Zb = h->Z; p.prow = h->prow;
     p.nN = h->nN; p.nV = h->nV; p.ldb = h->ldb;
-    p.ca = 2.0 / h->dt; p.cb = -0.5 / h->dt;
+    p.ca = 2.0 / h->dt; p.cb = -0.5 / h->dt; p.na = -2.0; p.nb = 1.0;  // BDF2: rhs = a_n + b_{n-1}
+    if (h->scheme == 1) { p.ca = 0.0; p.cb = 0.0; p.na = -1.0; p.nb = 0.0; }
     dim3 grid(h->npatch, h->ldb / 32), block(32, EP_WARPS);
     if (h->nonlinear) k_element_patch<true><<<grid, block, h->patch_smem, h->stream>>>(p);
     else k_element_patch<false><<<grid, block, h->patch_smem, h->stream>>>(p);
@@ -1241,7 +1283,7 @@ int enqueue_element(fcb_context* h, const double* u, double* a, double* b, const
     if (h->nshared > 0) {
         dim3 g2((h->nshared + 7) / 8, h->ldb / 32), b2(32, 8);
         k_patch_merge<<<g2, b2, 0, h->stream>>>(h->nshared, h->mptr, h->msrc, h->mnode, h->mrow, h->pscratch, a, b, bprev, h->Z,
-                                                h->nN, h->ldb);
+                                                p.mode, h->nN, h->ldb);
         h->launches += 1;
     }
     CK(cudaGetLastError());
@@ -1318,6 +1360,12 @@ int enqueue_step(fcb_context* h, int order, int parity, bool rhs_ready, PhaseMar
             k_ctrl_add<<<grid, block, 0, h->stream>>>(h->ncrow, h->crow, h->ccoef, h->na, h->uctrl, h->Z, h->ldb);
             h->launches += 1;
         }
+        if (h->scheme == 1 && h->ncrow_prev > 0 && h->na > 0) {
+            // Crank-Nicolson averages the body force over the step: + F u_ctrl^n / 2 (nsforms.py:226-229)
+            dim3 grid((h->ncrow_prev + 7) / 8, h->ldb / 32), block(32, 8);
+            k_ctrl_add<<<grid, block, 0, h->stream>>>(h->ncrow_prev, h->crow_prev, h->ccoef_prev, h->na, h->uctrl_prev, h->Z, h->ldb);
+            h->launches += 1;
+        }
     } else {
         dim3 grid((h->n + 7) / 8, h->ldb / 32), block(32, 8);
         k_rhs_build<<<grid, block, 0, h->stream>>>(h->n, h->Nv, h->perm, h->avec, h->bvec[1 - parity], order, h->na,
@@ -1337,6 +1385,8 @@ int enqueue_step(fcb_context* h, int order, int parity, bool rhs_ready, PhaseMar
     TRY(enqueue_element(h, nxt, h->avec, h->bvec[1 - parity], h->bvec[parity]));
     if (pm) pm->mark(FCB_PHASE_MEASURE);
     TRY(enqueue_measure(h, nxt));
+    if (h->scheme == 1 && h->na > 0)
+        CK(cudaMemcpyAsync(h->uctrl_prev, h->uctrl, (size_t)h->na * h->ldb * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     if (pm) pm->mark(FCB_NPHASES);
     CK(cudaGetLastError());
     return FCB_OK;
@@ -1417,7 +1467,7 @@ void destroy(fcb_context* h) {
         for (int j = 0; j < 2; ++j)
             if (h->g_loop[i][j]) cudaGraphExecDestroy(h->g_loop[i][j]);
     }
-    void* ptrs[] = {h->crow, h->ccoef, h->bc_dofs, h->cell_nodes, h->perm, h->iperm, h->Jinv, h->detJ, h->bc_shape, h->ctrl_rhs[0],
+    void* ptrs[] = {h->cn_ptr, h->cn_idx, h->cn_val, h->uctrl_prev, h->ccoef_prev, h->crow_prev, h->crow, h->ccoef, h->bc_dofs, h->cell_nodes, h->perm, h->iperm, h->Jinv, h->detJ, h->bc_shape, h->ctrl_rhs[0],
                     h->ctrl_rhs[1], h->sensor_ptr, h->sensor_idx, h->sensor_val, h->up[0], h->up[1], h->avec,
                     h->bvec[0], h->bvec[1], h->Z, h->epart, h->uctrl, h->y, h->dE, h->diverged, h->Ad, h->Bd, h->Cd,
                     h->Dd, h->Ky, h->Fu, h->xk[0], h->xk[1], h->series, h->counter, h->sweep_dbg,
@@ -1693,19 +1743,35 @@ int create_impl(fcb_context* h, const fcb_problem* p, int B) {
     TRY(upload(h, &h->bc_shape, p->bc_shape, (size_t)p->na * p->n_bc));
     for (int o = 0; o < 2; ++o) TRY(upload(h, &h->ctrl_rhs[o], p->ctrl_rhs[o], (size_t)p->na * p->n_free));
     TRY(upload(h, &h->bc_dofs, p->bc_dofs, (size_t)p->n_bc));
-    {
-        // the control terms of the BDF2 right-hand side touch only the rows next to the actuated boundaries / force support
+    // the control terms of the steady-state right-hand side touch only the rows next to the actuated boundaries / force support
+    auto sparse_rows = [&](const double* dense, int* count, int** drows, double** dcoef) -> int {
         std::vector<int> rows;
         for (int r = 0; r < p->n_free; ++r)
             for (int k = 0; k < p->na; ++k)
-                if (p->ctrl_rhs[1][(size_t)k * p->n_free + r] != 0.0) { rows.push_back(r); break; }
+                if (dense[(size_t)k * p->n_free + r] != 0.0) { rows.push_back(r); break; }
         std::vector<double> coef((size_t)p->na * rows.size());
         for (int k = 0; k < p->na; ++k)
-            for (size_t i = 0; i < rows.size(); ++i) coef[(size_t)k * rows.size() + i] = p->ctrl_rhs[1][(size_t)k * p->n_free + rows[i]];
-        h->ncrow = (int)rows.size();
-        TRY(upload(h, &h->crow, rows.data(), std::max<size_t>(rows.size(), 1)));
-        TRY(upload(h, &h->ccoef, coef.data(), std::max<size_t>(coef.size(), 1)));
+            for (size_t i = 0; i < rows.size(); ++i) coef[(size_t)k * rows.size() + i] = dense[(size_t)k * p->n_free + rows[i]];
+        *count = (int)rows.size();
+        TRY(upload(h, drows, rows.data(), std::max<size_t>(rows.size(), 1)));
+        TRY(upload(h, dcoef, coef.data(), std::max<size_t>(coef.size(), 1)));
         CK(cudaStreamSynchronize(h->stream));
+        return FCB_OK;
+    };
+    TRY(sparse_rows(p->ctrl_rhs[1], &h->ncrow, &h->crow, &h->ccoef));
+    h->scheme = p->scheme;
+    if (p->scheme == 1) {
+        if (!p->cn_ptr || !p->cn_idx || !p->cn_val || (p->na > 0 && !p->ctrl_rhs_prev))
+            return fail(h, FCB_ERR_INVALID, "scheme 1 (Crank-Nicolson) needs cn_ptr/cn_idx/cn_val and ctrl_rhs_prev");
+        const size_t nnz = (size_t)p->cn_ptr[p->n_free];
+        for (size_t j = 0; j < nnz; ++j)
+            if (p->cn_idx[j] < 0 || p->cn_idx[j] >= h->Nv) return fail(h, FCB_ERR_INVALID, "cn_idx out of the velocity range");
+        TRY(upload(h, &h->cn_ptr, p->cn_ptr, (size_t)p->n_free + 1));
+        TRY(upload(h, &h->cn_idx, p->cn_idx, std::max<size_t>(nnz, 1)));
+        TRY(upload(h, &h->cn_val, p->cn_val, std::max<size_t>(nnz, 1)));
+        if (p->na > 0) TRY(sparse_rows(p->ctrl_rhs_prev, &h->ncrow_prev, &h->crow_prev, &h->ccoef_prev));
+    } else if (p->scheme != 0) {
+        return fail(h, FCB_ERR_INVALID, "scheme must be 0 (BDF) or 1 (Crank-Nicolson)");
     }
     TRY(upload(h, &h->sensor_ptr, p->sensor_ptr, (size_t)p->ns + 1));
     const size_t snnz = p->ns ? (size_t)p->sensor_ptr[p->ns] : 0;
@@ -1746,6 +1812,7 @@ int create_impl(fcb_context* h, const fcb_problem* p, int B) {
     }
     TRY(upload<double>(h, &h->epart, nullptr, (size_t)h->nblk_total * L));
     TRY(upload<double>(h, &h->uctrl, nullptr, (size_t)(h->na > 0 ? h->na : 1) * L));
+    TRY(upload<double>(h, &h->uctrl_prev, nullptr, (size_t)(h->na > 0 ? h->na : 1) * L));
     TRY(upload<double>(h, &h->y, nullptr, (size_t)(h->ns > 0 ? h->ns : 1) * L));
     TRY(upload<double>(h, &h->dE, nullptr, L));
     TRY(upload<int>(h, &h->diverged, nullptr, L));
@@ -1800,6 +1867,17 @@ int fcb_set_state(fcb_handle h, const double* u_n, const double* u_nn, const dou
     TRY(copy_in(h, h->up[0], u_n, h->Nv));
     TRY(copy_in(h, h->up[1], u_nn ? u_nn : u_n, h->Nv));
     if (p_n) TRY(copy_in(h, h->up[0] + (size_t)h->Nv * L, p_n, h->nV));
+    if (h->scheme == 1) {
+        // Crank-Nicolson is self-starting: rhs = E u_n - N(u_n) + control terms, u_ctrl^{n} = 0 before the first step
+        CK(cudaMemsetAsync(h->uctrl_prev, 0, (size_t)(h->na > 0 ? h->na : 1) * L * sizeof(double), h->stream));
+        TRY(enqueue_element(h, h->up[0], h->avec, h->bvec[0], nullptr));
+        h->rhs_ready = true;
+        TRY(enqueue_measure(h, h->up[0]));
+        CK(cudaStreamSynchronize(h->stream));
+        h->order = 2;
+        h->have_state = true;
+        return FCB_OK;
+    }
     // b_{n-1} from u_nn, then (a_n, b_n) and the energy partials from u_n
     TRY(enqueue_element(h, h->up[1], h->avec, h->bvec[1], nullptr));
     // a BDF2 (re)start goes through the same fused arithmetic as a running simulation, so that it continues a run

@@ -67,7 +67,8 @@ class Ensemble:
         un = self._host(u_n, self.Nv)
         unn = self._host(u_nn, self.Nv) if u_nn is not None else None
         pn = self._host(p_n, self.nV) if p_n is not None else None
-        rc = self.lib.fcb_set_state(self.h, libfcb.as_voidp(un), libfcb.as_voidp(unn), libfcb.as_voidp(pn), int(order))
+        order = 2 if order == "cn" else int(order)  # Crank-Nicolson has one system; the library ignores the order then
+        rc = self.lib.fcb_set_state(self.h, libfcb.as_voidp(un), libfcb.as_voidp(unn), libfcb.as_voidp(pn), order)
         self._check(rc, "fcb_set_state")
         return self.measurement()
 

@@ -104,8 +104,8 @@ class FlowSolver(ABC):
             raise FileNotFoundError(f"Mesh file not found at {params_mesh.meshpath}")
         if params_restart is not None and params_restart.Trestartfrom < 0:
             raise ValueError(f"Trestartfrom must be non-negative, got {params_restart.Trestartfrom}")
-        if params_solver.time_scheme != "bdf":
-            raise NotImplementedError("only time_scheme='bdf' is implemented on the GPU path (SURVEY.md row a14)")
+        if params_solver.time_scheme not in ("bdf", "cn"):
+            raise ValueError(f"time_scheme must be 'bdf' or 'cn', got {params_solver.time_scheme!r}")
 
     # ── setup (flowsolver.py:169-201) ─────────────────────────────────────────
     def _setup(self) -> None:
@@ -252,6 +252,7 @@ class FlowSolver(ABC):
             self.params_control.actuator_list, self.params_control.sensor_list, self.fields.UP0.array,
             nonlinear=self.params_solver.is_eq_nonlinear, shift=self.params_solver.shift,
             pin_pressure=self._pin_pressure(), leaf_cells=pe.leaf_cells, top_levels=pe.top_levels,
+            time_scheme=self.params_solver.time_scheme,
         )
         if self.ensemble is not None:
             self.ensemble.close()
@@ -268,6 +269,9 @@ class FlowSolver(ABC):
         else:
             up_ic, u_n, u_nn, order = self._initialize_at_time(Tstart)
         tab = self.tables
+        cn = self.params_solver.time_scheme == "cn"
+        if cn:
+            order = "cn"  # self-starting (flowsolver.py:513)
         self.order = order
         self.iter = 0
         self.t = Tstart if Tstart else self.params_time.Tstart
@@ -392,7 +396,8 @@ class FlowSolver(ABC):
                 raise RuntimeError("Failed solving: Inf found in solution")
         self.iter += 1
         self.t = self.params_time.Tstart + self.iter * self.params_time.dt
-        self.order = 2
+        if self.params_solver.time_scheme != "cn":
+            self.order = 2
         self._refresh_fields()
         y = np.array(ens.y_meas, copy=True)
         if B > 1:
@@ -407,7 +412,7 @@ class FlowSolver(ABC):
         self.exporter.log(u_ctrl=uc_dev[:, 0], y_meas=self._traj0(y), dE=dE, t=self.t, runtime=runtime)
         if at_checkpoint:
             self.exporter.export_xdmf(self.fields.u_n, self.fields.u_nn, self.fields.p_n, time=self.t, adjust_baseflow=1.0)
-            self.exporter.write_metadata(restart_order=2)
+            self.exporter.write_metadata(restart_order="cn" if self.params_solver.time_scheme == "cn" else 2)
             self.exporter.write_timeseries()
         return self.y_meas
 

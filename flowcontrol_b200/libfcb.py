@@ -44,6 +44,7 @@ class fcb_problem(C.Structure):
         ("plan", fcb_plan * 2),
         ("ns", C.c_int32), ("sensor_ptr", c_i32p), ("sensor_idx", c_i32p), ("sensor_val", c_f64p),
         ("dt", C.c_double), ("nonlinear", C.c_int32),
+        ("scheme", C.c_int32), ("cn_ptr", c_i32p), ("cn_idx", c_i32p), ("cn_val", c_f64p), ("ctrl_rhs_prev", c_f64p),
     ]
 
 
@@ -162,4 +163,19 @@ class ProblemPack:
         s.sensor_val = _ptr(arr(prob.sensor_val, np.float64), c_f64p)
         s.dt = prob.dt
         s.nonlinear = int(prob.nonlinear)
+        s.scheme = 1 if prob.time_scheme == "cn" else 0
+        if prob.time_scheme == "cn":
+            # explicit operator E in solver row order: row r = canonical dof perm[r] (velocity rows only)
+            import scipy.sparse as sp
+
+            n, Nv = prob.sym.n, tab.Nv
+            perm = np.asarray(prob.sym.perm)
+            vel = np.flatnonzero(perm < Nv)
+            sel = sp.csr_matrix((np.ones(len(vel)), (vel, perm[vel])), shape=(n, Nv))
+            E = (sel @ prob.E_cn).tocsr()
+            E.sort_indices()
+            s.cn_ptr = _ptr(arr(E.indptr, np.int32), c_i32p)
+            s.cn_idx = _ptr(arr(E.indices, np.int32), c_i32p)
+            s.cn_val = _ptr(arr(E.data, np.float64), c_f64p)
+        s.ctrl_rhs_prev = _ptr(arr(prob.ctrl_rhs_prev, np.float64), c_f64p)
         self.struct = s

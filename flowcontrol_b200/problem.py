@@ -115,10 +115,14 @@ class FlowProblem:
         pin_pressure: bool = False,
         leaf_cells: int = 16,
         top_levels: int = 2,
+        time_scheme: str = "bdf",
         symbolic: SymbolicFactor | None = None,
     ):
         self.tab, self.blocks = tab, blocks
         self.Re, self.dt, self.nonlinear = float(Re), float(dt), bool(nonlinear)
+        if time_scheme not in ("bdf", "cn"):
+            raise ValueError(f"time_scheme must be 'bdf' or 'cn', got {time_scheme!r}")
+        self.time_scheme = time_scheme
         self.actuators, self.sensors = list(actuators), list(sensors)
         na = len(self.actuators)
         # an enclosed flow (all-Dirichlet velocity) has a constant-pressure null space: pin one dof
@@ -142,15 +146,35 @@ class FlowProblem:
             (dset.shape.ravel(), (np.repeat(np.arange(na), len(dset.dofs)), np.tile(dset.dofs, na))),
             shape=(na, tab.N),
         ) if na else sp.csr_matrix((0, tab.N))
-        for order, c in ((1, 1.0 / dt), (2, 1.5 / dt)):
+        self.E_cn = None
+        self.ctrl_rhs_prev = np.zeros((na, self.sym.n))
+        if time_scheme == "bdf":
+            orders = ((1, 1.0 / dt), (2, 1.5 / dt))
+        else:
+            # Crank-Nicolson (nsforms.py:191-236): one self-starting system, used for both plan slots
+            orders = ((2, 1.0 / dt),)
+        for order, c in orders:
             A = blocks.saddle_point(c, Re, U0v, shift=shift, linearised=True)
+            half_force = 1.0
+            if time_scheme == "cn":
+                # theta = 1/2: the linear velocity terms L = C + D + K/Re are half implicit, half explicit (operator E_cn on
+                # u_n); mass, pressure and continuity are fully implicit; the body force is averaged over the step
+                L = blocks.saddle_point(0.0, Re, U0v, shift=0.0, linearised=True).tocsr()[: tab.Nv, : tab.Nv]
+                A = (A - 0.5 * sp.bmat([[L, None], [None, sp.csr_matrix((tab.nV, tab.nV))]], format="csr")).tocsr()
+                self.E_cn = (blocks.Mv / dt - 0.5 * L).tocsr()
+                self.E_cn.sort_indices()
+                half_force = 0.5
+                self.ctrl_rhs_prev = np.ascontiguousarray((0.5 * force)[:, self.sym.perm])
             self.A_raw[order] = A
             fac = BlockFactor(self.sym, A)
             self.factors[order] = fac
             self.plans[order] = build_plan(fac, top_levels=top_levels)
             # rhs contribution per unit u_ctrl_k in solver row order: (F_k - A[:,Gamma] shape_k)[perm]
             lift = (A @ G.T).toarray().T if na else np.zeros((0, tab.N))
-            self.ctrl_rhs[order] = np.ascontiguousarray((force - lift)[:, self.sym.perm])
+            self.ctrl_rhs[order] = np.ascontiguousarray((half_force * force - lift)[:, self.sym.perm])
+        if time_scheme == "cn":
+            for d in (self.A_raw, self.factors, self.plans, self.ctrl_rhs):
+                d[1] = d[2]
         self.sensor_ptr, self.sensor_idx, self.sensor_val = sensor_matrix(tab, self.sensors)
 
     @property
@@ -161,9 +185,14 @@ class FlowProblem:
     def ns(self) -> int:
         return len(self.sensors)
 
-    def host_step_rhs(self, order: int, u_n, u_nn, u_ctrl) -> np.ndarray:
-        """Host restatement of k_rhs_build for one trajectory (setup/tests only)."""
+    def host_step_rhs(self, order: int, u_n, u_nn, u_ctrl, u_ctrl_prev=None) -> np.ndarray:
+        """Host restatement of the device right-hand side for one trajectory (setup/tests only)."""
         b = self.blocks
+        if self.time_scheme == "cn":
+            rv = self.E_cn @ u_n - (b.convection(u_n) if self.nonlinear else 0.0)
+            full = np.concatenate([rv, np.zeros(self.tab.nV)])
+            prev = np.zeros(self.na) if u_ctrl_prev is None else np.asarray(u_ctrl_prev, dtype=np.float64)
+            return (full[self.sym.perm] + np.asarray(u_ctrl, dtype=np.float64) @ self.ctrl_rhs[2] + prev @ self.ctrl_rhs_prev)
         if order == 1:
             rv = b.Mv @ u_n / self.dt - (b.convection(u_n) if self.nonlinear else 0.0)
         else:

@@ -103,6 +103,14 @@ typedef struct fcb_problem {
     /* scheme */
     double dt;
     int32_t nonlinear; /* ParamSolver.is_eq_nonlinear (nsforms.py:249,283-284) */
+    /* ParamSolver.time_scheme (flowsolverparameters.py:192): 0 = "bdf" (BDF1 start-up, then BDF2), 1 = "cn"
+     * (Crank-Nicolson, nsforms.py:191-236).  For "cn" both plans hold the same system, the per-step right-hand side is
+     * E u_n - N(u_n) + ctrl_rhs[1] u_ctrl^{n+1} + ctrl_rhs_prev u_ctrl^n, with E = M/dt - (C + D + K/Re)/2 given as CSR. */
+    int32_t scheme;
+    const int32_t* cn_ptr;       /* [n_free+1] CSR of E, rows in solver order (pressure rows empty) */
+    const int32_t* cn_idx;       /*            canonical velocity dof of each entry               */
+    const double* cn_val;
+    const double* ctrl_rhs_prev; /* [na*n_free] coefficient of the previous step's u_ctrl (averaged body force) */
 } fcb_problem;
 
 /* Controller bank: one discrete LTI controller per trajectory

@@ -492,7 +492,13 @@ class ZOHController:
 class FlowOracle:
     """Restates FlowSolver: base flow, IC, BDF1->BDF2 stepping, sensors, energy."""
 
-    def __init__(self, case: CaseSpec, vertices, triangles):
+    def __init__(self, case: CaseSpec, vertices, triangles, time_scheme: str = "bdf", nonlinear: bool = True):
+        """``time_scheme``: "bdf" (BDF1 start-up then BDF2, nsforms.py:238-305) or "cn" (Crank-Nicolson,
+        nsforms.py:191-236, flowsolver.py:678-690, 755-758)."""
+        if time_scheme not in ("bdf", "cn"):
+            raise ValueError(time_scheme)
+        self.time_scheme = time_scheme
+        self.nonlinear = bool(nonlinear)  # ParamSolver.is_eq_nonlinear: b0 of nsforms.py:219
         self.case = case
         self.mesh = TaylorHoodMesh(vertices, triangles)
         self.ops = Operators(self.mesh)
@@ -630,8 +636,16 @@ class FlowOracle:
         mask = np.ones(m.N)
         mask[dofs] = 0.0
         Dm, Id = sp.diags(mask), sp.diags(1.0 - mask)
-        for order, c in ((1, 1.0 / dt), (2, 1.5 / dt)):
+        orders = ((1, 1.0 / dt), (2, 1.5 / dt)) if self.time_scheme == "bdf" else (("cn", 1.0 / dt),)
+        for order, c in orders:
             A = self.ops.lhs(c, Re, self.UP0[: m.Nv], newton_terms=True)
+            if order == "cn":
+                # theta = 1/2 (nsforms.py:213-236): the linear velocity terms C + D + K/Re are split half implicit / half
+                # explicit; mass, pressure and continuity stay fully implicit
+                L = self.ops.lhs(0.0, Re, self.UP0[: m.Nv], newton_terms=True).tocsr()[: m.Nv, : m.Nv]
+                Lpad = sp.bmat([[L, None], [None, sp.csr_matrix((m.nV, m.nV))]], format="csr")
+                A = (A - 0.5 * Lpad).tocsr()
+                self.E_cn = (self.ops.Mv / dt - 0.5 * L).tocsr()  # explicit operator on u_n
             self.A_raw[order] = A
             Abc = (Dm @ A @ Dm + Id).tocsc()
             if self.case.pin_pressure:
@@ -645,9 +659,10 @@ class FlowOracle:
         self.u_n = self.ic[: m.Nv].copy()
         self.u_nn = self.u_n.copy()
         self.up = self.ic.copy()
-        self.order = 1
+        self.order = 1 if self.time_scheme == "bdf" else "cn"
         self.iter = 0
         self.t = 0.0
+        self.u_ctrl_prev = np.zeros(len(self.case.actuators))  # f_n_field starts at zero (flowsolver.py:681-690)
         if not self.lu:
             self.prepare()
         self.y_meas = self.measure(self.ic)
@@ -660,16 +675,20 @@ class FlowOracle:
         dt = self.case.dt
         u_ctrl = np.asarray(u_ctrl, dtype=float)
         # N(u_nn) was N(u_n) of the previous step: reuse it (same value, half the assembly cost)
-        Nn = o.convection(self.u_n)
+        Nn = o.convection(self.u_n) if self.nonlinear else np.zeros(m.Nv)
         Nnn = self.N_prev if (self.N_prev is not None and self.order == 2) else None
-        if self.order == 1:
+        fterm = self.force_rhs(u_ctrl)
+        if self.order == "cn":
+            rv = self.E_cn @ self.u_n - Nn  # b0 = 1 (nsforms.py:219, 229)
+            fterm = 0.5 * (fterm + self.force_rhs(self.u_ctrl_prev))  # body force averaged over the step (nsforms.py:233-234)
+        elif self.order == 1:
             rv = o.Mv @ self.u_n / dt - Nn
         else:
             if Nnn is None:
-                Nnn = o.convection(self.u_nn)
+                Nnn = o.convection(self.u_nn) if self.nonlinear else np.zeros(m.Nv)
             rv = o.Mv @ (4.0 * self.u_n - self.u_nn) / (2.0 * dt) - 2.0 * Nn + Nnn
         self._N_cur = Nn
-        rv = rv + self.force_rhs(u_ctrl)
+        rv = rv + fterm
         b = np.concatenate([rv, np.zeros(m.nV)])
         g = self.bc_pert.values(u_ctrl)
         dofs = self.bc_pert.dofs
@@ -690,7 +709,8 @@ class FlowOracle:
             return None
         self.iter += 1
         self.t = self.iter * self.case.dt
-        self.order = 2
+        self.order = 2 if self.time_scheme == "bdf" else "cn"
+        self.u_ctrl_prev = np.asarray(u_ctrl, dtype=float).copy()
         self.u_nn = self.u_n
         self.u_n = x[: m.Nv].copy()
         self.N_prev = self._N_cur

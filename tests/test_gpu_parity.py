@@ -463,3 +463,87 @@ def test_lift_drag_time_series_200_steps(root, cyl):
     cl, cd = fs.compute_force_coefficients(UP0[: tab.Nv] + up[: tab.Nv], UP0[tab.Nv :] + up[tab.Nv :])
     assert np.isclose(cl, cl0 + series[-1, 6, 0], rtol=1e-9, atol=1e-12) and np.isclose(cd, cd0 + series[-1, 7, 0], rtol=1e-9)
     ens.close()
+
+
+def test_crank_nicolson_cylinder_vs_oracle(root, cyl):
+    """time_scheme='cn' (nsforms.py:191-236) on the device: k_spmm (E u_n) + element pass (-N(u_n)) + current and
+    previous-step control terms, for slot (BC lifting) and body-force actuation (force averaged over the step), host-driven
+    and closed loop on the device, against the oracle's Crank-Nicolson step."""
+    from flowcontrol_b200.actuator import ActuatorForceGaussianV
+    from flowcontrol_b200.controller import Controller, ControllerBank
+    from flowcontrol_b200.ensemble import Ensemble
+    from flowcontrol_b200.problem import FlowProblem
+    from oracle import flow_oracle as fo
+
+    fs, prob_bdf, _, UP0 = cyl
+    tab = prob_bdf.tab
+    acts = list(fs.params_control.actuator_list) + [ActuatorForceGaussianV(sigma=0.3, position=np.array([1.5, 0.2]))]
+    prob = FlowProblem(tab, fs.blocks, 100.0, 0.005, fs.bc.bcu, acts, fs.params_control.sensor_list, UP0,
+                       time_scheme="cn", symbolic=prob_bdf.sym)
+    case = cases.cylinder(100.0)
+    case.actuators = list(case.actuators) + [fo.ActuatorSpec("force", fo.gaussian_v(0.3, (1.5, 0.2)))]
+    case.ic = (2.0, 0.0, 0.5, 1.0)
+    xy, tri = cases.load_mesh(case.mesh_file)
+    orc = FlowOracle(case, xy, tri, time_scheme="cn")
+    orc.set_base_flow(UP0)
+    orc.init_time_stepping()
+    B, track, nsteps = 40, 11, 60
+    amp = np.linspace(-1.0, 1.0, B)
+    ens = Ensemble(prob, B)
+    y0 = ens.set_state(orc.ic[: tab.Nv], None, orc.ic[tab.Nv :], order="cn")
+    assert np.allclose(y0[:, track], orc.y_meas, rtol=1e-12)
+    worst_y = 0.0
+    for k in range(nsteps):
+        t = (k + 1) * prob.dt
+        base = np.array([np.sin(40 * t), 0.5 * np.cos(25 * t), 2.0 * np.cos(30 * t)])
+        ens.step(base[:, None] * amp[None, :])
+        orc.step(base * amp[track])
+        worst_y = max(worst_y, np.abs(ens.y_meas[:, track] - orc.y_meas).max() / np.abs(orc.y_meas).max())
+    up = ens.fields(0)[:, track]
+    assert rel(up[: tab.Nv], orc.up[: tab.Nv]) < FIELD_TOL
+    assert rel(up[tab.Nv :], orc.up[tab.Nv :]) < FIELD_TOL
+    assert worst_y < SERIES_TOL
+    assert abs(ens.dE[track] - orc.dE) / orc.dE < SERIES_TOL
+    assert not ens.diverged.any()
+    # restart from the state reached (u_ctrl^n = 0 again, like a reference restart): continue on the device in closed
+    # loop (CUDA-graph replay) and compare with the oracle driven by the same controller
+    u_n = ens.fields(0)[:, track].copy()
+    kk = np.load(root / "tests/golden/Kopt_reduced13.npz")
+    Ky, Fu = np.array([[-1.0, 0.0, 0.0]]), np.array([[1.0], [1.0], [0.5]])
+    ens.set_state(u_n[: tab.Nv], None, u_n[tab.Nv :], order="cn")
+    ens.set_controllers(ControllerBank([Controller(kk["A"], kk["B"], kk["C"], kk["D"]) for _ in range(B)], prob.dt, Ky, Fu))
+    series = ens.run_closed_loop(16)
+    orc.init_time_stepping(ic=u_n)
+    K = ZOHController(kk["A"], kk["B"], kk["C"], kk["D"])
+    for s in range(16):
+        u = K.step(-orc.y_meas[0], prob.dt)
+        orc.step([u[0], u[0], 0.5 * u[0]])
+        assert np.allclose(series[s, 4:, 0], orc.y_meas, rtol=SERIES_TOL, atol=0)
+        assert np.isclose(series[s, 0, 0], orc.dE, rtol=SERIES_TOL)
+    assert np.abs(series - series[:, :, :1]).max() == 0.0
+    ens.close()
+
+
+def test_crank_nicolson_through_the_facade(root, cyl, tmp_path):
+    """ParamSolver(time_scheme='cn') through FlowSolver.step: self-starting, order stays 'cn' (flowsolver.py:513, 742)."""
+    from flowcontrol_b200.examples.cylinder import CylinderFlowSolver
+    from flowcontrol_b200.flowfield import Field
+
+    _, _, _, UP0 = cyl
+    fs = CylinderFlowSolver.make_default(path_out=tmp_path, num_steps=5)
+    fs.params_solver.time_scheme = "cn"
+    tab = fs.tables
+    fs._assign_steady_state(Field(UP0[: tab.Nv]), Field(UP0[tab.Nv :]))
+    fs.params_ic.xloc, fs.params_ic.yloc, fs.params_ic.radius, fs.params_ic.amplitude = 2.0, 0.0, 0.5, 1.0
+    fs.initialize_time_stepping(Tstart=0.0)
+    case = cases.cylinder(100.0)
+    case.ic = (2.0, 0.0, 0.5, 1.0)
+    xy, tri = cases.load_mesh(case.mesh_file)
+    orc = FlowOracle(case, xy, tri, time_scheme="cn")
+    orc.set_base_flow(UP0)
+    orc.init_time_stepping()
+    for k in range(5):
+        y = fs.step(u_ctrl=[0.1 * k, -0.05 * k])
+        orc.step([0.1 * k, -0.05 * k])
+        assert fs.order == "cn"
+        assert np.allclose(y, orc.y_meas, rtol=SERIES_TOL, atol=0)

@@ -259,3 +259,38 @@ def test_force_coefficient_rows_match_oracle_and_closed_surface_identity():
     q = 0.5 * uinf**2 * D
     assert np.isclose(rows[1][1] @ up[rows[1][0]], -0.25 * 2.0 / q, rtol=1e-12)   # drag
     assert np.isclose(rows[0][1] @ up[rows[0][0]], -0.25 * -3.0 / q, rtol=1e-12)  # lift
+
+
+def test_crank_nicolson_host_step_matches_oracle():
+    """time_scheme='cn' (nsforms.py:191-236): product operators (A_cn factor, explicit operator E_cn, averaged force,
+    BC lifting) vs the oracle's Crank-Nicolson step, BC + force actuators with time-varying u_ctrl."""
+    xy, tri = unit_square_mesh(10, jitter=0.15, seed=5)
+    tab = TaylorHoodTables.from_arrays(xy, tri)
+    blocks = ScalarBlocks(tab)
+    rng = np.random.default_rng(2)
+    acts = [ActuatorBCUniformU(), ActuatorForceGaussianV(sigma=0.15, position=np.array([0.4, 0.5]))]
+    sensors = [SensorPoint(sensor_type=SENSOR_TYPE.V, position=np.array([0.31, 0.52]))]
+    UP0 = np.concatenate([0.5 * rng.standard_normal(tab.Nv), rng.standard_normal(tab.nV)])
+    prob = FlowProblem(tab, blocks, 80.0, 0.01, _bcs(acts), acts, sensors, UP0, leaf_cells=4, time_scheme="cn")
+    case = fo.CaseSpec(
+        name="t", mesh_file="", Re=80.0, dt=0.01, uinf=1.0,
+        bcs_pert=[fo.DirichletSpec(lambda x, y: fo.near(y, 1.0), (0, 1), ("actuator", 0)),
+                  fo.DirichletSpec(lambda x, y: fo.near(x, 0.0), (0, 1), (0.0, 0.0)),
+                  fo.DirichletSpec(lambda x, y: fo.near(y, 0.0), (1,), (0.0,))],
+        bcs_full=[], actuators=[fo.ActuatorSpec("bc", fo.uniform_u()), fo.ActuatorSpec("force", fo.gaussian_v(0.15, (0.4, 0.5)))],
+        sensors=[fo.SensorSpec("point", comp=1, position=(0.31, 0.52))], initial_guess=None,
+    )
+    orc = fo.FlowOracle(case, xy, tri, time_scheme="cn")
+    orc.set_base_flow(UP0)
+    ic = np.concatenate([0.1 * rng.standard_normal(tab.Nv), np.zeros(tab.nV)])
+    orc.init_time_stepping(ic=ic)
+    u_n, prev = ic[: tab.Nv].copy(), np.zeros(2)
+    for uc in ([0.3, -0.7], [0.1, 0.4], [-0.2, 0.9], [0.0, 0.0]):
+        orc.step(uc)
+        b = prob.host_step_rhs(2, u_n, None, uc, prev)
+        x = np.zeros(tab.N)
+        x[prob.sym.perm] = prob.factors[2].solve(b)
+        x[prob.dirichlet.dofs] = prob.dirichlet.values(uc)
+        assert np.linalg.norm(x[: tab.Nv] - orc.up[: tab.Nv]) / np.linalg.norm(orc.up[: tab.Nv]) < 1e-10
+        assert np.linalg.norm(x[tab.Nv :] - orc.up[tab.Nv :]) / np.linalg.norm(orc.up[tab.Nv :]) < 1e-9
+        u_n, prev = x[: tab.Nv].copy(), np.asarray(uc, dtype=float)
