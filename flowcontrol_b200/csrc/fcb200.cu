@@ -95,6 +95,7 @@ __device__ __forceinline__ void emit_node(int mode, const double* bprev, double*
     if (mode == 2) {
         if (rx >= 0) Zb[(size_t)rx * ldb + b] += ax;
         if (ry >= 0) Zb[(size_t)ry * ldb + b] += ay;
+        if (rp >= 0) Zb[(size_t)rp * ldb + b] = 0.0;
         return;
     }
     if (mode == 1) {
@@ -487,6 +488,96 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(c[0]), "+d"(c[1])
                  : "d"(a), "d"(b));
+}
+
+
+// ---- block-sparse SpMM on the FP64 tensor cores (Crank-Nicolson explicit operator E u_n) --------------------------
+// Z[row] = sum_j E[row, j] X[j] for the free velocity rows, all trajectories.  The library re-packs the caller's CSR
+// (build_spmm): consecutive solver rows (a compact piece of the mesh in the nested-dissection order) form a block of
+// at most 64 rows whose distinct columns (<= SPMM_CMAX) are staged once in shared memory, 32 trajectories wide; inside a
+// block, rows with similar column sets are grouped by eight, and each group is stored as a dense 8 x K panel over the
+// union of its columns, in mma.m8n8k4 A-fragment order.  One CTA = one (block, 32-trajectory slice), one warp = one
+// group: per k-step one A fragment (a coalesced 256-byte load, prefetched four k-steps ahead in registers), four column
+// slots, four B fragments from shared memory and four DMMAs (8 rows x 4 columns x 32 trajectories).  All index loads
+// are addressed by the block number alone (fixed strides), so the two dependent chains (columns -> X rows, group
+// record -> panel) start together; four CTAs per SM overlap one another's gathers and DMMAs.
+// History (cylinder, 256 trajectories): scalar CSR row loop (k_spmm below, kept for A/B runs) 0.21 ms - one 256-byte
+// row segment of X per non-zero, bound by L1 wavefronts; persistent CTAs with a two-stage mbarrier ring 0.28 ms with
+// per-row bulk copies (issued lane by lane through the uniform datapath), 0.135 ms with a cp.async producer warp,
+// 0.115 ms with every warp gathering - one CTA per SM leaves too little slack around the per-item barrier.
+constexpr int SPMM_CMAX = 192;   // staged columns per block
+constexpr int SPMM_XS = 36;      // shared row stride in doubles (== 4 mod 16: k-steps with slots distinct mod 4 are conflict-free)
+constexpr int SPMM_WARPS = 8;    // warps = groups per block
+constexpr int SPMM_GREC = 12;    // ints per group record: first k-step, k-steps, 8 solver rows (-1 = none), 2 pad
+constexpr int SPMM_PF = 4;       // k-steps of panel prefetch
+constexpr int SPMM_SMEM = SPMM_CMAX * SPMM_XS * 8;
+
+struct SpmmArgs {
+    const int* ucols;              // [nblk][SPMM_CMAX] staged column (canonical velocity dof) per slot, -1 = none
+    const int* ginfo;              // [nblk][SPMM_WARPS][SPMM_GREC]
+    const unsigned short* kslots;  // [nk][4] slot of each of the k-step's columns
+    const double* avals;           // [nk][32] panel values in A-fragment order: lane l holds (row l/4, column l%4)
+    const double* X;
+    double* Z;
+    int ldb, nslice;
+};
+
+__global__ void __launch_bounds__(32 * SPMM_WARPS, 4) k_spmm_mma(const SpmmArgs p) {
+    extern __shared__ __align__(16) double xs[];  // [slot][SPMM_XS]
+    const int lane = threadIdx.x, w = threadIdx.y;
+    const int blk = blockIdx.x / p.nslice, b0 = (blockIdx.x - blk * p.nslice) * 32;
+    const size_t ldb = (size_t)p.ldb;
+    const int half = lane >> 4, l16 = lane & 15, kq = lane & 3, nq = lane >> 2;
+    // this half-warp gathers the staged columns c = 2 (w + 8 i) + half, i = 0..11; lane l16 = i holds the index of round i
+    const int c_mine = 2 * (w + SPMM_WARPS * l16) + half;
+    const int col = c_mine < SPMM_CMAX ? __ldg(p.ucols + (size_t)blk * SPMM_CMAX + c_mine) : -1;
+    const int* gi = p.ginfo + ((size_t)blk * SPMM_WARPS + w) * SPMM_GREC;
+    const int k0 = __ldg(gi), nk = __ldg(gi + 1), row = __ldg(gi + 2 + nq);
+#pragma unroll
+    for (int i = 0; i < SPMM_CMAX / (2 * SPMM_WARPS); ++i) {
+        const int cc = __shfl_sync(0xffffffffu, col, (lane & 16) + i);
+        if (cc >= 0) {
+            const uint32_t dst = smem_u32(xs + (size_t)(2 * (w + SPMM_WARPS * i) + half) * SPMM_XS + 2 * l16);
+            const double* src = p.X + (size_t)cc * ldb + b0 + 2 * l16;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    // panel prefetch, SPMM_PF k-steps deep (the panel array is padded so that reading past the group is harmless)
+    const double* av = p.avals + (size_t)k0 * 32 + lane;
+    const unsigned short* sl = p.kslots + (size_t)k0 * 4 + kq;
+    double a_cur[SPMM_PF], a_nxt[SPMM_PF];
+    int s_cur[SPMM_PF], s_nxt[SPMM_PF];
+#pragma unroll
+    for (int t = 0; t < SPMM_PF; ++t) { a_cur[t] = __ldg(av + 32 * t); s_cur[t] = __ldg(sl + 4 * t); }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    double acc[4][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { acc[j][0] = 0.0; acc[j][1] = 0.0; }
+    for (int t0 = 0; t0 < nk; t0 += SPMM_PF) {
+        av += 32 * SPMM_PF;
+        sl += 4 * SPMM_PF;
+        if (t0 + SPMM_PF < nk) {
+#pragma unroll
+            for (int t = 0; t < SPMM_PF; ++t) { a_nxt[t] = __ldg(av + 32 * t); s_nxt[t] = __ldg(sl + 4 * t); }
+        }
+#pragma unroll
+        for (int t = 0; t < SPMM_PF; ++t) {
+            if (t0 + t < nk) {  // warp-uniform
+                const double* xr = xs + s_cur[t] * SPMM_XS + nq;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma(acc[j], a_cur[t], xr[8 * j]);
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < SPMM_PF; ++t) { a_cur[t] = a_nxt[t]; s_cur[t] = s_nxt[t]; }
+    }
+    if (row >= 0) {
+        double* z = p.Z + (size_t)row * ldb + b0 + 2 * kq;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<double2*>(z + 8 * j) = make_double2(acc[j][0], acc[j][1]);
+    }
 }
 
 struct alignas(64) SweepMaps {
@@ -924,6 +1015,12 @@ struct fcb_context {
     double *cn_val = nullptr, *uctrl_prev = nullptr, *ccoef_prev = nullptr;
     int ncrow_prev = 0;
     int* crow_prev = nullptr;
+    // packed form of the same operator for k_spmm_mma (build_spmm)
+    int sp_nblk = 0, sp_smem = 0;
+    bool sp_csr = false;  // FCB_SPMM_CSR=1: run the scalar CSR kernel instead (A/B measurements)
+    int *sp_ucols = nullptr, *sp_ginfo = nullptr;
+    unsigned short* sp_kslots = nullptr;
+    double* sp_avals = nullptr;
     int ncrow = 0;           // solver rows with a non-zero control coefficient (BDF2), their coefficients [na, ncrow]
     int* crow = nullptr;
     double* ccoef = nullptr;
@@ -1258,17 +1355,26 @@ struct PhaseMark {
     }
 };
 
+// Crank-Nicolson: the rhs rows first receive E u (k_spmm); the element pass then adds -N(u) (nsforms.py:219-229)
+int enqueue_spmm(fcb_context* h, const double* u) {
+    if (h->sp_csr) {
+        dim3 grid((h->n + 7) / 8, h->ldb / 32), block(32, 8);
+        k_spmm<<<grid, block, 0, h->stream>>>(h->n, h->cn_ptr, h->cn_idx, h->cn_val, u, h->Z, h->ldb);
+    } else {
+        // items = (block, slice) with the slice fastest: the CTAs working on one block run together and its panels come from HBM once
+        SpmmArgs a{h->sp_ucols, h->sp_ginfo, h->sp_kslots, h->sp_avals, u, h->Z, h->ldb, h->ldb / 32};
+        k_spmm_mma<<<h->sp_nblk * (h->ldb / 32), dim3(32, SPMM_WARPS), h->sp_smem, h->stream>>>(a);
+    }
+    h->launches += 1;
+    CK(cudaGetLastError());
+    return FCB_OK;
+}
+
 // element pass on the state u: b <- b(u) and either a <- a(u) (bprev == nullptr) or, fused, the next step's
 // right-hand side rows Z[0,n) <- a(u) + bprev
 int enqueue_element(fcb_context* h, const double* u, double* a, double* b, const double* bprev) {
     PatchArgs p;
     p.mode = h->scheme == 1 ? 2 : (bprev ? 1 : 0);
-    if (h->scheme == 1) {
-        // Crank-Nicolson: the rhs rows first receive E u (k_spmm), the element pass then adds -N(u) (nsforms.py:219-229)
-        dim3 grid((h->n + 7) / 8, h->ldb / 32), block(32, 8);
-        k_spmm<<<grid, block, 0, h->stream>>>(h->n, h->cn_ptr, h->cn_idx, h->cn_val, u, h->Z, h->ldb);
-        h->launches += 1;
-    }
     p.pcell_ptr = h->pcell_ptr; p.pcnode = h->pcnode; p.pgeo = h->pgeo; p.plnode = h->plnode;
     p.pnode_ptr = h->pnode_ptr; p.pnode_dst = h->pnode_dst; p.psrc = h->psrc; p.pacc_rows = h->pacc_rows;
     p.u = u; p.a = a; p.b = b; p.scratch = h->pscratch; p.epart = h->epart;
@@ -1380,6 +1486,8 @@ int enqueue_step(fcb_context* h, int order, int parity, bool rhs_ready, PhaseMar
         k_bc_fill<<<grid, block, 0, h->stream>>>(h->nbc, h->bc_dofs, h->na, h->bc_shape, h->uctrl, nxt, h->ldb);
         h->launches += 1;
     }
+    if (pm) pm->mark(FCB_PHASE_SPMM);
+    if (h->scheme == 1) TRY(enqueue_spmm(h, nxt));
     if (pm) pm->mark(FCB_PHASE_ELEMENT);
     // b(u_new) replaces b_{n-1}; the rhs of the next step = a(u_new) + b_n, with b_n = bvec[parity]
     TRY(enqueue_element(h, nxt, h->avec, h->bvec[1 - parity], h->bvec[parity]));
@@ -1467,7 +1575,7 @@ void destroy(fcb_context* h) {
         for (int j = 0; j < 2; ++j)
             if (h->g_loop[i][j]) cudaGraphExecDestroy(h->g_loop[i][j]);
     }
-    void* ptrs[] = {h->cn_ptr, h->cn_idx, h->cn_val, h->uctrl_prev, h->ccoef_prev, h->crow_prev, h->crow, h->ccoef, h->bc_dofs, h->cell_nodes, h->perm, h->iperm, h->Jinv, h->detJ, h->bc_shape, h->ctrl_rhs[0],
+    void* ptrs[] = {h->sp_ucols, h->sp_ginfo, h->sp_kslots, h->sp_avals, h->cn_ptr, h->cn_idx, h->cn_val, h->uctrl_prev, h->ccoef_prev, h->crow_prev, h->crow, h->ccoef, h->bc_dofs, h->cell_nodes, h->perm, h->iperm, h->Jinv, h->detJ, h->bc_shape, h->ctrl_rhs[0],
                     h->ctrl_rhs[1], h->sensor_ptr, h->sensor_idx, h->sensor_val, h->up[0], h->up[1], h->avec,
                     h->bvec[0], h->bvec[1], h->Z, h->epart, h->uctrl, h->y, h->dE, h->diverged, h->Ad, h->Bd, h->Cd,
                     h->Dd, h->Ky, h->Fu, h->xk[0], h->xk[1], h->series, h->counter, h->sweep_dbg,
@@ -1484,6 +1592,176 @@ void destroy(fcb_context* h) {
         if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
+}
+
+// Re-pack the Crank-Nicolson operator (CSR, rows in solver order, columns = canonical velocity dofs) for k_spmm_mma.
+namespace spmm_pack {
+typedef std::array<uint64_t, SPMM_CMAX / 64> Bits;
+struct Group {
+    int nm = 0, members[8];
+    std::vector<int> slots;  // 4 per k-step, -1 = padding
+};
+struct Block {
+    int r1 = 0;              // one past the last solver row covered
+    std::vector<int> cols, rows;
+    std::vector<Group> groups;
+    int nk = 0, conflicts = 0;
+};
+
+// rows [r, r1) that fit `rowcap` non-empty rows and SPMM_CMAX distinct columns, grouped by eight
+inline void pack_block(const int32_t* ptr, const int32_t* idx, int n, int r, int rowcap, std::vector<int>& slot_of, Block& B) {
+    B = Block();
+    int r1 = r;
+    for (; r1 < n && (int)B.rows.size() < rowcap; ++r1) {
+        int fresh = 0;
+        for (int j = ptr[r1]; j < ptr[r1 + 1]; ++j) fresh += slot_of[idx[j]] < 0;
+        if ((int)B.cols.size() + fresh > SPMM_CMAX) break;
+        for (int j = ptr[r1]; j < ptr[r1 + 1]; ++j)
+            if (slot_of[idx[j]] < 0) { slot_of[idx[j]] = (int)B.cols.size(); B.cols.push_back(idx[j]); }
+        if (ptr[r1 + 1] > ptr[r1]) B.rows.push_back(r1);
+    }
+    B.r1 = r1;
+    const int R = (int)B.rows.size();
+    std::vector<Bits> bits((size_t)R);
+    std::vector<int> order((size_t)R);
+    for (int i = 0; i < R; ++i) {
+        order[i] = i;
+        bits[i].fill(0);
+        for (int j = ptr[B.rows[i]]; j < ptr[B.rows[i] + 1]; ++j) { const int sl = slot_of[idx[j]]; bits[i][sl >> 6] |= 1ull << (sl & 63); }
+    }
+    for (int c : B.cols) slot_of[c] = -1;
+    // seeds: the longest rows first (a vertex node and the edge nodes inside its neighbourhood make a tight panel);
+    // members: the rows that add the fewest new columns, longer rows first among equals
+    auto len = [&](int i) { return ptr[B.rows[i] + 1] - ptr[B.rows[i]]; };
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return len(x) > len(y); });
+    std::vector<char> used((size_t)R, 0);
+    for (int seed : order) {
+        if (used[seed]) continue;
+        Group G;
+        Bits uni = bits[seed];
+        G.members[G.nm++] = seed; used[seed] = 1;
+        while (G.nm < 8) {
+            int best = -1, best_cost = 1 << 30, best_len = -1;
+            for (int i = 0; i < R; ++i) {
+                if (used[i]) continue;
+                int cost = 0;
+                for (size_t q = 0; q < uni.size(); ++q) cost += __builtin_popcountll(bits[i][q] & ~uni[q]);
+                if (cost < best_cost || (cost == best_cost && len(i) > best_len)) { best_cost = cost; best = i; best_len = len(i); }
+            }
+            if (best < 0) break;
+            G.members[G.nm++] = best; used[best] = 1;
+            for (size_t q = 0; q < uni.size(); ++q) uni[q] |= bits[best][q];
+        }
+        // k-steps: four columns each, one from each residue class of the slot (mod 4) while they last
+        std::vector<int> bucket[4];
+        for (int sl = 0; sl < (int)B.cols.size(); ++sl)
+            if (uni[sl >> 6] >> (sl & 63) & 1) bucket[sl & 3].push_back(sl);
+        size_t K = 0, take[4] = {0, 0, 0, 0};
+        for (auto& bq : bucket) K += bq.size();
+        const int nk = (int)((K + 3) / 4);
+        for (int t = 0; t < nk; ++t) {
+            int got = 0;
+            bool clean = true;
+            for (int q = 0; q < 4; ++q)
+                if (take[q] < bucket[q].size()) { G.slots.push_back(bucket[q][take[q]++]); ++got; }
+            while (got < 4) {
+                size_t remaining = 0, left = 0;
+                int q = -1;
+                for (int qq = 0; qq < 4; ++qq) {
+                    remaining += bucket[qq].size() - take[qq];
+                    if (bucket[qq].size() - take[qq] > left) { left = bucket[qq].size() - take[qq]; q = qq; }
+                }
+                if (q < 0 || remaining <= (size_t)(nk - 1 - t) * 4) { G.slots.push_back(-1); ++got; continue; }  // fits later: pad
+                G.slots.push_back(bucket[q][take[q]++]);  // a class ran dry: two columns of one class cost a bank conflict
+                ++got;
+                clean = false;
+            }
+            B.conflicts += !clean;
+        }
+        B.nk += nk;
+        B.groups.push_back(std::move(G));
+    }
+}
+}  // namespace spmm_pack
+
+int build_spmm(fcb_context* h, const fcb_problem* p) {
+    using namespace spmm_pack;
+    const int n = p->n_free;
+    const int32_t *ptr = p->cn_ptr, *idx = p->cn_idx;
+    const double* val = p->cn_val;
+    for (int i = 0; i < n; ++i) {
+        if (ptr[i + 1] - ptr[i] > SPMM_CMAX) return fail(h, FCB_ERR_INVALID, "Crank-Nicolson operator row %d has more than %d entries", i, SPMM_CMAX);
+        for (int j = ptr[i] + 1; j < ptr[i + 1]; ++j)
+            if (idx[j] <= idx[j - 1]) return fail(h, FCB_ERR_INVALID, "cn_idx must be strictly increasing within a row");
+    }
+    std::vector<int> ucols, ginfo;
+    int nblk = 0;
+    std::vector<unsigned short> kslots;
+    std::vector<double> avals;
+    std::vector<int> slot_of((size_t)h->Nv, -1);
+    size_t nnz_total = 0, conflict_steps = 0, ngroups = 0, staged = 0;
+    Block B;
+    for (int r = 0; r < n;) {
+        int rowcap = 8 * SPMM_WARPS;
+        for (;; rowcap -= 8) {
+            pack_block(ptr, idx, n, r, rowcap, slot_of, B);
+            if ((int)B.groups.size() <= SPMM_WARPS) break;
+            if (rowcap <= 8) return fail(h, FCB_ERR_INVALID, "Crank-Nicolson operator rows near %d do not fit a panel block", r);
+        }
+        r = B.r1;
+        if (B.rows.empty()) continue;  // a run of continuity rows (no entries)
+        ++nblk;
+        ucols.insert(ucols.end(), B.cols.begin(), B.cols.end());
+        ucols.resize((size_t)nblk * SPMM_CMAX, -1);  // fixed strides: no descriptor load in front of the gathers
+        for (const Group& G : B.groups) {
+            const int gnk = (int)G.slots.size() / 4;
+            ginfo.push_back((int)(kslots.size() / 4));
+            ginfo.push_back(gnk);
+            for (int m = 0; m < 8; ++m) ginfo.push_back(m < G.nm ? B.rows[G.members[m]] : -1);
+            ginfo.push_back(0);
+            ginfo.push_back(0);
+            for (int t = 0; t < gnk; ++t) {
+                const size_t base = avals.size();
+                avals.resize(base + 32, 0.0);
+                for (int c = 0; c < 4; ++c) {
+                    const int sl = G.slots[t * 4 + c];
+                    kslots.push_back((unsigned short)(sl < 0 ? std::min(c, (int)B.cols.size() - 1) : sl));  // padding: zero panel column on a staged slot
+                    if (sl < 0) continue;
+                    const int col = B.cols[sl];
+                    for (int m = 0; m < G.nm; ++m) {
+                        const int row = B.rows[G.members[m]];
+                        const int32_t* f = std::lower_bound(idx + ptr[row], idx + ptr[row + 1], col);
+                        if (f != idx + ptr[row + 1] && *f == col) avals[base + m * 4 + c] = val[f - idx];
+                    }
+                }
+            }
+            for (int m = 0; m < G.nm; ++m) nnz_total += ptr[B.rows[G.members[m]] + 1] - ptr[B.rows[G.members[m]]];
+        }
+        for (size_t g = B.groups.size(); g < (size_t)SPMM_WARPS; ++g) {  // absent groups: no k-steps, no rows
+            ginfo.push_back(0);
+            ginfo.push_back(0);
+            for (int m = 0; m < 10; ++m) ginfo.push_back(-1);
+        }
+        conflict_steps += B.conflicts;
+        ngroups += B.groups.size();
+        staged += B.cols.size();
+    }
+    // the kernel prefetches SPMM_PF k-steps at a time: pad the panel arrays so that reads past the last group stay inside
+    avals.resize(avals.size() + 32 * 2 * SPMM_PF, 0.0);
+    kslots.resize(kslots.size() + 4 * 2 * SPMM_PF, 0);
+    h->sp_nblk = nblk;
+    h->sp_smem = SPMM_SMEM;
+    TRY(upload(h, &h->sp_ucols, ucols.data(), std::max<size_t>(ucols.size(), 1)));
+    TRY(upload(h, &h->sp_ginfo, ginfo.data(), std::max<size_t>(ginfo.size(), 1)));
+    TRY(upload(h, &h->sp_kslots, kslots.data(), std::max<size_t>(kslots.size(), 1)));
+    TRY(upload(h, &h->sp_avals, avals.data(), std::max<size_t>(avals.size(), 1)));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaFuncSetAttribute(k_spmm_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, h->sp_smem));
+    if (getenv("FCB_VERBOSE"))
+        fprintf(stderr, "[fcb] spmm: %d blocks, %zu groups, %zu k-steps (%zu with a bank conflict), nnz %zu, panel fill %.2f, staged columns %zu (%.2f x Nv)\n",
+                h->sp_nblk, ngroups, kslots.size() / 4, conflict_steps, nnz_total,
+                nnz_total ? (double)(kslots.size() / 4 * 32) / (double)nnz_total : 0.0, staged, (double)staged / h->Nv);
+    return FCB_OK;
 }
 
 // Group the cells into patches for k_element_patch.  The nested-dissection numbering of the solver is a
@@ -1770,6 +2048,8 @@ int create_impl(fcb_context* h, const fcb_problem* p, int B) {
         TRY(upload(h, &h->cn_idx, p->cn_idx, std::max<size_t>(nnz, 1)));
         TRY(upload(h, &h->cn_val, p->cn_val, std::max<size_t>(nnz, 1)));
         if (p->na > 0) TRY(sparse_rows(p->ctrl_rhs_prev, &h->ncrow_prev, &h->crow_prev, &h->ccoef_prev));
+        h->sp_csr = getenv("FCB_SPMM_CSR") && atoi(getenv("FCB_SPMM_CSR")) != 0;
+        TRY(build_spmm(h, p));
     } else if (p->scheme != 0) {
         return fail(h, FCB_ERR_INVALID, "scheme must be 0 (BDF) or 1 (Crank-Nicolson)");
     }
@@ -1870,6 +2150,7 @@ int fcb_set_state(fcb_handle h, const double* u_n, const double* u_nn, const dou
     if (h->scheme == 1) {
         // Crank-Nicolson is self-starting: rhs = E u_n - N(u_n) + control terms, u_ctrl^{n} = 0 before the first step
         CK(cudaMemsetAsync(h->uctrl_prev, 0, (size_t)(h->na > 0 ? h->na : 1) * L * sizeof(double), h->stream));
+        TRY(enqueue_spmm(h, h->up[0]));
         TRY(enqueue_element(h, h->up[0], h->avec, h->bvec[0], nullptr));
         h->rhs_ready = true;
         TRY(enqueue_measure(h, h->up[0]));
@@ -2031,10 +2312,11 @@ int fcb_profile_step(fcb_handle h, const double* u_ctrl, float* ms, int32_t* lau
         }
     }
     if (launches) {
-        launches[FCB_PHASE_RHS] = 1;
+        launches[FCB_PHASE_RHS] = 1 + (h->scheme == 1 && h->ncrow_prev > 0 ? 1 : 0);
         launches[FCB_PHASE_FORWARD] = pl.n_forward;
         launches[FCB_PHASE_BACKWARD] = pl.nlaunch - pl.n_forward + (pl.asm_n > 0 ? 1 : 0);
         launches[FCB_PHASE_POST] = h->nbc > 0 ? 1 : 0;
+        launches[FCB_PHASE_SPMM] = h->scheme == 1 ? 1 : 0;
         launches[FCB_PHASE_ELEMENT] = 1 + (h->nshared > 0 ? 1 : 0);
         launches[FCB_PHASE_MEASURE] = 1;
     }

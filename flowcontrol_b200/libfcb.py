@@ -19,8 +19,8 @@ c_i32p = C.POINTER(C.c_int32)
 c_i64p = C.POINTER(C.c_int64)
 c_f64p = C.POINTER(C.c_double)
 
-FCB_NPHASES = 6
-PHASE_NAMES = ("rhs", "forward", "backward", "post", "element", "measure")
+FCB_NPHASES = 7
+PHASE_NAMES = ("rhs", "forward", "backward", "post", "spmm", "element", "measure")
 
 
 class fcb_plan(C.Structure):

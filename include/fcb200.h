@@ -130,7 +130,7 @@ typedef struct fcb_controllers {
 
 /* Names of the phases timed by fcb_profile_step. */
 enum { FCB_PHASE_RHS = 0, FCB_PHASE_FORWARD = 1, FCB_PHASE_BACKWARD = 2, FCB_PHASE_POST = 3,
-       FCB_PHASE_ELEMENT = 4, FCB_PHASE_MEASURE = 5, FCB_NPHASES = 6 };
+       FCB_PHASE_SPMM = 4 /* Crank-Nicolson only */, FCB_PHASE_ELEMENT = 5, FCB_PHASE_MEASURE = 6, FCB_NPHASES = 7 };
 
 /* Create an ensemble of B trajectories on CUDA device `device`.
  * Replaces FlowSolver._prepare_systems (flowsolver.py:665-701). */

@@ -28,7 +28,7 @@ def near(a, b, tol=3e-16):
     return np.abs(a - b) <= tol
 
 
-def build_cylinder_problem(leaf_cells=16, top_levels=2):
+def build_cylinder_problem(leaf_cells=16, top_levels=2, time_scheme="bdf"):
     tab = TaylorHoodTables.from_file(ROOT / "data/meshes/cylinder_O1.npz")
     blocks = ScalarBlocks(tab)
     r = 0.5
@@ -45,7 +45,8 @@ def build_cylinder_problem(leaf_cells=16, top_levels=2):
     sensors = [SensorPoint(sensor_type=SENSOR_TYPE.V, position=np.array(p)) for p in ((3.0, 0.0), (3.1, 1.0), (3.1, -1.0))]
     UP0 = np.load(ROOT / "tests/golden/cylinder_baseflow.npz")["UP0"]
     t0 = time.time()
-    prob = FlowProblem(tab, blocks, 100.0, 0.005, bcs, acts, sensors, UP0, leaf_cells=leaf_cells, top_levels=top_levels)
+    prob = FlowProblem(tab, blocks, 100.0, 0.005, bcs, acts, sensors, UP0, leaf_cells=leaf_cells, top_levels=top_levels,
+                       time_scheme=time_scheme)
     print(f"problem setup {time.time() - t0:.1f}s  n_free={prob.sym.n} factor entries={prob.sym.factor_entries() / 1e6:.2f}M "
           f"launches={len(prob.plans[2].launch_ptr) - 1}", flush=True)
     return prob, UP0
@@ -65,7 +66,9 @@ if __name__ == "__main__":
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
     nsteps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
     import os
-    prob, UP0 = build_cylinder_problem(leaf_cells=int(os.environ.get("FCB_LEAF", "16")), top_levels=int(os.environ.get("FCB_TOP", "2")))
+    scheme = os.environ.get("FCB_SCHEME", "bdf")
+    prob, UP0 = build_cylinder_problem(leaf_cells=int(os.environ.get("FCB_LEAF", "16")), top_levels=int(os.environ.get("FCB_TOP", "2")),
+                                       time_scheme=scheme)
     tab = prob.tab
     ic = default_ic(tab, UP0)
     ens = Ensemble(prob, B)
@@ -95,6 +98,14 @@ if __name__ == "__main__":
     for name, v in prof.items():
         print(f"  phase {name:9s} {v['ms']:8.3f} ms  launches {v['launches']}")
     print(f"  total {tot:.3f} ms -> {B / tot * 1e3:.0f} trajectory-steps/s (un-graphed, with phase events)")
+    if scheme == "cn":
+        # k_spmm: algorithmic bytes = CSR (12 nnz + 4(n+1)) read once + 8 B per input row and output row per trajectory
+        ldb = 32 if B <= 32 else 64 if B <= 64 else -(-B // 128) * 128
+        nnz, n = prob.E_cn.nnz, prob.sym.n
+        by = 12 * nnz + 4 * (n + 1) + 8 * (tab.Nv + n) * ldb
+        ms = prof["spmm"]["ms"]
+        print(f"  k_spmm: nnz {nnz} rows {n}: {by / 1e6:.1f} MB algorithmic in {ms:.4f} ms -> {by / ms / 1e6:.0f} GB/s "
+              f"({by / ms / 1e6 / 6536:.1%} of the measured 6536 GB/s HBM peak)")
     # graph-replayed steps with device-resident inputs
     import torch
 
