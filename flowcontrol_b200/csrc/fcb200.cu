@@ -509,13 +509,12 @@ constexpr int SPMM_CMAX = 192;   // staged columns per block
 constexpr int SPMM_XS = 36;      // shared row stride in doubles (== 4 mod 16: k-steps with slots distinct mod 4 are conflict-free)
 constexpr int SPMM_WARPS = 8;    // warps = groups per block
 constexpr int SPMM_GREC = 12;    // ints per group record: first k-step, k-steps, 8 solver rows (-1 = none), 2 pad
-constexpr int SPMM_PF = 4;       // k-steps of panel prefetch
 constexpr int SPMM_SMEM = SPMM_CMAX * SPMM_XS * 8;
 
 struct SpmmArgs {
     const int* ucols;              // [nblk][SPMM_CMAX] staged column (canonical velocity dof) per slot, -1 = none
     const int* ginfo;              // [nblk][SPMM_WARPS][SPMM_GREC]
-    const unsigned short* kslots;  // [nk][4] slot of each of the k-step's columns
+    const unsigned short* kslots;  // [nk/4][4 columns][4 k-steps] slot of each k-step's columns, chunked by four k-steps
     const double* avals;           // [nk][32] panel values in A-fragment order: lane l holds (row l/4, column l%4)
     const double* X;
     double* Z;
@@ -543,36 +542,46 @@ __global__ void __launch_bounds__(32 * SPMM_WARPS, 4) k_spmm_mma(const SpmmArgs 
         }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
-    // panel prefetch, SPMM_PF k-steps deep (the panel array is padded so that reading past the group is harmless)
+    // panel prefetch: chunks of four k-steps (four coalesced 256-byte A loads + one 8-byte load of the lane's four
+    // slots), three chunks in registers - two are in flight while one is multiplied.  Groups start on chunk boundaries
+    // and the arrays are padded, so the unconditional loads of the first two chunks stay inside.
     const double* av = p.avals + (size_t)k0 * 32 + lane;
-    const unsigned short* sl = p.kslots + (size_t)k0 * 4 + kq;
-    double a_cur[SPMM_PF], a_nxt[SPMM_PF];
-    int s_cur[SPMM_PF], s_nxt[SPMM_PF];
-#pragma unroll
-    for (int t = 0; t < SPMM_PF; ++t) { a_cur[t] = __ldg(av + 32 * t); s_cur[t] = __ldg(sl + 4 * t); }
+    const uint2* sl = reinterpret_cast<const uint2*>(p.kslots) + (size_t)k0 + kq;  // [chunk][kq][4] u16
+    const int nch = (nk + 3) >> 2;
+    double a_buf[3][4];
+    uint2 s_buf[3];
+#define SPMM_LOAD(B, C)                                                         \
+    do {                                                                        \
+        _Pragma("unroll") for (int t = 0; t < 4; ++t) a_buf[B][t] = __ldg(av + ((C) * 4 + t) * 32); \
+        s_buf[B] = __ldg(sl + (C) * 4);                                         \
+    } while (0)
+    SPMM_LOAD(0, 0);
+    SPMM_LOAD(1, 1);
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     double acc[4][2];
 #pragma unroll
     for (int j = 0; j < 4; ++j) { acc[j][0] = 0.0; acc[j][1] = 0.0; }
-    for (int t0 = 0; t0 < nk; t0 += SPMM_PF) {
-        av += 32 * SPMM_PF;
-        sl += 4 * SPMM_PF;
-        if (t0 + SPMM_PF < nk) {
-#pragma unroll
-            for (int t = 0; t < SPMM_PF; ++t) { a_nxt[t] = __ldg(av + 32 * t); s_nxt[t] = __ldg(sl + 4 * t); }
-        }
-#pragma unroll
-        for (int t = 0; t < SPMM_PF; ++t) {
-            if (t0 + t < nk) {  // warp-uniform
-                const double* xr = xs + s_cur[t] * SPMM_XS + nq;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) dmma(acc[j], a_cur[t], xr[8 * j]);
-            }
-        }
-#pragma unroll
-        for (int t = 0; t < SPMM_PF; ++t) { a_cur[t] = a_nxt[t]; s_cur[t] = s_nxt[t]; }
+#define SPMM_CHUNK(B, C)                                                        \
+    do {                                                                        \
+        _Pragma("unroll") for (int t = 0; t < 4; ++t) {                         \
+            if ((C) * 4 + t < nk) {                                             \
+                const unsigned int pair = t < 2 ? s_buf[B].x : s_buf[B].y;      \
+                const double* xr = xs + ((pair >> (16 * (t & 1))) & 0xffffu) * SPMM_XS + nq; \
+                _Pragma("unroll") for (int j = 0; j < 4; ++j) dmma(acc[j], a_buf[B][t], xr[8 * j]); \
+            }                                                                   \
+        }                                                                       \
+    } while (0)
+    for (int c = 0; c < nch; c += 3) {
+        if (c + 2 < nch) SPMM_LOAD(2, c + 2);
+        SPMM_CHUNK(0, c);
+        if (c + 3 < nch) SPMM_LOAD(0, c + 3);
+        if (c + 1 < nch) SPMM_CHUNK(1, c + 1);
+        if (c + 4 < nch) SPMM_LOAD(1, c + 4);
+        if (c + 2 < nch) SPMM_CHUNK(2, c + 2);
     }
+#undef SPMM_LOAD
+#undef SPMM_CHUNK
     if (row >= 0) {
         double* z = p.Z + (size_t)row * ldb + b0 + 2 * kq;
 #pragma unroll
@@ -939,11 +948,21 @@ __global__ void __launch_bounds__(32 * CTRL_ROWS) k_controller(int nx, int ny, i
 }
 
 // series[step][col][b], columns (dE, u_ctrl_1..na, y_1..ns); single CTA, then the step counter ticks.
+// also accumulates, per trajectory and in time order, the sums the reference's cost functions are made of
+// (utils/optim.py:231-288): costs[0] += dE, costs[1] += sum_k u_ctrl_k^2, costs[2] = dE of the last step
 __global__ void k_log(int na, int ns, const double* __restrict__ dE, const double* __restrict__ uctrl,
                       const double* __restrict__ y, double* __restrict__ series, int* __restrict__ counter,
-                      int capacity, int ldb) {
+                      int capacity, double* __restrict__ costs, int ldb) {
     const int step = *counter;
     const int ncol = 1 + na + ns;
+    for (int b = threadIdx.x; b < ldb; b += blockDim.x) {
+        double u2 = 0.0;
+        for (int k = 0; k < na; ++k) u2 = fma(uctrl[(size_t)k * ldb + b], uctrl[(size_t)k * ldb + b], u2);
+        const double e = dE[b];
+        costs[b] += e;
+        costs[ldb + b] += u2;
+        costs[2 * ldb + b] = e;
+    }
     if (step < capacity) {
         double* row = series + (size_t)step * ncol * ldb;
         for (int i = threadIdx.x; i < ncol * ldb; i += blockDim.x) {
@@ -1035,6 +1054,7 @@ struct fcb_context {
     double* series = nullptr;
     int series_capacity = 0;
     int* counter = nullptr;
+    double* costs = nullptr;  // [3][ldb] running sums of the closed-loop run (k_log)
     // graphs: [parity] for a BDF2 step, [parity][xparity] for a closed-loop BDF2 step
     cudaGraphExec_t g_step[2] = {nullptr, nullptr};
     int g_step_nodes[2] = {0, 0};
@@ -1510,7 +1530,7 @@ int enqueue_controller(fcb_context* h, int xparity) {
 }
 
 int enqueue_log(fcb_context* h) {
-    k_log<<<1, 256, 0, h->stream>>>(h->na, h->ns, h->dE, h->uctrl, h->y, h->series, h->counter, h->series_capacity, h->ldb);
+    k_log<<<1, 256, 0, h->stream>>>(h->na, h->ns, h->dE, h->uctrl, h->y, h->series, h->counter, h->series_capacity, h->costs, h->ldb);
     h->launches += 1;
     CK(cudaGetLastError());
     return FCB_OK;
@@ -1575,7 +1595,7 @@ void destroy(fcb_context* h) {
         for (int j = 0; j < 2; ++j)
             if (h->g_loop[i][j]) cudaGraphExecDestroy(h->g_loop[i][j]);
     }
-    void* ptrs[] = {h->sp_ucols, h->sp_ginfo, h->sp_kslots, h->sp_avals, h->cn_ptr, h->cn_idx, h->cn_val, h->uctrl_prev, h->ccoef_prev, h->crow_prev, h->crow, h->ccoef, h->bc_dofs, h->cell_nodes, h->perm, h->iperm, h->Jinv, h->detJ, h->bc_shape, h->ctrl_rhs[0],
+    void* ptrs[] = {h->costs, h->sp_ucols, h->sp_ginfo, h->sp_kslots, h->sp_avals, h->cn_ptr, h->cn_idx, h->cn_val, h->uctrl_prev, h->ccoef_prev, h->crow_prev, h->crow, h->ccoef, h->bc_dofs, h->cell_nodes, h->perm, h->iperm, h->Jinv, h->detJ, h->bc_shape, h->ctrl_rhs[0],
                     h->ctrl_rhs[1], h->sensor_ptr, h->sensor_idx, h->sensor_val, h->up[0], h->up[1], h->avec,
                     h->bvec[0], h->bvec[1], h->Z, h->epart, h->uctrl, h->y, h->dE, h->diverged, h->Ad, h->Bd, h->Cd,
                     h->Dd, h->Ky, h->Fu, h->xk[0], h->xk[1], h->series, h->counter, h->sweep_dbg,
@@ -1608,19 +1628,22 @@ struct Block {
     int nk = 0, conflicts = 0;
 };
 
-// rows [r, r1) that fit `rowcap` non-empty rows and SPMM_CMAX distinct columns, grouped by eight
-inline void pack_block(const int32_t* ptr, const int32_t* idx, int n, int r, int rowcap, std::vector<int>& slot_of, Block& B) {
+// one block from the given (non-empty) rows; false if they touch more than SPMM_CMAX distinct columns
+inline bool pack_block(const int32_t* ptr, const int32_t* idx, const std::vector<int>& rows, std::vector<int>& slot_of, Block& B) {
     B = Block();
-    int r1 = r;
-    for (; r1 < n && (int)B.rows.size() < rowcap; ++r1) {
-        int fresh = 0;
-        for (int j = ptr[r1]; j < ptr[r1 + 1]; ++j) fresh += slot_of[idx[j]] < 0;
-        if ((int)B.cols.size() + fresh > SPMM_CMAX) break;
-        for (int j = ptr[r1]; j < ptr[r1 + 1]; ++j)
-            if (slot_of[idx[j]] < 0) { slot_of[idx[j]] = (int)B.cols.size(); B.cols.push_back(idx[j]); }
-        if (ptr[r1 + 1] > ptr[r1]) B.rows.push_back(r1);
+    B.rows = rows;
+    bool fits = true;
+    for (int r : rows)
+        for (int j = ptr[r]; j < ptr[r + 1] && fits; ++j)
+            if (slot_of[idx[j]] < 0) {
+                if ((int)B.cols.size() == SPMM_CMAX) { fits = false; break; }
+                slot_of[idx[j]] = (int)B.cols.size();
+                B.cols.push_back(idx[j]);
+            }
+    if (!fits) {
+        for (int c : B.cols) slot_of[c] = -1;
+        return false;
     }
-    B.r1 = r1;
     const int R = (int)B.rows.size();
     std::vector<Bits> bits((size_t)R);
     std::vector<int> order((size_t)R);
@@ -1681,6 +1704,38 @@ inline void pack_block(const int32_t* ptr, const int32_t* idx, int n, int r, int
         B.nk += nk;
         B.groups.push_back(std::move(G));
     }
+    return true;
+}
+
+// Recursive coordinate bisection of the rows (by the position of their mesh node) into k compact clusters of equal
+// size; the two velocity rows of a node stay together.  Compact 2-D clusters touch ~2.2 columns per row, consecutive
+// solver rows (which follow separators, i.e. curves) ~3.1.
+inline void bisect(std::vector<int>& rows, size_t lo, size_t hi, int k, const std::vector<int>& node, const double* xy,
+                   std::vector<std::vector<int>>& out) {
+    if (k <= 1 || hi - lo <= 1) {
+        out.emplace_back(rows.begin() + lo, rows.begin() + hi);
+        return;
+    }
+    double mn[2] = {1e300, 1e300}, mx[2] = {-1e300, -1e300};
+    for (size_t i = lo; i < hi; ++i)
+        for (int a = 0; a < 2; ++a) {
+            const double v = xy[2 * node[rows[i]] + a];
+            mn[a] = std::min(mn[a], v);
+            mx[a] = std::max(mx[a], v);
+        }
+    const int ax = (mx[0] - mn[0] >= mx[1] - mn[1]) ? 0 : 1;
+    std::sort(rows.begin() + lo, rows.begin() + hi, [&](int x, int y) {
+        const double vx = xy[2 * node[x] + ax], vy = xy[2 * node[y] + ax];
+        if (vx != vy) return vx < vy;
+        if (node[x] != node[y]) return node[x] < node[y];
+        return x < y;
+    });
+    const int k1 = k / 2;
+    size_t cut = lo + (size_t)std::llround((double)(hi - lo) * k1 / k);
+    while (cut > lo && cut < hi && node[rows[cut]] == node[rows[cut - 1]]) ++cut;
+    cut = std::min(std::max(cut, lo + 1), hi - 1);
+    bisect(rows, lo, cut, k1, node, xy, out);
+    bisect(rows, cut, hi, k - k1, node, xy, out);
 }
 }  // namespace spmm_pack
 
@@ -1699,33 +1754,48 @@ int build_spmm(fcb_context* h, const fcb_problem* p) {
     std::vector<unsigned short> kslots;
     std::vector<double> avals;
     std::vector<int> slot_of((size_t)h->Nv, -1);
-    size_t nnz_total = 0, conflict_steps = 0, ngroups = 0, staged = 0;
+    size_t nnz_total = 0, conflict_steps = 0, ngroups = 0, staged = 0, ksteps_total = 0;
     Block B;
-    for (int r = 0; r < n;) {
-        int rowcap = 8 * SPMM_WARPS;
-        for (;; rowcap -= 8) {
-            pack_block(ptr, idx, n, r, rowcap, slot_of, B);
-            if ((int)B.groups.size() <= SPMM_WARPS) break;
-            if (rowcap <= 8) return fail(h, FCB_ERR_INVALID, "Crank-Nicolson operator rows near %d do not fit a panel block", r);
-        }
-        r = B.r1;
-        if (B.rows.empty()) continue;  // a run of continuity rows (no entries)
+    std::vector<int> live, node((size_t)n, 0);
+    for (int r = 0; r < n; ++r) {
+        if (ptr[r + 1] > ptr[r]) live.push_back(r);
+        node[r] = p->perm[r] % h->nN;  // canonical dof -> mesh node (ux: node, uy: nN + node)
+    }
+    std::vector<std::vector<int>> work, clusters;
+    if (!live.empty()) bisect(live, 0, live.size(), (int)((live.size() + 8 * SPMM_WARPS - 3) / (8 * SPMM_WARPS - 2)), node, p->node_xy, work);
+    while (!work.empty()) {  // halve the clusters that are too tall or touch too many columns
+        std::vector<int> c = std::move(work.back());
+        work.pop_back();
+        if ((int)c.size() <= 8 * SPMM_WARPS && pack_block(ptr, idx, c, slot_of, B)) { clusters.push_back(std::move(c)); continue; }
+        if (c.size() <= 1) return fail(h, FCB_ERR_INVALID, "Crank-Nicolson operator row %d does not fit a panel block", c.empty() ? -1 : c[0]);
+        std::vector<std::vector<int>> halves;
+        bisect(c, 0, c.size(), 2, node, p->node_xy, halves);
+        for (auto& hc : halves) work.push_back(std::move(hc));
+    }
+    std::reverse(clusters.begin(), clusters.end());  // back to the spatial order of the bisection
+    for (const std::vector<int>& c : clusters) {
+        pack_block(ptr, idx, c, slot_of, B);
         ++nblk;
         ucols.insert(ucols.end(), B.cols.begin(), B.cols.end());
         ucols.resize((size_t)nblk * SPMM_CMAX, -1);  // fixed strides: no descriptor load in front of the gathers
         for (const Group& G : B.groups) {
             const int gnk = (int)G.slots.size() / 4;
-            ginfo.push_back((int)(kslots.size() / 4));
+            const size_t kbase = avals.size() / 32;  // first k-step of the group, a multiple of four
+            ginfo.push_back((int)kbase);
             ginfo.push_back(gnk);
             for (int m = 0; m < 8; ++m) ginfo.push_back(m < G.nm ? B.rows[G.members[m]] : -1);
             ginfo.push_back(0);
             ginfo.push_back(0);
+            const int gpad = (gnk + 3) & ~3;
+            avals.resize((kbase + gpad) * 32, 0.0);
+            kslots.resize((kbase + gpad) * 4, 0);
+            ksteps_total += gnk;
             for (int t = 0; t < gnk; ++t) {
-                const size_t base = avals.size();
-                avals.resize(base + 32, 0.0);
+                const size_t base = (kbase + t) * 32;
                 for (int c = 0; c < 4; ++c) {
                     const int sl = G.slots[t * 4 + c];
-                    kslots.push_back((unsigned short)(sl < 0 ? std::min(c, (int)B.cols.size() - 1) : sl));  // padding: zero panel column on a staged slot
+                    // padding columns: a zero panel column on some staged slot
+                    kslots[((kbase + t) / 4 * 4 + c) * 4 + (t & 3)] = (unsigned short)(sl < 0 ? std::min(c, (int)B.cols.size() - 1) : sl);
                     if (sl < 0) continue;
                     const int col = B.cols[sl];
                     for (int m = 0; m < G.nm; ++m) {
@@ -1746,9 +1816,9 @@ int build_spmm(fcb_context* h, const fcb_problem* p) {
         ngroups += B.groups.size();
         staged += B.cols.size();
     }
-    // the kernel prefetches SPMM_PF k-steps at a time: pad the panel arrays so that reads past the last group stay inside
-    avals.resize(avals.size() + 32 * 2 * SPMM_PF, 0.0);
-    kslots.resize(kslots.size() + 4 * 2 * SPMM_PF, 0);
+    // the kernel loads the first two chunks of a group unconditionally: two chunks of padding at the end
+    avals.resize(avals.size() + 32 * 8, 0.0);
+    kslots.resize(kslots.size() + 4 * 8, 0);
     h->sp_nblk = nblk;
     h->sp_smem = SPMM_SMEM;
     TRY(upload(h, &h->sp_ucols, ucols.data(), std::max<size_t>(ucols.size(), 1)));
@@ -1759,8 +1829,8 @@ int build_spmm(fcb_context* h, const fcb_problem* p) {
     CK(cudaFuncSetAttribute(k_spmm_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, h->sp_smem));
     if (getenv("FCB_VERBOSE"))
         fprintf(stderr, "[fcb] spmm: %d blocks, %zu groups, %zu k-steps (%zu with a bank conflict), nnz %zu, panel fill %.2f, staged columns %zu (%.2f x Nv)\n",
-                h->sp_nblk, ngroups, kslots.size() / 4, conflict_steps, nnz_total,
-                nnz_total ? (double)(kslots.size() / 4 * 32) / (double)nnz_total : 0.0, staged, (double)staged / h->Nv);
+                h->sp_nblk, ngroups, ksteps_total, conflict_steps, nnz_total,
+                nnz_total ? (double)(ksteps_total * 32) / (double)nnz_total : 0.0, staged, (double)staged / h->Nv);
     return FCB_OK;
 }
 
@@ -2097,6 +2167,7 @@ int create_impl(fcb_context* h, const fcb_problem* p, int B) {
     TRY(upload<double>(h, &h->dE, nullptr, L));
     TRY(upload<int>(h, &h->diverged, nullptr, L));
     TRY(upload<int>(h, &h->counter, nullptr, 1));
+    TRY(upload<double>(h, &h->costs, nullptr, 3 * L));
     CK(cudaStreamSynchronize(h->stream));
     return FCB_OK;
 }
@@ -2244,6 +2315,7 @@ int fcb_run_closed_loop(fcb_handle h, int32_t nsteps, double* series) {
     } else {
         CK(cudaMemsetAsync(h->counter, 0, sizeof(int), h->stream));
     }
+    CK(cudaMemsetAsync(h->costs, 0, 3 * (size_t)h->ldb * sizeof(double), h->stream));
     for (int s = 0; s < nsteps; ++s) TRY(run_one_step(h, true));
     if (series && nsteps > 0) {
         CK(cudaMemcpy2DAsync(series, (size_t)h->B * sizeof(double), h->series, (size_t)h->ldb * sizeof(double),
@@ -2259,6 +2331,14 @@ int fcb_get_fields(fcb_handle h, int32_t which, double* up) {
     CK(cudaSetDevice(h->device));
     const double* src = (which == 0) ? h->up[h->parity] : h->up[1 - h->parity];
     TRY(copy_out(h, up, src, which == 0 ? h->N : h->Nv));
+    CK(cudaStreamSynchronize(h->stream));
+    return FCB_OK;
+}
+
+int fcb_get_costs(fcb_handle h, double* costs) {
+    if (!h || !costs) return FCB_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    TRY(copy_out(h, costs, h->costs, 3));
     CK(cudaStreamSynchronize(h->stream));
     return FCB_OK;
 }

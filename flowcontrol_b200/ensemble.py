@@ -120,6 +120,14 @@ class Ensemble:
         self._check(rc, "fcb_run_closed_loop")
         return series
 
+    def costs(self, Tnorm: float = 1.0) -> dict:
+        """Per-trajectory costs of the last run_closed_loop, summed on the device (utils/optim.py:231-288):
+        ``energy_integral`` = compute_signal_cost(dE, Tnorm, 'integral'), ``energy_terminal`` = (…, 'terminal'),
+        ``control`` = compute_control_cost(u_ctrl, Tnorm).  Diverged trajectories carry inf/nan."""
+        out = np.empty((3, self.B))
+        self._check(self.lib.fcb_get_costs(self.h, libfcb.as_voidp(out)), "fcb_get_costs")
+        return {"energy_integral": out[0] * Tnorm, "control": out[1] * Tnorm, "energy_terminal": out[2].copy()}
+
     def fields(self, which: int = 0) -> np.ndarray:
         rows = self.N if which == 0 else self.Nv
         out = np.empty((rows, self.B))

@@ -69,6 +69,7 @@ EXPORTS = {
     "fcb_get_fields": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "fcb_get_measurement": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fcb_get_controller_state": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "fcb_get_costs": (C.c_int, [C.c_void_p, C.c_void_p]),
     "fcb_profile_step": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "fcb_launch_count": (C.c_int64, [C.c_void_p]),
     "fcb_stream": (C.c_void_p, [C.c_void_p]),

@@ -165,6 +165,12 @@ int fcb_get_fields(fcb_handle h, int32_t which, double* up);
 int fcb_get_measurement(fcb_handle h, double* y_meas, double* dE, int32_t* diverged);
 int fcb_get_controller_state(fcb_handle h, double* x);
 
+/* Cost sums of the last fcb_run_closed_loop, accumulated on the device step by step: costs [3 * B] =
+ * (sum_t dE, sum_t sum_k u_ctrl_k^2, dE of the last step).  Multiplied by Tnorm they are the reference's
+ * compute_signal_cost(dE, 'integral' | 'terminal') and compute_control_cost (src/utils/optim.py:231-288); an
+ * optimisation loop over controllers (fun_array, optim.py:48-66) reads 24 bytes per trajectory instead of the series. */
+int fcb_get_costs(fcb_handle h, double* costs);
+
 /* Runs one step with CUDA events between phases; ms[FCB_NPHASES] receives device times,
  * launches[FCB_NPHASES] (may be NULL) the kernel launches per phase. */
 int fcb_profile_step(fcb_handle h, const double* u_ctrl, float* ms, int32_t* launches);

@@ -547,3 +547,39 @@ def test_crank_nicolson_through_the_facade(root, cyl, tmp_path):
         orc.step([0.1 * k, -0.05 * k])
         assert fs.order == "cn"
         assert np.allclose(y, orc.y_meas, rtol=SERIES_TOL, atol=0)
+
+
+def test_device_cost_sums_match_reference_cost_functions(root, cyl):
+    """fcb_get_costs (running sums in k_log) vs the reference's cost functions applied to the logged series
+    (utils/optim.py:231-288), for a gain-swept controller family."""
+    from flowcontrol_b200.controller import Controller, ControllerBank
+    from flowcontrol_b200.costs import compute_control_cost, compute_signal_cost
+    from flowcontrol_b200.ensemble import Ensemble
+    from flowcontrol_b200.sharding import controller_gain_sweep
+
+    fs, prob, _, _ = cyl
+    tab = prob.tab
+    ic = fs._default_initial_perturbation()
+    B, nsteps = 40, 30
+    k = np.load(root / "tests/golden/Kopt_reduced13.npz")
+    ctrls = [Controller(k["A"], g * k["B"], k["C"], g * k["D"]) for g in controller_gain_sweep(B)]
+    ens = Ensemble(prob, B)
+    ens.set_state(ic[: tab.Nv], None, ic[tab.Nv :], order=1)
+    ens.set_controllers(ControllerBank(ctrls, prob.dt, np.array([[-1.0, 0.0, 0.0]]), np.array([[1.0], [1.0]])))
+    series = ens.run_closed_loop(nsteps)
+    Tnorm = prob.dt / (nsteps * prob.dt)
+    c = ens.costs(Tnorm)
+    assert np.allclose(c["energy_integral"], compute_signal_cost(series[:, 0, :], Tnorm, "integral"), rtol=1e-13)
+    assert np.array_equal(c["energy_terminal"], compute_signal_cost(series[:, 0, :], Tnorm, "terminal"))
+    assert np.allclose(c["control"], compute_control_cost(series[:, 1:3, :], Tnorm), rtol=1e-13)
+    b = 7  # one trajectory through the reference's scalar signature
+    assert np.isclose(c["control"][b], compute_control_cost(series[:, 1:3, b], Tnorm), rtol=1e-13)
+    # a run without logging accumulates the same sums
+    ens.set_state(ic[: tab.Nv], None, ic[tab.Nv :], order=1)
+    ens.set_controllers(ControllerBank(ctrls, prob.dt, np.array([[-1.0, 0.0, 0.0]]), np.array([[1.0], [1.0]])))
+    ens.run_closed_loop(nsteps, log=False)
+    c2 = ens.costs(Tnorm)
+    assert all(np.array_equal(c[k_], c2[k_]) for k_ in c)
+    with pytest.raises(ValueError):
+        compute_signal_cost(series[:, 0, 0], Tnorm, "mean")
+    ens.close()
