@@ -75,7 +75,7 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def build_problem():
+def build_problem(time_scheme="bdf"):
     import tempfile
 
     from flowcontrol_b200.examples.cylinder import CylinderFlowSolver
@@ -87,7 +87,7 @@ def build_problem():
     tab = fs.tables
     fs._assign_steady_state(Field(UP0[: tab.Nv]), Field(UP0[tab.Nv :]))
     prob = FlowProblem(tab, fs.blocks, 100.0, 0.005, fs.bc.bcu, fs.params_control.actuator_list,
-                       fs.params_control.sensor_list, UP0)
+                       fs.params_control.sensor_list, UP0, time_scheme=time_scheme)
     return fs, prob
 
 
@@ -141,7 +141,7 @@ def run_ours(args):
     from flowcontrol_b200.ensemble import Ensemble
     from flowcontrol_b200.sharding import gather_series, shard_bounds
 
-    fs, prob = build_problem()
+    fs, prob = build_problem(args.time_scheme)
     tab = prob.tab
     total = B_PER_GPU * world
     lo, hi = shard_bounds(total, rank, world)
@@ -228,6 +228,12 @@ def run_ours(args):
                  "note": "the sweeps run on the FP64 tensor pipe (mma.sync m8n8k4); peak = measured DMMA rate (profiles/r01_fp64_peak.log)"},
         "phase_ms": phase_ms,
     }
+    if prob.time_scheme == "cn":
+        # k_spmm_mma: packed operator read once + one 8-byte read per input row and one write per output row and trajectory
+        sp_bytes = 12 * prob.E_cn.nnz + 4 * (n + 1) + 8 * (tab.Nv + n) * ldb
+        roofline["spmm_kernel"] = {"ms_per_step": phase_ms["spmm"], "algorithmic_bytes_per_step": sp_bytes,
+                                   "achieved_gbs": sp_bytes / (phase_ms["spmm"] * 1e-3) / 1e9,
+                                   "hbm_frac": sp_bytes / (phase_ms["spmm"] * 1e-3) / 1e9 / hbm_peak}
 
     # ---- end to end through the public API with host buffers ---------------------------------------
     host_bank = HostBank(bank)
@@ -258,7 +264,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W, 3),
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic (shipped mesh O1, cached base flow, gain-swept controllers, default ParamIC perturbation)",
-            "config": {"workload": WORKLOAD, "trajectories_per_gpu": B_PER_GPU, "trajectories_total": total,
+            "config": {"workload": WORKLOAD + (" [time_scheme=cn variant]" if args.time_scheme == "cn" else ""), "trajectories_per_gpu": B_PER_GPU, "trajectories_total": total,
                        "dofs_per_trajectory": int(tab.N), "l2": "working set >> L2 (solve buffer 560 MB + packed factors 130 MB + state 430 MB per GPU vs 126 MB L2); no flush needed",
                        "parallelism": f"ensemble-sharded x{world}, time-series all-gather only"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches * world), "roofline": roofline,
@@ -300,6 +306,8 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--time-scheme", default="bdf", choices=["bdf", "cn"],
+                    help="bdf = the reference's default BDF1->BDF2 (the benchmark); cn = Crank-Nicolson variant (adds the SpMM kernel's roofline)")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)
