@@ -149,10 +149,13 @@ __global__ void __launch_bounds__(32 * EP_WARPS, 2) k_element_patch(const PatchA
     if (c0 < c1) { patch_load_ids(p, c0, ids); patch_load_cell(p, c0, ids, b, cur); }
     if (c0 + 1 < c1) patch_load_ids(p, c0 + 1, ids);
     // accumulators start at zero, except (fused right-hand side) the a rows of the patch's own nodes, which start from
-    // b_{n-1}: those loads are all in flight together with the first cell's gathers
+    // b_{n-1}: those 256-byte row segments go straight from global to shared memory (cp.async, 16 bytes per lane: lanes
+    // 0-15 the x row, 16-31 the y row), all in flight together with the first cell's gathers.  (Staged through
+    // registers, eight nodes at a time, this prologue was 40 % of the kernel's warp time.)
     if (p.mode == 1) {
         const size_t ldb = (size_t)p.ldb;
         const int chunk = (nn + EP_WARPS - 1) / EP_WARPS;
+        const int hy = lane >> 4, l16 = lane & 15;
         for (int j0 = w * chunk; j0 < min(nn, (w + 1) * chunk); j0 += 32) {
             const int cnt = min(32, min(nn, (w + 1) * chunk) - j0);
             int l_dst = -1;
@@ -161,25 +164,28 @@ __global__ void __launch_bounds__(32 * EP_WARPS, 2) k_element_patch(const PatchA
                 l_dst = __ldg(p.pnode_dst + n0 + j0 + lane);
                 l_src = __ldg(reinterpret_cast<const unsigned*>(p.psrc) + n0 + j0 + lane);
             }
-#pragma unroll 8
             for (int i = 0; i < cnt; ++i) {
                 const int dst = __shfl_sync(0xffffffffu, l_dst, i);
                 const unsigned src = __shfl_sync(0xffffffffu, l_src, i);
-                double v0 = 0.0, v1 = 0.0;
-                if (dst >= 0) {  // warp-uniform
-                    v0 = p.bprev[(size_t)dst * ldb + b];
-                    v1 = p.bprev[(size_t)(dst + p.nN) * ldb + b];
-                }
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const unsigned rk = (src >> (8 * k)) & 255u;
-                    if (rk != 255u) {
+                    if (rk != 255u) {  // warp-uniform
                         double* t = acc + (size_t)rk * 128 + lane;
-                        t[0] = k == 0 ? v0 : 0.0; t[32] = k == 0 ? v1 : 0.0; t[64] = 0.0; t[96] = 0.0;
+                        if (k == 0 && dst >= 0) {
+                            const double* g = p.bprev + (size_t)(dst + hy * p.nN) * ldb + blockIdx.y * 32 + 2 * l16;
+                            const uint32_t sdst = (uint32_t)__cvta_generic_to_shared(acc + (size_t)rk * 128 + hy * 32 + 2 * l16);
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst), "l"(g) : "memory");
+                        } else {
+                            t[0] = 0.0; t[32] = 0.0;
+                        }
+                        t[64] = 0.0; t[96] = 0.0;
                     }
                 }
             }
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
     } else {
         for (int i = w; i < nrows * 4; i += EP_WARPS) acc[i * 32 + lane] = 0.0;
     }
