@@ -80,6 +80,7 @@ struct PatchArgs {
     double* epart;                 // [npatch, ldb]
     const double* bprev;           // b of the previous state (fused BDF rhs), else NULL
     double* Zb;
+    int tab_off;                   // byte offset of the node tables (dst, src, 3 solver rows per node) behind the accumulators
     int mode;                      // 0: store a and b; 1: Zb rows = a + bprev, store b (BDF); 2: Zb rows += a (Crank-Nicolson)
     int nN, nV, ldb;
     double ca, cb, na, nb;         // a = ca M u + na N(u), b = cb M u + nb N(u)
@@ -87,14 +88,16 @@ struct PatchArgs {
 
 // a/b rows of one node go out: either as a and b, or (fused) as next-step rhs rows and b
 // rows of one node go out.  mode 0: a and b; mode 1 (fused BDF): next-step rhs rows Zb = a (+ bprev if ADD_BPREV, else the
-// caller's a already contains it) and b; mode 2 (Crank-Nicolson): Zb rows += a (k_spmm wrote E u_n there before)
+// caller's a already contains it) and b; mode 2 (Crank-Nicolson): Zb rows = E u_n + a (k_spmm_mma wrote E u_n there; the
+// patch kernel seeds its accumulators with it, the merge kernel adds in place)
 template <bool ADD_BPREV>
 __device__ __forceinline__ void emit_node(int mode, const double* bprev, double* Zb, int rx, int ry, int rp, double* a, double* bout,
                                           int nN, size_t ldb, int nd, int b, double ax, double ay, double bx, double by) {
     const size_t ox = (size_t)nd * ldb + b, oy = (size_t)(nd + nN) * ldb + b;
     if (mode == 2) {
-        if (rx >= 0) Zb[(size_t)rx * ldb + b] += ax;
-        if (ry >= 0) Zb[(size_t)ry * ldb + b] += ay;
+        // ADD_BPREV (k_patch_merge): add to E u_n in place; otherwise the accumulators were seeded with it
+        if (rx >= 0) Zb[(size_t)rx * ldb + b] = ADD_BPREV ? Zb[(size_t)rx * ldb + b] + ax : ax;
+        if (ry >= 0) Zb[(size_t)ry * ldb + b] = ADD_BPREV ? Zb[(size_t)ry * ldb + b] + ay : ay;
         if (rp >= 0) Zb[(size_t)rp * ldb + b] = 0.0;
         return;
     }
@@ -146,36 +149,82 @@ __global__ void __launch_bounds__(32 * EP_WARPS, 2) k_element_patch(const PatchA
     const int nrows = __ldg(p.pacc_rows + blockIdx.x);
     CellIn cur, nxt;
     int ids[6];
-    if (c0 < c1) { patch_load_ids(p, c0, ids); patch_load_cell(p, c0, ids, b, cur); }
-    if (c0 + 1 < c1) patch_load_ids(p, c0 + 1, ids);
+    // second level of dependent loads, all issued before anything waits: node ids of the first cell, the first 32
+    // entries of this warp's node tables (the cp.async of the solver rows follows below)
+    const int chunk = (nn + EP_WARPS - 1) / EP_WARPS;
+    const int j_lo = w * chunk, j_hi = min(nn, (w + 1) * chunk);
+    int l_dst0 = -1;
+    unsigned l_src0 = 0xffffffffu;
+    if (c0 < c1) patch_load_ids(p, c0, ids);
+    int l_rx0 = -1, l_ry0 = -1;  // Crank-Nicolson: the solver rows whose E u_n values seed the accumulators
+    if (j_lo + lane < j_hi) {
+        l_dst0 = __ldg(p.pnode_dst + n0 + j_lo + lane);
+        l_src0 = __ldg(reinterpret_cast<const unsigned*>(p.psrc) + n0 + j_lo + lane);
+        if (p.mode == 2) {
+            l_rx0 = __ldg(p.prow + (size_t)(n0 + j_lo + lane) * 3);
+            l_ry0 = __ldg(p.prow + (size_t)(n0 + j_lo + lane) * 3 + 1);
+        }
+    }
     // accumulators start at zero, except (fused right-hand side) the a rows of the patch's own nodes, which start from
     // b_{n-1}: those 256-byte row segments go straight from global to shared memory (cp.async, 16 bytes per lane: lanes
     // 0-15 the x row, 16-31 the y row), all in flight together with the first cell's gathers.  (Staged through
     // registers, eight nodes at a time, this prologue was 40 % of the kernel's warp time.)
-    if (p.mode == 1) {
-        const size_t ldb = (size_t)p.ldb;
-        const int chunk = (nn + EP_WARPS - 1) / EP_WARPS;
-        const int hy = lane >> 4, l16 = lane & 15;
-        for (int j0 = w * chunk; j0 < min(nn, (w + 1) * chunk); j0 += 32) {
-            const int cnt = min(32, min(nn, (w + 1) * chunk) - j0);
-            int l_dst = -1;
-            unsigned l_src = 0xffffffffu;
-            if (lane < cnt) {
-                l_dst = __ldg(p.pnode_dst + n0 + j0 + lane);
-                l_src = __ldg(reinterpret_cast<const unsigned*>(p.psrc) + n0 + j0 + lane);
+    // node tables of the patch (destination, accumulator rows, solver rows), staged for the write-out: the solver rows
+    // by 4-byte cp.async, destination and sources through the registers the preload below needs anyway
+    int* s_dst = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(acc) + p.tab_off);
+    unsigned* s_src = reinterpret_cast<unsigned*>(s_dst + nn);
+    int* s_row = s_dst + 2 * nn;
+    if (p.mode != 0)
+        for (int j = 3 * j_lo + lane; j < 3 * j_hi; j += 32) {
+            const uint32_t sd = (uint32_t)__cvta_generic_to_shared(s_row + j);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sd), "l"(p.prow + (size_t)n0 * 3 + j) : "memory");
+        }
+    // third level: the first cell's values (its ids have been in flight since above), then the ids of the second cell
+    if (c0 < c1) patch_load_cell(p, c0, ids, b, cur);
+    if (c0 + 1 < c1) patch_load_ids(p, c0 + 1, ids);
+    for (int j0 = j_lo; j0 < j_hi; j0 += 32) {
+        const int cnt = min(32, j_hi - j0);
+        int l_dst = l_dst0, l_rx = l_rx0, l_ry = l_ry0;
+        unsigned l_src = l_src0;
+        if (j0 > j_lo && lane < cnt) {
+            l_dst = __ldg(p.pnode_dst + n0 + j0 + lane);
+            l_src = __ldg(reinterpret_cast<const unsigned*>(p.psrc) + n0 + j0 + lane);
+            if (p.mode == 2) {
+                l_rx = __ldg(p.prow + (size_t)(n0 + j0 + lane) * 3);
+                l_ry = __ldg(p.prow + (size_t)(n0 + j0 + lane) * 3 + 1);
             }
+        }
+        if (lane < cnt) {
+            s_dst[j0 + lane] = l_dst;
+            s_src[j0 + lane] = l_src;
+        }
+        if (p.mode != 0) {
+            const size_t ldb = (size_t)p.ldb;
+            const int hy = lane >> 4, l16 = lane & 15;
             for (int i = 0; i < cnt; ++i) {
                 const int dst = __shfl_sync(0xffffffffu, l_dst, i);
                 const unsigned src = __shfl_sync(0xffffffffu, l_src, i);
+                // the 256-byte row segment this half-warp seeds its accumulator row with: b_{n-1} of the node (BDF) or the
+                // solver row of E u_n (Crank-Nicolson); nodes finished by k_patch_merge and eliminated rows start at zero
+                const double* g = nullptr;
+                if (p.mode == 1) {
+                    if (dst >= 0) g = p.bprev + (size_t)(dst + hy * p.nN) * ldb;
+                } else {
+                    const int rx = __shfl_sync(0xffffffffu, l_rx, i), ry = __shfl_sync(0xffffffffu, l_ry, i);
+                    const int r = hy ? ry : rx;
+                    if (dst >= 0 && r >= 0) g = p.Zb + (size_t)r * ldb;
+                }
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const unsigned rk = (src >> (8 * k)) & 255u;
                     if (rk != 255u) {  // warp-uniform
                         double* t = acc + (size_t)rk * 128 + lane;
-                        if (k == 0 && dst >= 0) {
-                            const double* g = p.bprev + (size_t)(dst + hy * p.nN) * ldb + blockIdx.y * 32 + 2 * l16;
+                        if (k == 0 && g) {
                             const uint32_t sdst = (uint32_t)__cvta_generic_to_shared(acc + (size_t)rk * 128 + hy * 32 + 2 * l16);
-                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst), "l"(g) : "memory");
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst), "l"(g + blockIdx.y * 32 + 2 * l16) : "memory");
+                        } else if (k == 0) {
+                            acc[(size_t)rk * 128 + hy * 32 + 2 * l16] = 0.0;
+                            acc[(size_t)rk * 128 + hy * 32 + 2 * l16 + 1] = 0.0;
                         } else {
                             t[0] = 0.0; t[32] = 0.0;
                         }
@@ -184,9 +233,10 @@ __global__ void __launch_bounds__(32 * EP_WARPS, 2) k_element_patch(const PatchA
                 }
             }
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-    } else {
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (p.mode == 0) {
         for (int i = w; i < nrows * 4; i += EP_WARPS) acc[i * 32 + lane] = 0.0;
     }
     __syncthreads();
@@ -244,29 +294,16 @@ __global__ void __launch_bounds__(32 * EP_WARPS, 2) k_element_patch(const PatchA
         cur = nxt;
     }
     __syncthreads();
-    // write-out: every warp takes a contiguous chunk of the patch's nodes; the lanes fetch the chunk's destinations
-    // with one coalesced load each, then the rows go out four nodes at a time (independent loads in flight)
+    // write-out: every warp takes a contiguous chunk of the patch's nodes (tables staged in shared memory by the
+    // prologue, so nothing here waits on global memory); the rows go out four nodes at a time
     const size_t ldb = (size_t)p.ldb;
-    const int chunk = (nn + EP_WARPS - 1) / EP_WARPS;
-    for (int j0 = w * chunk; j0 < min(nn, (w + 1) * chunk); j0 += 32) {
-        const int cnt = min(32, min(nn, (w + 1) * chunk) - j0);
-        int l_dst = 0, l_rx = -1, l_ry = -1, l_rp = -1;
-        unsigned l_src = 0xffffffffu;
-        if (lane < cnt) {
-            l_dst = __ldg(p.pnode_dst + n0 + j0 + lane);
-            l_src = __ldg(reinterpret_cast<const unsigned*>(p.psrc) + n0 + j0 + lane);
-            if (p.mode != 0) {
-                l_rx = __ldg(p.prow + (size_t)(n0 + j0 + lane) * 3 + 0);
-                l_ry = __ldg(p.prow + (size_t)(n0 + j0 + lane) * 3 + 1);
-                l_rp = __ldg(p.prow + (size_t)(n0 + j0 + lane) * 3 + 2);
-            }
-        }
+    {
 #pragma unroll 4
-        for (int i = 0; i < cnt; ++i) {
-            const int dst = __shfl_sync(0xffffffffu, l_dst, i);
-            const unsigned src = __shfl_sync(0xffffffffu, l_src, i);
-            const int rx = __shfl_sync(0xffffffffu, l_rx, i), ry = __shfl_sync(0xffffffffu, l_ry, i);
-            const int rp = __shfl_sync(0xffffffffu, l_rp, i);
+        for (int j = j_lo; j < j_hi; ++j) {
+            const int dst = s_dst[j];
+            const unsigned src = s_src[j];
+            int rx = -1, ry = -1, rp = -1;
+            if (p.mode != 0) { rx = s_row[3 * j]; ry = s_row[3 * j + 1]; rp = s_row[3 * j + 2]; }
             const double* s = acc + (size_t)(src & 255u) * 128 + lane;
             double v0 = s[0], v1 = s[32], v2 = s[64], v3 = s[96];
 #pragma unroll
@@ -1021,7 +1058,7 @@ struct fcb_context {
     int nblk_total = 0;  // rows of the energy partial sums (one per element patch)
     // patch form of the element kernel
     int use_pdl = 1;
-    int npatch = 0, nshared = 0, patch_smem = 0;
+    int npatch = 0, nshared = 0, patch_smem = 0, patch_tab_off = 0;
     int *pcell_ptr = nullptr, *pcnode = nullptr;
     double* pgeo = nullptr;
     int *pnode_ptr = nullptr, *pnode_dst = nullptr, *mptr = nullptr, *msrc = nullptr,
@@ -1405,7 +1442,7 @@ int enqueue_element(fcb_context* h, const double* u, double* a, double* b, const
     p.pnode_ptr = h->pnode_ptr; p.pnode_dst = h->pnode_dst; p.psrc = h->psrc; p.pacc_rows = h->pacc_rows;
     p.u = u; p.a = a; p.b = b; p.scratch = h->pscratch; p.epart = h->epart;
     p.bprev = bprev; p.Zb = h->Z; p.prow = h->prow;
-    p.nN = h->nN; p.nV = h->nV; p.ldb = h->ldb;
+    p.nN = h->nN; p.nV = h->nV; p.ldb = h->ldb; p.tab_off = h->patch_tab_off;
     p.ca = 2.0 / h->dt; p.cb = -0.5 / h->dt; p.na = -2.0; p.nb = 1.0;  // BDF2: rhs = a_n + b_{n-1}
     if (h->scheme == 1) { p.ca = 0.0; p.cb = 0.0; p.na = -1.0; p.nb = 0.0; }
     dim3 grid(h->npatch, h->ldb / 32), block(32, EP_WARPS);
@@ -1845,7 +1882,7 @@ int build_spmm(fcb_context* h, const fcb_problem* p) {
 // the list into chunks gives compact patches without needing coordinates.
 int build_patches(fcb_context* h, const fcb_problem* p, const std::vector<int>& iperm) {
     const int nT = p->nT, nN = p->nN;
-    int pc = 26;  // cells per patch (upper bound): 4 sub-patches of <= 7 cells, ~100 accumulator rows x 1 KB: two CTAs per SM
+    int pc = 24;  // cells per patch: 4 sub-patches of 6 cells, ~94 accumulator rows x 1 KB: two CTAs per SM (measured 18..30)
     const char* env = getenv("FCB_PATCH_CELLS");
     if (env && atoi(env) >= EP_WARPS && atoi(env) <= 40) pc = atoi(env);
     // Cell order: recursive coordinate bisection of the cell centroids (longer extent, median split) when node
@@ -1861,26 +1898,32 @@ int build_patches(fcb_context* h, const fcb_problem* p, const std::vector<int>& 
         }
         std::vector<int> order(nT);
         for (int e = 0; e < nT; ++e) order[e] = e;
-        struct Range { int lo, hi, below; };  // below: bisection levels below the patch level (-1: still above it)
-        std::vector<Range> stack{{0, nT, nT <= pc ? 0 : -1}};
-        if (nT <= pc) patch_range.push_back({0, nT});
+        // k-way bisection with proportional cuts: ceil(nT / pc) patches of equal size (not a power of two of them),
+        // then two median levels inside a patch order its cells into the four sub-patches
+        struct Range { int lo, hi, k, below; };  // k: patches this range still splits into; below: levels below the patch level
+        const int npatch_target = (nT + pc - 1) / pc;
+        std::vector<Range> stack{{0, nT, npatch_target, npatch_target <= 1 ? 0 : -1}};
+        if (npatch_target <= 1) patch_range.push_back({0, nT});
         while (!stack.empty()) {
             const Range r = stack.back();
             stack.pop_back();
-            if (r.hi - r.lo <= 1 || r.below >= 2) continue;  // two more levels order the cells of a patch into its 4 sub-patches
+            if (r.hi - r.lo <= 1 || r.below >= 2) continue;
             double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
             for (int k = r.lo; k < r.hi; ++k) {
                 x0 = std::min(x0, cx[order[k]]); x1 = std::max(x1, cx[order[k]]);
                 y0 = std::min(y0, cy[order[k]]); y1 = std::max(y1, cy[order[k]]);
             }
             const std::vector<double>& c = (x1 - x0 >= y1 - y0) ? cx : cy;
-            const int mid = r.lo + (r.hi - r.lo) / 2;
+            const int k1 = r.below < 0 ? r.k / 2 : 0;
+            const int mid = r.below < 0 ? r.lo + (int)std::llround((double)(r.hi - r.lo) * k1 / r.k) : r.lo + (r.hi - r.lo) / 2;
             std::nth_element(order.begin() + r.lo, order.begin() + mid, order.begin() + r.hi,
                              [&](int a, int b) { return c[a] < c[b] || (c[a] == c[b] && a < b); });
-            for (const auto& half : {std::pair<int, int>{r.lo, mid}, std::pair<int, int>{mid, r.hi}}) {
+            const int ks[2] = {k1, r.k - k1};
+            const std::pair<int, int> halves[2] = {{r.lo, mid}, {mid, r.hi}};
+            for (int hh = 0; hh < 2; ++hh) {
                 int below = r.below >= 0 ? r.below + 1 : -1;
-                if (r.below < 0 && half.second - half.first <= pc) { below = 0; patch_range.push_back(half); }
-                stack.push_back({half.first, half.second, below});
+                if (r.below < 0 && ks[hh] <= 1) { below = 0; patch_range.push_back(halves[hh]); }
+                stack.push_back({halves[hh].first, halves[hh].second, ks[hh], below});
             }
         }
         std::sort(patch_range.begin(), patch_range.end());
@@ -1979,7 +2022,10 @@ int build_patches(fcb_context* h, const fcb_problem* p, const std::vector<int>& 
             return fail(h, FCB_ERR_INVALID, "P2 node %d belongs to no cell", nd);
     h->npatch = npatch;
     h->nshared = (int)mnode.size();
-    h->patch_smem = max_nodes * 4 * 32 * (int)sizeof(double);
+    int max_nn = 0;
+    for (int q = 0; q < npatch; ++q) max_nn = std::max(max_nn, pnode_ptr[q + 1] - pnode_ptr[q]);
+    h->patch_tab_off = max_nodes * 4 * 32 * (int)sizeof(double);
+    h->patch_smem = h->patch_tab_off + ((5 * max_nn * (int)sizeof(int) + 15) & ~15);  // accumulators + node tables
     h->nblk_total = npatch;
     if (h->patch_smem > 220 * 1024) return fail(h, FCB_ERR_INVALID, "element patches too large for shared memory");
     CK(cudaFuncSetAttribute(k_element_patch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->patch_smem));
