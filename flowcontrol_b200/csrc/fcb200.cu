@@ -918,9 +918,14 @@ constexpr int MEAS_WARPS = 32;
 __global__ void __launch_bounds__(32 * MEAS_WARPS) k_measure(int ns, const int* __restrict__ sptr, const int* __restrict__ sidx,
                                                            const double* __restrict__ sval, const double* __restrict__ up,
                                                            double* __restrict__ y, const double* __restrict__ epart, int nblk,
-                                                           double* __restrict__ dE, int ldb) {
+                                                           double* __restrict__ dE, int na, const double* __restrict__ uctrl,
+                                                           double* __restrict__ uctrl_prev, int ldb) {
     const int b = blockIdx.x * 32 + threadIdx.x;
     const int ty = threadIdx.y;
+    // Crank-Nicolson: this step's control becomes "the previous step's" (the averaged body force of the next rhs); a
+    // memcpy node in the step graph for these few kB cost 70 us
+    if (uctrl_prev)
+        for (int k = ty; k < na; k += MEAS_WARPS) uctrl_prev[(size_t)k * ldb + b] = uctrl[(size_t)k * ldb + b];
     for (int s = ty; s < ns; s += MEAS_WARPS) {
         double acc = 0.0;
         for (int j = __ldg(sptr + s); j < __ldg(sptr + s + 1); ++j)
@@ -1459,10 +1464,10 @@ int enqueue_element(fcb_context* h, const double* u, double* a, double* b, const
     return FCB_OK;
 }
 
-int enqueue_measure(fcb_context* h, const double* up) {
+int enqueue_measure(fcb_context* h, const double* up, bool roll_ctrl = false) {
     dim3 grid(h->ldb / 32), block(32, MEAS_WARPS);
     k_measure<<<grid, block, 0, h->stream>>>(h->ns, h->sensor_ptr, h->sensor_idx, h->sensor_val, up, h->y, h->epart,
-                                             h->nblk_total, h->dE, h->ldb);
+                                             h->nblk_total, h->dE, h->na, h->uctrl, roll_ctrl ? h->uctrl_prev : nullptr, h->ldb);
     h->launches += 1;
     CK(cudaGetLastError());
     return FCB_OK;
@@ -1555,9 +1560,7 @@ int enqueue_step(fcb_context* h, int order, int parity, bool rhs_ready, PhaseMar
     // b(u_new) replaces b_{n-1}; the rhs of the next step = a(u_new) + b_n, with b_n = bvec[parity]
     TRY(enqueue_element(h, nxt, h->avec, h->bvec[1 - parity], h->bvec[parity]));
     if (pm) pm->mark(FCB_PHASE_MEASURE);
-    TRY(enqueue_measure(h, nxt));
-    if (h->scheme == 1 && h->na > 0)
-        CK(cudaMemcpyAsync(h->uctrl_prev, h->uctrl, (size_t)h->na * h->ldb * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    TRY(enqueue_measure(h, nxt, h->scheme == 1 && h->na > 0));
     if (pm) pm->mark(FCB_NPHASES);
     CK(cudaGetLastError());
     return FCB_OK;
@@ -1804,15 +1807,24 @@ int build_spmm(fcb_context* h, const fcb_problem* p) {
         if (ptr[r + 1] > ptr[r]) live.push_back(r);
         node[r] = p->perm[r] % h->nN;  // canonical dof -> mesh node (ux: node, uy: nN + node)
     }
+    // without coordinates, the position of a node in the solver's nested-dissection order stands in for them
+    std::vector<double> order_xy;
+    const double* xy = p->node_xy;
+    if (!xy) {
+        order_xy.assign((size_t)2 * h->nN, 0.0);
+        for (int r = n - 1; r >= 0; --r)
+            if (ptr[r + 1] > ptr[r]) order_xy[2 * (size_t)node[r]] = (double)r;
+        xy = order_xy.data();
+    }
     std::vector<std::vector<int>> work, clusters;
-    if (!live.empty()) bisect(live, 0, live.size(), (int)((live.size() + 8 * SPMM_WARPS - 3) / (8 * SPMM_WARPS - 2)), node, p->node_xy, work);
+    if (!live.empty()) bisect(live, 0, live.size(), (int)((live.size() + 8 * SPMM_WARPS - 3) / (8 * SPMM_WARPS - 2)), node, xy, work);
     while (!work.empty()) {  // halve the clusters that are too tall or touch too many columns
         std::vector<int> c = std::move(work.back());
         work.pop_back();
         if ((int)c.size() <= 8 * SPMM_WARPS && pack_block(ptr, idx, c, slot_of, B)) { clusters.push_back(std::move(c)); continue; }
         if (c.size() <= 1) return fail(h, FCB_ERR_INVALID, "Crank-Nicolson operator row %d does not fit a panel block", c.empty() ? -1 : c[0]);
         std::vector<std::vector<int>> halves;
-        bisect(c, 0, c.size(), 2, node, p->node_xy, halves);
+        bisect(c, 0, c.size(), 2, node, xy, halves);
         for (auto& hc : halves) work.push_back(std::move(hc));
     }
     std::reverse(clusters.begin(), clusters.end());  // back to the spatial order of the bisection

@@ -83,7 +83,7 @@ typedef struct fcb_problem {
     const int32_t* cell_nodes; /* [nT*6] P2 node ids, local order v0 v1 v2 m12 m02 m01 */
     const double* Jinv;        /* [nT*4] row-major d(ref)/d(phys)                      */
     const double* detJ;        /* [nT] |det J|                                         */
-    const double* node_xy;     /* [nN*2] P2 node coordinates, or NULL (only used to group cells into compact patches) */
+    const double* node_xy;     /* [nN*2] P2 node coordinates, or NULL (only used to group cells and operator rows into compact patches) */
     /* unknown numbering */
     int32_t n_free;
     const int32_t* perm;    /* [n_free] solver row -> canonical dof in [0, 2nN+nV) */
