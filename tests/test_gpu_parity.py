@@ -583,3 +583,42 @@ def test_device_cost_sums_match_reference_cost_functions(root, cyl):
     with pytest.raises(ValueError):
         compute_signal_cost(series[:, 0, 0], Tnorm, "mean")
     ens.close()
+
+
+def test_create_rejects_inconsistent_crank_nicolson_input(cyl):
+    """fcb_create fails loudly (negative status + message) when scheme = 1 comes without its operator, and the scalar CSR
+    SpMM kept for A/B runs (FCB_SPMM_CSR=1) gives the same step as the tensor-core panels to round-off."""
+    import ctypes as C
+    import os
+
+    from flowcontrol_b200 import libfcb
+    from flowcontrol_b200.ensemble import Ensemble
+    from flowcontrol_b200.problem import FlowProblem
+
+    fs, prob_bdf, _, UP0 = cyl
+    tab = prob_bdf.tab
+    lib = libfcb.load()
+    pack = libfcb.ProblemPack(prob_bdf)
+    pack.struct.scheme = 1  # claims Crank-Nicolson but carries no CSR operator
+    h = C.c_void_p()
+    rc = lib.fcb_create(C.byref(pack.struct), 32, 0, C.byref(h))
+    assert rc < 0 and not h.value
+    assert b"cn_ptr" in lib.fcb_last_error(None)
+    pack.struct.scheme = 7
+    assert lib.fcb_create(C.byref(pack.struct), 32, 0, C.byref(h)) < 0
+    prob = FlowProblem(tab, fs.blocks, 100.0, 0.005, fs.bc.bcu, fs.params_control.actuator_list,
+                       fs.params_control.sensor_list, UP0, time_scheme="cn", symbolic=prob_bdf.sym)
+    ic = fs._default_initial_perturbation(2.0, 0.0, 0.5)
+    ups = []
+    for csr in ("0", "1"):
+        os.environ["FCB_SPMM_CSR"] = csr
+        try:
+            ens = Ensemble(prob, 40)
+        finally:
+            os.environ.pop("FCB_SPMM_CSR")
+        ens.set_state(ic[: tab.Nv], None, ic[tab.Nv :], order="cn")
+        for k in range(5):
+            ens.step(np.full((2, 40), 0.1 * k))
+        ups.append(ens.fields(0)[:, 17].copy())
+        ens.close()
+    assert rel(ups[0], ups[1]) < 1e-13
