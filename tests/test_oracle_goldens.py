@@ -108,3 +108,40 @@ def test_cylinder_base_flow_recomputed(root):
     assert np.isclose(U0.max(), REF["cylinder"][0], rtol=1e-12)
     assert np.isclose(U0.mean(), REF["cylinder"][1], rtol=1e-12)
     assert np.allclose(UP, golden(root, "cylinder_baseflow.npz")["UP0"], atol=1e-11)
+
+
+def test_jacobian_frobenius_norm_matches_reference_golden(root):
+    """tests/integration/test_operatorgetter.py:23-26 locks ||A||_F of the linearised operator A = -dF/dUP0 (with the
+    perturbation Dirichlet rows replaced by identity rows, operatorgetter.py:80-81) to 55.37024024761875 on the
+    cylinder at Re=100.  The Frobenius norm does not depend on the dof numbering, so it pins the C + D + K/Re, pressure
+    and continuity blocks of BOTH the oracle and the product's setup (the blocks every LHS / explicit operator is made of)."""
+    import scipy.sparse as sp
+    import tempfile
+    from pathlib import Path
+
+    ref = 55.37024024761875
+    UP0 = golden(root, "cylinder_baseflow.npz")["UP0"]
+    case = cases.cylinder(100.0)
+    xy, tri = cases.load_mesh(case.mesh_file)
+    fo = FlowOracle(case, xy, tri)
+    fo.set_base_flow(UP0)
+    m = fo.mesh
+
+    def fro(L, dofs):
+        keep = np.ones(L.shape[0])
+        keep[dofs] = 0.0
+        A = (sp.diags(keep) @ L.tocsr()).tocsr()
+        return float(np.sqrt((A.data**2).sum() + len(dofs)))
+
+    assert np.isclose(fro(fo.ops.lhs(0.0, 100.0, UP0[: m.Nv], newton_terms=True), fo.bc_pert.dofs), ref, rtol=1e-11)
+    # the product's own blocks and Dirichlet set
+    from flowcontrol_b200.examples.cylinder import CylinderFlowSolver
+    from flowcontrol_b200.flowfield import Field
+    from flowcontrol_b200.problem import DirichletSet
+
+    fs = CylinderFlowSolver.make_default(path_out=Path(tempfile.mkdtemp()))
+    tab = fs.tables
+    fs._assign_steady_state(Field(UP0[: tab.Nv]), Field(UP0[tab.Nv :]))
+    L = fs.blocks.saddle_point(0.0, 100.0, UP0[: tab.Nv], shift=0.0, linearised=True)
+    dset = DirichletSet(tab, fs.bc.bcu, fs.params_control.actuator_list)
+    assert np.isclose(fro(L, dset.dofs), ref, rtol=1e-11)
