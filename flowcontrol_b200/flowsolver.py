@@ -59,6 +59,27 @@ def between(a, lo, hi, tol: float = 0.0):
     return (a >= lo - tol) & (a <= hi + tol)
 
 
+class HostLUSolver:
+    """``dolfin.LUSolver``-shaped view of the factorised LHS of one time-stepping order: ``solve(x, b)`` with ``b`` the
+    assembled right-hand side in canonical numbering (Dirichlet rows holding the boundary values, lifting already
+    applied, as ``SystemAssembler`` leaves it) fills ``x``: ``x[free] = A_ff^-1 b[free]``, ``x[bc] = b[bc]``."""
+
+    def __init__(self, problem: FlowProblem, order=2):
+        self.problem = problem
+        self.order = 2 if order == "cn" else int(order)
+
+    def set_operator(self, A=None) -> None:
+        """The operator is fixed at setup (flowsolver.py:697); kept for call compatibility."""
+
+    def solve(self, x, b) -> int:
+        prob = self.problem
+        b = np.asarray(b, dtype=np.float64)
+        x = np.asarray(x)
+        x[prob.sym.perm] = prob.factors[self.order].solve(b[prob.sym.perm])
+        x[prob.dirichlet.dofs] = b[prob.dirichlet.dofs]
+        return 1
+
+
 class FlowSolver(ABC):
     def __init__(
         self,
@@ -232,6 +253,9 @@ class FlowSolver(ABC):
         self.fields.UP0 = self.merge(U0, P0)
         self.E0 = 0.5 * float(U0.array @ (self.blocks.Mv @ U0.array))
         self.problem = None  # LHS depends on the base flow
+        if self.ensemble is not None:
+            self.ensemble.close()
+            self.ensemble = None
 
     def _define_initial_guess(self, initial_guess=None) -> np.ndarray:
         if initial_guess is not None:
@@ -245,24 +269,39 @@ class FlowSolver(ABC):
         return np.full_like(x, self.params_flow.uinf), np.zeros_like(x)
 
     # ── time stepping ─────────────────────────────────────────────────────────
-    def _build_problem(self) -> None:
+    def _make_problem(self) -> FlowProblem:
+        """Host setup of the constant operators (the reference's _prepare_systems, flowsolver.py:665-701)."""
         pe = self.params_ensemble
-        self.problem = FlowProblem(
+        return FlowProblem(
             self.tables, self.blocks, self.params_flow.Re, self.params_time.dt, self.bc.bcu,
             self.params_control.actuator_list, self.params_control.sensor_list, self.fields.UP0.array,
             nonlinear=self.params_solver.is_eq_nonlinear, shift=self.params_solver.shift,
             pin_pressure=self._pin_pressure(), leaf_cells=pe.leaf_cells, top_levels=pe.top_levels,
             time_scheme=self.params_solver.time_scheme,
         )
+
+    def _build_problem(self) -> None:
+        pe = self.params_ensemble
+        if self.problem is None:
+            self.problem = self._make_problem()
         if self.ensemble is not None:
             self.ensemble.close()
         self.ensemble = Ensemble(self.problem, pe.batch, pe.device)
+
+    def _make_solver(self, order=2) -> "HostLUSolver":
+        """The reference's linear-solver hook (flowsolver.py:812-814; docs/numerical-details.md:44-48): an object with
+        ``set_operator(A)`` and ``solve(x, b)``.  On this path the factor of the constant LHS lives on the device and
+        ``step()`` never calls the hook; the object returned here solves the same BC-applied system on the host with the
+        same multifrontal factor (setup checks, operator tooling).  Overriding it does not redirect the device solve."""
+        if self.problem is None:
+            self.problem = self._make_problem()
+        return HostLUSolver(self.problem, "cn" if self.params_solver.time_scheme == "cn" else order)
 
     def initialize_time_stepping(self, Tstart: float = 0.0, ic=None) -> None:
         """ic: None, a Field / array [N] shared by all trajectories, or an array [N, B]."""
         if self.fields.UP0 is None:
             raise RuntimeError("compute_steady_state or load_steady_state must be called first")
-        if self.problem is None:
+        if self.problem is None or self.ensemble is None:
             self._build_problem()
         if Tstart == 0.0:
             up_ic, u_n, u_nn, order = self._initialize_with_ic(ic)

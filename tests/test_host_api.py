@@ -123,3 +123,35 @@ def test_mesh_reader_on_reference_files(root):
         xy, tri = read_xdmf_mesh(ref / rel)
         d = np.load(root / "data" / "meshes" / f"{fixture}.npz")
         assert np.array_equal(xy, d["vertices"]) and np.array_equal(tri, d["triangles"])
+
+
+def test_make_solver_hook_solves_the_bc_applied_system(root, tmp_path):
+    """FlowSolver._make_solver (flowsolver.py:812-814): object with set_operator / solve(x, b); here a host view of the
+    multifrontal factor.  Checked against SuperLU on the oracle's BC-applied BDF2 matrix (lid cavity, pinned pressure)."""
+    import scipy.sparse.linalg as spla
+
+    from flowcontrol_b200.examples.lidcavity import LidCavityFlowSolver
+    from flowcontrol_b200.flowfield import Field
+    from oracle import cases
+    from oracle.flow_oracle import FlowOracle
+
+    UP0 = np.load(root / "tests/golden/lidcavity_baseflow.npz")["UP0"]
+    fs = LidCavityFlowSolver.make_default(Re=1000.0, path_out=tmp_path)
+    tab = fs.tables
+    fs._assign_steady_state(Field(UP0[: tab.Nv]), Field(UP0[tab.Nv :]))
+    solver = fs._make_solver(order=2)
+    solver.set_operator(None)
+    case = cases.lidcavity(1000.0)
+    xy, tri = cases.load_mesh(case.mesh_file)
+    orc = FlowOracle(case, xy, tri)
+    orc.set_base_flow(UP0)
+    orc.prepare()
+    rng = np.random.default_rng(0)
+    b = rng.standard_normal(tab.N)
+    b[orc.bc_pert.dofs] = 0.3 * rng.standard_normal(len(orc.bc_pert.dofs))
+    b[tab.Nv] = 0.0  # pinned pressure dof
+    x = np.zeros(tab.N)
+    assert solver.solve(x, b) == 1
+    ref = spla.splu(orc.A_bc[2]).solve(b)
+    assert np.linalg.norm(x - ref) / np.linalg.norm(ref) < 1e-9
+    assert fs.ensemble is None  # the hook alone never needs the GPU
