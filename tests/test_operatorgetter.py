@@ -1,0 +1,83 @@
+"""OperatorGetter (reference: src/flowcontrol/operatorgetter.py, tests/integration/test_operatorgetter.py) on the
+cylinder at Re=100: Frobenius-norm regression constant of the reference, finite-difference validation of A against the
+steady residual, lifting consistency of B, C rows vs Sensor.eval, and the frequency response against a dense solve."""
+import tempfile
+from pathlib import Path
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from flowcontrol_b200.operatorgetter import OperatorGetter, get_frequency_response_sequential
+
+
+@pytest.fixture(scope="module")
+def fs_cylinder(root):
+    from flowcontrol_b200.examples.cylinder import CylinderFlowSolver
+    from flowcontrol_b200.flowfield import Field
+
+    UP0 = np.load(root / "tests/golden/cylinder_baseflow.npz")["UP0"]
+    fs = CylinderFlowSolver.make_default(path_out=Path(tempfile.mkdtemp()))
+    tab = fs.tables
+    fs._assign_steady_state(Field(UP0[: tab.Nv]), Field(UP0[tab.Nv :]))
+    return fs, UP0
+
+
+def test_get_A_frobenius_regression_and_shapes(fs_cylinder):
+    fs, UP0 = fs_cylinder
+    og = OperatorGetter(fs)
+    A, E, B, C = og.get_all()
+    N = fs.tables.N
+    assert A.shape == (N, N) and E.shape == (N, N) and B.shape == (N, 2) and C.shape == (3, N)
+    assert np.isclose(np.sqrt((A.data**2).sum()), 55.37024024761875, rtol=1e-11)  # test_operatorgetter.py:23-26
+    assert abs(E[fs.tables.Nv :, :]).sum() == 0 and abs(E[:, fs.tables.Nv :]).sum() == 0  # no pressure mass
+    assert np.isclose(E.sum(), 2 * 20 * 30 - 2 * np.pi * 0.25, rtol=1e-3)  # two components x area of the domain minus cylinder
+
+
+def test_get_A_matches_finite_differences_of_the_steady_residual(fs_cylinder):
+    """A x = -(F(UP0 + h x) - F(UP0)) / h on interior dofs (test_operatorgetter.py:111-140)."""
+    from flowcontrol_b200.problem import DirichletSet
+    from flowcontrol_b200.steadystate import SteadyStateSolver
+
+    fs, UP0 = fs_cylinder
+    tab = fs.tables
+    A = OperatorGetter(fs).get_A()
+    dset = DirichletSet(tab, fs.bc.bcu, fs.params_control.actuator_list)
+    sol = SteadyStateSolver(tab, fs.blocks, fs.params_flow.Re, dset)
+    interior = np.setdiff1d(np.arange(tab.N), dset.dofs)
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(tab.N)
+    x[dset.dofs] = 0.0
+    h = 1e-6
+    fd = -(sol.residual(UP0 + h * x) - sol.residual(UP0)) / h
+    Ax = A @ x
+    assert np.linalg.norm(Ax[interior] - fd[interior]) / np.linalg.norm(fd[interior]) < 1e-5
+    assert np.array_equal(Ax[dset.dofs], x[dset.dofs])  # identity rows
+
+
+def test_B_lifting_and_C_rows(fs_cylinder):
+    fs, UP0 = fs_cylinder
+    tab = fs.tables
+    og = OperatorGetter(fs)
+    B, C = og.get_B(), og.get_C()
+    # a BC actuator only loads the rows of the cells touching its slot
+    assert 0 < np.count_nonzero(B[:, 0]) < 600 and 0 < np.count_nonzero(B[:, 1]) < 600
+    # the two slots are mirror images on a nearly symmetric mesh: similar column norms
+    assert np.isclose(np.linalg.norm(B[:, 0]), np.linalg.norm(B[:, 1]), rtol=0.05)
+    up = np.random.default_rng(1).standard_normal(tab.N)
+    for s, sensor in enumerate(fs.params_control.sensor_list):
+        assert np.isclose(C[s] @ up, sensor.eval(up), rtol=1e-12)  # test_sensor.py:172-181 / test_operatorgetter.py:238-254
+
+
+def test_frequency_response_matches_dense_solve():
+    rng = np.random.default_rng(3)
+    n = 30
+    A = sp.csr_matrix(-2.0 * np.eye(n) + 0.3 * rng.standard_normal((n, n)))
+    Q = sp.diags(rng.uniform(0.5, 2.0, n)).tocsr()
+    B, C = rng.standard_normal((n, 2)), rng.standard_normal((3, n))
+    ww = np.array([0.0, 0.7, 5.0])
+    H, w = get_frequency_response_sequential(A, B, C, Q, ww)
+    assert H.shape == (3, 2, 3) and np.array_equal(w, ww)
+    for i, wi in enumerate(ww):
+        ref = C @ np.linalg.solve(1j * wi * Q.toarray() - A.toarray(), B)
+        assert np.allclose(H[:, :, i], ref, rtol=1e-10, atol=1e-12)
