@@ -1103,6 +1103,7 @@ struct fcb_context {
     int series_capacity = 0;
     int* counter = nullptr;
     double* costs = nullptr;  // [3][ldb] running sums of the closed-loop run (k_log)
+    double *pin_in = nullptr, *pin_out = nullptr;  // pinned staging of fcb_step's host arguments
     // graphs: [parity] for a BDF2 step, [parity][xparity] for a closed-loop BDF2 step
     cudaGraphExec_t g_step[2] = {nullptr, nullptr};
     int g_step_nodes[2] = {0, 0};
@@ -1636,6 +1637,8 @@ void destroy(fcb_context* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->pin_in) cudaFreeHost(h->pin_in);
+    if (h->pin_out) cudaFreeHost(h->pin_out);
     for (int i = 0; i < 2; ++i) {
         if (h->g_step[i]) cudaGraphExecDestroy(h->g_step[i]);
         for (int j = 0; j < 2; ++j)
@@ -2232,6 +2235,12 @@ int create_impl(fcb_context* h, const fcb_problem* p, int B) {
     TRY(upload<int>(h, &h->diverged, nullptr, L));
     TRY(upload<int>(h, &h->counter, nullptr, 1));
     TRY(upload<double>(h, &h->costs, nullptr, 3 * L));
+    if (cudaMallocHost((void**)&h->pin_in, (size_t)std::max(h->na, 1) * h->B * sizeof(double)) != cudaSuccess ||
+        cudaMallocHost((void**)&h->pin_out, ((size_t)h->ns + 2) * h->B * sizeof(double)) != cudaSuccess) {
+        cudaGetLastError();  // no pinned memory: the step falls back to direct (blocking) copies
+        if (h->pin_in) cudaFreeHost(h->pin_in);
+        h->pin_in = h->pin_out = nullptr;
+    }
     CK(cudaStreamSynchronize(h->stream));
     return FCB_OK;
 }
@@ -2340,17 +2349,43 @@ int fcb_set_controllers(fcb_handle h, const fcb_controllers* c) {
     return FCB_OK;
 }
 
+// pageable host memory (plain numpy arrays): copies to and from it block the calling thread one by one; the step
+// stages them through pinned buffers of the handle instead, so that all transfers are asynchronous and the call
+// synchronises once
+static bool is_pageable_host(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return at.type == cudaMemoryTypeUnregistered;
+}
+
 int fcb_step(fcb_handle h, const double* u_ctrl, double* y_meas, double* dE, int32_t* diverged) {
     if (!h) return FCB_ERR_INVALID;
     if (!h->have_state) return fail(h, FCB_ERR_STATE, "fcb_step: call fcb_set_state first");
     if (h->na > 0 && !u_ctrl) return fail(h, FCB_ERR_INVALID, "fcb_step: u_ctrl is NULL");
     CK(cudaSetDevice(h->device));
-    if (h->na > 0) TRY(copy_in(h, h->uctrl, u_ctrl, h->na));
+    const size_t B = (size_t)h->B;
+    if (h->na > 0) {
+        if (h->pin_in && is_pageable_host(u_ctrl)) {
+            memcpy(h->pin_in, u_ctrl, (size_t)h->na * B * sizeof(double));
+            TRY(copy_in(h, h->uctrl, h->pin_in, h->na));
+        } else {
+            TRY(copy_in(h, h->uctrl, u_ctrl, h->na));
+        }
+    }
     TRY(run_one_step(h, false));
-    if (y_meas && h->ns > 0) TRY(copy_out(h, y_meas, h->y, h->ns));
-    if (dE) TRY(copy_out(h, dE, h->dE, 1));
-    if (diverged) TRY(copy_out(h, diverged, h->diverged, 1));
+    double* py = h->pin_out;                                   // [ns][B] y, [B] dE, then [B] ints
+    double* pe = h->pin_out ? h->pin_out + (size_t)h->ns * B : nullptr;
+    int32_t* pd = h->pin_out ? reinterpret_cast<int32_t*>(pe + B) : nullptr;
+    const bool sy = y_meas && h->ns > 0 && h->pin_out && is_pageable_host(y_meas);
+    const bool se = dE && h->pin_out && is_pageable_host(dE);
+    const bool sd = diverged && h->pin_out && is_pageable_host(diverged);
+    if (y_meas && h->ns > 0) TRY(copy_out(h, sy ? py : y_meas, h->y, h->ns));
+    if (dE) TRY(copy_out(h, se ? pe : dE, h->dE, 1));
+    if (diverged) TRY(copy_out(h, sd ? pd : diverged, h->diverged, 1));
     CK(cudaStreamSynchronize(h->stream));
+    if (sy) memcpy(y_meas, py, (size_t)h->ns * B * sizeof(double));
+    if (se) memcpy(dE, pe, B * sizeof(double));
+    if (sd) memcpy(diverged, pd, B * sizeof(int32_t));
     return FCB_OK;
 }
 
