@@ -43,6 +43,18 @@ def gather_series(local, total: int, group=None):
     return torch.cat([o[:, :, :w] for o, w in zip(out, widths)], dim=2)
 
 
+def gather_costs(local: dict, total: int, device=None, group=None) -> dict:
+    """All-gather the per-trajectory cost sums of every shard (``Ensemble.costs()``: dict of ``[B_local]`` arrays) into
+    dicts of ``[total]`` arrays on every rank: what an optimiser rank needs from a sharded controller sweep
+    (24 bytes per trajectory instead of the time series).  Implemented on top of ``gather_series``."""
+    import torch
+
+    keys = sorted(local)
+    block = torch.as_tensor(np.stack([np.asarray(local[k], dtype=np.float64) for k in keys])[None], device=device)
+    full = gather_series(block, total, group=group)[0].cpu().numpy()
+    return {k: full[i] for i, k in enumerate(keys)}
+
+
 def controller_gain_sweep(B: int, lo: float = 0.5, hi: float = 1.5) -> np.ndarray:
     """Deterministic gain family of config 2: g_b = lo + (hi-lo) b/(B-1)."""
     if B == 1:

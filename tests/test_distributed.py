@@ -37,7 +37,14 @@ def _worker(rank, world, port, total, q):
     lo, hi = shard_bounds(total, rank, world)
     full = torch.arange(5 * 3 * total, dtype=torch.float64).reshape(5, 3, total)
     out = gather_series(full[:, :, lo:hi].contiguous(), total)
-    q.put((rank, bool(torch.equal(out, full))))
+    ok = bool(torch.equal(out, full))
+    from flowcontrol_b200.sharding import gather_costs
+
+    costs = {"energy_integral": full[0, 0, lo:hi].numpy(), "control": full[1, 1, lo:hi].numpy(), "energy_terminal": full[2, 2, lo:hi].numpy()}
+    g = gather_costs(costs, total)
+    ok = ok and np.array_equal(g["energy_integral"], full[0, 0].numpy()) and np.array_equal(g["control"], full[1, 1].numpy()) \
+        and np.array_equal(g["energy_terminal"], full[2, 2].numpy())
+    q.put((rank, ok))
     dist.destroy_process_group()
 
 
