@@ -622,3 +622,30 @@ def test_create_rejects_inconsistent_crank_nicolson_input(cyl):
         ups.append(ens.fields(0)[:, 17].copy())
         ens.close()
     assert rel(ups[0], ups[1]) < 1e-13
+
+
+def test_crank_nicolson_any_ensemble_width(cyl):
+    """The Crank-Nicolson path (SpMM slices, seeded element pass) at ragged widths: B = 1, 33 and 300 give the same
+    trajectory to round-off, and identical inputs stay bit-identical inside an ensemble."""
+    from flowcontrol_b200.ensemble import Ensemble
+    from flowcontrol_b200.problem import FlowProblem
+
+    fs, prob_bdf, _, UP0 = cyl
+    tab = prob_bdf.tab
+    prob = FlowProblem(tab, fs.blocks, 100.0, 0.005, fs.bc.bcu, fs.params_control.actuator_list,
+                       fs.params_control.sensor_list, UP0, time_scheme="cn", symbolic=prob_bdf.sym)
+    ic = fs._default_initial_perturbation(2.0, 0.0, 0.5)
+    ref = None
+    for B in (1, 33, 300):
+        ens = Ensemble(prob, B)
+        ens.set_state(ic[: tab.Nv], None, ic[tab.Nv :], order="cn")
+        for k in range(6):
+            ens.step(np.full((2, B), 0.05 * k))
+        up = ens.fields(0)
+        assert np.isfinite(up).all() and not ens.diverged.any()
+        assert np.abs(up - up[:, :1]).max() == 0.0
+        if ref is None:
+            ref = up[:, 0].copy()
+        else:
+            assert rel(up[:, -1], ref) < 1e-12
+        ens.close()
