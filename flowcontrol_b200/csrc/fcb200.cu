@@ -8,15 +8,21 @@
 // row / cell / tile, so indices, geometry and matrix values are warp-uniform
 // (broadcast loads) and all state traffic is 256-byte coalesced.
 //
-// One time step (reference: FlowSolver.step, flowsolver.py:703-799):
-//   k_rhs_build   rhs = a_n + b_{n-1} (BDF2) | a_n/2 (BDF1) + sum_k u_ctrl_k (f_k - l_k)   [solver row order]
-//   k_front_sweep forward sweep  (one launch per elimination-tree height): y_t, u_t = sum_children u_c - E_t y_t
-//   k_front_sweep backward sweep (one launch per elimination-tree depth):  x_t = F11^-1 y_t - G_t x_struct(t)
-//   k_post        un-permute, Dirichlet values, non-finite flag
-//   k_element_patch per patch of cells: convection N(u) (7-point Radon rule) + mass M u, accumulated in shared memory into
-//                 a = (2/dt) M u - 2 N(u),  b = -(1/2dt) M u + N(u);  energy partials u.(M u)
-//   k_measure     sensors (sparse rows) + energy reduction (fixed order)
-// Closed loop adds k_controller before and k_log after, all inside one CUDA graph.
+// One time step (reference: FlowSolver.step, flowsolver.py:703-799), one CUDA graph:
+//   k_ctrl_add      rhs rows += sum_k u_ctrl_k (f_k - A[:,Gamma] s_k)            (the rhs itself was left in Z by the previous step)
+//   k_front_sweep   forward sweep, one launch per elimination-tree level:  y_t, u_t = sum_children u_c - E_t y_t
+//   k_gather_sum    right-hand side of the merged top of the tree
+//   k_front_sweep   backward sweep, one launch per level: x_t = F11^-1 y_t - G_t x_struct(t); also writes x in canonical
+//                   numbering (the new state) and raises the per-trajectory non-finite flag
+//   k_bc_fill       Dirichlet rows of the new state
+//   k_spmm_mma      Crank-Nicolson only: rhs rows = E u_n (block-sparse SpMM on the FP64 tensor cores)
+//   k_element_patch per patch of cells: convection N(u) (7-point Radon rule) + mass M u accumulated in shared memory,
+//                   a = (2/dt) M u - 2 N(u),  b = -(1/2dt) M u + N(u); emits the NEXT step's rhs rows a_n + b_{n-1}
+//                   (Crank-Nicolson: E u_n - N(u_n)) in solver order, b_n, and the energy partials u.(M u)
+//   k_patch_merge   nodes shared between patches: sum of the patches' partials
+//   k_measure       sensors (sparse rows) + energy reduction (fixed order)
+// Closed loop adds k_controller before and k_log (series row + running cost sums) after, inside the same graph.
+// k_rhs_build forms the rhs from a and b for the first (BDF1) step after fcb_set_state(order = 1) only.
 
 #include <cuda.h>
 #include <cuda_runtime.h>
