@@ -5,8 +5,11 @@
 
 One "step" advances every trajectory of the ensemble by one closed-loop time step:
 controller update -> RHS assembly -> sparse direct solve -> sensors/energy -> log.
-Weak scaling: every GPU owns 256 trajectories (its own gain-swept controller family);
-there is no collective inside the step, only an all-gather of the time series at the end.
+Weak scaling (default): every GPU owns 256 trajectories (its own gain-swept controller family); `--scaling strong
+--trajectories T` shards a FIXED ensemble of T trajectories over the GPUs instead (BASELINE configs[2]/[4] ask for 512 /
+1024 trajectories across 1/2/4/8 GPUs).  There is no collective inside the step, only an all-gather of the time series
+at the end (timed inside `value`, reported separately as `allgather_ms`).  Without torchrun, `--gpus N` (N > 1)
+re-launches this script under `python -m torch.distributed.run` with N ranks.
 """
 
 from __future__ import annotations
@@ -47,6 +50,10 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None  # perf_counter bounds of the timed region (samples are stamped on arrival)
+
+    def window(self, t0: float, t1: float):
+        self.t0, self.t1 = t0, t1
 
     def start(self):
         try:
@@ -60,19 +67,27 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
     def stop(self) -> dict:
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         self.thread.join(2)
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        # the sampler runs from before the warm-up (so that no process is forked near the timed region); the samples that
+        # arrived inside the timed window (+- one period) are the ones reported, the rest only back them up when the
+        # window was shorter than two sampling periods
+        rows = [r for t, r in self.rows if self.t0 is None or (self.t0 - 0.03 <= t <= self.t1 + 0.03)]
+        scope = "timed region"
+        if len(rows) < 2:
+            rows = [r for t, r in self.rows if self.t0 is None or t >= self.t0 - 2.0]
+            scope = "timed region and the 2 s of warm-up load before it (the region was shorter than two 20 ms samples)"
+        sm = [float(r[0]) for r in rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        reasons = sorted({n for r in rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "scope": scope}
 
 
 def build_problem(time_scheme="bdf"):
@@ -120,6 +135,17 @@ class HostBank:
         return np.ascontiguousarray((self.Fu @ u.T))
 
 
+def newest_kernel_summary():
+    """Latest offline ncu summary (tools/kernel_summary.py) with the measured DRAM traffic of the sweep launches."""
+    for path in sorted((ROOT / "profiles").glob("r*_kernel_summary.json"), reverse=True):
+        try:
+            k = json.loads(path.read_text())["kernels"]["k_front_sweep"]
+            return float(k["dram_bytes"]), f"profiles/{path.name}"
+        except Exception:
+            continue
+    return None, None
+
+
 def run_ours(args):
     import torch
 
@@ -134,16 +160,22 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
+    # the clock sampler (a forked nvidia-smi) starts here, long before the timed region, so that no rank forks a process
+    # or does anything the others do not between the barrier and the first event
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     if rank == 0:
         g.build()
     if world > 1:
         dist.barrier()
     from flowcontrol_b200.ensemble import Ensemble
-    from flowcontrol_b200.sharding import gather_series, shard_bounds
+    from flowcontrol_b200.sharding import SeriesGatherer, shard_bounds
 
     fs, prob = build_problem(args.time_scheme)
     tab = prob.tab
-    total = B_PER_GPU * world
+    strong = args.scaling == "strong"
+    total = args.trajectories if strong else B_PER_GPU * world
     lo, hi = shard_bounds(total, rank, world)
     B = hi - lo
     bank = controller_bank(prob, lo, hi, total)
@@ -153,7 +185,7 @@ def run_ours(args):
     ens.set_controllers(bank)
     stream = torch.cuda.ExternalStream(ens.stream, device=torch.device("cuda", local_rank))
     ncol = 1 + prob.na + prob.ns
-    K, W = args.steps, args.warmup
+    K, W = args.steps, max(args.warmup, 3)
 
     def barrier():
         if world > 1:
@@ -161,31 +193,32 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- device-resident closed loop (value) -------------------------------------------------
-    ens.run_closed_loop(max(W, 3), log=False)  # warm-up: BDF1 start-up step + graph capture + steady BDF2
+    ens.run_closed_loop(W, log=False)  # warm-up: BDF1 start-up step + graph capture + steady BDF2
     series_dev = torch.empty((K, ncol, B), dtype=torch.float64, device="cuda")
-    # one untimed logged pass of the same length: the library sizes its device-side series buffer and re-captures the
-    # step graphs for it on first use; neither belongs in the timed region
-    ens.run_closed_loop(K, log=True, out=series_dev)
-    if world > 1:
-        gather_series(torch.zeros_like(series_dev), total)  # warm-up: NCCL communicator + buffers exist before the timed region
+    gatherer = SeriesGatherer(K, ncol, total, torch.float64, torch.device("cuda", local_rank)) if world > 1 else None
+    # one untimed logged pass of the same length (the library allocates its series chunk buffer on first use) and one
+    # untimed all-gather (NCCL communicator, channels and the gatherer's buffers exist before the timed region)
+    with torch.cuda.stream(stream):
+        ens.run_closed_loop(K, log=True, out=series_dev)
+        if gatherer:
+            gatherer(series_dev)
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     l0 = ens.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    t_begin = time.perf_counter()
     with torch.cuda.stream(stream):
         e0.record(stream)
         ens.run_closed_loop(K, log=True, out=series_dev)
-        gathered = gather_series(series_dev, total) if world > 1 else series_dev
         e1.record(stream)
+        gathered = gatherer(series_dev) if gatherer else series_dev
+        e2.record(stream)
     barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    sampler.window(t_begin, time.perf_counter())
+    t = torch.tensor([e0.elapsed_time(e2), e1.elapsed_time(e2), e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
     launches = ens.launch_count() - l0
     if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    clocks = sampler.stop() if rank == 0 else None
-    ms = float(ms.item())
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, allgather_ms, loop_ms = (float(v) for v in t.tolist())
     value = total * K / (ms * 1e-3)
     finite = bool(torch.isfinite(gathered).all().item())
 
@@ -196,44 +229,50 @@ def run_ours(args):
     n = plan.n
     solve_ms = phase_ms["forward"] + phase_ms["backward"]
     solve_launches = prof_runs[0]["forward"]["launches"] + prof_runs[0]["backward"]["launches"]
-    ldb = (B + 31) // 32 * 32
-    # algorithmic bytes of one solve (all launches of both sweeps): factor values + gather indices read
-    # once; b read, y written, update vectors written and read once (forward); y read, x written (backward)
-    solve_bytes = 8 * plan.nnz + 4 * len(plan.i0) + 8 * (4 * n + 2 * plan.nU) * ldb
+    ldb = 32 if B <= 32 else (64 if B <= 64 else (B + 127) // 128 * 128)
+    # ALGORITHMIC bytes of one constant-LHS solve, SURVEY.md section 8(d) "Factor solve" (unique-touch model):
+    #   12 bytes per factor entry (value + index; the dense-block factor stores no per-entry index, the formula is kept as
+    #   the survey states it) read once per step + 8 * 2N per trajectory (right-hand side read, solution written).
+    # The update vectors of the multifrontal sweeps and the once-per-slab re-reads of the factor are NOT algorithmic:
+    # they show up in `traffic` (ncu DRAM bytes of the same launches) and in `traffic_over_algorithmic`.
+    solve_bytes = 12 * plan.nnz + 16 * tab.N * B
     solve_flops = 2.0 * plan.nnz * ldb
     hbm_peak, peak_src = peaks()
     achieved = solve_bytes / (solve_ms * 1e-3) / 1e9
-    # measured DRAM traffic of the same launches (ncu, profiles/r01_kernel_summary.json written by tools/kernel_summary.py)
-    traffic = None
-    ks = ROOT / "profiles" / "r01_kernel_summary.json"
-    if ks.exists():
-        try:
-            traffic = float(json.loads(ks.read_text())["kernels"]["k_front_sweep"]["dram_bytes"])
-        except Exception:
-            traffic = None
-    # element kernel (second largest): reads u and b_{n-1}, writes the next rhs rows and b_n; ~600 FP64 FMA per cell
-    elem_bytes = 8 * (3 * tab.Nv + n) * ldb
+    traffic, traffic_src = newest_kernel_summary() if B == B_PER_GPU else (None, None)
+    # internal byte model of the implementation (factor + gather lists once, rhs/y/x and the update vectors once each way)
+    impl_bytes = 8 * plan.nnz + 4 * len(plan.i0) + 8 * (4 * n + 2 * plan.nU) * ldb
+    # element kernel (second largest), SURVEY 8(d) rhs_assemble: 8 (4 Nv + N) state bytes per trajectory + geometry/index bytes
+    elem_bytes = 8 * (4 * tab.Nv + tab.N) * B + tab.nT * (24 + 40)
     elem_flops = 2.0 * 600 * tab.nT * ldb
     roofline = {
         "kernel": "k_front_sweep (multifrontal forward+backward sweeps on FP64 tensor cores, all launches of one solve)",
         "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-        "peak_source": peak_src, "traffic": traffic,
-        "traffic_note": "dram__bytes_read+write summed over the sweep launches of one step (ncu); algorithmic bytes assume the factor is read once",
+        "peak_source": peak_src,
+        "bytes_model": "SURVEY.md 8(d) factor solve: 12*nnz(factor) + 16*N*B per step (unique touch)",
+        "algorithmic_bytes_per_step": solve_bytes,
+        "traffic": traffic, "traffic_source": (f"offline ncu capture ({traffic_src}: dram__bytes_read+write over the sweep launches of "
+                                               "one step at B=256), not measured in this run") if traffic else None,
+        "traffic_over_algorithmic": (traffic / solve_bytes) if traffic else None,
+        "implementation_bytes_per_step": impl_bytes,
+        "implementation_gbs": impl_bytes / (solve_ms * 1e-3) / 1e9,
+        "timing": "CUDA events between the phases of un-graphed profile steps on the handle's stream (mean of 5, after the timed region)",
         "element_kernel": {"ms_per_step": phase_ms["element"], "achieved_gbs": elem_bytes / (phase_ms["element"] * 1e-3) / 1e9,
                            "hbm_frac": elem_bytes / (phase_ms["element"] * 1e-3) / 1e9 / hbm_peak,
                            "fp64_tflops": elem_flops / (phase_ms["element"] * 1e-3) / 1e12,
                            "fp64_frac_of_dfma_peak": elem_flops / (phase_ms["element"] * 1e-3) / 1e12 / 33.6,
-                           "algorithmic_bytes_per_step": elem_bytes},
+                           "algorithmic_bytes_per_step": elem_bytes,
+                           "bytes_model": "SURVEY.md 8(d) rhs_assemble: 8*(4*Nv + N)*B + nT*64"},
         "launches_per_step": solve_launches, "ms_per_launch": solve_ms / solve_launches, "ms_per_step": solve_ms,
-        "algorithmic_bytes_per_step": solve_bytes,
         "fp64": {"achieved_tflops": solve_flops / (solve_ms * 1e-3) / 1e12, "peak_tflops": FP64_PEAK_TFLOPS,
                  "frac": solve_flops / (solve_ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS,
-                 "note": "the sweeps run on the FP64 tensor pipe (mma.sync m8n8k4); peak = measured DMMA rate (profiles/r01_fp64_peak.log)"},
+                 "note": "the sweeps run on the FP64 tensor pipe (mma.sync m8n8k4); peak = measured DMMA rate (profiles/r01_fp64_peak.log); "
+                         "at B=256 the DMMA floor of one solve is 2*nnz*B / peak"},
         "phase_ms": phase_ms,
     }
     if prob.time_scheme == "cn":
-        # k_spmm_mma: packed operator read once + one 8-byte read per input row and one write per output row and trajectory
-        sp_bytes = 12 * prob.E_cn.nnz + 4 * (n + 1) + 8 * (tab.Nv + n) * ldb
+        # k_spmm_mma, SURVEY 8(d) SpMM: (12 nnz + 4 (n+1)) + 8 (n_in + n_out) B
+        sp_bytes = 12 * prob.E_cn.nnz + 4 * (n + 1) + 8 * (tab.Nv + n) * B
         roofline["spmm_kernel"] = {"ms_per_step": phase_ms["spmm"], "algorithmic_bytes_per_step": sp_bytes,
                                    "achieved_gbs": sp_bytes / (phase_ms["spmm"] * 1e-3) / 1e9,
                                    "hbm_frac": sp_bytes / (phase_ms["spmm"] * 1e-3) / 1e9 / hbm_peak}
@@ -251,26 +290,32 @@ def run_ours(args):
     t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e = {"value": total * K / float(t_e2e.item()), "unit": UNIT, "h2d_bytes_per_step": int(world * prob.na * B * 8),
-           "d2h_bytes_per_step": int(world * (prob.ns * B * 8 + B * 8 + B * 4)),
+    e2e = {"value": total * K / float(t_e2e.item()), "unit": UNIT, "h2d_bytes_per_step": int(total * prob.na * 8),
+           "d2h_bytes_per_step": int(total * (prob.ns * 8 + 8 + 4)),
            "note": "FlowSolver/Ensemble.step with host numpy buffers, controller bank stepped on the host"}
 
+    clocks = sampler.stop() if rank == 0 else None
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle.cpu_bench import time_oracle
 
         cpu = time_oracle(nsteps=20, warmup=3)
-        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "threads_per_worker", "per_core_steps_per_s")}
     ens.close()
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W, 3),
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
             "data": "synthetic (shipped mesh O1, cached base flow, gain-swept controllers, default ParamIC perturbation)",
-            "config": {"workload": WORKLOAD + (" [time_scheme=cn variant]" if args.time_scheme == "cn" else ""), "trajectories_per_gpu": B_PER_GPU, "trajectories_total": total,
-                       "dofs_per_trajectory": int(tab.N), "warmup_note": "W steps + one untimed logged pass of K steps (series buffer allocation, graph capture)", "l2": "working set >> L2 (solve buffer 560 MB + packed factors 130 MB + state 430 MB per GPU vs 126 MB L2); no flush needed",
+            "config": {"workload": WORKLOAD + (" [time_scheme=cn variant]" if args.time_scheme == "cn" else "")
+                       + (f" [strong scaling: {total} trajectories in total]" if strong else ""),
+                       "trajectories_per_gpu": B if strong else B_PER_GPU, "trajectories_total": total,
+                       "dofs_per_trajectory": int(tab.N), "warmup_note": "W steps + one untimed logged pass of K steps and one untimed all-gather (buffers, graph capture, NCCL channels)", "l2": "working set >> L2 (solve buffer 560 MB + packed factors 130 MB + state 430 MB per GPU vs 126 MB L2); no flush needed",
                        "parallelism": f"ensemble-sharded x{world}, time-series all-gather only"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches * world), "roofline": roofline,
+            "allgather_ms": allgather_ms, "loop_ms": loop_ms,
+            "timed_region": "K graph-replayed closed-loop steps + the all-gather of the [K, ncol, B] series (allgather_ms, a fixed cost per run: "
+                            "it is inside `value`, so `value` at small K understates the steady step rate loop_ms / K)",
             "all_finite": finite,
         }
         if cpu is not None:
@@ -295,7 +340,7 @@ def run_reference(args):
         "data": "synthetic (same mesh, base flow, controllers and IC as the CUDA arm)",
         "config": {"workload": WORKLOAD, "note": "FEniCS/PETSc/MUMPS cannot be installed here; numpy/scipy (SuperLU) port of the same step, "
                    "one trajectory per host core"},
-        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "threads_per_worker", "per_core_steps_per_s")},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -311,7 +356,17 @@ if __name__ == "__main__":
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--time-scheme", default="bdf", choices=["bdf", "cn"],
                     help="bdf = the reference's default BDF1->BDF2 (the benchmark); cn = Crank-Nicolson variant (adds the SpMM kernel's roofline)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: 256 trajectories per GPU (the benchmark); strong: a fixed ensemble of --trajectories sharded over the GPUs")
+    ap.add_argument("--trajectories", type=int, default=512, help="total ensemble width for --scaling strong")
     a = ap.parse_args()
+    if a.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # launched by hand without torchrun: spawn the ranks ourselves (one process per GPU, NCCL rendezvous on 127.0.0.1)
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={a.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", os.environ.get("MASTER_PORT", "29517"), str(Path(__file__).resolve())] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    if "WORLD_SIZE" in os.environ and int(os.environ["WORLD_SIZE"]) != a.gpus:
+        sys.exit(f"bench.py: --gpus {a.gpus} does not match WORLD_SIZE={os.environ['WORLD_SIZE']}")
     if a.impl == "reference":
         run_reference(a)
     else:

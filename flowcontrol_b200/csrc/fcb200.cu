@@ -1001,13 +1001,28 @@ __global__ void __launch_bounds__(32 * CTRL_ROWS) k_controller(int nx, int ny, i
     }
 }
 
+// Run control block of the device-resident loops (one per handle, in device memory): the graphs of a step read the series
+// pointer, its capacity and the step counter from here, so a run of any length replays the same graphs chunk by chunk.
+struct RunCtl {
+    double* series;         // [capacity][ncol][ldb] chunk buffer, or capacity == 0: logging off
+    const double* useries;  // [capacity][na][ldb] open-loop control inputs of the chunk
+    int capacity;
+    int step;               // step inside the current chunk
+};
+
+// open loop: this step's control inputs come from the staged chunk of the caller's u_ctrl series.  grid = ldb/32, block = 32
+__global__ void k_load_ctrl(int na, const RunCtl* __restrict__ ctl, double* __restrict__ uctrl, int ldb) {
+    const int b = blockIdx.x * 32 + threadIdx.x;
+    const double* src = ctl->useries + (size_t)ctl->step * na * ldb;
+    for (int k = 0; k < na; ++k) uctrl[(size_t)k * ldb + b] = src[(size_t)k * ldb + b];
+}
+
 // series[step][col][b], columns (dE, u_ctrl_1..na, y_1..ns); single CTA, then the step counter ticks.
 // also accumulates, per trajectory and in time order, the sums the reference's cost functions are made of
 // (utils/optim.py:231-288): costs[0] += dE, costs[1] += sum_k u_ctrl_k^2, costs[2] = dE of the last step
 __global__ void k_log(int na, int ns, const double* __restrict__ dE, const double* __restrict__ uctrl,
-                      const double* __restrict__ y, double* __restrict__ series, int* __restrict__ counter,
-                      int capacity, double* __restrict__ costs, int ldb) {
-    const int step = *counter;
+                      const double* __restrict__ y, RunCtl* __restrict__ ctl, double* __restrict__ costs, int ldb) {
+    const int step = ctl->step;
     const int ncol = 1 + na + ns;
     for (int b = threadIdx.x; b < ldb; b += blockDim.x) {
         double u2 = 0.0;
@@ -1017,8 +1032,8 @@ __global__ void k_log(int na, int ns, const double* __restrict__ dE, const doubl
         costs[ldb + b] += u2;
         costs[2 * ldb + b] = e;
     }
-    if (step < capacity) {
-        double* row = series + (size_t)step * ncol * ldb;
+    if (step < ctl->capacity) {
+        double* row = ctl->series + (size_t)step * ncol * ldb;
         for (int i = threadIdx.x; i < ncol * ldb; i += blockDim.x) {
             const int col = i / ldb, b = i - col * ldb;
             double v;
@@ -1029,7 +1044,7 @@ __global__ void k_log(int na, int ns, const double* __restrict__ dE, const doubl
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0) *counter = step + 1;
+    if (threadIdx.x == 0) ctl->step = step + 1;
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -1105,9 +1120,11 @@ struct fcb_context {
     double *Ad = nullptr, *Bd = nullptr, *Cd = nullptr, *Dd = nullptr, *Ky = nullptr, *Fu = nullptr;
     double* xk[2] = {nullptr, nullptr};
     int xparity = 0;
-    double* series = nullptr;
+    double* series = nullptr;   // chunk buffer of the device-resident loops [series_capacity][ncol][ldb]
+    double* useries = nullptr;  // open loop: staged control inputs of a chunk [series_capacity][na][ldb]
     int series_capacity = 0;
-    int* counter = nullptr;
+    int series_chunk = 1024;    // steps per chunk (FCB_SERIES_CHUNK): long runs stream their series out chunk by chunk
+    RunCtl* ctl = nullptr;
     double* costs = nullptr;  // [3][ldb] running sums of the closed-loop run (k_log)
     double *pin_in = nullptr, *pin_out = nullptr;  // pinned staging of fcb_step's host arguments
     // graphs: [parity] for a BDF2 step, [parity][xparity] for a closed-loop BDF2 step
@@ -1115,6 +1132,8 @@ struct fcb_context {
     int g_step_nodes[2] = {0, 0};
     cudaGraphExec_t g_loop[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
     int g_loop_nodes[2][2] = {{0, 0}, {0, 0}};
+    cudaGraphExec_t g_open[2] = {nullptr, nullptr};  // open-loop run: load u_ctrl -> step -> log
+    int g_open_nodes[2] = {0, 0};
     long long launches = 0;
     int phase_launches[FCB_NPHASES] = {0};
     cudaEvent_t ev[FCB_NPHASES + 1] = {nullptr};
@@ -1583,19 +1602,30 @@ int enqueue_controller(fcb_context* h, int xparity) {
 }
 
 int enqueue_log(fcb_context* h) {
-    k_log<<<1, 256, 0, h->stream>>>(h->na, h->ns, h->dE, h->uctrl, h->y, h->series, h->counter, h->series_capacity, h->costs, h->ldb);
+    k_log<<<1, 256, 0, h->stream>>>(h->na, h->ns, h->dE, h->uctrl, h->y, h->ctl, h->costs, h->ldb);
     h->launches += 1;
     CK(cudaGetLastError());
     return FCB_OK;
 }
 
-int capture(fcb_context* h, cudaGraphExec_t* exec, int* nodes, bool loop, int parity, int xparity) {
+int enqueue_load_ctrl(fcb_context* h) {
+    if (h->na <= 0) return FCB_OK;
+    k_load_ctrl<<<h->ldb / 32, 32, 0, h->stream>>>(h->na, h->ctl, h->uctrl, h->ldb);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    return FCB_OK;
+}
+
+enum RunMode { RUN_STEP = 0, RUN_CLOSED = 1, RUN_OPEN = 2 };
+
+int capture(fcb_context* h, cudaGraphExec_t* exec, int* nodes, int mode, int parity, int xparity) {
     const long long before = h->launches;
     CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
     int rc = FCB_OK;
-    if (loop) rc = enqueue_controller(h, xparity);
+    if (mode == RUN_CLOSED) rc = enqueue_controller(h, xparity);
+    if (mode == RUN_OPEN) rc = enqueue_load_ctrl(h);
     if (rc == FCB_OK) rc = enqueue_step(h, 2, parity, true, nullptr);
-    if (rc == FCB_OK && loop) rc = enqueue_log(h);
+    if (rc == FCB_OK && mode != RUN_STEP) rc = enqueue_log(h);
     cudaGraph_t graph = nullptr;
     cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
     *nodes = (int)(h->launches - before);
@@ -1620,20 +1650,21 @@ int copy_out(fcb_context* h, T* dst, const T* src, int rows) {
     return FCB_OK;
 }
 
-int run_one_step(fcb_context* h, bool loop) {
+int run_one_step(fcb_context* h, int mode) {
     if (h->order == 2 && h->rhs_ready) {
-        cudaGraphExec_t* exec = loop ? &h->g_loop[h->parity][h->xparity] : &h->g_step[h->parity];
-        int* nodes = loop ? &h->g_loop_nodes[h->parity][h->xparity] : &h->g_step_nodes[h->parity];
-        if (!*exec) TRY(capture(h, exec, nodes, loop, h->parity, h->xparity));
+        cudaGraphExec_t* exec = mode == RUN_CLOSED ? &h->g_loop[h->parity][h->xparity] : (mode == RUN_OPEN ? &h->g_open[h->parity] : &h->g_step[h->parity]);
+        int* nodes = mode == RUN_CLOSED ? &h->g_loop_nodes[h->parity][h->xparity] : (mode == RUN_OPEN ? &h->g_open_nodes[h->parity] : &h->g_step_nodes[h->parity]);
+        if (!*exec) TRY(capture(h, exec, nodes, mode, h->parity, h->xparity));
         CK(cudaGraphLaunch(*exec, h->stream));
         h->launches += *nodes;
     } else {
-        if (loop) TRY(enqueue_controller(h, h->xparity));
+        if (mode == RUN_CLOSED) TRY(enqueue_controller(h, h->xparity));
+        if (mode == RUN_OPEN) TRY(enqueue_load_ctrl(h));
         TRY(enqueue_step(h, h->order, h->parity, h->rhs_ready, nullptr));
-        if (loop) TRY(enqueue_log(h));
+        if (mode != RUN_STEP) TRY(enqueue_log(h));
     }
     h->parity ^= 1;
-    if (loop) h->xparity ^= 1;
+    if (mode == RUN_CLOSED) h->xparity ^= 1;
     h->order = 2;
     h->rhs_ready = true;
     return FCB_OK;
@@ -1647,13 +1678,14 @@ void destroy(fcb_context* h) {
     if (h->pin_out) cudaFreeHost(h->pin_out);
     for (int i = 0; i < 2; ++i) {
         if (h->g_step[i]) cudaGraphExecDestroy(h->g_step[i]);
+        if (h->g_open[i]) cudaGraphExecDestroy(h->g_open[i]);
         for (int j = 0; j < 2; ++j)
             if (h->g_loop[i][j]) cudaGraphExecDestroy(h->g_loop[i][j]);
     }
     void* ptrs[] = {h->costs, h->sp_ucols, h->sp_ginfo, h->sp_kslots, h->sp_avals, h->cn_ptr, h->cn_idx, h->cn_val, h->uctrl_prev, h->ccoef_prev, h->crow_prev, h->crow, h->ccoef, h->bc_dofs, h->cell_nodes, h->perm, h->iperm, h->Jinv, h->detJ, h->bc_shape, h->ctrl_rhs[0],
                     h->ctrl_rhs[1], h->sensor_ptr, h->sensor_idx, h->sensor_val, h->up[0], h->up[1], h->avec,
                     h->bvec[0], h->bvec[1], h->Z, h->epart, h->uctrl, h->y, h->dE, h->diverged, h->Ad, h->Bd, h->Cd,
-                    h->Dd, h->Ky, h->Fu, h->xk[0], h->xk[1], h->series, h->counter, h->sweep_dbg,
+                    h->Dd, h->Ky, h->Fu, h->xk[0], h->xk[1], h->series, h->useries, h->ctl, h->sweep_dbg,
                     h->pcell_ptr, h->pcnode, h->pgeo, h->pnode_ptr, h->pnode_dst, h->mptr, h->msrc, h->mnode, h->plnode, h->pscratch, h->prow, h->mrow, h->psrc, h->pacc_rows};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -2196,6 +2228,12 @@ int create_impl(fcb_context* h, const fcb_problem* p, int B) {
     } else if (p->scheme != 0) {
         return fail(h, FCB_ERR_INVALID, "scheme must be 0 (BDF) or 1 (Crank-Nicolson)");
     }
+    if (p->ns < 0 || (p->ns > 0 && (!p->sensor_ptr || p->sensor_ptr[0] != 0))) return fail(h, FCB_ERR_INVALID, "sensor_ptr must start at 0");
+    for (int i = 0; i < p->ns; ++i) {
+        if (p->sensor_ptr[i + 1] < p->sensor_ptr[i]) return fail(h, FCB_ERR_INVALID, "sensor_ptr must be non-decreasing (row %d)", i);
+        for (int j = p->sensor_ptr[i]; j < p->sensor_ptr[i + 1]; ++j)
+            if (p->sensor_idx[j] < 0 || p->sensor_idx[j] >= h->N) return fail(h, FCB_ERR_INVALID, "sensor_idx[%d] = %d is outside [0, %d)", j, p->sensor_idx[j], h->N);
+    }
     TRY(upload(h, &h->sensor_ptr, p->sensor_ptr, (size_t)p->ns + 1));
     const size_t snnz = p->ns ? (size_t)p->sensor_ptr[p->ns] : 0;
     TRY(upload(h, &h->sensor_idx, p->sensor_idx, snnz));
@@ -2239,7 +2277,11 @@ int create_impl(fcb_context* h, const fcb_problem* p, int B) {
     TRY(upload<double>(h, &h->y, nullptr, (size_t)(h->ns > 0 ? h->ns : 1) * L));
     TRY(upload<double>(h, &h->dE, nullptr, L));
     TRY(upload<int>(h, &h->diverged, nullptr, L));
-    TRY(upload<int>(h, &h->counter, nullptr, 1));
+    TRY(upload<RunCtl>(h, &h->ctl, nullptr, 1));
+    {
+        const char* env = getenv("FCB_SERIES_CHUNK");
+        if (env && atoi(env) >= 1 && atoi(env) <= (1 << 20)) h->series_chunk = atoi(env);
+    }
     TRY(upload<double>(h, &h->costs, nullptr, 3 * L));
     if (cudaMallocHost((void**)&h->pin_in, (size_t)std::max(h->na, 1) * h->B * sizeof(double)) != cudaSuccess ||
         cudaMallocHost((void**)&h->pin_out, ((size_t)h->ns + 2) * h->B * sizeof(double)) != cudaSuccess) {
@@ -2378,7 +2420,7 @@ int fcb_step(fcb_handle h, const double* u_ctrl, double* y_meas, double* dE, int
             TRY(copy_in(h, h->uctrl, u_ctrl, h->na));
         }
     }
-    TRY(run_one_step(h, false));
+    TRY(run_one_step(h, RUN_STEP));
     double* py = h->pin_out;                                   // [ns][B] y, [B] dE, then [B] ints
     double* pe = h->pin_out ? h->pin_out + (size_t)h->ns * B : nullptr;
     int32_t* pd = h->pin_out ? reinterpret_cast<int32_t*>(pe + B) : nullptr;
@@ -2395,36 +2437,65 @@ int fcb_step(fcb_handle h, const double* u_ctrl, double* y_meas, double* dE, int
     return FCB_OK;
 }
 
+// Device-resident run of nsteps steps (closed loop: controller -> step -> log; open loop: load u_ctrl -> step -> log), streamed
+// chunk by chunk: the handle owns one series buffer of `series_chunk` steps; after every chunk its rows go out to the
+// caller's array (asynchronously, in stream order) and the next chunk replays the SAME graphs -- the kernels read the
+// buffer, its capacity and the step counter from the RunCtl block, so neither the run length nor logging on/off ever
+// forces a re-capture, and a long run needs no series-sized device allocation.
+static int run_device_loop(fcb_handle h, int mode, int32_t nsteps, const double* u_series, double* series) {
+    CK(cudaSetDevice(h->device));
+    const int ncol = 1 + h->na + h->ns;
+    const int chunk = std::max(1, std::min(h->series_chunk, (int)nsteps));
+    const bool want_u = mode == RUN_OPEN && h->na > 0;
+    if (chunk > h->series_capacity) {
+        CK(cudaStreamSynchronize(h->stream));
+        if (h->series) cudaFree(h->series);
+        if (h->useries) cudaFree(h->useries);
+        h->series = h->useries = nullptr;
+        h->series_capacity = 0;
+        CK(cudaMalloc((void**)&h->series, (size_t)chunk * ncol * h->ldb * sizeof(double)));
+        CK(cudaMalloc((void**)&h->useries, (size_t)chunk * std::max(h->na, 1) * h->ldb * sizeof(double)));
+        CK(cudaMemsetAsync(h->useries, 0, (size_t)chunk * std::max(h->na, 1) * h->ldb * sizeof(double), h->stream));
+        h->series_capacity = chunk;
+    }
+    CK(cudaMemsetAsync(h->costs, 0, 3 * (size_t)h->ldb * sizeof(double), h->stream));
+    for (int c0 = 0; c0 < nsteps; c0 += chunk) {
+        const int nc = std::min(chunk, (int)nsteps - c0);
+        const RunCtl ctl{h->series, h->useries, series ? nc : 0, 0};
+        CK(cudaMemcpyAsync(h->ctl, &ctl, sizeof ctl, cudaMemcpyHostToDevice, h->stream));  // pageable source: staged before the call returns
+        if (want_u)
+            CK(cudaMemcpy2DAsync(h->useries, (size_t)h->ldb * sizeof(double), u_series + (size_t)c0 * h->na * h->B, (size_t)h->B * sizeof(double),
+                                 (size_t)h->B * sizeof(double), (size_t)nc * h->na, cudaMemcpyDefault, h->stream));
+        for (int s = 0; s < nc; ++s) TRY(run_one_step(h, mode));
+        if (series)
+            CK(cudaMemcpy2DAsync(series + (size_t)c0 * ncol * h->B, (size_t)h->B * sizeof(double), h->series, (size_t)h->ldb * sizeof(double),
+                                 (size_t)h->B * sizeof(double), (size_t)nc * ncol, cudaMemcpyDefault, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return FCB_OK;
+}
+
 int fcb_run_closed_loop(fcb_handle h, int32_t nsteps, double* series) {
     if (!h || nsteps < 0) return FCB_ERR_INVALID;
     if (!h->have_state) return fail(h, FCB_ERR_STATE, "fcb_run_closed_loop: call fcb_set_state first");
     if (!h->have_ctrl) return fail(h, FCB_ERR_STATE, "fcb_run_closed_loop: call fcb_set_controllers first");
+    return run_device_loop(h, RUN_CLOSED, nsteps, nullptr, series);
+}
+
+int fcb_run_open_loop(fcb_handle h, int32_t nsteps, const double* u_series, double* series) {
+    if (!h || nsteps < 0) return FCB_ERR_INVALID;
+    if (!h->have_state) return fail(h, FCB_ERR_STATE, "fcb_run_open_loop: call fcb_set_state first");
+    if (h->na > 0 && !u_series) return fail(h, FCB_ERR_INVALID, "fcb_run_open_loop: u_series is NULL");
+    return run_device_loop(h, RUN_OPEN, nsteps, u_series, series);
+}
+
+int fcb_set_controller_state(fcb_handle h, const double* x) {
+    if (!h) return FCB_ERR_INVALID;
+    if (!h->have_ctrl) return fail(h, FCB_ERR_STATE, "fcb_set_controller_state: no controllers set");
     CK(cudaSetDevice(h->device));
-    const int ncol = 1 + h->na + h->ns;
-    const int need = series ? nsteps : 0;
-    if (need > h->series_capacity) {
-        if (h->series) cudaFree(h->series);
-        h->series = nullptr;
-        CK(cudaMalloc((void**)&h->series, (size_t)need * ncol * h->ldb * sizeof(double)));
-        // the log kernel reads series/capacity from its launch arguments: re-capture
-        for (int i = 0; i < 2; ++i)
-            for (int j = 0; j < 2; ++j)
-                if (h->g_loop[i][j]) { cudaGraphExecDestroy(h->g_loop[i][j]); h->g_loop[i][j] = nullptr; }
-        h->series_capacity = need;
-    }
-    if (!series && h->series_capacity != 0) {
-        // logging disabled for this run: counter starts beyond capacity
-        int big = h->series_capacity;
-        CK(cudaMemcpyAsync(h->counter, &big, sizeof(int), cudaMemcpyHostToDevice, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-    } else {
-        CK(cudaMemsetAsync(h->counter, 0, sizeof(int), h->stream));
-    }
-    CK(cudaMemsetAsync(h->costs, 0, 3 * (size_t)h->ldb * sizeof(double), h->stream));
-    for (int s = 0; s < nsteps; ++s) TRY(run_one_step(h, true));
-    if (series && nsteps > 0) {
-        CK(cudaMemcpy2DAsync(series, (size_t)h->B * sizeof(double), h->series, (size_t)h->ldb * sizeof(double),
-                             (size_t)h->B * sizeof(double), (size_t)nsteps * ncol, cudaMemcpyDefault, h->stream));
+    if (h->nx > 0) {
+        if (x) TRY(copy_in(h, h->xk[h->xparity], x, h->nx));
+        else CK(cudaMemsetAsync(h->xk[h->xparity], 0, (size_t)h->nx * h->ldb * sizeof(double), h->stream));
     }
     CK(cudaStreamSynchronize(h->stream));
     return FCB_OK;

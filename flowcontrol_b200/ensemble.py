@@ -120,6 +120,26 @@ class Ensemble:
         self._check(rc, "fcb_run_closed_loop")
         return series
 
+    def run_open_loop(self, u_series, log: bool = True, out=None):
+        """Open-loop run on the device: ``u_series`` [nsteps, na, B] (numpy, or a torch CUDA tensor / device pointer with
+        ``nsteps`` given by its shape) holds every step's control inputs.  Returns the series like run_closed_loop."""
+        nsteps = int(u_series.shape[0])
+        if isinstance(u_series, np.ndarray):
+            u_series = np.ascontiguousarray(u_series, dtype=np.float64)
+            if u_series.shape != (nsteps, self.na, self.B):
+                raise ValueError(f"expected u_series of shape ({nsteps}, {self.na}, {self.B}), got {u_series.shape}")
+        series = None
+        if log:
+            series = out if out is not None else np.empty((nsteps, 1 + self.na + self.ns, self.B))
+        rc = self.lib.fcb_run_open_loop(self.h, nsteps, libfcb.as_voidp(u_series), libfcb.as_voidp(series))
+        self._check(rc, "fcb_run_open_loop")
+        return series
+
+    def set_controller_state(self, x=None) -> None:
+        """Controller states [nx, B] (None = zeros): Controller.reset / ensemble restart."""
+        xs = None if x is None else self._host(x, self._bank.nx)
+        self._check(self.lib.fcb_set_controller_state(self.h, libfcb.as_voidp(xs)), "fcb_set_controller_state")
+
     def costs(self, Tnorm: float = 1.0) -> dict:
         """Per-trajectory costs of the last run_closed_loop, summed on the device (utils/optim.py:231-288):
         ``energy_integral`` = compute_signal_cost(dE, Tnorm, 'integral'), ``energy_terminal`` = (…, 'terminal'),

@@ -66,6 +66,8 @@ EXPORTS = {
     "fcb_set_controllers": (C.c_int, [C.c_void_p, C.POINTER(fcb_controllers)]),
     "fcb_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fcb_run_closed_loop": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "fcb_run_open_loop": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "fcb_set_controller_state": (C.c_int, [C.c_void_p, C.c_void_p]),
     "fcb_get_fields": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
     "fcb_get_measurement": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fcb_get_controller_state": (C.c_int, [C.c_void_p, C.c_void_p]),

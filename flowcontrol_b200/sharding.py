@@ -23,24 +23,58 @@ def shard_bounds(total: int, rank: int, world: int) -> tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def gather_series(local, total: int, group=None):
-    """All-gather per-rank series blocks ``[nsteps, ncol, B_local]`` (torch tensor, trajectory
-    innermost) into ``[nsteps, ncol, total]`` on every rank.  Ragged shards are padded to the
-    widest shard for the collective and cropped afterwards."""
-    import torch
-    import torch.distributed as dist
+class SeriesGatherer:
+    """All-gather of per-rank series blocks ``[nsteps, ncol, B_local]`` (torch tensors, trajectory innermost) into
+    ``[nsteps, ncol, total]`` on every rank, with every buffer allocated ONCE: the collective is a single
+    ``all_gather_into_tensor`` into a preallocated ``[world, nsteps, ncol, wmax]`` block followed by one strided copy into
+    the preallocated result (no per-call allocation, no list-form all_gather, no torch.cat).  Ragged shards are staged
+    through a preallocated pad of the widest shard; even shards are sent in place."""
 
-    world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
-    widths = [shard_bounds(total, r, world)[1] - shard_bounds(total, r, world)[0] for r in range(world)]
-    wmax = max(widths)
-    nsteps, ncol, bl = local.shape
-    assert bl == widths[rank]
-    pad = torch.zeros((nsteps, ncol, wmax), dtype=local.dtype, device=local.device)
-    pad[:, :, :bl] = local
-    out = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(out, pad.contiguous(), group=group)
-    return torch.cat([o[:, :, :w] for o, w in zip(out, widths)], dim=2)
+    def __init__(self, nsteps: int, ncol: int, total: int, dtype, device, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.total = int(total)
+        bounds = [shard_bounds(total, r, self.world) for r in range(self.world)]
+        self.widths = [hi - lo for lo, hi in bounds]
+        self.offsets = [lo for lo, _ in bounds]
+        self.wmax = max(self.widths)
+        self.even = min(self.widths) == self.wmax
+        self.shape = (int(nsteps), int(ncol))
+        # [world * nsteps, ncol, wmax]: the concatenation-along-dim-0 form every backend (NCCL, gloo) accepts
+        self.recv = torch.empty((self.world * nsteps, ncol, self.wmax), dtype=dtype, device=device)
+        self.pad = None if self.even else torch.zeros((nsteps, ncol, self.wmax), dtype=dtype, device=device)
+        self.out = torch.empty((nsteps, ncol, self.total), dtype=dtype, device=device)
+
+    def __call__(self, local):
+        import torch.distributed as dist
+
+        nsteps, ncol = self.shape
+        if tuple(local.shape) != (nsteps, ncol, self.widths[self.rank]):
+            raise ValueError(f"expected a [{nsteps}, {ncol}, {self.widths[self.rank]}] block, got {tuple(local.shape)}")
+        send = local
+        if not self.even:
+            self.pad[:, :, : local.shape[2]].copy_(local)
+            send = self.pad
+        if not send.is_contiguous():
+            send = send.contiguous()
+        dist.all_gather_into_tensor(self.recv, send, group=self.group)
+        recv = self.recv.view(self.world, nsteps, ncol, self.wmax)
+        if self.even:
+            self.out.view(nsteps, ncol, self.world, self.wmax).copy_(recv.permute(1, 2, 0, 3))
+        else:
+            for r, (o, w) in enumerate(zip(self.offsets, self.widths)):
+                self.out[:, :, o : o + w].copy_(recv[r, :, :, :w])
+        return self.out
+
+
+def gather_series(local, total: int, group=None):
+    """One-shot form of :class:`SeriesGatherer` (allocates its buffers for this call)."""
+    nsteps, ncol, _ = local.shape
+    return SeriesGatherer(nsteps, ncol, total, local.dtype, local.device, group=group)(local)
 
 
 def gather_costs(local: dict, total: int, device=None, group=None) -> dict:

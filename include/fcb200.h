@@ -158,6 +158,18 @@ int fcb_step(fcb_handle h, const double* u_ctrl, double* y_meas, double* dE, int
  * (src/flowcontrol/exporter.py:191-224).  Requires fcb_set_controllers. */
 int fcb_run_closed_loop(fcb_handle h, int32_t nsteps, double* series);
 
+/* nsteps open-loop steps without host round trips: u_series [nsteps * na * B] holds the control inputs of every step
+ * (host or device memory); series as above.  Replaces the user loop `for _ in range(num_steps): fs.step(u_ctrl(t))` of
+ * the open-loop examples (src/examples/pinball/run_pinball_rotation_example.py:108-112,
+ * src/examples/lidcavity/batch_run_lidcavity.py:203-216).  Both loops stream their series out in chunks of
+ * FCB_SERIES_CHUNK steps (environment, default 1024): device memory for the series does not grow with nsteps. */
+int fcb_run_open_loop(fcb_handle h, int32_t nsteps, const double* u_series, double* series);
+
+/* Overwrite the controller states x [nx * B] (NULL = zeros): Controller.reset / restoring a checkpointed ensemble
+ * (src/flowcontrol/controller.py:161-163).  fcb_set_state does NOT touch the controller states: like the reference's
+ * restart (tests/integration/test_cylinder.py:95-112) the controller object lives on across a re-initialisation. */
+int fcb_set_controller_state(fcb_handle h, const double* x);
+
 /* Current fields in canonical numbering: up [ (2nN+nV) * B ].  which = 0: (u_, p_) of the
  * last step; 1: u_nn, only the 2nN velocity rows are written.  Replaces fs.fields.u_/p_/u_n/u_nn reads
  * (src/flowcontrol/flowfield.py:62-97). */

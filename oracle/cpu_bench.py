@@ -14,15 +14,25 @@ import os
 import time
 from pathlib import Path
 
-import numpy as np
+# One trajectory per worker process, one BLAS/OpenMP thread per worker: the thread caps must be in the environment BEFORE
+# numpy (and its BLAS) is imported, in the parent too, because spawned children import numpy while unpickling the worker
+# function -- setting them inside the worker is too late and 16-32 workers x all-core BLAS pools oversubscribe the host.
+THREAD_VARS = ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS", "VECLIB_MAXIMUM_THREADS")
+for _v in THREAD_VARS:
+    os.environ[_v] = "1"
+
+import numpy as np  # noqa: E402
 
 ROOT = Path(__file__).resolve().parent.parent
 
 
 def _worker(idx: int, nsteps: int, warmup: int, gain: float, ready, go, out):
-    os.environ["OMP_NUM_THREADS"] = "1"
-    os.environ["OPENBLAS_NUM_THREADS"] = "1"
-    os.environ["MKL_NUM_THREADS"] = "1"
+    try:  # belt and braces: cap an already-loaded BLAS pool as well
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(1)
+    except Exception:
+        pass
     from oracle import cases
     from oracle.flow_oracle import FlowOracle, ZOHController
 
@@ -53,7 +63,13 @@ def time_oracle(nsteps: int = 20, warmup: int = 3, workers: int | None = None) -
 
     Returns trajectory-steps/s over all workers, timed from a common start to the slowest finish."""
     ncpu = os.cpu_count() or 1
-    workers = workers or min(ncpu, 32)
+    try:
+        ncpu = min(ncpu, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    workers = workers or min(ncpu, 64)
+    for v in THREAD_VARS:  # inherited by the spawned children before they import numpy
+        os.environ[v] = "1"
     ctx = mp.get_context("spawn")
     ready, out = ctx.Queue(), ctx.Queue()
     go = ctx.Event()
@@ -75,6 +91,7 @@ def time_oracle(nsteps: int = 20, warmup: int = 3, workers: int | None = None) -
         "unit": "trajectory-steps/s",
         "cores": workers,
         "kind": "port",
+        "threads_per_worker": 1,
         "sample": f"{workers} trajectories x {nsteps} closed-loop steps of the cylinder Re=100 config, one process per core "
                   f"(host has {ncpu} logical CPUs); numpy/scipy SuperLU stand-in for the FEniCS/MUMPS path",
         "wall_s": wall,

@@ -38,6 +38,15 @@ def _worker(rank, world, port, total, q):
     full = torch.arange(5 * 3 * total, dtype=torch.float64).reshape(5, 3, total)
     out = gather_series(full[:, :, lo:hi].contiguous(), total)
     ok = bool(torch.equal(out, full))
+    # the preallocated form used by bench.py: same buffers on every call, non-contiguous shard views accepted
+    from flowcontrol_b200.sharding import SeriesGatherer
+
+    gat = SeriesGatherer(5, 3, total, torch.float64, "cpu")
+    o1 = gat(full[:, :, lo:hi])
+    p1 = o1.data_ptr()
+    ok = ok and bool(torch.equal(o1, full))
+    o2 = gat((2.0 * full)[:, :, lo:hi])
+    ok = ok and o2.data_ptr() == p1 and bool(torch.equal(o2, 2.0 * full))
     from flowcontrol_b200.sharding import gather_costs
 
     costs = {"energy_integral": full[0, 0, lo:hi].numpy(), "control": full[1, 1, lo:hi].numpy(), "energy_terminal": full[2, 2, lo:hi].numpy()}

@@ -355,10 +355,10 @@ def test_cavity_force_actuator_golden_trajectory(root, built_lib):
     assert np.isclose(ens.dE[0], 0.005000924582291293, rtol=1e-9)
     up = ens.fields(0)[:, 0]
     assert np.isclose(np.linalg.norm(up), float(gold["up_norm"]), rtol=1e-9)
-    # force actuation changes the answer linearly in u_ctrl at first order: just check it is wired
-    ens.step(np.full((1, B), 0.5))
-    y_forced = ens.y_meas[:, 0].copy()
-    assert np.all(np.isfinite(y_forced)) and not ens.diverged.any()
+    # the force actuator with u_ctrl != 0 is compared with the oracle in
+    # tests/test_gpu_configs.py::test_cavity_bdf_force_actuator_nonzero_control (open loop) and
+    # ::test_config3_cavity_static_gains_256 (closed loop, B = 256)
+    assert not ens.diverged.any()
     ens.close()
 
 
