@@ -919,6 +919,303 @@ __global__ void __launch_bounds__(32 * (KS ? 5 : NWC + 1), KS ? SV_MINCTAS4 : Sw
     if (dbg && lane == 0 && wid == 0) { dbg[4] = globaltimer_ns(); dbg[6] = (unsigned long long)nj; }
 }
 
+
+// ----------------------------------------------------------------------------------------------
+// Subtree clusters: the lower part of the elimination tree, swept with everything resident in shared memory.
+//
+// A cluster (multifrontal.py: choose_clusters) is a connected piece of the tree; one CTA sweeps it for 32 trajectories on
+// one resident vector S = [own unknowns of its fronts | boundary rows of its root] (row stride 36 doubles, so that the
+// B fragments below are bank-conflict free for consecutive rows):
+//   forward   S[own] = b (+ update vectors imported from lower clusters); per front, in elimination order, the right-looking
+//             update S[struct] += (-E) S[own of the front]; at the end y = S[own] goes to Z[n + row] and the boundary
+//             rows -- the update vector of the cluster's root -- to the U region, where the launches above pull it.
+//   backward  S[own] = y, S[boundary] = x of the ancestors; per front, in reverse: S[own] = [F11^-1 | -G] [S[own]; S[struct]];
+//             at the end x goes to the canonical state (and to Z[row] when a lower cluster gathers it).
+// The update vectors of the fronts inside a cluster therefore never exist in global memory, and a whole subtree costs one
+// launch per sweep instead of one per level.  The host compiles every (cluster, direction) into a program: a table of
+// operations (M x K products on the FP64 tensor cores, mma.m8n8k4), 16-bit tables of resident-row indices for the K
+// gathered rows and the M output rows, and the A fragments of all operations packed in consumption order, which a
+// producer warp streams through a ring of 16 KB chunks (cp.async.bulk + mbarrier) starting BEFORE the grid dependency is
+// resolved (factor values do not depend on the previous kernel).  A unit = 8 output rows x 16 trajectories (an even- and
+// an odd-column DMMA per k-step, C fragments = 4 consecutive trajectories per lane); warp w owns units w, w+8, ... of
+// an operation (up to 4), all in its half of the trajectories, so one 16-byte B load feeds all of them.
+// ----------------------------------------------------------------------------------------------
+constexpr int CL_NW = 16;         // consumer warps
+constexpr int CL_W = 32;          // trajectories per CTA
+constexpr int CL_XS = CL_W + 4;   // row stride of the resident vector (doubles)
+constexpr int CL_RMAX = 2;        // units per warp and operation -> at most 128 output rows per operation
+constexpr int CL_MAXROWS = 8 * CL_RMAX * CL_NW / 2;
+constexpr int CL_CHUNK = 64;      // A fragments (256 bytes each) per ring chunk
+constexpr int CL_STAGES = 3;
+constexpr int CL_HDR = 32;        // ints: nops, nown, mroot, nimp, ustore, vfrag0, off_grow, off_ops, off_tab16, off_aux, words,
+                                  //       write_z, imports: first entry of each consumer warp [12..28], off_gdof [29], store_y [30]
+constexpr int CL_OPREC = 8;       // ints: M, k-steps, row blocks, mode, krow table, orow table / first output row, k parts, k-steps per chunk
+constexpr int CL_RING_BYTES = CL_STAGES * CL_CHUNK * 256;
+constexpr int CL_RED_BYTES = 12 * 1024;  // k-split partial sums: (parts - 1) * units KB, units * parts <= CL_NW
+
+struct ClusterArgs {
+    const int* prog;       // programs of every (cluster, direction)
+    const int4* prog_loc;  // [clusters of this launch] (word offset, words, first own row if the own rows are one run else -1, own rows)
+    const double* vals;    // A fragments
+    double* Z;
+    double* xout;
+    int* diverged;
+    int n, Nv, ldb, nslab, backward, prog_max_words, srow_max;
+    unsigned long long* dbg;  // FCB_CLUSTER_DEBUG: 8 globaltimer stamps per CTA
+};
+
+__device__ __forceinline__ void cl_bar_consumers() { asm volatile("bar.sync 1, %0;" ::"n"(32 * CL_NW) : "memory"); }
+// one 256-byte row of the resident vector -> global memory, asynchronously (bulk copy engine)
+__device__ __forceinline__ void cl_row_out(double* dst, const double* src) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 256;" ::"l"(dst), "r"(smem_u32(src)) : "memory");
+}
+
+// grid = clusters of the tier x slabs of 32 trajectories (slab fastest: the CTAs of one cluster run together and share
+// its factor through L2); block = (32, CL_NW + 1)
+__global__ void __launch_bounds__(32 * (CL_NW + 1), 1) k_cluster_sweep(const ClusterArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x, wid = threadIdx.y;
+    const int cl = blockIdx.x / a.nslab, slab0 = (blockIdx.x - cl * a.nslab) * CL_W;
+    double* S = reinterpret_cast<double*>(smem);
+    unsigned char* ring = smem + (size_t)a.srow_max * CL_XS * 8;
+    double* red = reinterpret_cast<double*>(ring + CL_RING_BYTES);
+    int* prog = reinterpret_cast<int*>(ring + CL_RING_BYTES + CL_RED_BYTES);
+    const uint32_t bar_prog = smem_u32(prog) + (uint32_t)a.prog_max_words * 4u;
+    const uint32_t bar_full = bar_prog + 8, bar_empty = bar_full + 8 * CL_STAGES;
+    const int4 loc = __ldg(a.prog_loc + cl);
+    unsigned long long* dbg = a.dbg ? a.dbg + (size_t)blockIdx.x * 8 : nullptr;
+    if (dbg && lane == 0 && wid == 0) dbg[0] = globaltimer_ns();
+    if (lane == 0 && wid == 0) {
+        mbar_init(bar_prog, 1);
+        for (int s = 0; s < CL_STAGES; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, CL_NW);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(bar_prog, (uint32_t)loc.y * 4u);
+        bulk_g2s(smem_u32(prog), a.prog + loc.x, (uint32_t)loc.y * 4u, bar_prog);
+    }
+    __syncthreads();
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+    if (wid == CL_NW) {
+        // ---------------- producer warp: the A fragments of every operation, in order; static data, so no grid dependency ----
+        mbar_wait(bar_prog, 0);
+        const int nops = prog[0];
+        const int* ops = prog + prog[7];
+        size_t frag = (size_t)(unsigned)prog[5];
+        RingPos rp{0, 1};
+        for (int o = 0; o < nops; ++o) {
+            const int nks = ops[o * CL_OPREC + 1], nrb = ops[o * CL_OPREC + 2], cks = ops[o * CL_OPREC + 7];
+            for (int k0 = 0; k0 < nks; k0 += cks) {
+                const uint32_t nfr = (uint32_t)((min(nks, k0 + cks) - k0) * nrb);
+                mbar_wait(bar_empty + 8 * rp.s, rp.ph);
+                if (lane == 0) {
+                    mbar_expect_tx(bar_full + 8 * rp.s, nfr * 256u);
+                    bulk_g2s(smem_u32(ring) + rp.s * (CL_CHUNK * 256), a.vals + frag * 32, nfr * 256u, bar_full + 8 * rp.s);
+                }
+                frag += nfr;
+                rp.advance(CL_STAGES);
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumer warps ----------------
+    const int gid = lane >> 2, tig = lane & 3, half = wid & 1;
+    const int tid = wid * 32 + lane;
+    const size_t L = (size_t)a.ldb;
+    const int nown = loc.w;
+    const double* zsrc = a.Z + slab0 + (a.backward ? (size_t)a.n * L : 0);
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // the rows this cluster reads are complete and visible
+    // resident vector: every row segment (16 bytes per thread, 16 threads per row) goes straight from global to shared
+    // memory (cp.async), all in flight at once; a cluster whose own rows are one run of solver rows (every cluster of the
+    // lowest tier) starts them before its program has arrived
+    if (loc.z >= 0)
+        for (int idx = tid; idx < nown * 16; idx += 32 * CL_NW) {
+            const int i = idx >> 4, seg = (idx & 15) * 2;
+            const uint32_t dst = smem_u32(S + (size_t)i * CL_XS + seg);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(zsrc + (size_t)(loc.z + i) * L + seg) : "memory");
+        }
+    mbar_wait(bar_prog, 0);
+    if (dbg && tid == 0) dbg[1] = globaltimer_ns();  // program arrived
+    const int nops = prog[0];
+    const int* ops = prog + prog[7];
+    const int mroot = prog[2];
+    const int* grow = prog + prog[6];
+    const unsigned short* tab16 = reinterpret_cast<const unsigned short*>(prog + prog[8]);
+    const int* aux = prog + prog[9];
+    if (loc.z < 0)
+        for (int idx = tid; idx < nown * 16; idx += 32 * CL_NW) {
+            const int i = idx >> 4, seg = (idx & 15) * 2;
+            const uint32_t dst = smem_u32(S + (size_t)i * CL_XS + seg);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(zsrc + (size_t)grow[i] * L + seg) : "memory");
+        }
+    if (a.backward) {
+        for (int idx = tid; idx < mroot * 16; idx += 32 * CL_NW) {
+            const int j = idx >> 4, seg = (idx & 15) * 2;
+            const uint32_t dst = smem_u32(S + (size_t)(nown + j) * CL_XS + seg);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(a.Z + slab0 + (size_t)aux[j] * L + seg) : "memory");
+        }
+    } else {
+        for (int j = wid; j < mroot; j += CL_NW) S[(size_t)(nown + j) * CL_XS + lane] = 0.0;
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (dbg && tid == 0) dbg[2] = globaltimer_ns();  // resident vector loaded (this thread's part)
+    if (!a.backward && prog[3] > 0) {
+        // update vectors of lower clusters: every resident row is summed by one warp, in the order of the list
+        cl_bar_consumers();
+        const double* Zc = a.Z + slab0 + lane;
+        const int j1 = prog[12 + wid + 1];
+        for (int j = prog[12 + wid]; j < j1; j += 8) {
+            double v[8];
+            int d[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (j + u < j1) {
+                    v[u] = __ldcg(Zc + (size_t)aux[2 * (j + u)] * L);
+                    d[u] = aux[2 * (j + u) + 1];
+                }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (j + u < j1) S[(size_t)d[u] * CL_XS + lane] += v[u];
+        }
+    }
+    RingPos rp{0, 0};
+    const unsigned char* Sb = reinterpret_cast<const unsigned char*>(S + half * 16 + 2 * gid);  // B fragments: + byte offset of the row
+    for (int o = 0; o < nops; ++o) {
+        const int4 q0 = *reinterpret_cast<const int4*>(ops + o * CL_OPREC);
+        const int4 q1 = *reinterpret_cast<const int4*>(ops + o * CL_OPREC + 4);
+        const int M = q0.x, nks = q0.y, nrb = q0.z, mode = q0.w, kp = q1.z, cks = q1.w;
+        const int U = 2 * nrb;  // units (8 rows x 16 trajectories) of this operation
+        // slot s = wid + CL_NW * r of this warp: unit s % U (always in this warp's half of the trajectories), k part s / U.
+        // kp > 1 (few units, long K): U * kp <= CL_NW, one slot per warp, part p takes the groups of four k-steps g with
+        // g % kp == p; the partial sums meet in shared memory and part 0 finishes the unit
+        int un[CL_RMAX];
+        bool act[CL_RMAX];
+#pragma unroll
+        for (int r = 0; r < CL_RMAX; ++r) {
+            const int sl = wid + CL_NW * r;
+            act[r] = sl < U * kp;
+            un[r] = sl % U;
+        }
+        const int part = wid / U;  // only meaningful when kp > 1
+        // byte offsets of the gathered rows, grouped [k-step / 4][lane % 4][4]: one 16-byte load = this lane's rows of 4 k-steps
+        const unsigned* ko = reinterpret_cast<const unsigned*>(prog) + q1.x + tig * 4;
+        cl_bar_consumers();  // the rows the previous operation wrote are in place
+        double ce[CL_RMAX][2], co[CL_RMAX][2];
+#pragma unroll
+        for (int r = 0; r < CL_RMAX; ++r) ce[r][0] = ce[r][1] = co[r][0] = co[r][1] = 0.0;
+        for (int k0 = 0; k0 < nks; k0 += cks) {
+            mbar_wait(bar_full + 8 * rp.s, rp.ph);
+            if (dbg && tid == 0 && o == 0 && k0 == 0) dbg[3] = globaltimer_ns();  // first chunk of A fragments arrived
+            const double* ch = reinterpret_cast<const double*>(ring + rp.s * (CL_CHUNK * 256)) + lane;
+            const int k1 = min(nks, k0 + cks);
+            for (int ks = k0; ks < k1; ks += 4) {  // k0 and cks are multiples of 4
+                if (kp > 1 && ((ks >> 2) % kp) != part) continue;  // warp-uniform
+                const double* af = ch + (size_t)(ks - k0) * nrb * 32;
+                if (ks + 4 <= k1) {
+                    const uint4 o4 = *reinterpret_cast<const uint4*>(ko + (ks >> 2) * 16);
+                    const double2 b0 = *reinterpret_cast<const double2*>(Sb + o4.x), b1 = *reinterpret_cast<const double2*>(Sb + o4.y);
+                    const double2 b2 = *reinterpret_cast<const double2*>(Sb + o4.z), b3 = *reinterpret_cast<const double2*>(Sb + o4.w);
+#pragma unroll
+                    for (int r = 0; r < CL_RMAX; ++r)
+                        if (act[r]) {  // warp-uniform
+                            const double* ar = af + (un[r] >> 1) * 32;
+                            const double a0 = ar[0], a1 = ar[nrb * 32], a2 = ar[2 * nrb * 32], a3 = ar[3 * nrb * 32];
+                            dmma(ce[r], a0, b0.x); dmma(co[r], a0, b0.y);
+                            dmma(ce[r], a1, b1.x); dmma(co[r], a1, b1.y);
+                            dmma(ce[r], a2, b2.x); dmma(co[r], a2, b2.y);
+                            dmma(ce[r], a3, b3.x); dmma(co[r], a3, b3.y);
+                        }
+                } else {
+                    for (int kt = ks; kt < k1; ++kt) {
+                        const double2 bq = *reinterpret_cast<const double2*>(Sb + ko[(kt >> 2) * 16 + (kt & 3)]);
+#pragma unroll
+                        for (int r = 0; r < CL_RMAX; ++r)
+                            if (act[r]) {
+                                const double av = af[(size_t)(kt - ks) * nrb * 32 + (un[r] >> 1) * 32];
+                                dmma(ce[r], av, bq.x);
+                                dmma(co[r], av, bq.y);
+                            }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_empty + 8 * rp.s);
+            rp.advance(CL_STAGES);
+        }
+        if (kp > 1) {
+            // partial sums of parts 1.. -> shared memory; after the barrier part 0 adds them in order
+            if (act[0] && part > 0) {
+                double4* r4 = reinterpret_cast<double4*>(red) + ((size_t)(part - 1) * U + un[0]) * 32 + lane;
+                *r4 = make_double4(ce[0][0], co[0][0], ce[0][1], co[0][1]);
+            }
+            cl_bar_consumers();  // (for a backward operation this is also "every unit has read the front's own rows")
+            if (act[0] && part == 0) {
+                for (int pp = 1; pp < kp; ++pp) {
+                    const double4 v = reinterpret_cast<const double4*>(red)[((size_t)(pp - 1) * U + un[0]) * 32 + lane];
+                    ce[0][0] += v.x; co[0][0] += v.y; ce[0][1] += v.z; co[0][1] += v.w;
+                }
+            } else {
+                act[0] = false;
+            }
+        } else if (mode == 1) {
+            cl_bar_consumers();  // backward: the own rows are overwritten once every unit has read them
+        }
+        if (mode == 0) {
+            // forward: S[struct rows] += acc (the factor block is stored negated); units own disjoint (row, trajectory) tiles
+            const unsigned short* orow = tab16 + q1.y;
+#pragma unroll
+            for (int r = 0; r < CL_RMAX; ++r)
+                if (act[r]) {
+                    const unsigned row = orow[(un[r] >> 1) * 8 + gid];
+                    if (row != 0xffffu) {
+                        double4* pq = reinterpret_cast<double4*>(S + (size_t)row * CL_XS + half * 16 + 4 * tig);
+                        double4 v = *pq;
+                        v.x += ce[r][0]; v.y += co[r][0]; v.z += ce[r][1]; v.w += co[r][1];
+                        *pq = v;
+                    }
+                }
+        } else {
+#pragma unroll
+            for (int r = 0; r < CL_RMAX; ++r) {
+                const int rr = (un[r] >> 1) * 8 + gid;
+                if (act[r] && rr < M)
+                    *reinterpret_cast<double4*>(S + (size_t)(q1.y + rr) * CL_XS + half * 16 + 4 * tig) =
+                        make_double4(ce[r][0], co[r][0], ce[r][1], co[r][1]);
+            }
+        }
+    }
+    // ---- results leave as 256-byte rows through the bulk copy engine, one row per thread and instruction
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // this thread's writes to S, before the async proxy reads them
+    cl_bar_consumers();
+    if (dbg && tid == 0) { dbg[4] = globaltimer_ns(); dbg[6] = (unsigned long long)nops; }  // operations done
+    if (!a.backward) {
+        if (prog[30]) {
+            double* dst = a.Z + slab0 + (size_t)a.n * L;
+            for (int i = tid; i < nown; i += 32 * CL_NW) cl_row_out(dst + (size_t)grow[i] * L, S + (size_t)i * CL_XS);
+        }
+        const int ustore = prog[4];
+        if (ustore >= 0)
+            for (int j = tid; j < mroot; j += 32 * CL_NW) cl_row_out(a.Z + slab0 + (size_t)(ustore + j) * L, S + (size_t)(nown + j) * CL_XS);
+    } else {
+        const int write_z = prog[11];
+        const int* gdof = prog + prog[29];
+        for (int i = tid; i < nown; i += 32 * CL_NW) {
+            cl_row_out(a.xout + slab0 + (size_t)gdof[i] * L, S + (size_t)i * CL_XS);
+            if (write_z) cl_row_out(a.Z + slab0 + (size_t)grow[i] * L, S + (size_t)i * CL_XS);
+        }
+        bool bad = false;  // per-trajectory flag of a non-finite velocity
+        for (int i = wid; i < nown; i += CL_NW) bad = bad || (gdof[i] < a.Nv && !isfinite(S[(size_t)i * CL_XS + lane]));
+        if (bad) a.diverged[slab0 + lane] = 1;
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory stays valid until the copies have read it
+    if (dbg && tid == 0) dbg[5] = globaltimer_ns();
+}
+
 // sensors + energy.  grid = ldb/32, block = (32, MEAS_WARPS)
 constexpr int MEAS_WARPS = 32;
 __global__ void __launch_bounds__(32 * MEAS_WARPS) k_measure(int ns, const int* __restrict__ sptr, const int* __restrict__ sidx,
@@ -1059,6 +1356,14 @@ struct DevPlan {
     std::vector<Launch> launches;
     int n_forward = 0;
     long long nstages_total = 0, packed_doubles = 0;
+    // subtree clusters (k_cluster_sweep)
+    struct Tier { int first, count; };
+    std::vector<Tier> tiers;
+    int ncluster = 0, cl_srow_max = 0, cl_prog_max = 0, cl_smem = 0;
+    int* cprog = nullptr;
+    int4* cprog_loc[2] = {nullptr, nullptr};  // forward / backward: (word offset, words, first own row or -1, own rows) per cluster
+    double* cvals = nullptr;
+    long long cl_frags = 0;
 };
 
 }  // namespace
@@ -1070,6 +1375,7 @@ struct fcb_context {
     int kslots = 24;                        // ... and for k-split CTAs, whose 4 warps each need stages in flight (FCB_SWEEP_KSLOTS)
     int force_slots[4] = {48, 36, 12, 12};  // gathered rows per ring stage for those widths (FCB_SWEEP_SLOTS=a,b,c,d)
     unsigned long long* sweep_dbg = nullptr;  // FCB_SWEEP_DEBUG=<file>: per-CTA timeline of the sweeps of a profiled step
+    unsigned long long* cl_dbg = nullptr;     // FCB_CLUSTER_DEBUG=<file>: per-CTA timeline of the cluster sweeps (8 tiers x 2 directions x 8192 CTAs)
     cudaStream_t stream = nullptr;
     std::string error;
     int B = 0, ldb = 0;
@@ -1410,6 +1716,192 @@ int upload_plan(fcb_context* h, DevPlan& d, const fcb_plan& p, const int32_t* pe
     return FCB_OK;
 }
 
+
+// Compile the subtree clusters of a plan into device programs (see k_cluster_sweep) and upload them.
+int upload_clusters(fcb_context* h, DevPlan& d, const fcb_plan& p, const int32_t* perm) {
+    d.ncluster = p.ncluster;
+    d.tiers.clear();
+    if (p.ncluster <= 0) return FCB_OK;
+    if (p.ntier <= 0 || !p.tier_ptr || p.tier_ptr[0] != 0 || p.tier_ptr[p.ntier] != p.ncluster)
+        return fail(h, FCB_ERR_INVALID, "cluster plan: tier_ptr is malformed");
+    const int zrow = 2 * p.n + p.nU;
+    std::vector<int> prog;                 // all programs
+    std::vector<int4> loc[2];
+    std::vector<double> vals;              // A fragments, 32 doubles each
+    int srow_max = 0, prog_max = 0;
+    for (int q = 0; q < p.ncluster; ++q) {
+        const int f0 = p.cl_fptr[q], f1 = p.cl_fptr[q + 1], nf = f1 - f0;
+        if (nf <= 0 || f1 > p.nfront) return fail(h, FCB_ERR_INVALID, "cluster %d has no fronts", q);
+        std::vector<int> off(nf + 1, 0);
+        for (int k = 0; k < nf; ++k) {
+            const int f = f0 + k;
+            if (p.fr_w[f] < 0 || p.fr_m[f] < 0 || p.fr_c0[f] < 0 || p.fr_c0[f] + p.fr_w[f] > p.n || p.fr_sptr[f + 1] - p.fr_sptr[f] != p.fr_m[f] ||
+                (k > 0 && p.fr_c0[f] < p.fr_c0[f - 1] + p.fr_w[f - 1]))
+                return fail(h, FCB_ERR_INVALID, "cluster %d: front %d is malformed", q, f);
+            off[k + 1] = off[k] + p.fr_w[f];
+        }
+        const int nown = off[nf];
+        const int32_t* rs = p.fr_struct + p.fr_sptr[f1 - 1];
+        const int mroot = p.fr_m[f1 - 1];
+        const int srows = nown + mroot;
+        if (srows > 65000) return fail(h, FCB_ERR_INVALID, "cluster %d: %d resident rows do not fit 16-bit tables", q, srows);
+        srow_max = std::max(srow_max, srows);
+        auto local = [&](int g) -> int {  // solver row -> resident row
+            int lo = 0, hi = nf;  // last front with c0 <= g
+            while (lo < hi) {
+                const int mid = (lo + hi) / 2;
+                if (p.fr_c0[f0 + mid] <= g) lo = mid + 1;
+                else hi = mid;
+            }
+            if (lo > 0 && g < p.fr_c0[f0 + lo - 1] + p.fr_w[f0 + lo - 1]) return off[lo - 1] + g - p.fr_c0[f0 + lo - 1];
+            const int32_t* it = std::lower_bound(rs, rs + mroot, g);
+            if (it != rs + mroot && *it == g) return nown + (int)(it - rs);
+            return -1;
+        };
+        for (int dir = 0; dir < 2; ++dir) {
+            std::vector<int> ops;
+            std::vector<unsigned short> tab;  // 16-bit tables: output rows of the forward operations
+            std::vector<unsigned> ktab;       // byte offsets of the gathered rows, [k-step / 4][lane % 4][4] per operation
+            const long long frag0 = (long long)(vals.size() / 32);
+            // gathered rows of an operation -> ktab; returns its offset (a multiple of 16 entries)
+            auto add_ktab = [&](const std::vector<int>& rows) {
+                const int koff = (int)ktab.size(), ng = ((int)rows.size() + 15) / 16;
+                ktab.resize(ktab.size() + (size_t)ng * 16, 0u);
+                for (size_t kq = 0; kq < rows.size(); ++kq) {
+                    const size_t ks = kq >> 2, tg = kq & 3;
+                    ktab[koff + (ks >> 2) * 16 + tg * 4 + (ks & 3)] = (unsigned)rows[kq] * (unsigned)(CL_XS * 8);
+                }
+                return koff;
+            };
+            auto add_op = [&](int M, int K, int mode, int koff, int oarg, const double* V, int ldv, int r0, double sign) {
+                const int nrb = (M + 7) / 8, nks = (K + 3) / 4, cks = std::max(4, (CL_CHUNK / nrb) & ~3);
+                // few units and a long K: split K over the idle warps (parts take the groups of four k-steps round-robin)
+                int kp = 1;
+                while (kp < 4 && 2 * nrb * (kp * 2) <= CL_NW && (nks + 3) / 4 >= 2 * (kp * 2)) kp *= 2;
+                if ((kp - 1) * 2 * nrb * 1024 > CL_RED_BYTES) kp = 1;
+                const int rec[CL_OPREC] = {M, nks, nrb, mode, koff, oarg, kp, cks};
+                ops.insert(ops.end(), rec, rec + CL_OPREC);
+                const size_t v0 = vals.size();
+                vals.resize(v0 + (size_t)nks * nrb * 32, 0.0);
+                for (int r = 0; r < M; ++r) {
+                    const double* vr = V + (size_t)(r0 + r) * ldv;
+                    double* dst = vals.data() + v0 + (size_t)(r >> 3) * 32 + (size_t)(r & 7) * 4;
+                    for (int k = 0; k < K; ++k) dst[(size_t)(k >> 2) * nrb * 32 + (k & 3)] = sign * vr[k];
+                }
+            };
+            for (int kk = 0; kk < nf; ++kk) {
+                const int k = dir == 0 ? kk : nf - 1 - kk, f = f0 + k;
+                const int w = p.fr_w[f], m = p.fr_m[f];
+                const int32_t* st = p.fr_struct + p.fr_sptr[f];
+                if (w == 0) continue;
+                if (dir == 0) {
+                    if (m == 0) continue;
+                    std::vector<int> krows(w);
+                    for (int kq = 0; kq < w; ++kq) krows[kq] = off[k] + kq;
+                    const int koff = add_ktab(krows);
+                    for (int r0 = 0; r0 < m; r0 += CL_MAXROWS) {
+                        const int M = std::min(CL_MAXROWS, m - r0);
+                        const int ooff = (int)tab.size();
+                        for (int r = 0; r < ((M + 7) & ~7); ++r) {
+                            int lr = 0xffff;
+                            if (r < M) {
+                                lr = local(st[r0 + r]);
+                                if (lr < 0) return fail(h, FCB_ERR_INVALID, "cluster %d: boundary row %d of front %d is not resident", q, st[r0 + r], f);
+                            }
+                            tab.push_back((unsigned short)lr);
+                        }
+                        add_op(M, w, 0, koff, ooff, p.cl_vals + p.fr_eptr[f], w, r0, -1.0);
+                    }
+                } else {
+                    if (w > CL_MAXROWS) return fail(h, FCB_ERR_INVALID, "cluster %d: front %d is wider than %d", q, f, CL_MAXROWS);
+                    const int K = w + m;
+                    std::vector<int> krows(K);
+                    for (int kq = 0; kq < K; ++kq) {
+                        krows[kq] = kq < w ? off[k] + kq : local(st[kq - w]);
+                        if (krows[kq] < 0) return fail(h, FCB_ERR_INVALID, "cluster %d: boundary row %d of front %d is not resident", q, st[kq - w], f);
+                    }
+                    add_op(w, K, 1, add_ktab(krows), off[k], p.cl_vals + p.fr_bptr[f], K, 0, 1.0);
+                }
+            }
+            // imports (forward): sorted by consumer warp (resident row mod CL_NW), original order inside
+            std::vector<std::array<int, 2>> imp;
+            int wfirst[CL_NW + 1] = {0};
+            if (dir == 0) {
+                std::vector<std::array<int, 3>> tmp;
+                for (long long t = p.cl_iptr[q]; t < p.cl_iptr[q + 1]; ++t) {
+                    const int lr = local(p.imp_dst[t]);
+                    if (lr < 0 || p.imp_src[t] < 0 || p.imp_src[t] >= zrow) return fail(h, FCB_ERR_INVALID, "cluster %d: import %lld is malformed", q, t);
+                    tmp.push_back({lr % CL_NW, p.imp_src[t], lr});
+                }
+                std::stable_sort(tmp.begin(), tmp.end(), [](const std::array<int, 3>& x, const std::array<int, 3>& y) { return x[0] < y[0]; });
+                for (auto& e : tmp) { imp.push_back({e[1], e[2]}); ++wfirst[e[0] + 1]; }
+                for (int wq = 0; wq < CL_NW; ++wq) wfirst[wq + 1] += wfirst[wq];
+            }
+            // ---- lay the program out
+            const size_t base = prog.size();
+            std::vector<int> pr(CL_HDR, 0);
+            pr[0] = (int)(ops.size() / CL_OPREC); pr[1] = nown; pr[2] = mroot; pr[3] = (int)imp.size();
+            pr[4] = dir == 0 ? p.cl_ustore[q] : -1;
+            if (dir == 0 && p.cl_ustore[q] >= 0 && (p.cl_ustore[q] < 2 * p.n || p.cl_ustore[q] + mroot > zrow))
+                return fail(h, FCB_ERR_INVALID, "cluster %d: update vector outside the U region", q);
+            if (frag0 > 0x7fffffffLL) return fail(h, FCB_ERR_INVALID, "cluster factor too large for 32-bit fragment offsets");
+            pr[5] = (int)frag0;
+            pr[11] = (dir == 1 && p.cl_iptr[q + 1] > p.cl_iptr[q]) ? 1 : 0;  // x rows go to Z only if a lower cluster gathers them
+            for (int wq = 0; wq <= CL_NW; ++wq) pr[12 + wq] = wfirst[wq];
+            pr[6] = (int)pr.size();  // grow
+            for (int k = 0; k < nf; ++k)
+                for (int r = 0; r < p.fr_w[f0 + k]; ++r) pr.push_back(p.fr_c0[f0 + k] + r);
+            pr[30] = 1;  // the forward sweep stores y
+            pr[29] = (int)pr.size();  // gdof (backward)
+            if (dir == 1)
+                for (int k = 0; k < nf; ++k)
+                    for (int r = 0; r < p.fr_w[f0 + k]; ++r) pr.push_back(perm[p.fr_c0[f0 + k] + r]);
+            while (pr.size() % 4) pr.push_back(0);
+            pr[7] = (int)pr.size();  // ops (16-byte aligned: read as int4)
+            const int kbase = pr[7] + (int)ops.size();  // gathered-row tables right behind (16-byte aligned: read as uint4)
+            for (size_t o = 0; o < ops.size(); o += CL_OPREC) ops[o + 4] += kbase;
+            pr.insert(pr.end(), ops.begin(), ops.end());
+            pr.insert(pr.end(), ktab.begin(), ktab.end());
+            pr[8] = (int)pr.size();  // 16-bit tables
+            pr.resize(pr.size() + (tab.size() + 1) / 2, 0);
+            memcpy(pr.data() + pr[8], tab.data(), tab.size() * sizeof(unsigned short));
+            pr[9] = (int)pr.size();  // aux
+            if (dir == 0) for (auto& e : imp) { pr.push_back(e[0]); pr.push_back(e[1]); }
+            else for (int j = 0; j < mroot; ++j) {
+                if (rs[j] < 0 || rs[j] >= p.n) return fail(h, FCB_ERR_INVALID, "cluster %d: boundary row out of range", q);
+                pr.push_back(rs[j]);
+            }
+            while (pr.size() % 4) pr.push_back(0);
+            pr[10] = (int)pr.size();
+            prog_max = std::max(prog_max, (int)pr.size());
+            bool one_run = true;
+            for (int k = 1; k < nf; ++k) one_run = one_run && p.fr_c0[f0 + k] == p.fr_c0[f0 + k - 1] + p.fr_w[f0 + k - 1];
+            loc[dir].push_back(make_int4((int)base, (int)pr.size(), one_run ? p.fr_c0[f0] : -1, nown));
+            prog.insert(prog.end(), pr.begin(), pr.end());
+        }
+    }
+    d.cl_srow_max = srow_max;
+    d.cl_prog_max = prog_max;
+    d.cl_smem = srow_max * CL_XS * 8 + CL_RING_BYTES + CL_RED_BYTES + prog_max * 4 + 8 * (1 + 2 * CL_STAGES);
+    d.cl_frags = (long long)(vals.size() / 32);
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, h->device));
+    if (d.cl_smem > (int)prop.sharedMemPerBlockOptin)
+        return fail(h, FCB_ERR_INVALID, "subtree clusters need %d bytes of shared memory per CTA (%d resident rows, %d-word programs), the device offers %d: "
+                    "build the plan with a smaller cluster_rows", d.cl_smem, srow_max, prog_max, (int)prop.sharedMemPerBlockOptin);
+    for (int t = 0; t < p.ntier; ++t) d.tiers.push_back({p.tier_ptr[t], p.tier_ptr[t + 1] - p.tier_ptr[t]});
+    if (vals.empty()) vals.resize(32, 0.0);
+    TRY(upload(h, &d.cprog, prog.data(), prog.size()));
+    TRY(upload(h, &d.cprog_loc[0], loc[0].data(), loc[0].size()));
+    TRY(upload(h, &d.cprog_loc[1], loc[1].data(), loc[1].size()));
+    TRY(upload(h, &d.cvals, vals.data(), vals.size()));
+    CK(cudaStreamSynchronize(h->stream));
+    if (getenv("FCB_VERBOSE"))
+        fprintf(stderr, "[fcb200] clusters: %d in %d tiers, max %d resident rows, programs <= %d words, %lld A fragments, %d B smem per CTA\n",
+                p.ncluster, p.ntier, srow_max, prog_max, d.cl_frags, d.cl_smem);
+    return FCB_OK;
+}
+
 void fill_tables(double phi[7][6], double dphi[7][6][2], double w[7], double mass[6][6]) {
     const double s15 = std::sqrt(15.0);
     const double a1 = (6.0 - s15) / 21.0, a2 = (6.0 + s15) / 21.0;
@@ -1499,6 +1991,7 @@ int enqueue_measure(fcb_context* h, const double* up, bool roll_ctrl = false) {
     return FCB_OK;
 }
 
+
 constexpr size_t DBG_PER_LAUNCH = 8 * 8192;  // 8 timeline slots for up to 8192 CTAs
 
 template <int NWC, bool KS>
@@ -1520,7 +2013,29 @@ void launch_sweep(fcb_context* h, const DevPlan& pl, const DevPlan::Launch& L, i
                        h->ldb, L.nstages, L.slots, xout, h->diverged, h->Nv, dbg);
 }
 
+void launch_clusters(fcb_context* h, const DevPlan& pl, const DevPlan::Tier& t, int backward, double* xout) {
+    ClusterArgs a;
+    const int tier_index = (int)(&t - pl.tiers.data());
+    a.dbg = (h->cl_dbg && tier_index < 8) ? h->cl_dbg + (size_t)(tier_index * 2 + backward) * DBG_PER_LAUNCH : nullptr;
+    a.prog = pl.cprog; a.prog_loc = pl.cprog_loc[backward] + t.first; a.vals = pl.cvals; a.Z = h->Z; a.xout = xout;
+    a.diverged = h->diverged; a.n = pl.n; a.Nv = h->Nv; a.ldb = h->ldb; a.nslab = h->ldb / CL_W; a.backward = backward;
+    a.prog_max_words = pl.cl_prog_max; a.srow_max = pl.cl_srow_max;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(t.count * a.nslab);
+    cfg.blockDim = dim3(32, CL_NW + 1);
+    cfg.dynamicSmemBytes = pl.cl_smem;
+    cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = h->use_pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, k_cluster_sweep, a);
+    h->launches += 1;
+}
+
 int enqueue_solve(fcb_context* h, const DevPlan& pl, double* xout, PhaseMark* pm) {
+    for (const DevPlan::Tier& t : pl.tiers) launch_clusters(h, pl, t, 0, xout);  // forward: the subtree clusters first, tier by tier
     for (int l = 0; l < pl.nlaunch; ++l) {
         if (pm && l == pl.n_forward) pm->mark(FCB_PHASE_BACKWARD);
         if (l == pl.n_forward && pl.asm_n > 0) {
@@ -1543,6 +2058,7 @@ int enqueue_solve(fcb_context* h, const DevPlan& pl, double* xout, PhaseMark* pm
         h->launches += 1;
     }
     if (pm && pl.n_forward >= pl.nlaunch) pm->mark(FCB_PHASE_BACKWARD);
+    for (size_t t = pl.tiers.size(); t-- > 0;) launch_clusters(h, pl, pl.tiers[t], 1, xout);  // backward: clusters last, top tier first
     CK(cudaGetLastError());
     return FCB_OK;
 }
@@ -1685,13 +2201,14 @@ void destroy(fcb_context* h) {
     void* ptrs[] = {h->costs, h->sp_ucols, h->sp_ginfo, h->sp_kslots, h->sp_avals, h->cn_ptr, h->cn_idx, h->cn_val, h->uctrl_prev, h->ccoef_prev, h->crow_prev, h->crow, h->ccoef, h->bc_dofs, h->cell_nodes, h->perm, h->iperm, h->Jinv, h->detJ, h->bc_shape, h->ctrl_rhs[0],
                     h->ctrl_rhs[1], h->sensor_ptr, h->sensor_idx, h->sensor_val, h->up[0], h->up[1], h->avec,
                     h->bvec[0], h->bvec[1], h->Z, h->epart, h->uctrl, h->y, h->dE, h->diverged, h->Ad, h->Bd, h->Cd,
-                    h->Dd, h->Ky, h->Fu, h->xk[0], h->xk[1], h->series, h->useries, h->ctl, h->sweep_dbg,
+                    h->Dd, h->Ky, h->Fu, h->xk[0], h->xk[1], h->series, h->useries, h->ctl, h->sweep_dbg, h->cl_dbg,
                     h->pcell_ptr, h->pcnode, h->pgeo, h->pnode_ptr, h->pnode_dst, h->mptr, h->msrc, h->mnode, h->plnode, h->pscratch, h->prow, h->mrow, h->psrc, h->pacc_rows};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (int i = 0; i < 2; ++i) {
         void* pp[] = {h->plan[i].srec, h->plan[i].jrec, h->plan[i].cta_sptr, h->plan[i].cta_jptr, h->plan[i].vals,
-                      h->plan[i].asm_ptr, h->plan[i].asm_src, h->plan[i].asm_dst};
+                      h->plan[i].asm_ptr, h->plan[i].asm_src, h->plan[i].asm_dst, h->plan[i].cprog, h->plan[i].cprog_loc[0],
+                      h->plan[i].cprog_loc[1], h->plan[i].cvals};
         for (void* q : pp)
             if (q) cudaFree(q);
     }
@@ -2140,6 +2657,10 @@ int create_impl(fcb_context* h, const fcb_problem* p, int B) {
         if (env && atoi(env) >= 12 && atoi(env) <= 96 && atoi(env) % 12 == 0) h->kslots = atoi(env);
         env = getenv("FCB_SWEEP_MAXWARPS");
         if (env && (atoi(env) == 1 || atoi(env) == 2 || atoi(env) == 4)) h->max_nwc = atoi(env);  // 8 would need a 260-column box
+        if (getenv("FCB_CLUSTER_DEBUG")) {
+            CK(cudaMalloc((void**)&h->cl_dbg, 16 * DBG_PER_LAUNCH * sizeof(unsigned long long)));
+            CK(cudaMemset(h->cl_dbg, 0, 16 * DBG_PER_LAUNCH * sizeof(unsigned long long)));
+        }
         if (getenv("FCB_SWEEP_DEBUG")) {
             size_t nl = (size_t)std::max(p->plan[0].nlaunch, p->plan[1].nlaunch);
             CK(cudaMalloc((void**)&h->sweep_dbg, nl * DBG_PER_LAUNCH * sizeof(unsigned long long)));
@@ -2238,7 +2759,11 @@ int create_impl(fcb_context* h, const fcb_problem* p, int B) {
     const size_t snnz = p->ns ? (size_t)p->sensor_ptr[p->ns] : 0;
     TRY(upload(h, &h->sensor_idx, p->sensor_idx, snnz));
     TRY(upload(h, &h->sensor_val, p->sensor_val, snnz));
-    for (int o = 0; o < 2; ++o) TRY(upload_plan(h, h->plan[o], p->plan[o], p->perm));
+    for (int o = 0; o < 2; ++o) {
+        TRY(upload_plan(h, h->plan[o], p->plan[o], p->perm));
+        TRY(upload_clusters(h, h->plan[o], p->plan[o], p->perm));
+    }
+    CK(cudaFuncSetAttribute(k_cluster_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin));
     const size_t L = (size_t)h->ldb;
     for (int i = 0; i < 2; ++i) {
         TRY(upload<double>(h, &h->up[i], nullptr, (size_t)h->N * L));
@@ -2551,6 +3076,21 @@ int fcb_profile_step(fcb_handle h, const double* u_ctrl, float* ms, int32_t* lau
     h->order = 2;
     h->rhs_ready = true;
     for (int i = 0; i < FCB_NPHASES; ++i) CK(cudaEventElapsedTime(&ms[i], h->ev[i], h->ev[i + 1]));
+    if (h->cl_dbg) {
+        std::vector<unsigned long long> host(16 * DBG_PER_LAUNCH);
+        CK(cudaMemcpy(host.data(), h->cl_dbg, host.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        if (FILE* f = fopen(getenv("FCB_CLUSTER_DEBUG"), "wb")) {
+            const int nt = (int)std::min<size_t>(pl.tiers.size(), 8);
+            fwrite(&nt, sizeof(int), 1, f);
+            for (int t = 0; t < nt; ++t)
+                for (int dir = 0; dir < 2; ++dir) {
+                    const int nc = std::min(pl.tiers[t].count * (h->ldb / CL_W), 8192);
+                    fwrite(&nc, sizeof(int), 1, f);
+                    fwrite(host.data() + (size_t)(t * 2 + dir) * DBG_PER_LAUNCH, sizeof(unsigned long long), (size_t)nc * 8, f);
+                }
+            fclose(f);
+        }
+    }
     if (h->sweep_dbg) {
         const char* path = getenv("FCB_SWEEP_DEBUG");
         std::vector<unsigned long long> host((size_t)pl.nlaunch * DBG_PER_LAUNCH);
@@ -2569,8 +3109,8 @@ int fcb_profile_step(fcb_handle h, const double* u_ctrl, float* ms, int32_t* lau
     }
     if (launches) {
         launches[FCB_PHASE_RHS] = 1 + (h->scheme == 1 && h->ncrow_prev > 0 ? 1 : 0);
-        launches[FCB_PHASE_FORWARD] = pl.n_forward;
-        launches[FCB_PHASE_BACKWARD] = pl.nlaunch - pl.n_forward + (pl.asm_n > 0 ? 1 : 0);
+        launches[FCB_PHASE_FORWARD] = pl.n_forward + (int)pl.tiers.size();
+        launches[FCB_PHASE_BACKWARD] = pl.nlaunch - pl.n_forward + (pl.asm_n > 0 ? 1 : 0) + (int)pl.tiers.size();
         launches[FCB_PHASE_POST] = h->nbc > 0 ? 1 : 0;
         launches[FCB_PHASE_SPMM] = h->scheme == 1 ? 1 : 0;
         launches[FCB_PHASE_ELEMENT] = 1 + (h->nshared > 0 ? 1 : 0);

@@ -31,6 +31,11 @@ class fcb_plan(C.Structure):
         ("i0", c_i32p), ("i1", c_i32p), ("i2", c_i32p), ("e0", c_i32p), ("e1", c_i32p), ("vals", c_f64p),
         ("nlaunch", C.c_int32), ("launch_ptr", c_i32p), ("n_forward_launches", C.c_int32),
         ("asm_n", C.c_int32), ("asm_ptr", c_i32p), ("asm_src", c_i32p), ("asm_dst", c_i32p),
+        ("ntier", C.c_int32), ("tier_ptr", c_i32p),
+        ("ncluster", C.c_int32), ("cl_fptr", c_i32p), ("cl_ustore", c_i32p), ("cl_iptr", c_i64p),
+        ("imp_src", c_i32p), ("imp_dst", c_i32p),
+        ("nfront", C.c_int32), ("fr_c0", c_i32p), ("fr_w", c_i32p), ("fr_m", c_i32p), ("fr_sptr", c_i64p), ("fr_struct", c_i32p),
+        ("fr_eptr", c_i64p), ("fr_bptr", c_i64p), ("cl_vals", c_f64p),
     ]
 
 
@@ -160,6 +165,15 @@ class ProblemPack:
             q.asm_ptr = _ptr(arr(p.asm_ptr, np.int32), c_i32p)
             q.asm_src = _ptr(arr(p.asm_src if len(p.asm_src) else np.zeros(1), np.int32), c_i32p)
             q.asm_dst = _ptr(arr(p.asm_dst if len(p.asm_dst) else np.zeros(1), np.int32), c_i32p)
+            pad = lambda a: a if len(a) else np.zeros(1)  # noqa: E731
+            q.ntier = len(p.tier_ptr) - 1
+            q.ncluster = len(p.cl_fptr) - 1
+            q.nfront = len(p.fr_c0)
+            for name in ("tier_ptr", "cl_fptr", "cl_ustore", "imp_src", "imp_dst", "fr_c0", "fr_w", "fr_m", "fr_struct"):
+                setattr(q, name, _ptr(arr(pad(getattr(p, name)), np.int32), c_i32p))
+            for name in ("cl_iptr", "fr_sptr", "fr_eptr", "fr_bptr"):
+                setattr(q, name, _ptr(arr(pad(getattr(p, name)), np.int64), c_i64p))
+            q.cl_vals = _ptr(arr(pad(p.cl_vals), np.float64), c_f64p)
         s.ns = prob.ns
         s.sensor_ptr = _ptr(arr(prob.sensor_ptr, np.int32), c_i32p)
         s.sensor_idx = _ptr(arr(prob.sensor_idx, np.int32), c_i32p)

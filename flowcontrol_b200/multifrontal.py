@@ -242,10 +242,29 @@ class SolvePlan:
     asm_ptr: np.ndarray = None
     asm_src: np.ndarray = None
     asm_dst: np.ndarray = None
+    # Subtree clusters (csrc/fcb200.cu: k_cluster_sweep): connected pieces of the lower elimination tree that one CTA sweeps
+    # with ALL their unknowns resident in shared memory (right-looking inside the piece, so the update vectors of the
+    # fronts inside a cluster never exist in global memory).  Clusters of tier t only need the update vectors of cluster
+    # roots of tiers < t; all tiers run before the pull-form launches above in the forward sweep and after them in the
+    # backward sweep.  Fronts are listed cluster by cluster in elimination order.
+    tier_ptr: np.ndarray = None  # int32 [ntier+1] cluster ranges
+    cl_fptr: np.ndarray = None  # int32 [ncluster+1] front ranges
+    cl_ustore: np.ndarray = None  # int32 [ncluster] first Z row of the root's update vector (-1: none)
+    cl_iptr: np.ndarray = None  # int64 [ncluster+1] ranges of imp_src / imp_dst
+    imp_src: np.ndarray = None  # int32 Z row (update vector of a lower cluster's root)
+    imp_dst: np.ndarray = None  # int32 solver row it is added to
+    fr_c0: np.ndarray = None  # int32 [nfront] first solver row of the front's own unknowns
+    fr_w: np.ndarray = None  # int32 own unknowns
+    fr_m: np.ndarray = None  # int32 boundary (struct) rows
+    fr_sptr: np.ndarray = None  # int64 [nfront+1] ranges of fr_struct
+    fr_struct: np.ndarray = None  # int32 solver rows of the boundary
+    fr_eptr: np.ndarray = None  # int64 [nfront] offsets into cl_vals: E (m x w, row-major)
+    fr_bptr: np.ndarray = None  # int64 [nfront] offsets into cl_vals: [F11^-1 | -G] (w x (w+m), row-major)
+    cl_vals: np.ndarray = None
 
     @property
     def nnz(self) -> int:
-        return int(self.vals.size)
+        return int(self.vals.size) + (int(self.cl_vals.size) if self.cl_vals is not None else 0)
 
     @property
     def zrow(self) -> int:
@@ -277,20 +296,100 @@ def top_inverse(fac: BlockFactor, top: list[int]) -> tuple[np.ndarray, np.ndarra
     return trows, X
 
 
-def build_plan(fac: BlockFactor, top_levels: int = 2) -> SolvePlan:
+def choose_clusters(sym: SymbolicFactor, in_top: np.ndarray, max_rows: int, max_height: int, max_width: int = 128,
+                    min_tier_clusters: int = 24):
+    """Greedy bottom-up grouping of supernodes into clusters (connected subtrees) whose resident vector --- the own
+    unknowns of every front of the cluster plus the boundary rows of its root --- has at most ``max_rows`` rows.
+
+    Returns (cluster id per supernode or -1, list of clusters as supernode lists in elimination order, tier per cluster).
+    A supernode above ``max_height``, in the merged top, wider than ``max_width`` or with a non-clustered child stays in the
+    pull-form plan (so everything above a pull supernode is pull as well)."""
+    sns = sym.supernodes
+    nS = len(sns)
+    cl_of = np.full(nS, -1, dtype=np.int64)
+    open_cl: dict[int, tuple[int, list[int]]] = {}  # root -> (own rows, members) of clusters that may still grow
+    clusters: list[list[int]] = []
+    is_pull = np.zeros(nS, dtype=bool)
+
+    def close(c: int) -> None:
+        _, members = open_cl.pop(c)
+        for j in members:
+            cl_of[j] = len(clusters)
+        clusters.append(members)
+
+    for i, s in enumerate(sns):  # post-order: children first
+        w, m = s.c1 - s.c0, len(s.struct)
+        ch = sym.children[i]
+        eligible = (not in_top[i]) and s.height <= max_height and w <= max_width and not any(is_pull[c] for c in ch) and max_rows > 0
+        if not eligible:
+            for c in ch:
+                if c in open_cl:
+                    close(c)
+            is_pull[i] = True
+            continue
+        own = w + sum(open_cl[c][0] for c in ch if c in open_cl)
+        if own + m <= max_rows:
+            members: list[int] = []
+            for c in ch:
+                if c in open_cl:
+                    members += open_cl.pop(c)[1]
+            open_cl[i] = (own, members + [i])
+        else:
+            for c in ch:
+                if c in open_cl:
+                    close(c)
+            if w + m <= max_rows:
+                open_cl[i] = (w, [i])
+            else:
+                is_pull[i] = True
+    for c in sorted(open_cl):
+        close(c)
+    # tiers: a cluster comes after the clusters its fronts import from
+    tier = np.zeros(len(clusters), dtype=np.int64)
+    order = sorted(range(len(clusters)), key=lambda q: clusters[q][-1])  # by root: children's clusters have smaller roots
+    for q in order:
+        t = 0
+        for j in clusters[q]:
+            for c in sym.children[j]:
+                if cl_of[c] != q and cl_of[c] >= 0:
+                    t = max(t, tier[cl_of[c]] + 1)
+        tier[q] = t
+    # a tier with only a handful of clusters is a launch that leaves most of the GPU idle: its fronts (and everything
+    # above them) go back to the pull-form launches, which split one front over many CTAs
+    ntier = int(tier.max()) + 1 if len(clusters) else 0
+    for t in range(1, ntier):
+        if int((tier == t).sum()) < min_tier_clusters:
+            keep = [q for q in range(len(clusters)) if tier[q] < t]
+            cl_of[:] = -1
+            for new_q, q in enumerate(keep):
+                cl_of[clusters[q]] = new_q
+            clusters = [clusters[q] for q in keep]
+            tier = tier[keep]
+            break
+    return cl_of, clusters, tier
+
+
+def build_plan(fac: BlockFactor, top_levels: int = 2, cluster_rows: int = 0, cluster_height: int = 6,
+               min_tier_clusters: int = 24) -> SolvePlan:
+    """``cluster_rows`` = 0 disables the shared-memory subtree clusters (every front goes through the pull-form launches)."""
     sym = fac.sym
     sns = sym.supernodes
     n = sym.n
     nS = len(sns)
-    uoff = np.zeros(nS + 1, dtype=np.int64)
-    for i, s in enumerate(sns):
-        uoff[i + 1] = uoff[i] + len(s.struct)
-    nU = int(uoff[-1])
-    UB = 2 * n  # first row of the U region
-    ZROW = 2 * n + nU
     top = [i for i, s in enumerate(sns) if s.depth < top_levels]  # post-order, closed under ancestors
     in_top = np.zeros(nS, dtype=bool)
     in_top[top] = True
+    cl_of, clusters, cl_tier = choose_clusters(sym, in_top, cluster_rows, cluster_height, min_tier_clusters=min_tier_clusters)
+    in_cluster = cl_of >= 0
+    # update vectors live in global memory only for cluster roots and for the fronts of the pull-form plan
+    needs_u = np.array([(not in_top[i]) and len(s.struct) > 0 and ((not in_cluster[i]) or clusters[cl_of[i]][-1] == i)
+                        for i, s in enumerate(sns)], dtype=bool)
+    uoff = np.zeros(nS + 1, dtype=np.int64)
+    for i, s in enumerate(sns):
+        uoff[i + 1] = uoff[i] + (len(s.struct) if needs_u[i] else 0)
+    nU = int(uoff[-1])
+    UB = 2 * n  # first row of the U region
+    ZROW = 2 * n + nU
 
     def child_sources(i: int, rows: np.ndarray, absent: int) -> tuple[np.ndarray, np.ndarray]:
         """Z rows of the (at most two) children's update vectors that hit the given solver rows."""
@@ -312,7 +411,7 @@ def build_plan(fac: BlockFactor, top_levels: int = 2) -> SolvePlan:
     launch_ptr = [0]
     max_h = max(s.height for s in sns)
     for h in range(max_h + 1):
-        for i in (i for i, s in enumerate(sns) if s.height == h and not in_top[i]):
+        for i in (i for i, s in enumerate(sns) if s.height == h and not in_top[i] and not in_cluster[i]):
             s = sns[i]
             w, m = s.c1 - s.c0, len(s.struct)
             if w == 0 and m == 0:
@@ -361,7 +460,7 @@ def build_plan(fac: BlockFactor, top_levels: int = 2) -> SolvePlan:
             launch_ptr.append(len(blocks))
     max_d = max(s.depth for s in sns)
     for dpt in range(max_d + 1):
-        for i in (i for i, s in enumerate(sns) if s.depth == dpt and not in_top[i]):
+        for i in (i for i, s in enumerate(sns) if s.depth == dpt and not in_top[i] and not in_cluster[i]):
             s = sns[i]
             w = s.c1 - s.c0
             if w == 0:
@@ -400,6 +499,44 @@ def build_plan(fac: BlockFactor, top_levels: int = 2) -> SolvePlan:
             e1p.append(b["e1"])
             epos += int(M[q])
     cat = lambda xs, dt: np.concatenate(xs).astype(dt) if xs else np.zeros(0, dt)  # noqa: E731
+    # ---- clusters, tier by tier; inside a tier the heaviest first (they start first on the device)
+    def cl_work(q: int) -> int:
+        return sum((sns[j].c1 - sns[j].c0) * ((sns[j].c1 - sns[j].c0) + 2 * len(sns[j].struct)) for j in clusters[q])
+
+    ntier = int(cl_tier.max()) + 1 if len(clusters) else 0
+    cl_order = sorted(range(len(clusters)), key=lambda q: (cl_tier[q], -cl_work(q)))
+    tier_ptr = np.zeros(ntier + 1, dtype=np.int32)
+    for q in cl_order:
+        tier_ptr[cl_tier[q] + 1] += 1
+    tier_ptr = np.cumsum(tier_ptr).astype(np.int32)
+    cl_fptr, cl_ustore, cl_iptr = [0], [], [0]
+    imp_src, imp_dst = [], []
+    fr_c0, fr_w, fr_m, fr_sptr, fr_struct, fr_eptr, fr_bptr, cl_vparts = [], [], [], [0], [], [], [], []
+    cvpos = 0
+    for q in cl_order:
+        members = clusters[q]
+        root = members[-1]
+        cl_ustore.append(UB + int(uoff[root]) if needs_u[root] else -1)
+        for j in members:
+            sj = sns[j]
+            w, m = sj.c1 - sj.c0, len(sj.struct)
+            E, Finv, G = fac.blocks[j]
+            fr_c0.append(sj.c0); fr_w.append(w); fr_m.append(m)
+            fr_struct.append(sj.struct.astype(np.int32))
+            fr_sptr.append(fr_sptr[-1] + m)
+            fr_eptr.append(cvpos)
+            cl_vparts.append(np.ascontiguousarray(E, dtype=np.float64).ravel())
+            cvpos += m * w
+            fr_bptr.append(cvpos)
+            cl_vparts.append(np.ascontiguousarray(np.concatenate([Finv, -G], axis=1), dtype=np.float64).ravel())
+            cvpos += w * (w + m)
+            for c in sym.children[j]:
+                if cl_of[c] != cl_of[j]:  # the root of a lower cluster: its update vector is imported
+                    mc = len(sns[c].struct)
+                    imp_src.append(UB + uoff[c] + np.arange(mc, dtype=np.int64))
+                    imp_dst.append(sns[c].struct.astype(np.int64))
+        cl_fptr.append(len(fr_c0))
+        cl_iptr.append(int(sum(len(a) for a in imp_src)))
     return SolvePlan(
         n=n, nU=nU, blk_K=K, blk_M=M,
         blk_nsrc=np.array([b["nsrc"] for b in blocks], dtype=np.int32),
@@ -410,7 +547,54 @@ def build_plan(fac: BlockFactor, top_levels: int = 2) -> SolvePlan:
         launch_ptr=np.array(launch_ptr, dtype=np.int32), n_forward_launches=n_fwd,
         asm_ptr=np.array(asm_ptr, dtype=np.int32), asm_src=np.array(asm_src, dtype=np.int32),
         asm_dst=np.array(asm_dst, dtype=np.int32),
+        tier_ptr=tier_ptr, cl_fptr=np.array(cl_fptr, dtype=np.int32), cl_ustore=np.array(cl_ustore, dtype=np.int32),
+        cl_iptr=np.array(cl_iptr, dtype=np.int64), imp_src=cat(imp_src, np.int32), imp_dst=cat(imp_dst, np.int32),
+        fr_c0=np.array(fr_c0, dtype=np.int32), fr_w=np.array(fr_w, dtype=np.int32), fr_m=np.array(fr_m, dtype=np.int32),
+        fr_sptr=np.array(fr_sptr, dtype=np.int64), fr_struct=cat(fr_struct, np.int32),
+        fr_eptr=np.array(fr_eptr, dtype=np.int64), fr_bptr=np.array(fr_bptr, dtype=np.int64),
+        cl_vals=cat(cl_vparts, np.float64),
     )
+
+
+def _cluster_sweep_host(plan: SolvePlan, Z: np.ndarray, q: int, forward: bool) -> None:
+    """Numpy emulation of k_cluster_sweep for cluster ``q`` (same local vector, same order of operations)."""
+    n = plan.n
+    f0, f1 = int(plan.cl_fptr[q]), int(plan.cl_fptr[q + 1])
+    c0, w, m = plan.fr_c0[f0:f1], plan.fr_w[f0:f1], plan.fr_m[f0:f1]
+    off = np.concatenate([[0], np.cumsum(w)])
+    nown = int(off[-1])
+    root_struct = plan.fr_struct[plan.fr_sptr[f1 - 1] : plan.fr_sptr[f1]]
+    # solver row -> local row of the resident vector
+    loc = {}
+    for k in range(f1 - f0):
+        for r in range(int(w[k])):
+            loc[int(c0[k]) + r] = int(off[k]) + r
+    for j, g in enumerate(root_struct):
+        loc[int(g)] = nown + j
+    S = np.zeros((nown + len(root_struct), Z.shape[1]))
+    own_rows = np.concatenate([np.arange(c0[k], c0[k] + w[k]) for k in range(f1 - f0)]) if f1 > f0 else np.zeros(0, dtype=np.int64)
+    if forward:
+        S[:nown] = Z[own_rows]
+        for t in range(int(plan.cl_iptr[q]), int(plan.cl_iptr[q + 1])):
+            S[loc[int(plan.imp_dst[t])]] += Z[plan.imp_src[t]]
+        for k in range(f1 - f0):
+            f = f0 + k
+            st = np.array([loc[int(g)] for g in plan.fr_struct[plan.fr_sptr[f] : plan.fr_sptr[f + 1]]], dtype=np.int64)
+            E = plan.cl_vals[plan.fr_eptr[f] : plan.fr_eptr[f] + int(m[k]) * int(w[k])].reshape(int(m[k]), int(w[k]))
+            if len(st):
+                S[st] -= E @ S[off[k] : off[k + 1]]
+        Z[n + own_rows] = S[:nown]
+        if plan.cl_ustore[q] >= 0:
+            Z[plan.cl_ustore[q] : plan.cl_ustore[q] + len(root_struct)] = S[nown:]
+    else:
+        S[:nown] = Z[n + own_rows]
+        S[nown:] = Z[root_struct]
+        for k in reversed(range(f1 - f0)):
+            f = f0 + k
+            st = np.array([loc[int(g)] for g in plan.fr_struct[plan.fr_sptr[f] : plan.fr_sptr[f + 1]]], dtype=np.int64)
+            Bm = plan.cl_vals[plan.fr_bptr[f] : plan.fr_bptr[f] + int(w[k]) * int(w[k] + m[k])].reshape(int(w[k]), int(w[k] + m[k]))
+            S[off[k] : off[k + 1]] = Bm @ np.concatenate([S[off[k] : off[k + 1]], S[st]])
+        Z[own_rows] = S[:nown]
 
 
 def apply_plan_host(plan: SolvePlan, b_perm: np.ndarray) -> np.ndarray:
@@ -422,6 +606,10 @@ def apply_plan_host(plan: SolvePlan, b_perm: np.ndarray) -> np.ndarray:
     n = plan.n
     Z = np.zeros((plan.z_rows, b.shape[1]))
     Z[:n] = b
+    ntier = len(plan.tier_ptr) - 1 if plan.tier_ptr is not None else 0
+    for t in range(ntier):
+        for q in range(int(plan.tier_ptr[t]), int(plan.tier_ptr[t + 1])):
+            _cluster_sweep_host(plan, Z, q, True)
     q_asm = int(plan.launch_ptr[plan.n_forward_launches])  # first block after the forward launches
     for q in range(len(plan.blk_K) + 1):
         if q == q_asm:
@@ -446,6 +634,9 @@ def apply_plan_host(plan: SolvePlan, b_perm: np.ndarray) -> np.ndarray:
                 has = extra >= 0
                 acc[has] += Z[extra[has]]
         Z[plan.blk_out0[q] : plan.blk_out0[q] + M] = acc
+    for t in reversed(range(ntier)):
+        for q in range(int(plan.tier_ptr[t]), int(plan.tier_ptr[t + 1])):
+            _cluster_sweep_host(plan, Z, q, False)
     assert not Z[plan.zrow].any()
     x = Z[:n]
     return x[:, 0] if squeeze else x

@@ -115,6 +115,8 @@ class FlowProblem:
         pin_pressure: bool = False,
         leaf_cells: int = 16,
         top_levels: int = 2,
+        cluster_rows: int | None = None,
+        cluster_height: int | None = None,
         time_scheme: str = "bdf",
         symbolic: SymbolicFactor | None = None,
     ):
@@ -168,7 +170,14 @@ class FlowProblem:
             self.A_raw[order] = A
             fac = BlockFactor(self.sym, A)
             self.factors[order] = fac
-            self.plans[order] = build_plan(fac, top_levels=top_levels)
+            # shared-memory subtree clusters of the GPU solve (k_cluster_sweep): OFF by default -- measured on B200 they cut
+            # the sweeps' DRAM traffic (bottom four forward levels 500 -> 200 MB) but run slower than the pull-form launches
+            # they replace; cluster_rows / FCB_CLUSTER_ROWS > 0 turns them on (512 rows fit one CTA per SM)
+            import os
+
+            crow = int(os.environ.get("FCB_CLUSTER_ROWS", 0 if cluster_rows is None else cluster_rows))
+            chgt = int(os.environ.get("FCB_CLUSTER_HEIGHT", 6 if cluster_height is None else cluster_height))
+            self.plans[order] = build_plan(fac, top_levels=top_levels, cluster_rows=crow, cluster_height=chgt)
             # rhs contribution per unit u_ctrl_k in solver row order: (F_k - A[:,Gamma] shape_k)[perm]
             lift = (A @ G.T).toarray().T if na else np.zeros((0, tab.N))
             self.ctrl_rhs[order] = np.ascontiguousarray((half_force * force - lift)[:, self.sym.perm])

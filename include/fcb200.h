@@ -71,6 +71,33 @@ typedef struct fcb_plan {
     const int32_t* asm_ptr; /* [asm_n+1] */
     const int32_t* asm_src;
     const int32_t* asm_dst; /* [asm_n] */
+    /* Subtree clusters (multifrontal.py: choose_clusters): connected pieces of the lower elimination tree that ONE CTA
+     * sweeps with all their unknowns resident in shared memory (k_cluster_sweep).  Inside a cluster the sweep is
+     * right-looking on one resident vector S = [own rows of its fronts | boundary rows of its root]:
+     *   forward   S[own] = b (+ imported update vectors); per front, in order:  S[struct] -= E S[own of the front];
+     *             at the end  y = S[own] -> Z[n + row],  update vector of the root = S[boundary] -> Z[cl_ustore ...]
+     *   backward  S[own] = y, S[boundary] = x of the ancestors; per front, in reverse:  S[own] = [F11^-1 | -G] [S[own]; S[struct]];
+     *             at the end  x = S[own] -> Z[row] and the canonical state
+     * so the update vectors of the fronts inside a cluster never exist in global memory.  Clusters of tier t import only
+     * update vectors of cluster roots of lower tiers; all tiers run before the forward launches above and after the
+     * backward launches.  ncluster may be 0.  Fronts are listed cluster by cluster in elimination order. */
+    int32_t ntier;
+    const int32_t* tier_ptr;   /* [ntier+1] cluster ranges                                          */
+    int32_t ncluster;
+    const int32_t* cl_fptr;    /* [ncluster+1] front ranges                                         */
+    const int32_t* cl_ustore;  /* [ncluster] first Z row of the root's update vector, or -1         */
+    const int64_t* cl_iptr;    /* [ncluster+1] ranges of imp_src / imp_dst                          */
+    const int32_t* imp_src;    /* Z row of an imported update-vector entry                          */
+    const int32_t* imp_dst;    /* solver row it is added to (a row resident in the cluster)         */
+    int32_t nfront;
+    const int32_t* fr_c0;      /* [nfront] first solver row of the front's own unknowns             */
+    const int32_t* fr_w;       /* [nfront] own unknowns                                             */
+    const int32_t* fr_m;       /* [nfront] boundary rows                                            */
+    const int64_t* fr_sptr;    /* [nfront+1] ranges of fr_struct                                    */
+    const int32_t* fr_struct;  /* solver rows of the boundary, increasing                           */
+    const int64_t* fr_eptr;    /* [nfront] offset of E (m x w, row-major) in cl_vals                */
+    const int64_t* fr_bptr;    /* [nfront] offset of [F11^-1 | -G] (w x (w+m), row-major) in cl_vals */
+    const double* cl_vals;
 } fcb_plan;
 
 /* Everything that is constant over a run and shared by the whole ensemble.

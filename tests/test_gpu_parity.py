@@ -649,3 +649,50 @@ def test_crank_nicolson_any_ensemble_width(cyl):
         else:
             assert rel(up[:, -1], ref) < 1e-12
         ens.close()
+
+
+@pytest.mark.parametrize("rows,height", [(512, 6), (300, 2)])
+def test_subtree_cluster_sweeps_match_oracle(root, built_lib, rows, height):
+    """The shared-memory subtree clusters (k_cluster_sweep; optional path of the constant-LHS solve, off by default): same
+    trajectory as the oracle for two cuts of the elimination tree (one and several tiers, k-split operations, imported
+    update vectors), ragged ensemble width, trajectory-dependent lid actuation."""
+    from flowcontrol_b200.ensemble import Ensemble
+    from flowcontrol_b200.examples import lidcavity as ex
+    from flowcontrol_b200.flowfield import Field
+    from flowcontrol_b200.problem import FlowProblem
+
+    UP0 = np.load(root / "tests/golden/lidcavity_baseflow.npz")["UP0"]
+    import tempfile
+    from pathlib import Path
+
+    fs = ex.LidCavityFlowSolver.make_default(Re=1000.0, path_out=Path(tempfile.mkdtemp()))
+    tab = fs.tables
+    fs._assign_steady_state(Field(UP0[: tab.Nv]), Field(UP0[tab.Nv :]))
+    prob = FlowProblem(tab, fs.blocks, 1000.0, 0.005, fs.bc.bcu, fs.params_control.actuator_list, fs.params_control.sensor_list,
+                       UP0, pin_pressure=True, cluster_rows=rows, cluster_height=height)
+    assert len(prob.plans[2].cl_fptr) - 1 > 0  # the plan really has clusters
+    case = cases.lidcavity(1000.0)
+    xy, tri = cases.load_mesh(case.mesh_file)
+    B = 72
+    probe = [0, 35, 71]
+    amp = 0.02 + 0.1 * np.arange(B) / (B - 1)
+    oracles = []
+    for b in probe:
+        orc = FlowOracle(case, xy, tri)
+        orc.set_base_flow(UP0)
+        orc.init_time_stepping()
+        oracles.append(orc)
+    ens = Ensemble(prob, B)
+    ens.set_state(oracles[0].ic[: tab.Nv], None, oracles[0].ic[tab.Nv :], order=1)
+    for k in range(6):
+        uc = (amp * np.cos(0.9 * k))[None, :]
+        ens.step(uc)
+        for orc, b in zip(oracles, probe):
+            orc.step([uc[0, b]])
+            assert np.allclose(ens.y_meas[:, b], orc.y_meas, rtol=SERIES_TOL, atol=0)
+            assert np.isclose(ens.dE[b], orc.dE, rtol=SERIES_TOL)
+    up = ens.fields(0)
+    for orc, b in zip(oracles, probe):
+        assert rel(up[: tab.Nv, b], orc.up[: tab.Nv]) < FIELD_TOL
+    assert not ens.diverged.any()
+    ens.close()

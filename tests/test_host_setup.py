@@ -133,12 +133,30 @@ def test_multifrontal_matches_superlu_and_plan_matches_factor(small):
     Aff = A[sym.perm][:, sym.perm].tocsc()
     xref = spla.splu(Aff).solve(b)
     assert np.linalg.norm(x - xref) / np.linalg.norm(xref) < 1e-11
-    plan0 = build_plan(fac, top_levels=0)
+    plan0 = build_plan(fac, top_levels=0, cluster_rows=0)
     assert np.abs(apply_plan_host(plan0, b) - x).max() < 1e-12 * np.abs(x).max()
     assert plan0.i0.max() <= plan0.zrow and plan0.nnz == sym.factor_entries() and len(plan0.asm_dst) == 0
     for tl in (1, 2, 4, 99):  # merged top of the tree (explicit inverse of the top Schur complement)
-        assert np.abs(apply_plan_host(build_plan(fac, top_levels=tl), b) - x).max() < 1e-12 * np.abs(x).max()
-    plan = build_plan(fac, top_levels=2)
+        assert np.abs(apply_plan_host(build_plan(fac, top_levels=tl, cluster_rows=0), b) - x).max() < 1e-12 * np.abs(x).max()
+    # shared-memory subtree clusters below the pull-form launches: every cut (rows resident per cluster, height limit)
+    # gives the same solution, produces every x and y row exactly once, and keeps the factor entry count
+    seen_tiers = set()
+    for rows, hmax in ((40, 1), (60, 99), (120, 2), (120, 99), (400, 3), (10000, 99)):  # (min_tier_clusters keeps small upper tiers out)
+        pc = build_plan(fac, top_levels=2, cluster_rows=rows, cluster_height=hmax, min_tier_clusters=1 if rows != 120 else 6)
+        assert np.abs(apply_plan_host(pc, b) - x).max() < 1e-12 * np.abs(x).max(), (rows, hmax)
+        ncl = len(pc.cl_fptr) - 1
+        assert ncl > 0 and pc.tier_ptr[-1] == ncl
+        seen_tiers.add(len(pc.tier_ptr) - 1)
+        own = np.concatenate([np.arange(c, c + w) for c, w in zip(pc.fr_c0, pc.fr_w)])
+        bwp = np.arange(len(pc.blk_K)) >= pc.launch_ptr[pc.n_forward_launches]
+        pull = [np.arange(o, o + r) for o, r in zip(pc.blk_out0[bwp], pc.blk_M[bwp])]
+        assert sorted(np.concatenate([own] + pull).tolist()) == list(range(sym.n))
+        for q in range(ncl):  # the resident vector of a cluster respects the requested size
+            f0, f1 = pc.cl_fptr[q], pc.cl_fptr[q + 1]
+            assert pc.fr_w[f0:f1].sum() + pc.fr_m[f1 - 1] <= rows
+        assert pc.nU <= plan0.nU  # update vectors inside clusters never reach global memory
+    assert max(seen_tiers) >= 2  # some cut produced clusters that import from lower clusters
+    plan = build_plan(fac, top_levels=2, cluster_rows=0)
     # every x row and every y row is produced exactly once; blocks of one launch never read rows
     # that the same launch writes
     n = sym.n
