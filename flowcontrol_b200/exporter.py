@@ -1,12 +1,12 @@
 """Timeseries logging and checkpoint export (host side).
 
 Mirrors /root/reference/src/flowcontrol/exporter.py:42-290: same record columns
-(``time, dE, runtime, u_ctrl_i, y_meas_i``), same CSV and JSON-sidecar contents.
-The reference writes fields through dolfin's XDMF/HDF5 checkpoint writer
-(utils/io.py:21-39); no HDF5 library exists here, so each checkpoint is one
-``.npz`` per field file name (``U_restartT.npz`` next to where the ``.xdmf`` would
-be) holding the appended snapshots in canonical numbering.  SURVEY.md section
-8(f) row f2 tracks the byte-level XDMF writer.
+(``time, dE, runtime, u_ctrl_i, y_meas_i``), same CSV and JSON-sidecar contents, and the same field files: the
+reference writes fields through dolfin's XDMF/HDF5 checkpoint writer (utils/io.py:21-39); xdmf_checkpoint.py writes and
+reads that layout (``<name>.xdmf`` + ``<name>.h5`` with ``/<fn>/<fn>_<k>/{vector,cell_dofs,x_cell_dofs,cells,mesh/...}``)
+without dolfin or libhdf5.  An ensemble (batch > 1) stores one function per trajectory in the same files: trajectory 0
+under the reference's function name, trajectory b as ``<name>_traj<b:04d>``, so every trajectory can be restarted on its
+own (by this package or by the reference) and the whole ensemble can be restarted trajectory by trajectory.
 """
 
 from __future__ import annotations
@@ -17,35 +17,68 @@ import logging
 import numpy as np
 import pandas as pd
 
+from . import xdmf_checkpoint as xc
 from .flowfield import Field, FlowFieldCollection, SimPaths
 
 logger = logging.getLogger(__name__)
 
 
-def _npz_path(path):
-    return path.with_suffix(".npz")
+def _kind(tab, size: int) -> str:
+    if size == tab.Nv:
+        return "V"
+    if size == tab.nV:
+        return "P"
+    raise ValueError(f"a field of {size} dofs is neither a velocity ({tab.Nv}) nor a pressure ({tab.nV}) field")
 
 
-def write_checkpoint(path, name: str, data: np.ndarray, time: float, append: bool) -> None:
-    p = _npz_path(path)
-    p.parent.mkdir(parents=True, exist_ok=True)
-    if append and p.exists():
-        old = np.load(p)
-        snaps = np.concatenate([old["snapshots"], data[None]], axis=0)
-        times = np.concatenate([old["times"], [time]])
-    else:
-        snaps, times = data[None], np.array([time])
-    np.savez(p, snapshots=snaps, times=times, name=name)
+def write_checkpoint(path, name: str, data: np.ndarray, time: float, append: bool, tab) -> None:
+    """``write_xdmf`` of utils/io.py:21-39.  ``data`` [n] is one function, [n, B] one function per trajectory."""
+    data = np.asarray(data, dtype=np.float64)
+    if data.ndim == 1:
+        xc.write_checkpoint(path, name, tab, data, _kind(tab, data.shape[0]), time, append=append)
+        return
+    for b in range(data.shape[1]):
+        xc.write_checkpoint(path, xc.trajectory_name(name, b), tab, data[:, b], _kind(tab, data.shape[0]), time,
+                            append=append or b > 0)
 
 
-def read_checkpoint(path, counter: int = -1) -> np.ndarray:
-    return np.load(_npz_path(path))["snapshots"][counter]
+def checkpoint_function_name(path) -> str:
+    """Name of the first function stored in an XDMF checkpoint file."""
+    import re
+    from pathlib import Path
+
+    m = re.search(r'<Grid Name="([^"]+)" GridType="Collection"', Path(path).read_text())
+    if not m:
+        raise ValueError(f"{path}: not an XDMF function checkpoint")
+    return m.group(1)
+
+
+def read_checkpoint(path, counter: int = -1, tab=None, name: str | None = None, batch: int = 1) -> np.ndarray:
+    """``read_xdmf`` of utils/io.py:42-50: canonical dof vector [n]; with ``batch`` > 1 every trajectory, [n, batch]
+    (a file that holds a single function is broadcast)."""
+    import re
+    from pathlib import Path
+
+    if tab is None:
+        raise ValueError("read_checkpoint needs the mesh tables")
+    name = name or checkpoint_function_name(path)
+    text = Path(path).read_text()
+    kind = "V" if re.search(rf'Name="{re.escape(name)}" Center="Other" AttributeType="Vector"', text) else "P"
+    first = xc.read_checkpoint(path, name, tab, kind, counter)
+    if batch <= 1:
+        return first
+    out = np.empty((first.size, batch))
+    out[:, 0] = first
+    for b in range(1, batch):
+        fn = xc.trajectory_name(name, b)
+        out[:, b] = xc.read_checkpoint(path, fn, tab, kind, counter) if f'<Grid Name="{fn}" GridType="Collection"' in text else first
+    return out
 
 
 class FlowExporter:
     def __init__(self, paths: SimPaths, fields: FlowFieldCollection, V=None, P=None, Tstart: float = 0.0,
-                 dt: float = 0.0, save_every: int = 0) -> None:
-        self.paths, self.fields, self.V, self.P = paths, fields, V, P
+                 dt: float = 0.0, save_every: int = 0, tab=None) -> None:
+        self.paths, self.fields, self.V, self.P, self.tab = paths, fields, V, P, tab
         self._Tstart, self._dt, self._save_every = Tstart, dt, save_every
         self._records: list[dict] = []
         self._checkpoints_written = 0
@@ -54,15 +87,19 @@ class FlowExporter:
 
     def export_xdmf(self, u_n: Field, u_nn: Field, p_n: Field, time: float, append: bool = True,
                     write_mesh: bool = False, adjust_baseflow: float = 0.0) -> None:
-        """Write (U, Uprev, P) snapshots, optionally as full fields (exporter.py:85-165)."""
+        """Write (U, Uprev, P) snapshots, optionally as full fields (exporter.py:85-165).  The arguments are Fields
+        (one trajectory) or arrays [n, B] (every trajectory of an ensemble: one function per trajectory in the same files)."""
         U0v, P0v = self.fields.U0.vector()[:], self.fields.P0.vector()[:]
-        self.fields.Usave = Field(u_n.vector()[:] + adjust_baseflow * U0v)
-        self.fields.Usave_n = Field(u_nn.vector()[:] + adjust_baseflow * U0v)
-        self.fields.Psave = Field(p_n.vector()[:] + adjust_baseflow * P0v)
+        arr = lambda f: f.vector()[:] if isinstance(f, Field) else np.asarray(f, dtype=np.float64)  # noqa: E731
+        base = lambda v, ref: ref if v.ndim == 1 else ref[:, None]  # noqa: E731
+        U, Un, Pn = arr(u_n), arr(u_nn), arr(p_n)
+        U, Un, Pn = U + adjust_baseflow * base(U, U0v), Un + adjust_baseflow * base(Un, U0v), Pn + adjust_baseflow * base(Pn, P0v)
+        first = lambda v: v if v.ndim == 1 else v[:, 0]  # noqa: E731
+        self.fields.Usave, self.fields.Usave_n, self.fields.Psave = Field(first(U)), Field(first(Un)), Field(first(Pn))
         self._checkpoints_written += 1
-        write_checkpoint(self.paths.U_restart, "U", self.fields.Usave.array, time, append)
-        write_checkpoint(self.paths.Uprev_restart, "U_n", self.fields.Usave_n.array, time, append)
-        write_checkpoint(self.paths.P_restart, "P", self.fields.Psave.array, time, append)
+        write_checkpoint(self.paths.U_restart, "U", U, time, append, self.tab)
+        write_checkpoint(self.paths.Uprev_restart, "U_n", Un, time, append, self.tab)
+        write_checkpoint(self.paths.P_restart, "P", Pn, time, append, self.tab)
 
     def log_ic(self, t: float, y_meas, dE: float) -> None:
         row = {"time": t, "dE": dE, "runtime": 0.0}

@@ -46,8 +46,10 @@ class Vector:
 class Field:
     """A dof vector on V (2nN), P (nV) or W (2nN+nV) in canonical numbering."""
 
-    def __init__(self, data=None, size: int | None = None, fetch: Callable[[], np.ndarray] | None = None, Nv: int | None = None):
+    def __init__(self, data=None, size: int | None = None, fetch: Callable[[], np.ndarray] | None = None, Nv: int | None = None,
+                 fetch_all: Callable[[], np.ndarray] | None = None):
         self._fetch = fetch
+        self._fetch_all = fetch_all  # ensemble runs: every trajectory, [n, B]
         self._data = None if data is None else np.array(data, dtype=np.float64, copy=True)
         if self._data is None and fetch is None:
             self._data = np.zeros(int(size))
@@ -62,6 +64,13 @@ class Field:
     @array.setter
     def array(self, value) -> None:
         self._data = np.asarray(value, dtype=np.float64)
+
+    @property
+    def ensemble(self) -> np.ndarray:
+        """[n, B]: this field for every trajectory of the ensemble (a single run or a host-side field gives [n, 1])."""
+        if self._fetch_all is not None:
+            return np.asarray(self._fetch_all(), dtype=np.float64)
+        return self.array[:, None]
 
     def vector(self) -> Vector:
         return Vector(self)

@@ -145,7 +145,7 @@ class FlowSolver(ABC):
             sensor.load(self)
         self.bc = self._make_bcs()
         self.exporter = FlowExporter(self.paths, self.fields, Tstart=self.params_time.Tstart,
-                                     dt=self.params_time.dt, save_every=self.params_save.save_every)
+                                     dt=self.params_time.dt, save_every=self.params_save.save_every, tab=self.tables)
         self.problem: FlowProblem | None = None
         self.ensemble: Ensemble | None = None
         self.first_step = True
@@ -225,8 +225,8 @@ class FlowSolver(ABC):
             raise ValueError(f"method must be 'newton' or 'picard', got {method!r}")
         U0, P0 = Field(UP[: tab.Nv]), Field(UP[tab.Nv :])
         if self.params_save.save_every:
-            write_checkpoint(self.paths.U0, "U0", U0.array, 0.0, append=False)
-            write_checkpoint(self.paths.P0, "P0", P0.array, 0.0, append=False)
+            write_checkpoint(self.paths.U0, "U0", U0.array, 0.0, append=False, tab=tab)
+            write_checkpoint(self.paths.P0, "P0", P0.array, 0.0, append=False, tab=tab)
             self.paths.steady_meta.parent.mkdir(parents=True, exist_ok=True)
             self.paths.steady_meta.write_text(json.dumps({"mesh_cells": int(tab.nT)}, indent=2))
         self._assign_steady_state(U0, P0)
@@ -234,7 +234,8 @@ class FlowSolver(ABC):
     def load_steady_state(self, path_u_p: Sequence[Path] | None = None) -> None:
         paths = path_u_p or (self.paths.U0, self.paths.P0)
         self._check_steady_state_compatible(Path(paths[0]))
-        self._assign_steady_state(Field(read_checkpoint(Path(paths[0]))), Field(read_checkpoint(Path(paths[1]))))
+        self._assign_steady_state(Field(read_checkpoint(Path(paths[0]), tab=self.tables)),
+                                  Field(read_checkpoint(Path(paths[1]), tab=self.tables)))
 
     def _check_steady_state_compatible(self, u0_path: Path) -> None:
         try:
@@ -335,9 +336,14 @@ class FlowSolver(ABC):
             up = up + self.params_ic.amplitude * (pert if up.ndim == 1 else pert[:, None])
         u_n = up[: tab.Nv]
         if self.params_save.save_every:
-            first = up if up.ndim == 1 else up[:, 0]
-            self.exporter.export_xdmf(Field(first[: tab.Nv]), Field(first[: tab.Nv]), Field(first[tab.Nv :]), time=0.0,
-                                      append=False, write_mesh=True, adjust_baseflow=1.0)
+            B = self.params_ensemble.batch
+            if B == 1:
+                self.exporter.export_xdmf(Field(up[: tab.Nv]), Field(up[: tab.Nv]), Field(up[tab.Nv :]), time=0.0,
+                                          append=False, write_mesh=True, adjust_baseflow=1.0)
+            else:  # every trajectory gets its own function from the first snapshot on (the counters stay aligned)
+                up_all = up if up.ndim == 2 else np.repeat(up[:, None], B, axis=1)
+                self.exporter.export_xdmf(up_all[: tab.Nv], up_all[: tab.Nv], up_all[tab.Nv :], time=0.0,
+                                          append=False, write_mesh=True, adjust_baseflow=1.0)
         return up, u_n, u_n, 1
 
     def _find_restart_from_json(self, Tstart: float):
@@ -369,13 +375,16 @@ class FlowSolver(ABC):
         """Restart from a checkpoint: read full fields, subtract the base flow (flowsolver.py:599-663)."""
         found = self._find_restart_from_json(Tstart) or self._find_restart_from_params(Tstart)
         meta, counter, base = found
-        U = read_checkpoint(base / meta["files"]["U"], counter)
-        Uprev = read_checkpoint(base / meta["files"]["Uprev"], counter)
-        P = read_checkpoint(base / meta["files"]["P"], counter)
+        B = self.params_ensemble.batch  # an ensemble restarts trajectory by trajectory (files of a single run are broadcast)
+        U = read_checkpoint(base / meta["files"]["U"], counter, tab=self.tables, batch=B)
+        Uprev = read_checkpoint(base / meta["files"]["Uprev"], counter, tab=self.tables, batch=B)
+        P = read_checkpoint(base / meta["files"]["P"], counter, tab=self.tables, batch=B)
         if self.params_save.save_every:
-            self.exporter.export_xdmf(Field(U), Field(Uprev), Field(P), time=Tstart, append=False, write_mesh=True,
-                                      adjust_baseflow=0.0)
+            self.exporter.export_xdmf(Field(U) if B == 1 else U, Field(Uprev) if B == 1 else Uprev, Field(P) if B == 1 else P,
+                                      time=Tstart, append=False, write_mesh=True, adjust_baseflow=0.0)
         U0v, P0v = self.fields.U0.array, self.fields.P0.array
+        if B > 1:
+            U0v, P0v = U0v[:, None], P0v[:, None]
         u_n, u_nn, p_n = U - U0v, Uprev - U0v, P - P0v
         return np.concatenate([u_n, p_n]), u_n, u_nn, meta["restart_order"]
 
@@ -386,27 +395,31 @@ class FlowSolver(ABC):
         return self._traj0(a) if self.params_ensemble.batch == 1 else np.array(a.T, copy=True)
 
     def _refresh_fields(self) -> None:
-        """Lazy views of trajectory 0 (use ``self.ensemble.fields()`` for all trajectories)."""
+        """Lazy views of the device state.  ``field.vector().get_local()`` / ``field.array`` is trajectory 0 (the
+        reference's single-run accessors, flowfield.py:62-97); ``field.ensemble`` is the [n, B] array of EVERY trajectory."""
         tab, ens = self.tables, self.ensemble
         cache: dict = {}
 
-        def cur():
+        def cur_all():
             if "cur" not in cache:
-                cache["cur"] = ens.fields(0)[:, 0]
+                cache["cur"] = ens.fields(0)
             return cache["cur"]
 
-        def prev():
+        def prev_all():
             if "prev" not in cache:
-                cache["prev"] = ens.fields(1)[:, 0]
+                cache["prev"] = ens.fields(1)
             return cache["prev"]
 
+        def view(get_all, lo=None, hi=None, Nv=None):
+            return Field(fetch=lambda: get_all()[lo:hi, 0], fetch_all=lambda: get_all()[lo:hi], Nv=Nv)
+
         f = self.fields
-        f.up_ = Field(fetch=cur, Nv=tab.Nv)
-        f.u_ = Field(fetch=lambda: cur()[: tab.Nv])
-        f.p_ = Field(fetch=lambda: cur()[tab.Nv :])
-        f.u_n = Field(fetch=lambda: cur()[: tab.Nv])
-        f.p_n = Field(fetch=lambda: cur()[tab.Nv :])
-        f.u_nn = Field(fetch=prev)
+        f.up_ = view(cur_all, Nv=tab.Nv)
+        f.u_ = view(cur_all, 0, tab.Nv)
+        f.p_ = view(cur_all, tab.Nv, None)
+        f.u_n = view(cur_all, 0, tab.Nv)
+        f.p_n = view(cur_all, tab.Nv, None)
+        f.u_nn = view(prev_all)
 
     def step(self, u_ctrl) -> np.ndarray | None:
         """Advance every trajectory by one step (flowsolver.py:703-799)."""
@@ -450,7 +463,11 @@ class FlowSolver(ABC):
         dE = float(ens.dE[0]) if self._niter_multiple_of(self.iter, self.params_save.energy_every) else np.nan
         self.exporter.log(u_ctrl=uc_dev[:, 0], y_meas=self._traj0(y), dE=dE, t=self.t, runtime=runtime)
         if at_checkpoint:
-            self.exporter.export_xdmf(self.fields.u_n, self.fields.u_nn, self.fields.p_n, time=self.t, adjust_baseflow=1.0)
+            if B == 1:
+                self.exporter.export_xdmf(self.fields.u_n, self.fields.u_nn, self.fields.p_n, time=self.t, adjust_baseflow=1.0)
+            else:  # every trajectory, so that the ensemble can be restarted trajectory by trajectory
+                self.exporter.export_xdmf(self.fields.u_n.ensemble, self.fields.u_nn.ensemble, self.fields.p_n.ensemble,
+                                          time=self.t, adjust_baseflow=1.0)
             self.exporter.write_metadata(restart_order="cn" if self.params_solver.time_scheme == "cn" else 2)
             self.exporter.write_timeseries()
         return self.y_meas

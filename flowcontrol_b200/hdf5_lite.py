@@ -243,3 +243,140 @@ def read_xdmf_mesh(xdmf_path: str | Path) -> tuple[np.ndarray, np.ndarray]:
         h5 = HDF5LiteFile(xdmf_path.parent / tfile)
     tri = np.asarray(h5.read(tpath)).astype(np.int32)
     return np.ascontiguousarray(xy), np.ascontiguousarray(tri)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Writer (same subset as the reader: superblock 0, version-1 object headers, old-style groups, contiguous datasets)
+# ---------------------------------------------------------------------------------------------------------------------
+_LEAF_K, _INTERNAL_K = 4, 16  # libhdf5 defaults: symbol-table nodes hold up to 2*4 entries, B-tree nodes up to 2*16 children
+
+
+def _pad8(b: bytes) -> bytes:
+    return b + b"\x00" * (-len(b) % 8)
+
+
+def _message(mtype: int, data: bytes) -> bytes:
+    data = _pad8(data)
+    return struct.pack("<HHB3x", mtype, len(data), 0) + data
+
+
+def _datatype_message(dt: np.dtype) -> bytes:
+    dt = np.dtype(dt)
+    if dt.kind in "iu":
+        bits = 0x08 if dt.kind == "i" else 0x00
+        return struct.pack("<BBBBI", 0x10 | 0, bits, 0, 0, dt.itemsize) + struct.pack("<HH", 0, 8 * dt.itemsize)
+    if dt.kind == "f" and dt.itemsize == 8:
+        return struct.pack("<BBBBI", 0x10 | 1, 0x20, 63, 0, 8) + struct.pack("<HHBBBBI", 0, 64, 52, 11, 0, 52, 1023)
+    if dt.kind == "f" and dt.itemsize == 4:
+        return struct.pack("<BBBBI", 0x10 | 1, 0x20, 31, 0, 4) + struct.pack("<HHBBBBI", 0, 32, 23, 8, 0, 23, 127)
+    raise HDF5LiteError(f"datatype {dt} unsupported by the writer")
+
+
+class _Writer:
+    def __init__(self):
+        self.buf = bytearray(96)  # superblock, filled in at the end
+
+    def alloc(self, data: bytes) -> int:
+        self.buf += b"\x00" * (-len(self.buf) % 8)
+        addr = len(self.buf)
+        self.buf += data
+        return addr
+
+    def dataset(self, arr: np.ndarray) -> int:
+        arr = np.ascontiguousarray(arr)
+        if arr.dtype.byteorder == ">":
+            arr = arr.astype(arr.dtype.newbyteorder("<"))
+        daddr = self.alloc(arr.tobytes()) if arr.size else _UNDEF
+        space = struct.pack("<BBB5x", 1, arr.ndim, 0) + b"".join(struct.pack("<Q", d) for d in arr.shape)
+        msgs = [_message(0x01, space), _message(0x03, _datatype_message(arr.dtype)),
+                _message(0x05, struct.pack("<BBBB", 2, 2, 2, 0)),  # fill value v2: late allocation, never written, undefined
+                _message(0x08, struct.pack("<BBQQ", 3, 1, daddr, arr.nbytes))]
+        body = b"".join(msgs)
+        return self.alloc(struct.pack("<BBHII4x", 1, 0, len(msgs), 1, len(body)) + body)
+
+    def group(self, entries: dict) -> tuple[int, int, int]:
+        """entries: name -> (object header address, btree, heap) with btree = heap = None for datasets.
+        Returns (object header, btree, heap) addresses of the new group."""
+        names = sorted(entries)  # libhdf5 keeps symbol tables sorted by name
+        if len(names) > 2 * _LEAF_K * 2 * _INTERNAL_K:
+            raise HDF5LiteError("too many entries in one group for a single-level B-tree")
+        heap_data = bytearray(8)  # offset 0: the empty string
+        name_off = {}
+        for nm in names:
+            name_off[nm] = len(heap_data)
+            heap_data += _pad8(nm.encode() + b"\x00")
+        data_addr = self.alloc(bytes(heap_data))
+        heap_addr = self.alloc(b"HEAP" + struct.pack("<B3xQQQ", 0, len(heap_data), 1, data_addr))
+        chunks = [names[i : i + 2 * _LEAF_K] for i in range(0, len(names), 2 * _LEAF_K)] or [[]]
+        snods, keys = [], [0]
+        for chunk in chunks:
+            body = b"SNOD" + struct.pack("<BBH", 1, 0, len(chunk))
+            for nm in chunk:
+                obj, bt, hp = entries[nm]
+                if bt is None:
+                    body += struct.pack("<QQII16x", name_off[nm], obj, 0, 0)
+                else:
+                    body += struct.pack("<QQIIQQ", name_off[nm], obj, 1, 0, bt, hp)
+            body += b"\x00" * (8 + 2 * _LEAF_K * 40 - len(body))
+            snods.append(self.alloc(body))
+            keys.append(name_off[chunk[-1]] if chunk else 0)
+        node = b"TREE" + struct.pack("<BBHQQ", 0, 0, len(snods), _UNDEF, _UNDEF) + struct.pack("<Q", keys[0])
+        for child, key in zip(snods, keys[1:]):
+            node += struct.pack("<QQ", child, key)
+        node += b"\x00" * (24 + (2 * _INTERNAL_K + 1) * 8 + 2 * _INTERNAL_K * 8 - len(node))
+        btree = self.alloc(node)
+        msg = _message(0x11, struct.pack("<QQ", btree, heap_addr))
+        header = self.alloc(struct.pack("<BBHII4x", 1, 0, 1, 1, len(msg)) + msg)
+        return header, btree, heap_addr
+
+    def finish(self, root: tuple[int, int, int]) -> bytes:
+        header, btree, heap = root
+        eof = len(self.buf)
+        sb = _SIG + struct.pack("<BBBBBBBBHHI", 0, 0, 0, 0, 0, 8, 8, 0, _LEAF_K, _INTERNAL_K, 0)
+        sb += struct.pack("<QQQQ", 0, _UNDEF, eof, _UNDEF)
+        sb += struct.pack("<QQIIQQ", 0, header, 1, 0, btree, heap)
+        assert len(sb) == 96
+        self.buf[:96] = sb
+        return bytes(self.buf)
+
+
+def write_hdf5(path: str | Path, datasets: dict[str, np.ndarray]) -> None:
+    """Write ``{"/group/sub/name": array}`` as an HDF5 file (contiguous datasets in old-style groups: the layout libhdf5
+    1.8/1.10 reads and the layout dolfin's own files use)."""
+    tree: dict = {}
+    for full, arr in datasets.items():
+        parts = [p for p in full.split("/") if p]
+        if not parts:
+            raise HDF5LiteError("dataset needs a name")
+        node = tree
+        for p in parts[:-1]:
+            node = node.setdefault(p, {})
+            if not isinstance(node, dict):
+                raise HDF5LiteError(f"{full}: {p} is a dataset")
+        node[parts[-1]] = np.asarray(arr)
+    w = _Writer()
+
+    def emit(node: dict) -> tuple[int, int, int]:
+        entries = {}
+        for name, child in node.items():
+            entries[name] = emit(child) if isinstance(child, dict) else (w.dataset(child), None, None)
+        return w.group(entries)
+
+    Path(path).write_bytes(w.finish(emit(tree)))
+
+
+def read_all(path: str | Path) -> dict[str, np.ndarray]:
+    """Every dataset of a file as ``{"/group/name": array}`` (used to append to checkpoint files)."""
+    f = HDF5LiteFile(path)
+    out: dict[str, np.ndarray] = {}
+
+    def walk(prefix: str, addr: int) -> None:
+        for name, child in f._group_entries(addr).items():
+            is_group = any(mtype == 0x11 for mtype, _ in f._messages(child))
+            if is_group:
+                walk(f"{prefix}/{name}", child)
+            else:
+                out[f"{prefix}/{name}"] = f.read(f"{prefix}/{name}")
+
+    walk("", f.root_header)
+    return out

@@ -203,8 +203,8 @@ def test_facade_regression_with_restart(root, tmp_path, cyl):
     fs = CylinderFlowSolver.make_default(Re=100, path_out=tmp_path, num_steps=10, save_every=5)
     tab = fs.tables
     # base flow from the fixture (computing it takes ~40 s of SuperLU; covered by the slow CPU test)
-    write_checkpoint(fs.paths.U0, "U0", UP0[: tab.Nv], 0.0, append=False)
-    write_checkpoint(fs.paths.P0, "P0", UP0[tab.Nv :], 0.0, append=False)
+    write_checkpoint(fs.paths.U0, "U0", UP0[: tab.Nv], 0.0, append=False, tab=tab)
+    write_checkpoint(fs.paths.P0, "P0", UP0[tab.Nv :], 0.0, append=False, tab=tab)
     fs.load_steady_state()
     assert np.isclose(fs.fields.U0.vector().get_local().max(), 1.1921615450014942, rtol=1e-9)
     fs.initialize_time_stepping(ic=None)
@@ -696,3 +696,61 @@ def test_subtree_cluster_sweeps_match_oracle(root, built_lib, rows, height):
         assert rel(up[: tab.Nv, b], orc.up[: tab.Nv]) < FIELD_TOL
     assert not ens.diverged.any()
     ens.close()
+
+
+def test_facade_ensemble_checkpoint_and_restart(root, tmp_path, built_lib):
+    """Ensemble (batch = 5) through the FlowSolver facade: the XDMF/HDF5 checkpoints hold one function per trajectory, a
+    restarted ensemble continues EVERY trajectory exactly where it was (the restart goes through full fields and back, so
+    to round-off of one addition), the reference-shaped accessors give trajectory 0 and ``.ensemble`` all of them, and a
+    single-trajectory run restarts from the same files (trajectory 0)."""
+    from flowcontrol_b200.examples import lidcavity as ex
+    from flowcontrol_b200.exporter import read_checkpoint, write_checkpoint
+    from flowcontrol_b200.hdf5_lite import HDF5LiteFile
+
+    UP0 = np.load(root / "tests/golden/lidcavity_baseflow.npz")["UP0"]
+    B, dt = 5, 0.005
+
+    def make(batch, Tstart=0.0, num_steps=6):
+        fs = ex.LidCavityFlowSolver.make_default(Re=1000, path_out=tmp_path, num_steps=num_steps, save_every=3, Tstart=Tstart, batch=batch)
+        tab = fs.tables
+        write_checkpoint(fs.paths.U0, "U0", UP0[: tab.Nv], 0.0, append=False, tab=tab)
+        write_checkpoint(fs.paths.P0, "P0", UP0[tab.Nv :], 0.0, append=False, tab=tab)
+        fs.load_steady_state()
+        return fs
+
+    fs = make(B)
+    tab = fs.tables
+    rng = np.random.default_rng(4)
+    loc = rng.uniform(0.3, 0.7, size=(B, 2))
+    ic = np.stack([0.1 * fs._default_initial_perturbation(xloc=x, yloc=y, radius=0.1) for x, y in loc], axis=1)
+    fs.params_ic.amplitude = 0.0
+    fs.initialize_time_stepping(ic=ic)
+    amp = np.linspace(-0.05, 0.08, B)
+    for k in range(6):
+        y = fs.step(u_ctrl=(amp * np.cos(0.7 * k))[:, None])
+        assert y.shape == (B, 2)
+    up_full = fs.fields.up_.ensemble.copy()  # [N, B]
+    assert up_full.shape == (tab.N, B) and np.array_equal(fs.fields.up_.vector().get_local(), up_full[:, 0])
+    assert np.array_equal(fs.fields.u_nn.ensemble.shape, (tab.Nv, B))
+    assert rel(up_full[:, 1], up_full[:, 0]) > 1e-3  # the trajectories really differ
+    h5 = HDF5LiteFile(fs.paths.U_restart.with_suffix(".h5"))
+    assert h5.keys("/") == ["U"] + [f"U_traj{b:04d}" for b in range(1, B)] and h5.keys("/U_traj0003") == [f"U_traj0003_{k}" for k in range(3)]
+    # snapshot 1 (t = 3 dt) is the full field U0 + u of every trajectory
+    snap = read_checkpoint(fs.paths.U_restart, 1, tab=tab, batch=B)
+    assert snap.shape == (tab.Nv, B)
+    # restart every trajectory at t = 3 dt and redo steps 4..6
+    fs2 = make(B, Tstart=3 * dt, num_steps=3)
+    fs2.initialize_time_stepping(Tstart=3 * dt)
+    assert fs2.order == 2
+    for k in range(3, 6):
+        fs2.step(u_ctrl=(amp * np.cos(0.7 * k))[:, None])
+    up2 = fs2.fields.up_.ensemble
+    for b in range(B):
+        assert rel(up2[: tab.Nv, b], up_full[: tab.Nv, b]) < 1e-12
+    assert np.allclose(fs2.y_meas, fs.y_meas, rtol=1e-9, atol=1e-14)
+    # a single run restarts from the same files: trajectory 0
+    fs1 = make(1, Tstart=3 * dt, num_steps=3)
+    fs1.initialize_time_stepping(Tstart=3 * dt)
+    for k in range(3, 6):
+        fs1.step(u_ctrl=[amp[0] * np.cos(0.7 * k)])
+    assert rel(fs1.fields.u_.vector().get_local(), up_full[: tab.Nv, 0]) < 1e-12

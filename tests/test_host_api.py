@@ -58,19 +58,34 @@ def _paths(tmp_path):
                     mesh=tmp_path / "m.xdmf", **kw)
 
 
+def _small_tab():
+    from flowcontrol_b200.mesh import TaylorHoodTables
+    from util import unit_square_mesh
+
+    xy, tri = unit_square_mesh(3, jitter=0.1, seed=2)
+    return TaylorHoodTables.from_arrays(xy, tri)
+
+
 def test_exporter_columns_csv_and_sidecar(tmp_path):
-    """Column names/order and JSON keys of exporter.py:186-262."""
-    fields = FlowFieldCollection(U0=Field(np.ones(4)), P0=Field(np.zeros(2)))
-    ex = FlowExporter(_paths(tmp_path), fields, Tstart=0.0, dt=0.005, save_every=5)
+    """Column names/order and JSON keys of exporter.py:186-262; field snapshots through the XDMF/HDF5 checkpoint files."""
+    tab = _small_tab()
+    rng = np.random.default_rng(0)
+    U0, P0 = rng.standard_normal(tab.Nv), rng.standard_normal(tab.nV)
+    fields = FlowFieldCollection(U0=Field(U0), P0=Field(P0))
+    ex = FlowExporter(_paths(tmp_path), fields, Tstart=0.0, dt=0.005, save_every=5, tab=tab)
     ex.log_ic(0.0, np.array([0.1, 0.2]), 0.5)
     ex.log(np.array([1.0]), np.array([0.3, 0.4]), 0.4, 0.005, 1e-3)
     df = ex.to_dataframe()
     assert list(df.columns) == ["time", "dE", "runtime", "y_meas_1", "y_meas_2", "u_ctrl_1"]
     assert np.isnan(df.loc[0, "u_ctrl_1"]) and df.loc[1, "u_ctrl_1"] == 1.0
-    ex.export_xdmf(Field(np.arange(4.0)), Field(np.zeros(4)), Field(np.ones(2)), time=0.025, append=False, adjust_baseflow=1.0)
-    ex.export_xdmf(Field(2 * np.arange(4.0)), Field(np.arange(4.0)), Field(np.ones(2)), time=0.05, adjust_baseflow=1.0)
-    assert np.allclose(read_checkpoint(tmp_path / "U_restart.xdmf", 1), 2 * np.arange(4.0) + 1)
-    assert np.allclose(fields.Usave.array, 2 * np.arange(4.0) + 1)
+    u1, u2, p1 = rng.standard_normal(tab.Nv), rng.standard_normal(tab.Nv), rng.standard_normal(tab.nV)
+    ex.export_xdmf(Field(u1), Field(np.zeros(tab.Nv)), Field(p1), time=0.025, append=False, adjust_baseflow=1.0)
+    ex.export_xdmf(Field(u2), Field(u1), Field(p1), time=0.05, adjust_baseflow=1.0)
+    assert np.array_equal(read_checkpoint(tmp_path / "U_restart.xdmf", 1, tab=tab), u2 + U0)
+    assert np.array_equal(read_checkpoint(tmp_path / "U_restart.xdmf", 0, tab=tab), u1 + U0)
+    assert np.array_equal(read_checkpoint(tmp_path / "Uprev_restart.xdmf", -1, tab=tab), u1 + U0)
+    assert np.array_equal(read_checkpoint(tmp_path / "P_restart.xdmf", -1, tab=tab), p1 + P0)
+    assert np.allclose(fields.Usave.array, u2 + U0)
     ex.write_metadata(restart_order=2)
     ex.write_timeseries()
     meta = json.loads((tmp_path / "meta.json").read_text())
@@ -79,6 +94,59 @@ def test_exporter_columns_csv_and_sidecar(tmp_path):
     assert list(pd.read_csv(tmp_path / "ts.csv").columns) == list(df.columns)
     ex.reset()
     assert ex.to_dataframe().empty
+
+
+def test_xdmf_checkpoint_layout_roundtrip_and_foreign_numbering(tmp_path):
+    """The dolfin write_checkpoint layout (utils/io.py:21-50): XDMF attributes and HDF5 dataset tree, appended time steps
+    that share the first mesh, one function per trajectory of an ensemble, and a file written with ANOTHER dof numbering,
+    cell order and cell-vertex order (what dolfin itself would write) read back into canonical numbering."""
+    from flowcontrol_b200 import xdmf_checkpoint as xc
+    from flowcontrol_b200.exporter import write_checkpoint
+    from flowcontrol_b200.hdf5_lite import HDF5LiteFile, read_all, write_hdf5
+
+    tab = _small_tab()
+    rng = np.random.default_rng(1)
+    f = tmp_path / "U.xdmf"
+    snaps = rng.standard_normal((3, tab.Nv))
+    for k, t in enumerate((0.0, 0.05, 0.1)):
+        xc.write_checkpoint(f, "U", tab, snaps[k], "V", t, append=k > 0)
+    text = f.read_text()
+    assert text.count('ItemType="FiniteElementFunction" ElementFamily="CG" ElementDegree="2" ElementCell="triangle" Name="U"') == 3
+    assert text.count("<Topology") == 1 and text.count("xi:include") == 2  # later steps share the first step's mesh
+    assert xc.checkpoint_times(f, "U") == [0.0, 0.05, 0.1]
+    h5 = HDF5LiteFile(tmp_path / "U.h5")
+    assert h5.keys("/U") == ["U_0", "U_1", "U_2"]
+    assert h5.keys("/U/U_0") == ["cell_dofs", "cells", "mesh", "vector", "x_cell_dofs"] and h5.keys("/U/U_0/mesh") == ["geometry", "topology"]
+    assert h5.read("/U/U_1/vector").shape == (tab.Nv, 1) and h5.read("/U/U_0/cell_dofs").shape == (12 * tab.nT, 1)
+    assert np.array_equal(h5.read("/U/U_0/x_cell_dofs").ravel(), 12 * np.arange(tab.nT + 1))
+    topo = h5.read("/U/U_0/mesh/topology")
+    assert np.all(np.diff(topo, axis=1) > 0)  # dolfin orders the vertices of a cell
+    for k in range(3):
+        assert np.array_equal(xc.read_checkpoint(f, "U", tab, "V", k), snaps[k])
+    # pressure function added to the same file
+    pv = rng.standard_normal(tab.nV)
+    xc.write_checkpoint(f, "P", tab, pv, "P", 0.1, append=True)
+    assert np.array_equal(xc.read_checkpoint(f, "P", tab, "P", -1), pv) and np.array_equal(xc.read_checkpoint(f, "U", tab, "V", -1), snaps[2])
+    # ensemble: one function per trajectory
+    ens = rng.standard_normal((tab.Nv, 4))
+    g = tmp_path / "E.xdmf"
+    write_checkpoint(g, "U", ens, 0.0, append=False, tab=tab)
+    write_checkpoint(g, "U", 2 * ens, 0.05, append=True, tab=tab)
+    assert np.array_equal(read_checkpoint(g, 0, tab=tab, batch=4), ens) and np.array_equal(read_checkpoint(g, -1, tab=tab, batch=4), 2 * ens)
+    assert np.array_equal(read_checkpoint(g, -1, tab=tab), 2 * ens[:, 0])  # a single run restarts from trajectory 0
+    assert HDF5LiteFile(tmp_path / "E.h5").keys("/") == ["U", "U_traj0001", "U_traj0002", "U_traj0003"]
+    # foreign numbering: permute dofs, cell order and the vertex order inside the cells, keep the dolfin conventions
+    data = read_all(tmp_path / "U.h5")
+    perm = rng.permutation(tab.Nv)  # file dof j holds canonical dof perm[j]
+    inv = np.argsort(perm)
+    corder = rng.permutation(tab.nT)
+    cd = xc.cell_dofs(tab, "V")[corder]
+    foreign = {"/U/U_0/vector": snaps[1][perm][:, None], "/U/U_0/cell_dofs": inv[cd].ravel()[:, None],
+               "/U/U_0/x_cell_dofs": data["/U/U_0/x_cell_dofs"], "/U/U_0/cells": corder[:, None].astype(np.int64),
+               "/U/U_0/mesh/topology": data["/U/U_0/mesh/topology"][corder], "/U/U_0/mesh/geometry": data["/U/U_0/mesh/geometry"]}
+    write_hdf5(tmp_path / "F.h5", foreign)
+    (tmp_path / "F.xdmf").write_text(text.replace("U.h5", "F.h5"))
+    assert np.array_equal(xc.read_checkpoint(tmp_path / "F.xdmf", "U", tab, "V", 0), snaps[1])
 
 
 def test_param_defaults_match_reference():
