@@ -29,3 +29,12 @@ def test_control_cost_sums_all_channels():
     ub = rng.standard_normal((40, 2, 5))
     c = compute_control_cost(ub, 0.1)
     assert c.shape == (5,) and np.allclose(c, [compute_control_cost(ub[:, :, b], 0.1) for b in range(5)])
+
+
+def test_fun_array_point_by_point_fallback():
+    """utils/optim.py:48-66: any callable is evaluated row by row, output [n_points, 1]."""
+    from flowcontrol_b200.costs import fun_array
+
+    X = np.arange(12.0).reshape(4, 3)
+    out = fun_array(X, lambda x, p=1.0: p * float(x @ x), p=2.0)
+    assert out.shape == (4, 1) and np.allclose(out[:, 0], 2.0 * (X * X).sum(axis=1))

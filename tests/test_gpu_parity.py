@@ -754,3 +754,47 @@ def test_facade_ensemble_checkpoint_and_restart(root, tmp_path, built_lib):
     for k in range(3, 6):
         fs1.step(u_ctrl=[amp[0] * np.cos(0.7 * k)])
     assert rel(fs1.fields.u_.vector().get_local(), up_full[: tab.Nv, 0]) < 1e-12
+
+
+def test_fun_array_runs_a_controller_population_as_ensembles(root, cyl):
+    """fun_array (utils/optim.py:48-66) with an EnsembleCost: a population of controller parameters evaluated as ensembles
+    on the device (two chunks, the second partial) gives the costs of the point-by-point loop of the reference -- each point
+    simulated on its own through the host loop with compute_signal_cost / compute_control_cost."""
+    from flowcontrol_b200.controller import Controller
+    from flowcontrol_b200.costs import EnsembleCost, compute_control_cost, compute_signal_cost, fun_array
+    from flowcontrol_b200.ensemble import Ensemble
+
+    fs, prob, _, _ = cyl
+    tab = prob.tab
+    ic = fs._default_initial_perturbation()
+    k = np.load(root / "tests/golden/Kopt_reduced13.npz")
+
+    def make_controller(x):  # two parameters: loop gain and a scaling of the feed-through
+        return Controller(k["A"], x[0] * k["B"], k["C"], x[0] * x[1] * k["D"])
+
+    B, nsteps, pen = 32, 12, 0.3
+    rng = np.random.default_rng(8)
+    X = np.column_stack([rng.uniform(0.5, 1.5, 40), rng.uniform(0.0, 2.0, 40)])
+    ens = Ensemble(prob, B)
+    cost = EnsembleCost(ens, make_controller, ic[: tab.Nv], nsteps, Ky=[[-1.0, 0.0, 0.0]], Fu=[[1.0], [1.0]], u_penalty=pen, p_n=ic[tab.Nv :])
+    J = fun_array(X, cost)
+    assert J.shape == (40, 1) and np.all(np.isfinite(J)) and not cost.last["diverged"].any()
+    assert np.isclose(cost(X[3]), J[3, 0], rtol=1e-13)  # scalar signature
+    # the reference's loop, point by point, for a few points (host-stepped controller, logged series, reference cost functions)
+    for i in (0, 17, 39):
+        K = make_controller(X[i])
+        e1 = Ensemble(prob, 1)
+        e1.set_state(ic[: tab.Nv], None, ic[tab.Nv :], order=1)
+        dE, us = [], []
+        for _ in range(nsteps):
+            u = K.step(-e1.y_meas[0, 0], prob.dt)
+            e1.step(np.array([[u[0]], [u[0]]]))
+            dE.append(e1.dE[0])
+            us.append([u[0], u[0]])
+        Tnorm = prob.dt / (nsteps * prob.dt)
+        ref = compute_signal_cost(np.array(dE), Tnorm, "integral") + pen * compute_control_cost(np.array(us), Tnorm)
+        assert np.isclose(J[i, 0], ref, rtol=1e-10)
+        e1.close()
+    # any other callable is looped over as in the reference
+    assert np.array_equal(fun_array(X[:3], lambda x: x.sum()), X[:3].sum(axis=1)[:, None])
+    ens.close()
