@@ -1216,6 +1216,84 @@ __global__ void __launch_bounds__(32 * (CL_NW + 1), 1) k_cluster_sweep(const Clu
     if (dbg && tid == 0) dbg[5] = globaltimer_ns();
 }
 
+
+// ----------------------------------------------------------------------------------------------
+// Matrix assembly (steady-state Newton / Picard, operator tooling): the U-dependent blocks of the linearised operator,
+//   C_ab = int (U . grad phi_b) phi_a          (advection by U; the same block for both velocity components)
+//   D^{ij}_ab = int phi_b (d_j U_i) phi_a      (i = row / test component, j = column / trial component)
+// per cell (7-point Radon rule, exact for these degree-5 integrands) scattered into CSR value arrays of the scalar P2 pattern
+// through a precomputed position map pos[cell][a][b].  Cells are coloured so that cells of one colour share no P2 node:
+// one launch per colour, plain read-modify-write, no atomics, bit-reproducible.  One warp = one cell x 32 base-flow
+// candidates (trajectory innermost like everything else), so a Newton step for an ensemble of base flows (Re-continuation,
+// several actuation levels) is assembled in one pass.  grid = (ceil(cells of the colour / 4), ldb / 32), block = (32, 4)
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_assemble_advection(int c0, int ncell, const int* __restrict__ colour_cells,
+                                                           const int* __restrict__ cell_nodes, const double* __restrict__ Jinv,
+                                                           const double* __restrict__ detJ, const int* __restrict__ pos,
+                                                           const double* __restrict__ U, double* __restrict__ C, double* __restrict__ D,
+                                                           int nN, size_t nnz, int ldb) {
+    const int ci = blockIdx.x * blockDim.y + threadIdx.y;
+    if (ci >= ncell) return;
+    const int e = __ldg(colour_cells + c0 + ci);
+    const int b = blockIdx.y * 32 + threadIdx.x;
+    const size_t L = (size_t)ldb;
+    double ux[6], uy[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const int nd = __ldg(cell_nodes + (size_t)e * 6 + i);
+        ux[i] = U[(size_t)nd * L + b];
+        uy[i] = U[(size_t)(nd + nN) * L + b];
+    }
+    const double g00 = __ldg(Jinv + (size_t)e * 4), g01 = __ldg(Jinv + (size_t)e * 4 + 1), g10 = __ldg(Jinv + (size_t)e * 4 + 2),
+                 g11 = __ldg(Jinv + (size_t)e * 4 + 3), det = __ldg(detJ + e);
+    double ud0[7], ud1[7], G00[7], G01[7], G10[7], G11[7];
+#pragma unroll
+    for (int q = 0; q < 7; ++q) {
+        double vx = 0.0, vy = 0.0, ax0 = 0.0, ax1 = 0.0, ay0 = 0.0, ay1 = 0.0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            vx = fma(c_phi[q][i], ux[i], vx);
+            vy = fma(c_phi[q][i], uy[i], vy);
+            ax0 = fma(c_dphi[q][i][0], ux[i], ax0);
+            ax1 = fma(c_dphi[q][i][1], ux[i], ax1);
+            ay0 = fma(c_dphi[q][i][0], uy[i], ay0);
+            ay1 = fma(c_dphi[q][i][1], uy[i], ay1);
+        }
+        const double wq = c_w[q] * det;
+        ud0[q] = wq * (vx * g00 + vy * g01);  // wq U . grad phi_b = dphi_ref[b][0] ud0 + dphi_ref[b][1] ud1
+        ud1[q] = wq * (vx * g10 + vy * g11);
+        G00[q] = wq * (ax0 * g00 + ax1 * g10);  // d_x U_x
+        G01[q] = wq * (ax0 * g01 + ax1 * g11);  // d_y U_x
+        G10[q] = wq * (ay0 * g00 + ay1 * g10);  // d_x U_y
+        G11[q] = wq * (ay0 * g01 + ay1 * g11);  // d_y U_y
+    }
+    const int* pe = pos + (size_t)e * 36;
+    for (int a = 0; a < 6; ++a) {
+#pragma unroll
+        for (int bb = 0; bb < 6; ++bb) {
+            double cab = 0.0, dxx = 0.0, dxy = 0.0, dyx = 0.0, dyy = 0.0;
+#pragma unroll
+            for (int q = 0; q < 7; ++q) {
+                const double pa = c_phi[q][a];
+                cab = fma(pa, fma(c_dphi[q][bb][0], ud0[q], c_dphi[q][bb][1] * ud1[q]), cab);
+                const double pab = pa * c_phi[q][bb];
+                dxx = fma(pab, G00[q], dxx);
+                dxy = fma(pab, G01[q], dxy);
+                dyx = fma(pab, G10[q], dyx);
+                dyy = fma(pab, G11[q], dyy);
+            }
+            const size_t p0 = (size_t)__ldg(pe + a * 6 + bb) * L + b;
+            C[p0] += cab;
+            if (D) {
+                D[p0] += dxx;
+                D[nnz * L + p0] += dxy;
+                D[2 * nnz * L + p0] += dyx;
+                D[3 * nnz * L + p0] += dyy;
+            }
+        }
+    }
+}
+
 // sensors + energy.  grid = ldb/32, block = (32, MEAS_WARPS)
 constexpr int MEAS_WARPS = 32;
 __global__ void __launch_bounds__(32 * MEAS_WARPS) k_measure(int ns, const int* __restrict__ sptr, const int* __restrict__ sidx,
@@ -3116,6 +3194,89 @@ int fcb_profile_step(fcb_handle h, const double* u_ctrl, float* ms, int32_t* lau
         launches[FCB_PHASE_ELEMENT] = 1 + (h->nshared > 0 ? 1 : 0);
         launches[FCB_PHASE_MEASURE] = 1;
     }
+    return FCB_OK;
+}
+
+
+int fcb_assemble_advection(const fcb_assembly* m, int32_t B, int32_t device, const double* U, double* C, double* D) {
+    fcb_context* h = nullptr;  // errors go to fcb_last_error(NULL)
+    if (!m || !U || !C || B <= 0) return fail(h, FCB_ERR_INVALID, "fcb_assemble_advection: bad arguments");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(h, FCB_ERR_NO_DEVICE, "fcb_assemble_advection: no CUDA device available (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(h, FCB_ERR_INVALID, "fcb_assemble_advection: device %d out of range", device);
+    if (m->nT <= 0 || m->nN <= 0 || m->nnz <= 0 || m->ncolour <= 0 || !m->cell_nodes || !m->Jinv || !m->detJ || !m->colour_ptr || !m->colour_cells || !m->pos)
+        return fail(h, FCB_ERR_INVALID, "fcb_assemble_advection: incomplete mesh description");
+    if (m->colour_ptr[0] != 0 || m->colour_ptr[m->ncolour] != m->nT) return fail(h, FCB_ERR_INVALID, "fcb_assemble_advection: colour_ptr must cover every cell");
+    {   // ranges, and the colouring contract: cells of one colour share no P2 node (otherwise the plain scatter would race)
+        std::vector<int> seen((size_t)m->nN, -1);
+        for (int c = 0; c < m->ncolour; ++c) {
+            if (m->colour_ptr[c + 1] < m->colour_ptr[c]) return fail(h, FCB_ERR_INVALID, "fcb_assemble_advection: colour_ptr must be non-decreasing");
+            for (int k = m->colour_ptr[c]; k < m->colour_ptr[c + 1]; ++k) {
+                const int e = m->colour_cells[k];
+                if (e < 0 || e >= m->nT) return fail(h, FCB_ERR_INVALID, "fcb_assemble_advection: colour_cells out of range");
+                for (int i = 0; i < 6; ++i) {
+                    const int nd = m->cell_nodes[(size_t)e * 6 + i];
+                    if (nd < 0 || nd >= m->nN) return fail(h, FCB_ERR_INVALID, "fcb_assemble_advection: cell_nodes out of range");
+                    if (seen[nd] == c) return fail(h, FCB_ERR_INVALID, "fcb_assemble_advection: two cells of colour %d share node %d", c, nd);
+                    seen[nd] = c;
+                }
+            }
+        }
+        for (size_t k = 0; k < (size_t)m->nT * 36; ++k)
+            if (m->pos[k] < 0 || m->pos[k] >= m->nnz) return fail(h, FCB_ERR_INVALID, "fcb_assemble_advection: pos out of range");
+    }
+#define CKA(call)                                                                                                        \
+    do {                                                                                                                 \
+        cudaError_t e_ = (call);                                                                                         \
+        if (e_ != cudaSuccess) {                                                                                         \
+            for (void* q_ : bufs) cudaFree(q_);                                                                          \
+            return fail(h, FCB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);     \
+        }                                                                                                                \
+    } while (0)
+    std::vector<void*> bufs;
+    CKA(cudaSetDevice(device));
+    {
+        double phi[7][6], dphi[7][6][2], w[7], mass[6][6];
+        fill_tables(phi, dphi, w, mass);
+        CKA(cudaMemcpyToSymbol(c_phi, phi, sizeof phi));
+        CKA(cudaMemcpyToSymbol(c_dphi, dphi, sizeof dphi));
+        CKA(cudaMemcpyToSymbol(c_w, w, sizeof w));
+        CKA(cudaMemcpyToSymbol(c_mass, mass, sizeof mass));
+    }
+    const int ldb = (B + 31) / 32 * 32;
+    const size_t L = (size_t)ldb, Nv = 2 * (size_t)m->nN, nnz = (size_t)m->nnz;
+    int *d_cells = nullptr, *d_nodes = nullptr, *d_pos = nullptr;
+    double *d_J = nullptr, *d_det = nullptr, *d_U = nullptr, *d_C = nullptr, *d_D = nullptr;
+    auto dev_alloc = [&](void** p, size_t bytes) { cudaError_t e = cudaMalloc(p, bytes); if (e == cudaSuccess) bufs.push_back(*p); return e; };
+    CKA(dev_alloc((void**)&d_cells, (size_t)m->nT * sizeof(int)));
+    CKA(dev_alloc((void**)&d_nodes, (size_t)m->nT * 6 * sizeof(int)));
+    CKA(dev_alloc((void**)&d_pos, (size_t)m->nT * 36 * sizeof(int)));
+    CKA(dev_alloc((void**)&d_J, (size_t)m->nT * 4 * sizeof(double)));
+    CKA(dev_alloc((void**)&d_det, (size_t)m->nT * sizeof(double)));
+    CKA(dev_alloc((void**)&d_U, Nv * L * sizeof(double)));
+    CKA(dev_alloc((void**)&d_C, nnz * L * sizeof(double)));
+    if (D) CKA(dev_alloc((void**)&d_D, 4 * nnz * L * sizeof(double)));
+    CKA(cudaMemcpy(d_cells, m->colour_cells, (size_t)m->nT * sizeof(int), cudaMemcpyDefault));
+    CKA(cudaMemcpy(d_nodes, m->cell_nodes, (size_t)m->nT * 6 * sizeof(int), cudaMemcpyDefault));
+    CKA(cudaMemcpy(d_pos, m->pos, (size_t)m->nT * 36 * sizeof(int), cudaMemcpyDefault));
+    CKA(cudaMemcpy(d_J, m->Jinv, (size_t)m->nT * 4 * sizeof(double), cudaMemcpyDefault));
+    CKA(cudaMemcpy(d_det, m->detJ, (size_t)m->nT * sizeof(double), cudaMemcpyDefault));
+    CKA(cudaMemset(d_U, 0, Nv * L * sizeof(double)));
+    CKA(cudaMemcpy2D(d_U, L * sizeof(double), U, (size_t)B * sizeof(double), (size_t)B * sizeof(double), Nv, cudaMemcpyDefault));
+    CKA(cudaMemset(d_C, 0, nnz * L * sizeof(double)));
+    if (D) CKA(cudaMemset(d_D, 0, 4 * nnz * L * sizeof(double)));
+    for (int c = 0; c < m->ncolour; ++c) {
+        const int c0 = m->colour_ptr[c], nc = m->colour_ptr[c + 1] - c0;
+        if (nc == 0) continue;
+        k_assemble_advection<<<dim3((nc + 3) / 4, ldb / 32), dim3(32, 4)>>>(c0, nc, d_cells, d_nodes, d_J, d_det, d_pos, d_U, d_C, d_D, m->nN, nnz, ldb);
+    }
+    CKA(cudaGetLastError());
+    CKA(cudaMemcpy2D(C, (size_t)B * sizeof(double), d_C, L * sizeof(double), (size_t)B * sizeof(double), nnz, cudaMemcpyDefault));
+    if (D) CKA(cudaMemcpy2D(D, (size_t)B * sizeof(double), d_D, L * sizeof(double), (size_t)B * sizeof(double), 4 * nnz, cudaMemcpyDefault));
+    CKA(cudaDeviceSynchronize());
+    for (void* q_ : bufs) cudaFree(q_);
+#undef CKA
     return FCB_OK;
 }
 

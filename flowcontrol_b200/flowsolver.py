@@ -209,13 +209,21 @@ class FlowSolver(ABC):
         return f
 
     def compute_steady_state(self, u_ctrl: list, method: str = "newton", initial_guess: Field | None = None,
-                             max_iter: int = 10, **kwargs) -> None:
+                             max_iter: int = 10, assembly: str = "host", **kwargs) -> None:
+        """``assembly="device"`` assembles the Newton / Picard matrices on the GPU (assembly.py, fcb_assemble_advection)."""
         self.set_actuators_u_ctrl(u_ctrl)
         tab = self.tables
         extra = [tab.Nv] if self._pin_pressure() else []
         dset = DirichletSet(tab, self._make_BCs().bcu, self.params_control.actuator_list, extra_zero_dofs=extra)
+        if assembly not in ("host", "device"):
+            raise ValueError(f"assembly must be 'host' or 'device', got {assembly!r}")
+        assembler = None
+        if assembly == "device":
+            from .assembly import DeviceAdvectionAssembler
+
+            assembler = DeviceAdvectionAssembler(tab, self.blocks, device=self.params_ensemble.device)
         ss = SteadyStateSolver(tab, self.blocks, self.params_flow.Re, dset, force=self._force_vector(u_ctrl),
-                               verbose=bool(self.verbose))
+                               verbose=bool(self.verbose), assembler=assembler)
         UP = self._define_initial_guess(initial_guess)
         if method == "newton":
             UP = ss.newton(UP, u_ctrl, max_iter=max_iter, **kwargs)

@@ -53,6 +53,15 @@ class fcb_problem(C.Structure):
     ]
 
 
+class fcb_assembly(C.Structure):
+    _fields_ = [
+        ("nT", C.c_int32), ("nN", C.c_int32),
+        ("cell_nodes", c_i32p), ("Jinv", c_f64p), ("detJ", c_f64p),
+        ("ncolour", C.c_int32), ("colour_ptr", c_i32p), ("colour_cells", c_i32p),
+        ("nnz", C.c_int32), ("pos", c_i32p),
+    ]
+
+
 class fcb_controllers(C.Structure):
     _fields_ = [
         ("nx", C.c_int32), ("ny", C.c_int32), ("nu", C.c_int32),
@@ -77,6 +86,7 @@ EXPORTS = {
     "fcb_get_measurement": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fcb_get_controller_state": (C.c_int, [C.c_void_p, C.c_void_p]),
     "fcb_get_costs": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "fcb_assemble_advection": (C.c_int, [C.POINTER(fcb_assembly), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fcb_profile_step": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "fcb_launch_count": (C.c_int64, [C.c_void_p]),
     "fcb_stream": (C.c_void_p, [C.c_void_p]),

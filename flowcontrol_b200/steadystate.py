@@ -3,8 +3,9 @@
 Restates /root/reference/src/flowcontrol/steadystate.py:60-159 (Newton through
 ``dolfin.solve(F == 0, ...)`` with dolfin's NewtonSolver defaults, hand-rolled
 Picard loop) on the scalar blocks of fem.py with SciPy's SuperLU as the direct
-solver.  Not on the per-step hot path (SURVEY.md section 8(f) row f1 is the GPU
-version of this).
+solver.  Not on the per-step hot path.  SURVEY.md section 8(f) row f1: the iteration matrices can be assembled on the GPU
+(``assembler=DeviceAdvectionAssembler(...)``: per-element matrices scattered into CSR through a position map, coloured);
+the factorisation of each iterate stays on the host.
 """
 
 from __future__ import annotations
@@ -30,8 +31,11 @@ def _constrain_rows(A: sp.csr_matrix, dofs: np.ndarray) -> sp.csc_matrix:
 
 class SteadyStateSolver:
     def __init__(self, tab: TaylorHoodTables, blocks: ScalarBlocks, Re: float, dirichlet: DirichletSet,
-                 force: np.ndarray | None = None, verbose: bool = False):
+                 force: np.ndarray | None = None, verbose: bool = False, assembler=None):
+        """``assembler``: an object with ``saddle_point(c, Re, U, linearised=...)`` that assembles the iteration matrix;
+        None = the host blocks (fem.py), a ``DeviceAdvectionAssembler`` (assembly.py) = element matrices on the GPU."""
         self.tab, self.blocks, self.Re, self.dirichlet = tab, blocks, Re, dirichlet
+        self.asm = assembler if assembler is not None else blocks
         self.force = np.zeros(tab.Nv) if force is None else force
         self.verbose = verbose
         self._Kv = sp.block_diag([blocks.K, blocks.K], format="csr")
@@ -46,7 +50,7 @@ class SteadyStateSolver:
         b[dofs] = g
         UP = np.array(UP0, dtype=np.float64)
         for i in range(max_iter):
-            A = self.blocks.saddle_point(0.0, self.Re, UP[: tab.Nv], linearised=False)
+            A = self.asm.saddle_point(0.0, self.Re, UP[: tab.Nv], linearised=False)
             UP1 = spla.splu(_constrain_rows(A, dofs)).solve(b)
             rel = np.linalg.norm(UP1 - UP) / (np.linalg.norm(UP) + 1e-14)
             UP = UP1
@@ -81,6 +85,6 @@ class SteadyStateSolver:
                 return UP
             if it == max_iter:
                 break
-            J = self.blocks.saddle_point(0.0, self.Re, UP[: tab.Nv], linearised=True)
+            J = self.asm.saddle_point(0.0, self.Re, UP[: tab.Nv], linearised=True)
             UP = UP - spla.splu(_constrain_rows(J, dofs)).solve(b)
         raise RuntimeError("Newton solver did not converge")

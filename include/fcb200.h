@@ -210,6 +210,29 @@ int fcb_get_controller_state(fcb_handle h, double* x);
  * optimisation loop over controllers (fun_array, optim.py:48-66) reads 24 bytes per trajectory instead of the series. */
 int fcb_get_costs(fcb_handle h, double* costs);
 
+/* Mesh side of the matrix assembly: cells, their P2 nodes and geometry, a colouring in which cells of one colour share no
+ * P2 node (flowcontrol_b200.mesh.TaylorHoodTables.element_colouring), and the position map of every element-matrix entry
+ * in the CSR pattern of a scalar P2 operator (rows / columns = P2 nodes). */
+typedef struct fcb_assembly {
+    int32_t nT, nN;
+    const int32_t* cell_nodes;   /* [nT*6] */
+    const double* Jinv;          /* [nT*4] */
+    const double* detJ;          /* [nT]   */
+    int32_t ncolour;
+    const int32_t* colour_ptr;   /* [ncolour+1] ranges of colour_cells */
+    const int32_t* colour_cells; /* [nT] cells, colour by colour */
+    int32_t nnz;                 /* entries of the scalar P2 pattern */
+    const int32_t* pos;          /* [nT*36] entry (local row a, local column b) of cell e -> index into the pattern */
+} fcb_assembly;
+
+/* Assemble, for B velocity fields U [2nN * B] at once, the U-dependent blocks of the linearised operator on the scalar
+ * P2 pattern: C [nnz * B] with C_ab = int (U.grad phi_b) phi_a, and (D != NULL) D [4 * nnz * B] = D^xx, D^xy, D^yx, D^yy
+ * with D^ij_ab = int phi_b (d_j U_i) phi_a.  Replaces the dolfin assembly of the Jacobian / Picard operator in the
+ * steady-state solver (src/flowcontrol/steadystate.py:95, 139-147 -> nsforms.py:137-183) and of the linearised
+ * operator in OperatorGetter.get_A (src/flowcontrol/operatorgetter.py:25-83).  Stateless: needs no handle; host or
+ * device pointers. */
+int fcb_assemble_advection(const fcb_assembly* m, int32_t B, int32_t device, const double* U, double* C, double* D);
+
 /* Runs one step with CUDA events between phases; ms[FCB_NPHASES] receives device times,
  * launches[FCB_NPHASES] (may be NULL) the kernel launches per phase. */
 int fcb_profile_step(fcb_handle h, const double* u_ctrl, float* ms, int32_t* launches);

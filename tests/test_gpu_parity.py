@@ -798,3 +798,53 @@ def test_fun_array_runs_a_controller_population_as_ensembles(root, cyl):
     # any other callable is looped over as in the reference
     assert np.array_equal(fun_array(X[:3], lambda x: x.sum()), X[:3].sum(axis=1)[:, None])
     ens.close()
+
+
+def test_device_matrix_assembly_matches_host_and_oracle(root, built_lib):
+    """fcb_assemble_advection (k_assemble_advection: per-element matrices of C(U) and D^ij(U), scattered into CSR through the
+    position map, one launch per colour) for an ensemble of velocity fields vs the host blocks (fem.py) and vs the oracle's
+    independent assembly (16-point rule), and bit-reproducible."""
+    from flowcontrol_b200.assembly import DeviceAdvectionAssembler
+    from flowcontrol_b200.fem import ScalarBlocks
+    from flowcontrol_b200.mesh import TaylorHoodTables
+    from oracle.flow_oracle import Operators, TaylorHoodMesh
+
+    tab = TaylorHoodTables.from_file(root / "data/meshes/lidcavity_mesh64.npz")
+    blocks = ScalarBlocks(tab)
+    asm = DeviceAdvectionAssembler(tab, blocks)
+    rng = np.random.default_rng(11)
+    B = 5
+    U = rng.standard_normal((tab.Nv, B))
+    Cv, Dv = asm.values(U)
+    Cv2, Dv2 = asm.values(U)
+    assert np.array_equal(Cv, Cv2) and np.array_equal(Dv, Dv2)
+    xy, tri = cases.load_mesh("lidcavity_mesh64")
+    ops = Operators(TaylorHoodMesh(xy, tri))
+    for b in (0, 3):
+        Ch, Dh = blocks.advection(U[:, b])
+        Cd = asm._csr(Cv[:, b])
+        assert abs(Cd - Ch).max() < 1e-13 * abs(Ch).max()
+        Co, Do = ops.advection_blocks(U[:, b])
+        assert abs(Cd - Co).max() < 1e-12 * abs(Co).max()
+        for i in range(2):
+            for j in range(2):
+                Dd = asm._csr(Dv[2 * i + j, :, b])
+                assert abs(Dd - Dh[i, j]).max() < 1e-13 * abs(Dh[i, j]).max()
+                assert abs(Dd - Do[i, j]).max() < 1e-12 * abs(Do[i, j]).max()
+    A_dev = asm.saddle_point(1.5 / 0.005, 100.0, U[:, 1])
+    A_host = blocks.saddle_point(1.5 / 0.005, 100.0, U[:, 1])
+    assert abs(A_dev - A_host).max() < 1e-12 * abs(A_host).max()
+
+
+def test_steady_state_newton_with_device_assembly(root, tmp_path, built_lib):
+    """the base flow of the cylinder (Re=100; 3 Picard + Newton as tests/integration/test_cylinder.py)
+    with every iteration matrix assembled on the GPU reproduces the reference's golden constants and the committed base flow."""
+    from flowcontrol_b200.examples.cylinder import CylinderFlowSolver
+
+    fs = CylinderFlowSolver.make_default(Re=100, path_out=tmp_path)
+    fs.compute_steady_state(method="picard", max_iter=3, tol=1e-7, u_ctrl=[0.0, 0.0], assembly="device")
+    fs.compute_steady_state(method="newton", max_iter=25, u_ctrl=[0.0, 0.0], initial_guess=fs.fields.UP0, assembly="device")
+    U0 = fs.fields.U0.vector().get_local()
+    assert np.isclose(U0.max(), 1.1921615450014942, rtol=1e-9) and np.isclose(U0.mean(), 0.336746427968607, rtol=1e-9)  # test_cylinder.py:66-67
+    UP0 = np.load(root / "tests/golden/cylinder_baseflow.npz")["UP0"]
+    assert rel(fs.fields.UP0.vector().get_local(), UP0) < 1e-9

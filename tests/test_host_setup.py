@@ -312,3 +312,27 @@ def test_crank_nicolson_host_step_matches_oracle():
         assert np.linalg.norm(x[: tab.Nv] - orc.up[: tab.Nv]) / np.linalg.norm(orc.up[: tab.Nv]) < 1e-10
         assert np.linalg.norm(x[tab.Nv :] - orc.up[tab.Nv :]) / np.linalg.norm(orc.up[tab.Nv :]) < 1e-9
         u_n, prev = x[: tab.Nv].copy(), np.asarray(uc, dtype=float)
+
+
+def test_assembly_position_map_is_bit_exact(small):
+    """Integer maps of the device matrix assembly (assembly.py): every element-matrix entry (cell, a, b) lands on the CSR
+    entry (node_a, node_b) of the scalar P2 pattern, and cells of one colour share no node (atomic-free scatter)."""
+    import scipy.sparse as sp
+
+    from flowcontrol_b200.assembly import DeviceAdvectionAssembler
+
+    _, _, tab, blocks, _ = small
+    asm = DeviceAdvectionAssembler(tab, blocks)
+    cn = np.asarray(tab.cell_nodes)
+    rows, cols = np.repeat(cn, 6, axis=1).ravel(), np.tile(cn, (1, 6)).ravel()
+    row_of = np.repeat(np.arange(tab.nN), np.diff(asm.indptr))
+    assert np.array_equal(row_of[asm.pos], rows) and np.array_equal(asm.indices[asm.pos], cols)
+    counts = np.bincount(asm.pos, minlength=len(asm.indices))
+    ref = sp.coo_matrix((np.ones(len(rows)), (rows, cols)), shape=(tab.nN, tab.nN)).tocsr()
+    ref.sort_indices()
+    assert np.array_equal(ref.indices, asm.indices) and np.array_equal(ref.data.astype(np.int64), counts)
+    cptr, ccells = tab.element_colouring()
+    assert sorted(ccells.tolist()) == list(range(tab.nT))
+    for c in range(len(cptr) - 1):
+        nodes = cn[ccells[cptr[c] : cptr[c + 1]]].ravel()
+        assert len(np.unique(nodes)) == len(nodes)
