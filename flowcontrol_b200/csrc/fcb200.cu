@@ -1429,6 +1429,7 @@ struct DevPlan {
     int n = 0, nU = 0, njobs = 0, nlaunch = 0;
     int *srec = nullptr, *jrec = nullptr, *cta_sptr = nullptr, *cta_jptr = nullptr;
     int asm_n = 0, *asm_ptr = nullptr, *asm_src = nullptr, *asm_dst = nullptr;
+    std::vector<int> asm_lptr;  // [nlaunch+1]: gather-sum rows [asm_lptr[l], asm_lptr[l+1]) run right before launch l
     double* vals = nullptr;
     struct Launch { int grid, nwc, nslab, nstages, slots, cta_off, ksplit; };
     std::vector<Launch> launches;
@@ -1779,6 +1780,12 @@ int upload_plan(fcb_context* h, DevPlan& d, const fcb_plan& p, const int32_t* pe
     TRY(upload(h, &d.cta_jptr, cta_jptr.data(), cta_jptr.size()));
     TRY(upload(h, &d.vals, packed.data(), packed.size()));
     d.asm_n = p.asm_n;
+    d.asm_lptr.assign((size_t)p.nlaunch + 1, 0);
+    for (int l = 0; l <= p.nlaunch; ++l) {
+        d.asm_lptr[l] = p.asm_lptr ? p.asm_lptr[l] : (l <= p.n_forward_launches ? 0 : p.asm_n);
+        if (d.asm_lptr[l] < 0 || d.asm_lptr[l] > p.asm_n || (l > 0 && d.asm_lptr[l] < d.asm_lptr[l - 1]))
+            return fail(h, FCB_ERR_INVALID, "plan: asm_lptr is malformed");
+    }
     if (p.asm_n > 0) {
         for (int i = 0; i < p.asm_n; ++i) {
             if (p.asm_dst[i] < 0 || p.asm_dst[i] >= zrow || p.asm_ptr[i + 1] < p.asm_ptr[i])
@@ -2116,9 +2123,11 @@ int enqueue_solve(fcb_context* h, const DevPlan& pl, double* xout, PhaseMark* pm
     for (const DevPlan::Tier& t : pl.tiers) launch_clusters(h, pl, t, 0, xout);  // forward: the subtree clusters first, tier by tier
     for (int l = 0; l < pl.nlaunch; ++l) {
         if (pm && l == pl.n_forward) pm->mark(FCB_PHASE_BACKWARD);
-        if (l == pl.n_forward && pl.asm_n > 0) {
-            dim3 grid((pl.asm_n + 7) / 8, h->ldb / 32), block(32, 8);
-            k_gather_sum<<<grid, block, 0, h->stream>>>(pl.asm_n, pl.asm_ptr, pl.asm_src, pl.asm_dst, h->Z, h->ldb);
+        if (const int nsum = pl.asm_lptr[l + 1] - pl.asm_lptr[l]; nsum > 0) {
+            // gather-sums of this launch: virtual update vectors of fronts with more than two children, top right-hand side
+            const int r0 = pl.asm_lptr[l];
+            dim3 grid((nsum + 7) / 8, h->ldb / 32), block(32, 8);
+            k_gather_sum<<<grid, block, 0, h->stream>>>(nsum, pl.asm_ptr + r0, pl.asm_src, pl.asm_dst + r0, h->Z, h->ldb);
             h->launches += 1;
         }
         const DevPlan::Launch& L = pl.launches[l];
@@ -3188,7 +3197,11 @@ int fcb_profile_step(fcb_handle h, const double* u_ctrl, float* ms, int32_t* lau
     if (launches) {
         launches[FCB_PHASE_RHS] = 1 + (h->scheme == 1 && h->ncrow_prev > 0 ? 1 : 0);
         launches[FCB_PHASE_FORWARD] = pl.n_forward + (int)pl.tiers.size();
-        launches[FCB_PHASE_BACKWARD] = pl.nlaunch - pl.n_forward + (pl.asm_n > 0 ? 1 : 0) + (int)pl.tiers.size();
+        int nsum_f = 0, nsum_b = 0;
+        for (int l = 0; l < pl.nlaunch; ++l)
+            if (pl.asm_lptr[l + 1] > pl.asm_lptr[l]) (l < pl.n_forward ? nsum_f : nsum_b) += 1;
+        launches[FCB_PHASE_FORWARD] += nsum_f;
+        launches[FCB_PHASE_BACKWARD] = pl.nlaunch - pl.n_forward + nsum_b + (int)pl.tiers.size();
         launches[FCB_PHASE_POST] = h->nbc > 0 ? 1 : 0;
         launches[FCB_PHASE_SPMM] = h->scheme == 1 ? 1 : 0;
         launches[FCB_PHASE_ELEMENT] = 1 + (h->nshared > 0 ? 1 : 0);

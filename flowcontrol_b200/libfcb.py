@@ -30,7 +30,7 @@ class fcb_plan(C.Structure):
         ("blk_iptr", c_i64p), ("blk_vptr", c_i64p), ("blk_eptr", c_i64p),
         ("i0", c_i32p), ("i1", c_i32p), ("i2", c_i32p), ("e0", c_i32p), ("e1", c_i32p), ("vals", c_f64p),
         ("nlaunch", C.c_int32), ("launch_ptr", c_i32p), ("n_forward_launches", C.c_int32),
-        ("asm_n", C.c_int32), ("asm_ptr", c_i32p), ("asm_src", c_i32p), ("asm_dst", c_i32p),
+        ("asm_n", C.c_int32), ("asm_ptr", c_i32p), ("asm_src", c_i32p), ("asm_dst", c_i32p), ("asm_lptr", c_i32p),
         ("ntier", C.c_int32), ("tier_ptr", c_i32p),
         ("ncluster", C.c_int32), ("cl_fptr", c_i32p), ("cl_ustore", c_i32p), ("cl_iptr", c_i64p),
         ("imp_src", c_i32p), ("imp_dst", c_i32p),
@@ -175,6 +175,7 @@ class ProblemPack:
             q.asm_ptr = _ptr(arr(p.asm_ptr, np.int32), c_i32p)
             q.asm_src = _ptr(arr(p.asm_src if len(p.asm_src) else np.zeros(1), np.int32), c_i32p)
             q.asm_dst = _ptr(arr(p.asm_dst if len(p.asm_dst) else np.zeros(1), np.int32), c_i32p)
+            q.asm_lptr = _ptr(arr(p.asm_lptr, np.int32), c_i32p)
             pad = lambda a: a if len(a) else np.zeros(1)  # noqa: E731
             q.ntier = len(p.tier_ptr) - 1
             q.ncluster = len(p.cl_fptr) - 1

@@ -29,7 +29,7 @@ import numpy as np
 import scipy.sparse as sp
 
 from .mesh import TaylorHoodTables
-from .ordering import TreeNode, dissect, postorder
+from .ordering import TreeNode, amalgamate, dissect, postorder
 
 
 @dataclass
@@ -48,11 +48,13 @@ class Supernode:
 class SymbolicFactor:
     """Ordering + supernode structure shared by every matrix on one mesh/BC set."""
 
-    def __init__(self, tab: TaylorHoodTables, free_mask: np.ndarray, leaf_cells: int = 8):
-        """``free_mask[N]`` is True for unknowns kept in the solve (non-Dirichlet)."""
+    def __init__(self, tab: TaylorHoodTables, free_mask: np.ndarray, leaf_cells: int = 8, amalgamate_above: int = 0):
+        """``free_mask[N]`` is True for unknowns kept in the solve (non-Dirichlet).  ``amalgamate_above`` = h > 0 merges every
+        tree node whose children have height >= h with those children (ordering.amalgamate): half the levels above height h."""
         self.N = tab.N
         nN, nV = tab.nN, tab.nV
-        tree = dissect(tab, leaf_cells=leaf_cells)
+        tree = amalgamate(dissect(tab, leaf_cells=leaf_cells), amalgamate_above)
+        self.amalgamate_above = int(amalgamate_above)
         po = postorder(tree)
 
         def dofs_of(nodes: np.ndarray) -> np.ndarray:
@@ -242,6 +244,7 @@ class SolvePlan:
     asm_ptr: np.ndarray = None
     asm_src: np.ndarray = None
     asm_dst: np.ndarray = None
+    asm_lptr: np.ndarray = None  # int32 [nlaunch+1]: gather-sum rows [asm_lptr[l], asm_lptr[l+1]) run right before launch l
     # Subtree clusters (csrc/fcb200.cu: k_cluster_sweep): connected pieces of the lower elimination tree that one CTA sweeps
     # with ALL their unknowns resident in shared memory (right-looking inside the piece, so the update vectors of the
     # fronts inside a cluster never exist in global memory).  Clusters of tier t only need the update vectors of cluster
@@ -387,28 +390,55 @@ def build_plan(fac: BlockFactor, top_levels: int = 2, cluster_rows: int = 0, clu
     uoff = np.zeros(nS + 1, dtype=np.int64)
     for i, s in enumerate(sns):
         uoff[i + 1] = uoff[i] + (len(s.struct) if needs_u[i] else 0)
-    nU = int(uoff[-1])
     UB = 2 * n  # first row of the U region
+    # A front gathers b and at most TWO update vectors (the sweep kernel's three source planes and two seed lists).  A front
+    # with more children -- the amalgamated levels of the tree -- first sums groups of its children's update vectors into
+    # "virtual" update vectors: rows of a gather-sum that runs right before the launch of the front's level.
+    nvirt = int(uoff[-1])  # virtual vectors live behind the real ones in the U region
+    sources: dict[int, list[tuple[np.ndarray, int]]] = {}  # front -> [(solver rows of the vector, sorted; first Z row)]
+    presum: dict[int, list[tuple[int, list[int]]]] = {}  # front -> [(destination Z row, source Z rows in fixed order)]
+    for i, s in enumerate(sns):
+        if in_top[i] or in_cluster[i]:
+            continue
+        plain = [(sns[c].struct.astype(np.int64), UB + int(uoff[c])) for c in sym.children[i] if len(sns[c].struct)]
+        if len(plain) <= 2:
+            sources[i] = plain
+            continue
+        half = (len(plain) + 1) // 2
+        srcs, pre = [], []
+        for grp in (plain[:half], plain[half:]):
+            if len(grp) == 1:
+                srcs.append(grp[0])
+                continue
+            rows = np.unique(np.concatenate([g[0] for g in grp]))
+            base = UB + nvirt
+            nvirt += len(rows)
+            contrib: list[list[int]] = [[] for _ in rows]
+            for st, zb in grp:  # children in order: a fixed summation order per row
+                for k, q in enumerate(np.searchsorted(rows, st)):
+                    contrib[q].append(zb + k)
+            pre += [(base + q, c) for q, c in enumerate(contrib)]
+            srcs.append((rows, base))
+        sources[i], presum[i] = srcs, pre
+    nU = nvirt
     ZROW = 2 * n + nU
 
     def child_sources(i: int, rows: np.ndarray, absent: int) -> tuple[np.ndarray, np.ndarray]:
-        """Z rows of the (at most two) children's update vectors that hit the given solver rows."""
+        """Z rows of the (at most two) update vectors feeding front ``i`` that hit the given solver rows."""
         srcs = [np.full(len(rows), absent, dtype=np.int64), np.full(len(rows), absent, dtype=np.int64)]
-        ch = sym.children[i]
-        if len(ch) > 2:
-            raise NotImplementedError("solve plan assumes a binary dissection tree")
-        for slot, c in enumerate(ch):
-            st = sns[c].struct
+        for slot, (st, zb) in enumerate(sources[i]):
             if len(st) == 0 or len(rows) == 0:
                 continue
             pos = np.searchsorted(st, rows)
             pos_c = np.minimum(pos, len(st) - 1)
             hit = st[pos_c] == rows
-            srcs[slot][hit] = UB + uoff[c] + pos_c[hit]
+            srcs[slot][hit] = zb + pos_c[hit]
         return srcs[0], srcs[1]
 
     blocks: list[dict] = []
     launch_ptr = [0]
+    asm_ptr, asm_src, asm_dst = [0], [], []
+    asm_lptr = [0]  # gather-sum rows [asm_lptr[l], asm_lptr[l+1]) run right before launch l
     max_h = max(s.height for s in sns)
     for h in range(max_h + 1):
         for i in (i for i, s in enumerate(sns) if s.height == h and not in_top[i] and not in_cluster[i]):
@@ -416,18 +446,22 @@ def build_plan(fac: BlockFactor, top_levels: int = 2, cluster_rows: int = 0, clu
             w, m = s.c1 - s.c0, len(s.struct)
             if w == 0 and m == 0:
                 continue
+            for dst, srcs in presum.get(i, []):
+                asm_src.extend(srcs)
+                asm_ptr.append(len(asm_src))
+                asm_dst.append(dst)
             own = np.arange(s.c0, s.c1, dtype=np.int64)
             a1, a2 = child_sources(i, own, ZROW)
-            has_children = bool(sym.children[i])
+            has_children = bool(sources[i])
             e0, e1 = child_sources(i, s.struct, -1)
             blocks.append(dict(K=w, M=m, nsrc=3 if has_children else 1, out0=UB + int(uoff[i]), ystore=n + s.c0,
                                i0=own, i1=a1, i2=a2, vals=-fac.blocks[i][0], e0=e0 if has_children else None,
                                e1=e1 if has_children else None))
         if len(blocks) > launch_ptr[-1]:
             launch_ptr.append(len(blocks))
+            asm_lptr.append(len(asm_dst))
     n_fwd = len(launch_ptr) - 1
     # merged top: assemble r_T into the y rows of the top unknowns, then x_T = S^-1 r_T
-    asm_ptr, asm_src, asm_dst = [0], [], []
     if top:
         trows, Sinv = top_inverse(fac, top)
         frontier = [c for t in top for c in sym.children[t] if not in_top[c]]
@@ -458,6 +492,7 @@ def build_plan(fac: BlockFactor, top_levels: int = 2, cluster_rows: int = 0, clu
             pos += w
         if len(blocks) > launch_ptr[-1]:
             launch_ptr.append(len(blocks))
+            asm_lptr.append(len(asm_dst))
     max_d = max(s.depth for s in sns)
     for dpt in range(max_d + 1):
         for i in (i for i, s in enumerate(sns) if s.depth == dpt and not in_top[i] and not in_cluster[i]):
@@ -472,6 +507,7 @@ def build_plan(fac: BlockFactor, top_levels: int = 2, cluster_rows: int = 0, clu
                                e0=None, e1=None))
         if len(blocks) > launch_ptr[-1]:
             launch_ptr.append(len(blocks))
+            asm_lptr.append(len(asm_dst))
     nb = len(blocks)
     K = np.array([b["K"] for b in blocks], dtype=np.int32)
     M = np.array([b["M"] for b in blocks], dtype=np.int32)
@@ -546,7 +582,7 @@ def build_plan(fac: BlockFactor, top_levels: int = 2, cluster_rows: int = 0, clu
         i0=i0, i1=i1, i2=i2, e0=cat(e0p, np.int32), e1=cat(e1p, np.int32), vals=cat(vparts, np.float64),
         launch_ptr=np.array(launch_ptr, dtype=np.int32), n_forward_launches=n_fwd,
         asm_ptr=np.array(asm_ptr, dtype=np.int32), asm_src=np.array(asm_src, dtype=np.int32),
-        asm_dst=np.array(asm_dst, dtype=np.int32),
+        asm_dst=np.array(asm_dst, dtype=np.int32), asm_lptr=np.array(asm_lptr, dtype=np.int32),
         tier_ptr=tier_ptr, cl_fptr=np.array(cl_fptr, dtype=np.int32), cl_ustore=np.array(cl_ustore, dtype=np.int32),
         cl_iptr=np.array(cl_iptr, dtype=np.int64), imp_src=cat(imp_src, np.int32), imp_dst=cat(imp_dst, np.int32),
         fr_c0=np.array(fr_c0, dtype=np.int32), fr_w=np.array(fr_w, dtype=np.int32), fr_m=np.array(fr_m, dtype=np.int32),
@@ -610,13 +646,15 @@ def apply_plan_host(plan: SolvePlan, b_perm: np.ndarray) -> np.ndarray:
     for t in range(ntier):
         for q in range(int(plan.tier_ptr[t]), int(plan.tier_ptr[t + 1])):
             _cluster_sweep_host(plan, Z, q, True)
-    q_asm = int(plan.launch_ptr[plan.n_forward_launches])  # first block after the forward launches
-    for q in range(len(plan.blk_K) + 1):
-        if q == q_asm:
-            for i, dst in enumerate(plan.asm_dst):
-                Z[dst] = Z[plan.asm_src[plan.asm_ptr[i] : plan.asm_ptr[i + 1]]].sum(axis=0)
-        if q == len(plan.blk_K):
-            break
+    first_block = {int(plan.launch_ptr[l]): l for l in range(len(plan.launch_ptr) - 1)}
+    for q in range(len(plan.blk_K)):
+        if q in first_block:  # gather-sums scheduled right before this launch (virtual update vectors, top right-hand side)
+            l = first_block[q]
+            for i in range(int(plan.asm_lptr[l]), int(plan.asm_lptr[l + 1])):
+                acc = np.zeros(Z.shape[1])
+                for src in plan.asm_src[plan.asm_ptr[i] : plan.asm_ptr[i + 1]]:  # fixed order, as on the device
+                    acc = acc + Z[src]
+                Z[plan.asm_dst[i]] = acc
         K, M = int(plan.blk_K[q]), int(plan.blk_M[q])
         sl = slice(plan.blk_iptr[q], plan.blk_iptr[q] + K)
         x = Z[plan.i0[sl]]

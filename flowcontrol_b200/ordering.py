@@ -118,3 +118,40 @@ def postorder(nodes: list[TreeNode]) -> list[int]:
             for c in reversed(nodes[t].children):
                 stack.append((c, False))
     return out
+
+
+def amalgamate(nodes: list[TreeNode], min_child_height: int) -> list[TreeNode]:
+    """Merge tree nodes pairwise along the depth: a node whose two children both have height >= ``min_child_height``
+    absorbs them (its separator becomes the union of the three separators, its children are the four grandchildren), and
+    the same rule is then applied to the grandchildren.  The elimination tree above the small fronts gets half as many
+    levels -- half as many dependent launches in the GPU sweeps -- for slightly larger dense fronts (the two absorbed
+    separators are not coupled to each other, their zero block is stored).  ``min_child_height`` <= 0 returns the tree
+    unchanged.  The result is a new list (index 0 = root) with parent / children / depth rebuilt."""
+    if min_child_height <= 0:
+        return nodes
+    height = [0] * len(nodes)
+    for t in reversed(postorder(nodes)[::-1]):  # children before parents
+        pass
+    for t in postorder(nodes):
+        for c in nodes[t].children:
+            height[t] = max(height[t], height[c] + 1)
+    out: list[TreeNode] = []
+
+    def build(t: int, parent: int, depth: int) -> int:
+        nd = nodes[t]
+        kids = list(nd.children)
+        own = nd.own_nodes
+        if len(kids) == 2 and all(height[c] >= min_child_height for c in kids) and all(len(nodes[c].children) == 2 for c in kids):
+            own = np.concatenate([nodes[kids[0]].own_nodes, nodes[kids[1]].own_nodes, nd.own_nodes])
+            kids = [g for c in kids for g in nodes[c].children]
+        me = len(out)
+        out.append(TreeNode(cells=nd.cells, parent=parent, own_nodes=own, bnd_nodes=nd.bnd_nodes, depth=depth))
+        for c in kids:
+            out[me].children.append(build(c, me, depth + 1))
+        return me
+
+    import sys
+
+    sys.setrecursionlimit(max(sys.getrecursionlimit(), 10000))
+    build(0, -1, 0)
+    return out

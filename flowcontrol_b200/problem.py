@@ -117,6 +117,7 @@ class FlowProblem:
         top_levels: int = 2,
         cluster_rows: int | None = None,
         cluster_height: int | None = None,
+        amalgamate_above: int | None = None,
         time_scheme: str = "bdf",
         symbolic: SymbolicFactor | None = None,
     ):
@@ -131,7 +132,14 @@ class FlowProblem:
         extra = [tab.Nv] if pin_pressure else []
         self.dirichlet = DirichletSet(tab, bcs, self.actuators, extra_zero_dofs=extra)
         dset = self.dirichlet
-        self.sym = symbolic or SymbolicFactor(tab, dset.free, leaf_cells=leaf_cells)
+        # amalgamated upper tree (ordering.amalgamate): fronts whose children have height >= amalgamate_above absorb them, which
+        # halves the dependent levels above; the merged root then IS the old two-level top, so only one level is inverted densely
+        import os
+
+        amal = int(os.environ.get("FCB_AMALGAMATE", 0 if amalgamate_above is None else amalgamate_above))
+        self.sym = symbolic or SymbolicFactor(tab, dset.free, leaf_cells=leaf_cells, amalgamate_above=amal)
+        if getattr(self.sym, "amalgamate_above", 0) > 0:
+            top_levels = min(top_levels, 1)
         if not np.array_equal(np.sort(self.sym.perm), np.flatnonzero(dset.free)):
             raise ValueError("symbolic factorisation was built for a different Dirichlet set")
         # force vectors F_k = blkdiag(M,M) shape_k  (FORCE actuators), zero for BC actuators

@@ -65,12 +65,15 @@ typedef struct fcb_plan {
     int32_t nlaunch;
     const int32_t* launch_ptr; /* [nlaunch+1] block ranges; blocks of a launch are independent      */
     int32_t n_forward_launches;
-    /* gather-sum executed after the forward launches: Z[asm_dst[i]] = sum of Z[asm_src[j]], asm_ptr[i] <= j < asm_ptr[i+1]
-     * (right-hand side of the merged top of the elimination tree); asm_n may be 0 */
+    /* gather-sums: Z[asm_dst[i]] = sum of Z[asm_src[j]], asm_ptr[i] <= j < asm_ptr[i+1], in that order.  Rows
+     * [asm_lptr[l], asm_lptr[l+1]) run right before launch l: the right-hand side of the merged top of the elimination tree,
+     * and the "virtual" update vectors of fronts with more than two children (amalgamated levels).  asm_lptr == NULL: every
+     * row runs before launch n_forward_launches.  asm_n may be 0 */
     int32_t asm_n;
-    const int32_t* asm_ptr; /* [asm_n+1] */
+    const int32_t* asm_ptr;  /* [asm_n+1] */
     const int32_t* asm_src;
-    const int32_t* asm_dst; /* [asm_n] */
+    const int32_t* asm_dst;  /* [asm_n] */
+    const int32_t* asm_lptr; /* [nlaunch+1] or NULL */
     /* Subtree clusters (multifrontal.py: choose_clusters): connected pieces of the lower elimination tree that ONE CTA
      * sweeps with all their unknowns resident in shared memory (k_cluster_sweep).  Inside a cluster the sweep is
      * right-looking on one resident vector S = [own rows of its fronts | boundary rows of its root]:

@@ -156,6 +156,20 @@ def test_multifrontal_matches_superlu_and_plan_matches_factor(small):
             assert pc.fr_w[f0:f1].sum() + pc.fr_m[f1 - 1] <= rows
         assert pc.nU <= plan0.nU  # update vectors inside clusters never reach global memory
     assert max(seen_tiers) >= 2  # some cut produced clusters that import from lower clusters
+    # amalgamated upper tree: fronts with four children (virtual update vectors summed right before their launch)
+    for above in (1, 2):
+        syma = SymbolicFactor(tab, d.free, leaf_cells=4, amalgamate_above=above)
+        assert max(len(c) for c in syma.children) == 4 and max(s_.height for s_ in syma.supernodes) < max(s_.height for s_ in sym.supernodes)
+        faca = BlockFactor(syma, A)
+        ba = rng.standard_normal((syma.n, 2))
+        xa = spla.splu(A[syma.perm][:, syma.perm].tocsc()).solve(ba)
+        assert np.linalg.norm(faca.solve(ba) - xa) / np.linalg.norm(xa) < 1e-11
+        for tl, rows in ((1, 0), (0, 0), (1, 80)):
+            pa = build_plan(faca, top_levels=tl, cluster_rows=rows, min_tier_clusters=1)
+            assert np.abs(apply_plan_host(pa, ba) - xa).max() < 1e-11 * np.abs(xa).max(), (above, tl, rows)
+            if rows == 0:
+                assert pa.asm_lptr[-1] == len(pa.asm_dst) and len(pa.asm_lptr) == len(pa.launch_ptr)
+                assert len(pa.asm_dst) > (len(pa.launch_ptr) > 1 and tl) * 0  # gather-sum rows exist for the four-child fronts
     plan = build_plan(fac, top_levels=2, cluster_rows=0)
     # every x row and every y row is produced exactly once; blocks of one launch never read rows
     # that the same launch writes
