@@ -106,6 +106,145 @@ def build_problem(time_scheme="bdf"):
     return fs, prob
 
 
+def build_workload(name: str):
+    """Other BASELINE configurations as strong-scaling workloads (open loop): returns (problem, ic [N] or fn(lo, hi) -> [N, B],
+    u_of_step(k, lo, hi) -> [na, B], description)."""
+    import tempfile
+
+    from flowcontrol_b200.flowfield import Field
+    from flowcontrol_b200.problem import FlowProblem
+
+    sys.path.insert(0, str(ROOT / "tools"))
+    import make_goldens_r2 as mk  # amplitudes / initial conditions of the configurations (shared with the parity tests)
+
+    if name == "pinball":
+        from flowcontrol_b200.actuator import CYLINDER_ACTUATION_MODE
+        from flowcontrol_b200.examples.pinball import PinballFlowSolver
+
+        UP0 = np.load(ROOT / "tests/golden/pinball_Re100_baseflow.npz")["UP0"]
+        fs = PinballFlowSolver.make_default(Re=100.0, mode_actuation=CYLINDER_ACTUATION_MODE.ROTATION, path_out=Path(tempfile.mkdtemp()))
+        tab = fs.tables
+        fs._assign_steady_state(Field(UP0[: tab.Nv]), Field(UP0[tab.Nv :]))
+        prob = FlowProblem(tab, fs.blocks, 100.0, 0.005, fs.bc.bcu, fs.params_control.actuator_list, fs.params_control.sensor_list, UP0)
+        ic = fs._default_initial_perturbation(2.0, 0.0, 0.5)
+        return prob, (lambda lo, hi, total: ic), (lambda k, lo, hi, total: mk.pinball_u((k + 1) * 0.005, mk.pinball_amplitudes(total)[:, lo:hi])), \
+            "fluidic pinball Re=100 (mesh_middle), three rotation actuators with Gaussian pulses, open loop (BASELINE configs[2])"
+    if name == "lidcavity":
+        from flowcontrol_b200.examples import lidcavity as ex
+
+        UP0 = np.load(ROOT / "tests/golden/lidcavity_Re8000_baseflow.npz")["UP0"]
+        prob = ex.make_problem(Re=8000.0, UP0=UP0)
+        tab = prob.tab
+        fs = ex.LidCavityFlowSolver.make_default(Re=8000.0, path_out=Path(tempfile.mkdtemp()))
+        fs._assign_steady_state(Field(UP0[: tab.Nv]), Field(UP0[tab.Nv :]))
+
+        def ic(lo, hi, total):
+            loc = mk.lid_ics(total)[lo:hi]
+            return np.stack([0.1 * fs._default_initial_perturbation(xloc=x, yloc=y, radius=0.1) for x, y in loc], axis=1)
+
+        return prob, ic, (lambda k, lo, hi, total: np.zeros((1, hi - lo))), \
+            "lid-driven cavity Re=8000 (mesh64), random Gaussian-vortex initial conditions, open loop (BASELINE configs[4])"
+    raise ValueError(name)
+
+
+def run_open_workload(args):
+    """Strong / weak scaling of the open-loop configurations (pinball B=512, lid cavity B=1024): same timing rules as the
+    headline benchmark, the device-resident loop is fcb_run_open_loop."""
+    import torch
+
+    import __graft_entry__ as g
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        g.build()
+    if world > 1:
+        dist.barrier()
+    from flowcontrol_b200.ensemble import Ensemble
+    from flowcontrol_b200.sharding import SeriesGatherer, shard_bounds
+
+    prob, ic_of, u_of, desc = build_workload(args.workload)
+    tab = prob.tab
+    total = args.trajectories if args.scaling == "strong" else args.trajectories * world
+    lo, hi = shard_bounds(total, rank, world)
+    B = hi - lo
+    K, W = args.steps, max(args.warmup, 3)
+    ens = Ensemble(prob, B, device=local_rank)
+    ic = ic_of(lo, hi, total)
+    ens.set_state(ic[: tab.Nv], None, ic[tab.Nv :], order=1)
+    useries = torch.as_tensor(np.stack([u_of(k, lo, hi, total) for k in range(W + 2 * K)]), device="cuda").contiguous()
+    stream = torch.cuda.ExternalStream(ens.stream, device=torch.device("cuda", local_rank))
+    ncol = 1 + prob.na + prob.ns
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    series_dev = torch.empty((K, ncol, B), dtype=torch.float64, device="cuda")
+    gatherer = SeriesGatherer(K, ncol, total, torch.float64, torch.device("cuda", local_rank)) if world > 1 else None
+    with torch.cuda.stream(stream):
+        ens.run_open_loop(useries[:W], log=False)
+        ens.run_open_loop(useries[W : W + K], log=True, out=series_dev)
+        if gatherer:
+            gatherer(series_dev)
+    barrier()
+    l0 = ens.launch_count()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    t_begin = time.perf_counter()
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        ens.run_open_loop(useries[W + K :], log=True, out=series_dev)
+        e1.record(stream)
+        gathered = gatherer(series_dev) if gatherer else series_dev
+        e2.record(stream)
+    barrier()
+    sampler.window(t_begin, time.perf_counter())
+    t = torch.tensor([e0.elapsed_time(e2), e1.elapsed_time(e2)], dtype=torch.float64, device="cuda")
+    launches = ens.launch_count() - l0
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, allgather_ms = (float(v) for v in t.tolist())
+    finite = bool(torch.isfinite(gathered).all().item())
+    prof = [ens.profile_step(np.zeros((prob.na, B))) for _ in range(4)][1:]
+    phase_ms = {k: float(np.mean([p[k]["ms"] for p in prof])) for k in prof[0]}
+    # end to end with host buffers
+    u_host = [np.ascontiguousarray(u_of(k, lo, hi, total)) for k in range(K)]
+    for k in range(3):
+        ens.step(u_host[k])
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(K):
+        ens.step(u_host[k])
+    torch.cuda.synchronize()
+    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if rank == 0 else None
+    ens.close()
+    if rank == 0:
+        print(json.dumps({
+            "metric": f"trajectory-steps/s ({args.workload} open-loop ensemble)", "value": total * K / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic (shipped mesh, committed base-flow fixture, seeded amplitudes / initial conditions of the configuration)",
+            "config": {"workload": desc, "trajectories_total": total, "trajectories_per_gpu": B, "dofs_per_trajectory": int(tab.N),
+                       "l2": "working set >> L2; no flush needed", "parallelism": f"ensemble-sharded x{world}, time-series all-gather only"},
+            "clocks": clocks, "e2e": {"value": total * K / float(t_e2e.item()), "unit": UNIT, "h2d_bytes_per_step": int(total * prob.na * 8),
+                                      "d2h_bytes_per_step": int(total * (prob.ns * 8 + 12))},
+            "gpu_launches": int(launches * world), "allgather_ms": allgather_ms, "phase_ms": phase_ms, "all_finite": finite}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def controller_bank(prob, lo: int, hi: int, total: int):
     from flowcontrol_b200.controller import Controller, ControllerBank
     from flowcontrol_b200.sharding import controller_gain_sweep
@@ -358,7 +497,9 @@ if __name__ == "__main__":
                     help="bdf = the reference's default BDF1->BDF2 (the benchmark); cn = Crank-Nicolson variant (adds the SpMM kernel's roofline)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: 256 trajectories per GPU (the benchmark); strong: a fixed ensemble of --trajectories sharded over the GPUs")
-    ap.add_argument("--trajectories", type=int, default=512, help="total ensemble width for --scaling strong")
+    ap.add_argument("--trajectories", type=int, default=512, help="total ensemble width for --scaling strong (per GPU for weak scaling of --workload pinball/lidcavity)")
+    ap.add_argument("--workload", default="cylinder", choices=["cylinder", "pinball", "lidcavity"],
+                    help="cylinder = the headline benchmark (BASELINE configs[1]); pinball / lidcavity = configs[2] / configs[4] as open-loop scaling runs")
     a = ap.parse_args()
     if a.gpus > 1 and "WORLD_SIZE" not in os.environ:
         # launched by hand without torchrun: spawn the ranks ourselves (one process per GPU, NCCL rendezvous on 127.0.0.1)
@@ -369,5 +510,7 @@ if __name__ == "__main__":
         sys.exit(f"bench.py: --gpus {a.gpus} does not match WORLD_SIZE={os.environ['WORLD_SIZE']}")
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload != "cylinder":
+        run_open_workload(a)
     else:
         run_ours(a)

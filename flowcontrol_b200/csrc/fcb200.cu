@@ -68,6 +68,12 @@ __constant__ double c_mass[6][6];     // reference mass matrix (int phi_a phi_b 
 // Z[row(dof)] = a + b_{n-1} (solver order), so no separate rhs pass reads a and b again.
 // ----------------------------------------------------------------------------------------------
 constexpr int EP_WARPS = 4;
+#ifndef FCB_EP_MINCTAS
+#define FCB_EP_MINCTAS 2   // CTAs per SM the element kernel is compiled for (2 => 255 registers per thread)
+#endif
+#ifndef FCB_EP_PREFETCH
+#define FCB_EP_PREFETCH 1  // 1: the next cell's node values are prefetched into registers while the current cell is integrated
+#endif
 
 struct PatchArgs {
     const int* pcell_ptr;          // [npatch*EP_WARPS+1] cell ranges of every warp
@@ -146,7 +152,7 @@ __device__ __forceinline__ void patch_load_cell(const PatchArgs& p, int slot, co
 
 // grid = (npatch, ldb/32), block = (32, EP_WARPS), dynamic smem = max accumulator rows * 4 * 32 doubles
 template <bool NONLINEAR>
-__global__ void __launch_bounds__(32 * EP_WARPS, 2) k_element_patch(const PatchArgs p) {
+__global__ void __launch_bounds__(32 * EP_WARPS, FCB_EP_MINCTAS) k_element_patch(const PatchArgs p) {
     extern __shared__ __align__(16) double acc[];  // [row][4][32]
     const int lane = threadIdx.x, w = threadIdx.y;
     const int b = blockIdx.y * 32 + lane;
@@ -248,8 +254,13 @@ __global__ void __launch_bounds__(32 * EP_WARPS, 2) k_element_patch(const PatchA
     __syncthreads();
     double e_acc = 0.0;
     for (int r = c0; r < c1; ++r) {
+#if FCB_EP_PREFETCH
         if (r + 1 < c1) patch_load_cell(p, r + 1, ids, b, nxt);
         if (r + 2 < c1) patch_load_ids(p, r + 2, ids);
+#else
+        if (r > c0) patch_load_cell(p, r, ids, b, cur);           // no register prefetch: more CTAs per SM hide the latency
+        if (r + 1 < c1) patch_load_ids(p, r + 1, ids);
+#endif
         double rx[6], ry[6];
 #pragma unroll
         for (int i = 0; i < 6; ++i) { rx[i] = 0.0; ry[i] = 0.0; }
@@ -297,7 +308,9 @@ __global__ void __launch_bounds__(32 * EP_WARPS, 2) k_element_patch(const PatchA
             s[64] += p.cb * mx + p.nb * rx[i];
             s[96] += p.cb * my + p.nb * ry[i];
         }
+#if FCB_EP_PREFETCH
         cur = nxt;
+#endif
     }
     __syncthreads();
     // write-out: every warp takes a contiguous chunk of the patch's nodes (tables staged in shared memory by the
@@ -554,7 +567,13 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
 // row segment of X per non-zero, bound by L1 wavefronts; persistent CTAs with a two-stage mbarrier ring 0.28 ms with
 // per-row bulk copies (issued lane by lane through the uniform datapath), 0.135 ms with a cp.async producer warp,
 // 0.115 ms with every warp gathering - one CTA per SM leaves too little slack around the per-item barrier.
-constexpr int SPMM_CMAX = 192;   // staged columns per block
+#ifndef FCB_SPMM_CMAX
+#define FCB_SPMM_CMAX 192
+#endif
+#ifndef FCB_SPMM_MINCTAS
+#define FCB_SPMM_MINCTAS 4
+#endif
+constexpr int SPMM_CMAX = FCB_SPMM_CMAX;   // staged columns per block (a multiple of 64)
 constexpr int SPMM_XS = 36;      // shared row stride in doubles (== 4 mod 16: k-steps with slots distinct mod 4 are conflict-free)
 constexpr int SPMM_WARPS = 8;    // warps = groups per block
 constexpr int SPMM_GREC = 12;    // ints per group record: first k-step, k-steps, 8 solver rows (-1 = none), 2 pad
@@ -570,7 +589,7 @@ struct SpmmArgs {
     int ldb, nslice;
 };
 
-__global__ void __launch_bounds__(32 * SPMM_WARPS, 4) k_spmm_mma(const SpmmArgs p) {
+__global__ void __launch_bounds__(32 * SPMM_WARPS, FCB_SPMM_MINCTAS) k_spmm_mma(const SpmmArgs p) {
     extern __shared__ __align__(16) double xs[];  // [slot][SPMM_XS]
     const int lane = threadIdx.x, w = threadIdx.y;
     const int blk = blockIdx.x / p.nslice, b0 = (blockIdx.x - blk * p.nslice) * 32;

@@ -22,7 +22,7 @@ class Ensemble:
         self.B = int(batch)
         self.device = int(device)
         self.lib = libfcb.load()
-        self._pack = libfcb.ProblemPack(problem)
+        self._pack = libfcb.ProblemPack(problem, batch=self.B)
         h = C.c_void_p()
         rc = self.lib.fcb_create(C.byref(self._pack.struct), self.B, self.device, C.byref(h))
         if rc != 0:

@@ -100,6 +100,11 @@ def load() -> C.CDLL:
     """Load libfcb200.so and declare every entry point of include/fcb200.h."""
     global _lib
     if _lib is None:
+        import os
+
+        global LIB_PATH
+        if os.environ.get("FCB_LIB"):  # tuning builds of the same library (tools/spmm_variants.sh); never a different code path
+            LIB_PATH = Path(os.environ["FCB_LIB"]).resolve()
         if not LIB_PATH.exists():
             raise ImportError(
                 f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
@@ -138,8 +143,9 @@ def as_voidp(x) -> C.c_void_p:
 class ProblemPack:
     """Keeps the numpy arrays referenced by an ``fcb_problem`` alive."""
 
-    def __init__(self, prob):
+    def __init__(self, prob, batch: int | None = None):
         tab = prob.tab
+        plans = prob.plans if batch is None else prob.plans_for_batch(batch)
         keep = self.keep = []
 
         def arr(a, dt):
@@ -161,7 +167,7 @@ class ProblemPack:
         s.bc_shape = _ptr(arr(prob.dirichlet.shape, np.float64), c_f64p)
         for o in (1, 2):
             s.ctrl_rhs[o - 1] = _ptr(arr(prob.ctrl_rhs[o], np.float64), c_f64p)
-            p, q = prob.plans[o], s.plan[o - 1]
+            p, q = plans[o], s.plan[o - 1]
             q.n, q.nU, q.nblocks = p.n, p.nU, len(p.blk_K)
             for name in ("blk_K", "blk_M", "blk_nsrc", "blk_out0", "blk_ystore", "i0", "i1", "i2", "e0", "e1"):
                 setattr(q, name, _ptr(arr(getattr(p, name), np.int32), c_i32p))

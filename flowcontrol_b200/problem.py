@@ -186,6 +186,7 @@ class FlowProblem:
             crow = int(os.environ.get("FCB_CLUSTER_ROWS", 0 if cluster_rows is None else cluster_rows))
             chgt = int(os.environ.get("FCB_CLUSTER_HEIGHT", 6 if cluster_height is None else cluster_height))
             self.plans[order] = build_plan(fac, top_levels=top_levels, cluster_rows=crow, cluster_height=chgt)
+            self._plan_args = (top_levels, cluster_rows is None and "FCB_CLUSTER_ROWS" not in os.environ)
             # rhs contribution per unit u_ctrl_k in solver row order: (F_k - A[:,Gamma] shape_k)[perm]
             lift = (A @ G.T).toarray().T if na else np.zeros((0, tab.N))
             self.ctrl_rhs[order] = np.ascontiguousarray((half_force * force - lift)[:, self.sym.perm])
@@ -193,6 +194,21 @@ class FlowProblem:
             for d in (self.A_raw, self.factors, self.plans, self.ctrl_rhs):
                 d[1] = d[2]
         self.sensor_ptr, self.sensor_idx, self.sensor_val = sensor_matrix(tab, self.sensors)
+
+    def plans_for_batch(self, B: int) -> dict:
+        """Solve plans for an ensemble of ``B`` trajectories.  Up to 32 trajectories (one 32-wide slab: the single-trajectory
+        latency case, BASELINE configs[0]) every launch of the sweeps is pure latency, and sweeping the bottom four levels of
+        the tree as shared-memory subtree clusters (one launch per sweep instead of four) is faster (measured on B200,
+        cylinder B=1: 0.337 vs 0.359 ms per step); wider ensembles use the pull-form launches throughout.  An explicit
+        ``cluster_rows`` / FCB_CLUSTER_ROWS setting is always respected."""
+        top_levels, auto = self._plan_args
+        if not auto or B > 32:
+            return self.plans
+        if getattr(self, "_plans_small", None) is None:
+            built = {o: build_plan(self.factors[o], top_levels=top_levels, cluster_rows=512, cluster_height=3)
+                     for o in sorted(set(self.factors))}
+            self._plans_small = {o: built[o] for o in self.plans} if self.time_scheme != "cn" else {1: built[2], 2: built[2]}
+        return self._plans_small
 
     @property
     def na(self) -> int:

@@ -848,3 +848,63 @@ def test_steady_state_newton_with_device_assembly(root, tmp_path, built_lib):
     assert np.isclose(U0.max(), 1.1921615450014942, rtol=1e-9) and np.isclose(U0.mean(), 0.336746427968607, rtol=1e-9)  # test_cylinder.py:66-67
     UP0 = np.load(root / "tests/golden/cylinder_baseflow.npz")["UP0"]
     assert rel(fs.fields.UP0.vector().get_local(), UP0) < 1e-9
+
+
+def test_run_loops_chunked_series_open_loop_and_controller_state(root, cyl, monkeypatch):
+    """The device-resident loops (include/fcb200.h): (a) the series is streamed in chunks -- a run with 7-step chunks gives
+    bit for bit the series of a run with one chunk; (b) fcb_run_open_loop == stepping with fcb_step from the host;
+    (c) fcb_set_controller_state restores the controller states (Controller.reset, controller.py:161-163): a repeated
+    closed-loop run reproduces the first one exactly, and fcb_set_state alone does not touch them."""
+    from flowcontrol_b200.controller import Controller, ControllerBank
+    from flowcontrol_b200.ensemble import Ensemble
+    from flowcontrol_b200.sharding import controller_gain_sweep
+
+    fs, prob, _, _ = cyl
+    tab = prob.tab
+    ic = fs._default_initial_perturbation()
+    B, n = 40, 23
+    k = np.load(root / "tests/golden/Kopt_reduced13.npz")
+    bank = ControllerBank([Controller(k["A"], g * k["B"], k["C"], g * k["D"]) for g in controller_gain_sweep(B)], prob.dt,
+                          np.array([[-1.0, 0.0, 0.0]]), np.array([[1.0], [1.0]]))
+
+    def closed(chunk):
+        if chunk:
+            monkeypatch.setenv("FCB_SERIES_CHUNK", str(chunk))
+        else:
+            monkeypatch.delenv("FCB_SERIES_CHUNK", raising=False)
+        e = Ensemble(prob, B)
+        e.set_state(ic[: tab.Nv], None, ic[tab.Nv :], order=1)
+        e.set_controllers(bank)
+        return e, e.run_closed_loop(n)
+
+    e1, s1 = closed(0)
+    e7, s7 = closed(7)
+    assert np.array_equal(s1, s7) and np.array_equal(e1.fields(0), e7.fields(0))
+    e7.close()
+    # (c) same handle: new state, controller states still those of the end of the run -> different series; reset -> identical
+    x_end = e1.controller_state().copy()
+    assert np.abs(x_end).max() > 0
+    e1.set_state(ic[: tab.Nv], None, ic[tab.Nv :], order=1)
+    assert np.array_equal(e1.controller_state(), x_end)
+    e1.set_controller_state(None)
+    assert np.abs(e1.controller_state()).max() == 0.0
+    s1b = e1.run_closed_loop(n)
+    assert np.array_equal(s1b, s1)
+    e1.set_controller_state(x_end)
+    assert np.array_equal(e1.controller_state(), x_end)
+    e1.close()
+    # (b) open loop: device-resident run vs host-driven steps
+    rng = np.random.default_rng(5)
+    useries = 0.1 * rng.standard_normal((n, 2, B))
+    eo = Ensemble(prob, B)
+    eo.set_state(ic[: tab.Nv], None, ic[tab.Nv :], order=1)
+    so = eo.run_open_loop(useries)
+    eh = Ensemble(prob, B)
+    eh.set_state(ic[: tab.Nv], None, ic[tab.Nv :], order=1)
+    for s_ in range(n):
+        eh.step(useries[s_])
+        assert np.array_equal(so[s_, 3:, :], eh.y_meas) and np.array_equal(so[s_, 0, :], eh.dE)
+        assert np.array_equal(so[s_, 1:3, :], useries[s_])
+    assert np.array_equal(eo.fields(0), eh.fields(0))
+    eo.close()
+    eh.close()
