@@ -848,6 +848,15 @@ def test_steady_state_newton_with_device_assembly(root, tmp_path, built_lib):
     assert np.isclose(U0.max(), 1.1921615450014942, rtol=1e-9) and np.isclose(U0.mean(), 0.336746427968607, rtol=1e-9)  # test_cylinder.py:66-67
     UP0 = np.load(root / "tests/golden/cylinder_baseflow.npz")["UP0"]
     assert rel(fs.fields.UP0.vector().get_local(), UP0) < 1e-9
+    # lid-driven cavity Re=1000 (enclosed flow, pinned pressure; 40 Picard iterations as tests/integration/test_lidcavity.py)
+    from flowcontrol_b200.examples.lidcavity import LidCavityFlowSolver
+
+    fl = LidCavityFlowSolver.make_default(Re=1000, path_out=tmp_path / "lid")
+    fl.compute_steady_state(method="picard", max_iter=40, tol=1e-7, u_ctrl=[0.0], assembly="device")
+    L0 = np.load(root / "tests/golden/lidcavity_baseflow.npz")["UP0"]
+    Nv = fl.tables.Nv
+    assert rel(fl.fields.UP0.vector().get_local()[:Nv], L0[:Nv]) < 1e-9
+    assert np.isclose(fl.fields.U0.vector().get_local().mean(), 0.0020234251738529907, rtol=1e-6)  # test_lidcavity.py:48
 
 
 def test_run_loops_chunked_series_open_loop_and_controller_state(root, cyl, monkeypatch):
