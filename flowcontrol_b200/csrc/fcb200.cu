@@ -1313,6 +1313,191 @@ __global__ void __launch_bounds__(128) k_assemble_advection(int c0, int ncell, c
     }
 }
 
+
+// ----------------------------------------------------------------------------------------------
+// Numeric multifrontal factorisation (setup): fronts are dense (w+m) x (w+m) matrices, row-major, leading dimension w+m,
+// all in one workspace; a level of the elimination tree (fronts of equal height) is one launch of each kernel.
+//   k_ff_assemble  F = entries of the sparse matrix + Schur complements of the children (extend-add, children in order)
+//   k_ff_invert    F11 <- F11^-1 in place (Gauss-Jordan, partial pivoting), copy to the output, growth estimate
+//   k_ff_gemm      mode 0: E = F21 F11^-1   mode 1: G = F11^-1 F12   mode 2: F22 -= E F12   (32 x 32 tiles, FP64 FMA)
+// ----------------------------------------------------------------------------------------------
+struct FrontDesc {
+    long long foff, eoff, ioff;  // workspace / E,G output / F11^-1 output offsets (doubles)
+    int w, m;
+};
+
+// grid = fronts of the level, block = 512
+__global__ void __launch_bounds__(512) k_ff_assemble(const int* __restrict__ fronts, const FrontDesc* __restrict__ fd, const long long* __restrict__ a_ptr,
+                                                    const int* __restrict__ a_src, const int* __restrict__ a_dst, const double* __restrict__ avals,
+                                                    const long long* __restrict__ c_ptr, const int* __restrict__ c_front,
+                                                    const long long* __restrict__ c_lptr, const int* __restrict__ c_loc, double* __restrict__ W) {
+    const int f = fronts[blockIdx.x];
+    const FrontDesc d = fd[f];
+    const int s = d.w + d.m;
+    double* F = W + d.foff;
+    for (long long k = a_ptr[f] + threadIdx.x; k < a_ptr[f + 1]; k += blockDim.x) F[a_dst[k]] = avals[a_src[k]];
+    for (long long c = c_ptr[f]; c < c_ptr[f + 1]; ++c) {
+        __syncthreads();  // children one after the other: a fixed summation order for the entries two children share
+        const FrontDesc dc = fd[c_front[c]];
+        const int sc = dc.w + dc.m, mc = dc.m;
+        const double* CB = W + dc.foff + (size_t)dc.w * sc + dc.w;  // Schur complement of the child (its F22 after elimination)
+        const int* loc = c_loc + c_lptr[c];
+        for (long long t = threadIdx.x; t < (long long)mc * mc; t += blockDim.x) {
+            const int i = (int)(t / mc), j = (int)(t - (long long)i * mc);
+            F[(size_t)loc[i] * s + loc[j]] += CB[(size_t)i * sc + j];
+        }
+    }
+}
+
+// grid = fronts of the level, block = 512; dynamic shared memory: w ints (pivot rows)
+__global__ void __launch_bounds__(512) k_ff_invert(const int* __restrict__ fronts, const FrontDesc* __restrict__ fd, double* __restrict__ W,
+                                                  double* __restrict__ Finv, double* __restrict__ growth) {
+    extern __shared__ int piv[];
+    __shared__ double red_v[16];
+    __shared__ int red_i[16];
+    __shared__ double s_scale;
+    const int f = fronts[blockIdx.x];
+    const FrontDesc d = fd[f];
+    const int w = d.w, s = d.w + d.m, tid = threadIdx.x, nt = blockDim.x;
+    double* A = W + d.foff;  // F11 = rows / columns [0, w), leading dimension s
+    // max |F11| (growth estimate)
+    double mx = 0.0;
+    for (int t = tid; t < w * w; t += nt) mx = fmax(mx, fabs(A[(size_t)(t / w) * s + (t % w)]));
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((tid & 31) == 0) red_v[tid >> 5] = mx;
+    __syncthreads();
+    if (tid == 0) {
+        double v = 0.0;
+        for (int k = 0; k < nt / 32; ++k) v = fmax(v, red_v[k]);
+        s_scale = v;
+    }
+    __syncthreads();
+    for (int k = 0; k < w; ++k) {
+        // pivot: largest |A[i][k]|, i >= k (ties: the smallest row, deterministic)
+        double bv = -1.0;
+        int bi = k;
+        for (int i = k + tid; i < w; i += nt) {
+            const double v = fabs(A[(size_t)i * s + k]);
+            if (v > bv) { bv = v; bi = i; }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if ((tid & 31) == 0) { red_v[tid >> 5] = bv; red_i[tid >> 5] = bi; }
+        __syncthreads();
+        if (tid == 0) {
+            double v = red_v[0];
+            int ix = red_i[0];
+            for (int q = 1; q < nt / 32; ++q)
+                if (red_v[q] > v || (red_v[q] == v && red_i[q] < ix)) { v = red_v[q]; ix = red_i[q]; }
+            piv[k] = ix;
+        }
+        __syncthreads();
+        const int p = piv[k];
+        if (p != k)
+            for (int j = tid; j < w; j += nt) {
+                const double t0 = A[(size_t)k * s + j];
+                A[(size_t)k * s + j] = A[(size_t)p * s + j];
+                A[(size_t)p * s + j] = t0;
+            }
+        __syncthreads();
+        const double pinv = 1.0 / A[(size_t)k * s + k];
+        __syncthreads();
+        // row k: the pivot column becomes the unit vector's image
+        for (int j = tid; j < w; j += nt) A[(size_t)k * s + j] = (j == k ? 1.0 : A[(size_t)k * s + j]) * pinv;
+        __syncthreads();
+        // every other row i: A[i][:] -= A[i][k] * row k, with A[i][k] replaced by 0 first
+        for (int i = tid >> 5; i < w; i += nt >> 5) {
+            if (i == k) continue;
+            const double fk = A[(size_t)i * s + k];
+            __syncwarp();
+            for (int j = tid & 31; j < w; j += 32) {
+                const double rk = A[(size_t)k * s + j];
+                const double v = (j == k ? 0.0 : A[(size_t)i * s + j]);
+                A[(size_t)i * s + j] = fma(-fk, rk, v);
+            }
+        }
+        __syncthreads();
+    }
+    // undo the row exchanges as column exchanges, last first
+    for (int k = w - 1; k >= 0; --k) {
+        const int p = piv[k];
+        if (p != k)
+            for (int i = tid; i < w; i += nt) {
+                const double t0 = A[(size_t)i * s + k];
+                A[(size_t)i * s + k] = A[(size_t)i * s + p];
+                A[(size_t)i * s + p] = t0;
+            }
+        __syncthreads();
+    }
+    double mi = 0.0;
+    double* out = Finv + d.ioff;
+    for (int t = tid; t < w * w; t += nt) {
+        const double v = A[(size_t)(t / w) * s + (t % w)];
+        out[t] = v;
+        mi = isfinite(v) ? fmax(mi, fabs(v)) : INFINITY;  // a NaN / Inf anywhere flags the front as singular
+    }
+    for (int o = 16; o > 0; o >>= 1) mi = fmax(mi, __shfl_xor_sync(0xffffffffu, mi, o));
+    __syncthreads();
+    if ((tid & 31) == 0) red_v[tid >> 5] = mi;
+    __syncthreads();
+    if (tid == 0) {
+        double v = 0.0;
+        for (int k = 0; k < nt / 32; ++k) v = fmax(v, red_v[k]);
+        growth[f] = (w > 0) ? (isfinite(v) ? v * s_scale : INFINITY) : 0.0;
+    }
+}
+
+// grid = (fronts of the level, tiles); block = (16, 16), each thread 2 x 2 outputs of a 32 x 32 tile
+__global__ void __launch_bounds__(256) k_ff_gemm(int mode, const int* __restrict__ fronts, const FrontDesc* __restrict__ fd, double* __restrict__ W,
+                                                double* __restrict__ Eo, double* __restrict__ Go) {
+    __shared__ double As[32][33], Bs[32][33];
+    const int f = fronts[blockIdx.x];
+    const FrontDesc d = fd[f];
+    const int w = d.w, m = d.m, s = w + m;
+    double* F = W + d.foff;
+    // C [M x N] = (or -=) A [M x K] B [K x N]
+    int M, N, K, lda, ldb, ldc;
+    const double *A, *B;
+    double* Cc;
+    if (mode == 0)      { M = m; N = w; K = w; A = F + (size_t)w * s; lda = s; B = F; ldb = s; Cc = Eo + d.eoff; ldc = w; }
+    else if (mode == 1) { M = w; N = m; K = w; A = F; lda = s; B = F + w; ldb = s; Cc = Go + d.eoff; ldc = m; }
+    else                { M = m; N = m; K = w; A = Eo + d.eoff; lda = w; B = F + w; ldb = s; Cc = F + (size_t)w * s + w; ldc = s; }
+    const int tn = (N + 31) / 32, tm = (M + 31) / 32;
+    for (int tile = blockIdx.y; tile < tm * tn; tile += gridDim.y) {
+        const int r0 = (tile / tn) * 32, c0 = (tile % tn) * 32;
+        const int tx = threadIdx.x, ty = threadIdx.y;
+        double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+        for (int k0 = 0; k0 < K; k0 += 32) {
+            for (int q = ty; q < 32; q += 16)
+                for (int r = tx; r < 32; r += 16) {
+                    As[q][r] = (r0 + q < M && k0 + r < K) ? A[(size_t)(r0 + q) * lda + k0 + r] : 0.0;
+                    Bs[q][r] = (k0 + q < K && c0 + r < N) ? B[(size_t)(k0 + q) * ldb + c0 + r] : 0.0;
+                }
+            __syncthreads();
+#pragma unroll 8
+            for (int kk = 0; kk < 32; ++kk) {
+                const double a0 = As[ty][kk], a1 = As[ty + 16][kk], b0 = Bs[kk][tx], b1 = Bs[kk][tx + 16];
+                acc[0][0] = fma(a0, b0, acc[0][0]); acc[0][1] = fma(a0, b1, acc[0][1]);
+                acc[1][0] = fma(a1, b0, acc[1][0]); acc[1][1] = fma(a1, b1, acc[1][1]);
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int r = r0 + ty + 16 * i, c = c0 + tx + 16 * j;
+                if (r < M && c < N) {
+                    double* o = Cc + (size_t)r * ldc + c;
+                    *o = (mode == 2) ? *o - acc[i][j] : acc[i][j];
+                }
+            }
+    }
+}
+
 // sensors + energy.  grid = ldb/32, block = (32, MEAS_WARPS)
 constexpr int MEAS_WARPS = 32;
 __global__ void __launch_bounds__(32 * MEAS_WARPS) k_measure(int ns, const int* __restrict__ sptr, const int* __restrict__ sidx,
@@ -3309,6 +3494,113 @@ int fcb_assemble_advection(const fcb_assembly* m, int32_t B, int32_t device, con
     CKA(cudaDeviceSynchronize());
     for (void* q_ : bufs) cudaFree(q_);
 #undef CKA
+    return FCB_OK;
+}
+
+
+int fcb_factorize(const fcb_symbolic* sy, int32_t device, const double* avals, int64_t nnz, double* E, double* Finv, double* G, double* growth) {
+    fcb_context* h = nullptr;  // errors go to fcb_last_error(NULL)
+    if (!sy || !avals || !E || !Finv || !G || !growth || nnz < 0) return fail(h, FCB_ERR_INVALID, "fcb_factorize: bad arguments");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(h, FCB_ERR_NO_DEVICE, "fcb_factorize: no CUDA device available (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(h, FCB_ERR_INVALID, "fcb_factorize: device %d out of range", device);
+    const int nf = sy->nfront;
+    if (nf <= 0 || sy->nlevel <= 0 || !sy->w || !sy->m || !sy->level_ptr || !sy->level_fronts || !sy->a_ptr || !sy->c_ptr || !sy->c_lptr)
+        return fail(h, FCB_ERR_INVALID, "fcb_factorize: incomplete symbolic structure");
+    if (sy->level_ptr[0] != 0 || sy->level_ptr[sy->nlevel] != nf) return fail(h, FCB_ERR_INVALID, "fcb_factorize: level_ptr must cover every front");
+    std::vector<FrontDesc> fd((size_t)nf);
+    long long foff = 0, eoff = 0, ioff = 0;
+    int wmax = 0;
+    for (int f = 0; f < nf; ++f) {
+        const int w = sy->w[f], m = sy->m[f];
+        if (w < 0 || m < 0) return fail(h, FCB_ERR_INVALID, "fcb_factorize: negative front size");
+        fd[f] = {foff, eoff, ioff, w, m};
+        foff += (long long)(w + m) * (w + m);
+        eoff += (long long)m * w;
+        ioff += (long long)w * w;
+        wmax = std::max(wmax, w);
+        for (long long k = sy->a_ptr[f]; k < sy->a_ptr[f + 1]; ++k)
+            if (sy->a_src[k] < 0 || sy->a_src[k] >= nnz || sy->a_dst[k] < 0 || sy->a_dst[k] >= (long long)(w + m) * (w + m))
+                return fail(h, FCB_ERR_INVALID, "fcb_factorize: matrix entry map of front %d out of range", f);
+        for (long long c = sy->c_ptr[f]; c < sy->c_ptr[f + 1]; ++c) {
+            const int ch = sy->c_front[c];
+            if (ch < 0 || ch >= nf || sy->c_lptr[c + 1] - sy->c_lptr[c] != sy->m[ch]) return fail(h, FCB_ERR_INVALID, "fcb_factorize: child list of front %d is malformed", f);
+            for (long long t = sy->c_lptr[c]; t < sy->c_lptr[c + 1]; ++t)
+                if (sy->c_loc[t] < 0 || sy->c_loc[t] >= w + m) return fail(h, FCB_ERR_INVALID, "fcb_factorize: extend-add map of front %d out of range", f);
+        }
+    }
+    {   // children must sit in earlier levels
+        std::vector<int> level_of((size_t)nf, -1);
+        for (int l = 0; l < sy->nlevel; ++l)
+            for (int k = sy->level_ptr[l]; k < sy->level_ptr[l + 1]; ++k) {
+                const int f = sy->level_fronts[k];
+                if (f < 0 || f >= nf || level_of[f] >= 0) return fail(h, FCB_ERR_INVALID, "fcb_factorize: level_fronts is not a permutation");
+                level_of[f] = l;
+            }
+        for (int f = 0; f < nf; ++f)
+            for (long long c = sy->c_ptr[f]; c < sy->c_ptr[f + 1]; ++c)
+                if (level_of[sy->c_front[c]] >= level_of[f]) return fail(h, FCB_ERR_INVALID, "fcb_factorize: a child of front %d is not in an earlier level", f);
+    }
+    std::vector<void*> bufs;
+#define CKF(call)                                                                                                        \
+    do {                                                                                                                 \
+        cudaError_t e_ = (call);                                                                                         \
+        if (e_ != cudaSuccess) {                                                                                         \
+            for (void* q_ : bufs) cudaFree(q_);                                                                          \
+            return fail(h, FCB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);     \
+        }                                                                                                                \
+    } while (0)
+    CKF(cudaSetDevice(device));
+    auto dev_copy = [&](void** p, const void* src, size_t bytes) {
+        cudaError_t e = cudaMalloc(p, std::max<size_t>(bytes, 16));
+        if (e != cudaSuccess) return e;
+        bufs.push_back(*p);
+        return src ? cudaMemcpy(*p, src, bytes, cudaMemcpyDefault) : cudaMemset(*p, 0, std::max<size_t>(bytes, 16));
+    };
+    const long long nch = sy->c_ptr[nf];
+    int *d_fronts, *d_asrc, *d_adst, *d_cfront, *d_cloc;
+    long long *d_aptr, *d_cptr, *d_clptr;
+    FrontDesc* d_fd;
+    double *d_av, *d_W, *d_E, *d_I, *d_G, *d_gr;
+    CKF(dev_copy((void**)&d_fronts, sy->level_fronts, (size_t)nf * 4));
+    CKF(dev_copy((void**)&d_fd, fd.data(), (size_t)nf * sizeof(FrontDesc)));
+    CKF(dev_copy((void**)&d_aptr, sy->a_ptr, (size_t)(nf + 1) * 8));
+    CKF(dev_copy((void**)&d_asrc, sy->a_src, (size_t)sy->a_ptr[nf] * 4));
+    CKF(dev_copy((void**)&d_adst, sy->a_dst, (size_t)sy->a_ptr[nf] * 4));
+    CKF(dev_copy((void**)&d_cptr, sy->c_ptr, (size_t)(nf + 1) * 8));
+    CKF(dev_copy((void**)&d_cfront, sy->c_front, (size_t)nch * 4));
+    CKF(dev_copy((void**)&d_clptr, sy->c_lptr, (size_t)(nch + 1) * 8));
+    CKF(dev_copy((void**)&d_cloc, sy->c_loc, (size_t)sy->c_lptr[nch] * 4));
+    CKF(dev_copy((void**)&d_av, avals, (size_t)nnz * 8));
+    CKF(dev_copy((void**)&d_W, nullptr, (size_t)foff * 8));
+    CKF(dev_copy((void**)&d_E, nullptr, (size_t)eoff * 8));
+    CKF(dev_copy((void**)&d_G, nullptr, (size_t)eoff * 8));
+    CKF(dev_copy((void**)&d_I, nullptr, (size_t)ioff * 8));
+    CKF(dev_copy((void**)&d_gr, nullptr, (size_t)nf * 8));
+    for (int l = 0; l < sy->nlevel; ++l) {
+        const int k0 = sy->level_ptr[l], nl = sy->level_ptr[l + 1] - k0;
+        if (nl <= 0) continue;
+        int tiles = 1;
+        for (int k = k0; k < k0 + nl; ++k) {
+            const int f = sy->level_fronts[k], w = sy->w[f], m = sy->m[f];
+            tiles = std::max(tiles, ((std::max(w, m) + 31) / 32) * ((std::max(w, m) + 31) / 32));
+        }
+        tiles = std::min(tiles, 1024);
+        k_ff_assemble<<<nl, 512>>>(d_fronts + k0, d_fd, d_aptr, d_asrc, d_adst, d_av, d_cptr, d_cfront, d_clptr, d_cloc, d_W);
+        k_ff_invert<<<nl, 512, (size_t)std::max(wmax, 1) * sizeof(int)>>>(d_fronts + k0, d_fd, d_W, d_I, d_gr);
+        k_ff_gemm<<<dim3(nl, tiles), dim3(16, 16)>>>(0, d_fronts + k0, d_fd, d_W, d_E, d_G);
+        k_ff_gemm<<<dim3(nl, tiles), dim3(16, 16)>>>(1, d_fronts + k0, d_fd, d_W, d_E, d_G);
+        k_ff_gemm<<<dim3(nl, tiles), dim3(16, 16)>>>(2, d_fronts + k0, d_fd, d_W, d_E, d_G);
+        CKF(cudaGetLastError());
+    }
+    CKF(cudaMemcpy(E, d_E, (size_t)eoff * 8, cudaMemcpyDefault));
+    CKF(cudaMemcpy(G, d_G, (size_t)eoff * 8, cudaMemcpyDefault));
+    CKF(cudaMemcpy(Finv, d_I, (size_t)ioff * 8, cudaMemcpyDefault));
+    CKF(cudaMemcpy(growth, d_gr, (size_t)nf * 8, cudaMemcpyDefault));
+    CKF(cudaDeviceSynchronize());
+    for (void* q_ : bufs) cudaFree(q_);
+#undef CKF
     return FCB_OK;
 }
 

@@ -209,8 +209,9 @@ class FlowSolver(ABC):
         return f
 
     def compute_steady_state(self, u_ctrl: list, method: str = "newton", initial_guess: Field | None = None,
-                             max_iter: int = 10, assembly: str = "host", **kwargs) -> None:
-        """``assembly="device"`` assembles the Newton / Picard matrices on the GPU (assembly.py, fcb_assemble_advection)."""
+                             max_iter: int = 10, assembly: str = "host", factor: str = "host", **kwargs) -> None:
+        """``assembly="device"`` assembles the Newton / Picard matrices on the GPU (assembly.py, fcb_assemble_advection);
+        ``factor="device"`` factorises every iterate on the GPU (devfactor.py, fcb_factorize)."""
         self.set_actuators_u_ctrl(u_ctrl)
         tab = self.tables
         extra = [tab.Nv] if self._pin_pressure() else []
@@ -223,7 +224,8 @@ class FlowSolver(ABC):
 
             assembler = DeviceAdvectionAssembler(tab, self.blocks, device=self.params_ensemble.device)
         ss = SteadyStateSolver(tab, self.blocks, self.params_flow.Re, dset, force=self._force_vector(u_ctrl),
-                               verbose=bool(self.verbose), assembler=assembler)
+                               verbose=bool(self.verbose), assembler=assembler, factor=factor, device=self.params_ensemble.device,
+                               leaf_cells=self.params_ensemble.leaf_cells)
         UP = self._define_initial_guess(initial_guess)
         if method == "newton":
             UP = ss.newton(UP, u_ctrl, max_iter=max_iter, **kwargs)
@@ -285,7 +287,7 @@ class FlowSolver(ABC):
             self.tables, self.blocks, self.params_flow.Re, self.params_time.dt, self.bc.bcu,
             self.params_control.actuator_list, self.params_control.sensor_list, self.fields.UP0.array,
             nonlinear=self.params_solver.is_eq_nonlinear, shift=self.params_solver.shift,
-            pin_pressure=self._pin_pressure(), leaf_cells=pe.leaf_cells, top_levels=pe.top_levels,
+            pin_pressure=self._pin_pressure(), leaf_cells=pe.leaf_cells, top_levels=pe.top_levels, factor_device=pe.device,
             time_scheme=self.params_solver.time_scheme,
         )
 

@@ -62,6 +62,15 @@ class fcb_assembly(C.Structure):
     ]
 
 
+class fcb_symbolic(C.Structure):
+    _fields_ = [
+        ("nfront", C.c_int32), ("w", c_i32p), ("m", c_i32p),
+        ("nlevel", C.c_int32), ("level_ptr", c_i32p), ("level_fronts", c_i32p),
+        ("a_ptr", c_i64p), ("a_src", c_i32p), ("a_dst", c_i32p),
+        ("c_ptr", c_i64p), ("c_front", c_i32p), ("c_lptr", c_i64p), ("c_loc", c_i32p),
+    ]
+
+
 class fcb_controllers(C.Structure):
     _fields_ = [
         ("nx", C.c_int32), ("ny", C.c_int32), ("nu", C.c_int32),
@@ -87,6 +96,7 @@ EXPORTS = {
     "fcb_get_controller_state": (C.c_int, [C.c_void_p, C.c_void_p]),
     "fcb_get_costs": (C.c_int, [C.c_void_p, C.c_void_p]),
     "fcb_assemble_advection": (C.c_int, [C.POINTER(fcb_assembly), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fcb_factorize": (C.c_int, [C.POINTER(fcb_symbolic), C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fcb_profile_step": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "fcb_launch_count": (C.c_int64, [C.c_void_p]),
     "fcb_stream": (C.c_void_p, [C.c_void_p]),

@@ -118,6 +118,7 @@ class FlowProblem:
         cluster_rows: int | None = None,
         cluster_height: int | None = None,
         amalgamate_above: int | None = None,
+        factor_device: int | None = None,
         time_scheme: str = "bdf",
         symbolic: SymbolicFactor | None = None,
     ):
@@ -176,7 +177,13 @@ class FlowProblem:
                 half_force = 0.5
                 self.ctrl_rhs_prev = np.ascontiguousarray((0.5 * force)[:, self.sym.perm])
             self.A_raw[order] = A
-            fac = BlockFactor(self.sym, A)
+            if factor_device is None:
+                fac = BlockFactor(self.sym, A)
+            else:  # numeric factorisation on the GPU (devfactor.py); the index maps are shared by the BDF1 / BDF2 matrices
+                from .devfactor import DeviceBlockFactor
+
+                fac = DeviceBlockFactor(self.sym, A, maps=getattr(self, "_front_maps", None), device=factor_device)
+                self._front_maps = fac.maps
             self.factors[order] = fac
             # shared-memory subtree clusters of the GPU solve (k_cluster_sweep): OFF by default -- measured on B200 they cut
             # the sweeps' DRAM traffic (bottom four forward levels 500 -> 200 MB) but run slower than the pull-form launches

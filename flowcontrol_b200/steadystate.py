@@ -4,8 +4,9 @@ Restates /root/reference/src/flowcontrol/steadystate.py:60-159 (Newton through
 ``dolfin.solve(F == 0, ...)`` with dolfin's NewtonSolver defaults, hand-rolled
 Picard loop) on the scalar blocks of fem.py with SciPy's SuperLU as the direct
 solver.  Not on the per-step hot path.  SURVEY.md section 8(f) row f1: the iteration matrices can be assembled on the GPU
-(``assembler=DeviceAdvectionAssembler(...)``: per-element matrices scattered into CSR through a position map, coloured);
-the factorisation of each iterate stays on the host.
+(``assembler=DeviceAdvectionAssembler(...)``: per-element matrices scattered into CSR through a position map, coloured)
+and factorised on the GPU (``factor="device"``: devfactor.DeviceBlockFactor, multifrontal fronts inverted and multiplied
+by hand-written kernels); the two triangular sweeps per iterate (one right-hand side) run on the host from those blocks.
 """
 
 from __future__ import annotations
@@ -31,14 +32,43 @@ def _constrain_rows(A: sp.csr_matrix, dofs: np.ndarray) -> sp.csc_matrix:
 
 class SteadyStateSolver:
     def __init__(self, tab: TaylorHoodTables, blocks: ScalarBlocks, Re: float, dirichlet: DirichletSet,
-                 force: np.ndarray | None = None, verbose: bool = False, assembler=None):
+                 force: np.ndarray | None = None, verbose: bool = False, assembler=None, factor: str = "host", device: int = 0,
+                 leaf_cells: int = 16):
         """``assembler``: an object with ``saddle_point(c, Re, U, linearised=...)`` that assembles the iteration matrix;
-        None = the host blocks (fem.py), a ``DeviceAdvectionAssembler`` (assembly.py) = element matrices on the GPU."""
+        None = the host blocks (fem.py), a ``DeviceAdvectionAssembler`` (assembly.py) = element matrices on the GPU.
+        ``factor``: "host" = SuperLU on the row-constrained matrix; "device" = multifrontal factorisation of the free-free
+        block on the GPU (devfactor.py; the Dirichlet unknowns are eliminated with their prescribed values, which is the
+        same linear system)."""
         self.tab, self.blocks, self.Re, self.dirichlet = tab, blocks, Re, dirichlet
         self.asm = assembler if assembler is not None else blocks
+        if factor not in ("host", "device"):
+            raise ValueError(f"factor must be 'host' or 'device', got {factor!r}")
+        self.factor, self.device = factor, int(device)
+        self._sym = self._maps = None
+        self._leaf_cells = leaf_cells
         self.force = np.zeros(tab.Nv) if force is None else force
         self.verbose = verbose
         self._Kv = sp.block_diag([blocks.K, blocks.K], format="csr")
+
+    def _solve(self, A: sp.csr_matrix, b: np.ndarray, dofs: np.ndarray) -> np.ndarray:
+        """Solve the system whose rows ``dofs`` are replaced by identity rows (x[dofs] = b[dofs])."""
+        if self.factor == "host":
+            return spla.splu(_constrain_rows(A, dofs)).solve(b)
+        from .devfactor import DeviceBlockFactor
+        from .multifrontal import SymbolicFactor
+
+        if self._sym is None:
+            self._sym = SymbolicFactor(self.tab, self.dirichlet.free, leaf_cells=self._leaf_cells)
+        perm = self._sym.perm
+        A = sp.csr_matrix(A)
+        xc = b[dofs]
+        rhs = (b - A[:, dofs] @ xc)[perm]
+        fac = DeviceBlockFactor(self._sym, A, maps=self._maps, device=self.device)
+        self._maps = fac.maps  # same sparsity in the next iteration: only the values are uploaded again
+        x = np.empty_like(b)
+        x[dofs] = xc
+        x[perm] = fac.solve(rhs)
+        return x
 
     def picard(self, UP0: np.ndarray, u_ctrl, max_iter: int = 10, tol: float = 1e-8) -> np.ndarray:
         """Fixed-point iteration with the advection velocity frozen at the previous
@@ -51,7 +81,7 @@ class SteadyStateSolver:
         UP = np.array(UP0, dtype=np.float64)
         for i in range(max_iter):
             A = self.asm.saddle_point(0.0, self.Re, UP[: tab.Nv], linearised=False)
-            UP1 = spla.splu(_constrain_rows(A, dofs)).solve(b)
+            UP1 = self._solve(A, b, dofs)
             rel = np.linalg.norm(UP1 - UP) / (np.linalg.norm(UP) + 1e-14)
             UP = UP1
             logger.info("Picard %d/%d  rel_err = %.3e", i + 1, max_iter, rel)
@@ -86,5 +116,5 @@ class SteadyStateSolver:
             if it == max_iter:
                 break
             J = self.asm.saddle_point(0.0, self.Re, UP[: tab.Nv], linearised=True)
-            UP = UP - spla.splu(_constrain_rows(J, dofs)).solve(b)
+            UP = UP - self._solve(J, b, dofs)
         raise RuntimeError("Newton solver did not converge")

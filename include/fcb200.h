@@ -236,6 +236,34 @@ typedef struct fcb_assembly {
  * device pointers. */
 int fcb_assemble_advection(const fcb_assembly* m, int32_t B, int32_t device, const double* U, double* C, double* D);
 
+/* Symbolic side of the numeric multifrontal factorisation (flowcontrol_b200/devfactor.py: FrontMaps): the fronts of the
+ * elimination tree (w own unknowns, m boundary rows; a front is the dense (w+m) x (w+m) matrix over [own | boundary]),
+ * grouped in levels (children before parents), where the entries of the sparse matrix go, and where the boundary rows of
+ * every child sit in its parent's front. */
+typedef struct fcb_symbolic {
+    int32_t nfront;
+    const int32_t* w;            /* [nfront] */
+    const int32_t* m;            /* [nfront] */
+    int32_t nlevel;
+    const int32_t* level_ptr;    /* [nlevel+1] ranges of level_fronts */
+    const int32_t* level_fronts; /* [nfront] fronts, level by level */
+    const int64_t* a_ptr;        /* [nfront+1] ranges of a_src / a_dst */
+    const int32_t* a_src;        /* index into the CSR value array */
+    const int32_t* a_dst;        /* row * (w+m) + column inside the front */
+    const int64_t* c_ptr;        /* [nfront+1] ranges of c_front */
+    const int32_t* c_front;      /* children */
+    const int64_t* c_lptr;       /* [number of children + 1] ranges of c_loc */
+    const int32_t* c_loc;        /* position of each boundary row of the child in the parent's front */
+} fcb_symbolic;
+
+/* Numeric multifrontal factorisation on the GPU: for every front, F11^-1 (w x w, Gauss-Jordan with partial pivoting),
+ * E = F21 F11^-1 (m x w), G = F11^-1 F12 (w x m), all row-major and concatenated front by front, plus growth[nfront] =
+ * max|F11^-1| max|F11| (singularity check).  avals [nnz]: values of the permuted matrix in CSR order.  Replaces the numeric
+ * phase of MUMPS behind dolfin.LUSolver.set_operator / dolfin.solve (src/flowcontrol/flowsolver.py:694-697,
+ * steadystate.py:95, 142-144).  Stateless; host or device pointers. */
+int fcb_factorize(const fcb_symbolic* s, int32_t device, const double* avals, int64_t nnz, double* E, double* Finv, double* G,
+                  double* growth);
+
 /* Runs one step with CUDA events between phases; ms[FCB_NPHASES] receives device times,
  * launches[FCB_NPHASES] (may be NULL) the kernel launches per phase. */
 int fcb_profile_step(fcb_handle h, const double* u_ctrl, float* ms, int32_t* launches);

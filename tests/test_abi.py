@@ -32,7 +32,7 @@ def test_struct_layout_matches_header(root):
 
     from flowcontrol_b200 import libfcb
 
-    src = '#include <stdio.h>\n#include "fcb200.h"\nint main(){printf("%zu %zu %zu %zu\\n", sizeof(fcb_plan), sizeof(fcb_problem), sizeof(fcb_controllers), sizeof(fcb_assembly));return 0;}\n'
+    src = '#include <stdio.h>\n#include "fcb200.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n", sizeof(fcb_plan), sizeof(fcb_problem), sizeof(fcb_controllers), sizeof(fcb_assembly), sizeof(fcb_symbolic));return 0;}\n'
     with tempfile.TemporaryDirectory() as d:
         c = Path(d) / "s.c"
         c.write_text(src)
@@ -40,7 +40,7 @@ def test_struct_layout_matches_header(root):
         subprocess.run(["gcc", f"-I{root / 'include'}", str(c), "-o", str(exe)], check=True)
         sizes = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     assert sizes == [ctypes.sizeof(libfcb.fcb_plan), ctypes.sizeof(libfcb.fcb_problem), ctypes.sizeof(libfcb.fcb_controllers),
-                     ctypes.sizeof(libfcb.fcb_assembly)]
+                     ctypes.sizeof(libfcb.fcb_assembly), ctypes.sizeof(libfcb.fcb_symbolic)]
 
 
 def test_no_cpu_fallback(built_lib):

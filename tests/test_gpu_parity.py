@@ -917,3 +917,81 @@ def test_run_loops_chunked_series_open_loop_and_controller_state(root, cyl, monk
     assert np.array_equal(eo.fields(0), eh.fields(0))
     eo.close()
     eh.close()
+
+
+def test_device_factorisation_matches_host_blocks_and_drives_the_step(root, built_lib):
+    """fcb_factorize (k_ff_assemble / k_ff_invert / k_ff_gemm: multifrontal fronts assembled, inverted with partial pivoting
+    and multiplied on the GPU) gives the blocks of the host factorisation (multifrontal.BlockFactor, LAPACK) to round-off,
+    flags a singular matrix, and a FlowProblem factorised on the device steps like the oracle."""
+    import tempfile
+    from pathlib import Path
+
+    import scipy.sparse as sp
+
+    from flowcontrol_b200.devfactor import DeviceBlockFactor, FrontMaps
+    from flowcontrol_b200.ensemble import Ensemble
+    from flowcontrol_b200.examples import lidcavity as ex
+    from flowcontrol_b200.flowfield import Field
+    from flowcontrol_b200.multifrontal import BlockFactor
+    from flowcontrol_b200.problem import FlowProblem
+
+    UP0 = np.load(root / "tests/golden/lidcavity_baseflow.npz")["UP0"]
+    fs = ex.LidCavityFlowSolver.make_default(Re=1000.0, path_out=Path(tempfile.mkdtemp()))
+    tab = fs.tables
+    fs._assign_steady_state(Field(UP0[: tab.Nv]), Field(UP0[tab.Nv :]))
+    kw = dict(pin_pressure=True)
+    prob_h = FlowProblem(tab, fs.blocks, 1000.0, 0.005, fs.bc.bcu, fs.params_control.actuator_list, fs.params_control.sensor_list, UP0, **kw)
+    prob_d = FlowProblem(tab, fs.blocks, 1000.0, 0.005, fs.bc.bcu, fs.params_control.actuator_list, fs.params_control.sensor_list, UP0,
+                         symbolic=prob_h.sym, factor_device=0, **kw)
+    for order in (1, 2):
+        worst = 0.0
+        for (E, Fi, G), (E2, Fi2, G2) in zip(prob_h.factors[order].blocks, prob_d.factors[order].blocks):
+            for a, b in ((E, E2), (Fi, Fi2), (G, G2)):
+                if a.size:
+                    worst = max(worst, float(np.abs(a - b).max() / np.abs(a).max()))
+        assert worst < 1e-9, worst
+    rng = np.random.default_rng(2)
+    b = rng.standard_normal(prob_h.sym.n)
+    xh, xd = prob_h.factors[2].solve(b), prob_d.factors[2].solve(b)
+    assert rel(xd, xh) < 1e-11
+    # the maps are reused for a matrix with the same sparsity; a singular matrix is reported
+    A2 = prob_h.A_raw[2]
+    maps = prob_d.factors[2].maps
+    again = DeviceBlockFactor(prob_h.sym, A2, maps=maps)
+    assert again.maps is maps and np.array_equal(again.blocks[0][1], prob_d.factors[2].blocks[0][1])
+    dead = sp.csr_matrix(A2).copy().tolil()
+    r = int(prob_h.sym.perm[0])
+    dead[r, :] = 0.0
+    dead[:, r] = 0.0
+    with pytest.raises(np.linalg.LinAlgError):
+        DeviceBlockFactor(prob_h.sym, dead.tocsr() + 0.0 * sp.csr_matrix(A2), maps=None)
+    # the device-factorised problem steps like the oracle
+    case = cases.lidcavity(1000.0)
+    xy, tri = cases.load_mesh(case.mesh_file)
+    orc = FlowOracle(case, xy, tri)
+    orc.set_base_flow(UP0)
+    orc.init_time_stepping()
+    B = 48
+    ens = Ensemble(prob_d, B)
+    ens.set_state(orc.ic[: tab.Nv], None, orc.ic[tab.Nv :], order=1)
+    for k in range(5):
+        uc = 0.04 * np.cos(0.8 * k)
+        orc.step([uc])
+        ens.step(np.full((1, B), uc))
+        assert np.allclose(ens.y_meas[:, 7], orc.y_meas, rtol=SERIES_TOL, atol=0)
+    assert rel(ens.fields(0)[: tab.Nv, 7], orc.up[: tab.Nv]) < FIELD_TOL
+    ens.close()
+
+
+def test_steady_state_newton_fully_on_device_assembly_and_factorisation(root, tmp_path, built_lib):
+    """Newton / Picard base flow of the cylinder with every iteration matrix assembled AND factorised on
+    the GPU (the two sweeps of the single right-hand side run on the host from the device-computed blocks)."""
+    from flowcontrol_b200.examples.cylinder import CylinderFlowSolver
+
+    fs = CylinderFlowSolver.make_default(Re=100, path_out=tmp_path)
+    fs.compute_steady_state(method="picard", max_iter=3, tol=1e-7, u_ctrl=[0.0, 0.0], assembly="device", factor="device")
+    fs.compute_steady_state(method="newton", max_iter=25, u_ctrl=[0.0, 0.0], initial_guess=fs.fields.UP0, assembly="device", factor="device")
+    U0 = fs.fields.U0.vector().get_local()
+    assert np.isclose(U0.max(), 1.1921615450014942, rtol=1e-9) and np.isclose(U0.mean(), 0.336746427968607, rtol=1e-9)  # test_cylinder.py:66-67
+    UP0 = np.load(root / "tests/golden/cylinder_baseflow.npz")["UP0"]
+    assert rel(fs.fields.UP0.vector().get_local(), UP0) < 1e-9

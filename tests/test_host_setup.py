@@ -350,3 +350,31 @@ def test_assembly_position_map_is_bit_exact(small):
     for c in range(len(cptr) - 1):
         nodes = cn[ccells[cptr[c] : cptr[c + 1]]].ravel()
         assert len(np.unique(nodes)) == len(nodes)
+
+
+def test_front_maps_of_the_device_factorisation_reproduce_the_host_factor(small):
+    """devfactor.FrontMaps (integer maps of the GPU numeric factorisation: matrix entry -> front position, child boundary ->
+    parent front position, levels) drive a numpy emulation of the device algorithm to exactly the host factor's blocks."""
+    import scipy.sparse as sp
+
+    from flowcontrol_b200.devfactor import FrontMaps
+
+    _, _, tab, blocks, _ = small
+    rng = np.random.default_rng(3)
+    U0 = 0.3 * rng.standard_normal(tab.Nv)
+    acts = [ActuatorBCUniformU()]
+    d = DirichletSet(tab, _bcs(acts), acts)
+    A = blocks.saddle_point(300.0, 100.0, U0)
+    for above in (0, 2):
+        sym = SymbolicFactor(tab, d.free, leaf_cells=4, amalgamate_above=above)
+        fac = BlockFactor(sym, A)
+        Ap = sp.csr_matrix(A)[sym.perm][:, sym.perm].tocsr()
+        Ap.sort_indices()
+        maps = FrontMaps(sym, Ap)
+        assert maps.a_ptr[-1] == Ap.nnz and sorted(maps.a_src.tolist()) == list(range(Ap.nnz))  # every entry lands in exactly one front
+        for lv in range(len(maps.level_ptr) - 1):  # children sit in earlier levels
+            lvl = set(maps.level_fronts[maps.level_ptr[lv] : maps.level_ptr[lv + 1]].tolist())
+            for f in lvl:
+                assert not (set(sym.children[f]) & lvl)
+        for (E, Fi, G), (E2, Fi2, G2) in zip(fac.blocks, maps.emulate(Ap.data)):
+            assert np.array_equal(E, E2) and np.array_equal(Fi, Fi2) and np.array_equal(G, G2)
