@@ -100,6 +100,18 @@ class OperatorGetter:
             np.add.at(C[s], idx[ptr[s] : ptr[s + 1]], val[ptr[s] : ptr[s + 1]])
         return C
 
+    def get_frequency_response(self, ww, device: int | None = None, UP0=None):
+        """H(w) = C (jwE - A)^-1 B of the linearised flow (utils/linalg.py:192-240).  ``device=None``: one host sparse LU
+        per frequency (get_frequency_response_sequential); ``device=d``: one multifrontal factorisation per frequency on
+        GPU ``d`` (devfactor.frequency_response_device)."""
+        A, E, B, C = self.get_A(UP0=UP0), self.get_mass_matrix(), self.get_B(UP0=UP0), self.get_C()
+        if device is None:
+            return get_frequency_response_sequential(A, B, C, E, ww)
+        from .devfactor import frequency_response_device
+
+        pe = getattr(self.flowsolver, "params_ensemble", None)
+        return frequency_response_device(A, B, C, E, ww, self.flowsolver.tables, device=device, leaf_cells=getattr(pe, "leaf_cells", 16))
+
     def get_all(self, autodiff: bool = True, u_ctrl=None) -> tuple:
         """(A, E, B, C) in one call (operatorgetter.py:242-267)."""
         return self.get_A(autodiff=autodiff, u_ctrl=u_ctrl), self.get_mass_matrix(), self.get_B(), self.get_C()
