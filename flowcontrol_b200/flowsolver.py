@@ -280,21 +280,23 @@ class FlowSolver(ABC):
         return np.full_like(x, self.params_flow.uinf), np.zeros_like(x)
 
     # ── time stepping ─────────────────────────────────────────────────────────
-    def _make_problem(self) -> FlowProblem:
-        """Host setup of the constant operators (the reference's _prepare_systems, flowsolver.py:665-701)."""
+    def _make_problem(self, factor_device: int | None = None) -> FlowProblem:
+        """Setup of the constant operators (the reference's _prepare_systems, flowsolver.py:665-701).  ``factor_device``: GPU
+        that does the numeric factorisation (the time-stepping path, which needs the GPU anyway); None = host (the
+        ``_make_solver`` hook and other host-side tooling)."""
         pe = self.params_ensemble
         return FlowProblem(
             self.tables, self.blocks, self.params_flow.Re, self.params_time.dt, self.bc.bcu,
             self.params_control.actuator_list, self.params_control.sensor_list, self.fields.UP0.array,
             nonlinear=self.params_solver.is_eq_nonlinear, shift=self.params_solver.shift,
-            pin_pressure=self._pin_pressure(), leaf_cells=pe.leaf_cells, top_levels=pe.top_levels, factor_device=pe.device,
+            pin_pressure=self._pin_pressure(), leaf_cells=pe.leaf_cells, top_levels=pe.top_levels, factor_device=factor_device,
             time_scheme=self.params_solver.time_scheme,
         )
 
     def _build_problem(self) -> None:
         pe = self.params_ensemble
         if self.problem is None:
-            self.problem = self._make_problem()
+            self.problem = self._make_problem(factor_device=pe.device)
         if self.ensemble is not None:
             self.ensemble.close()
         self.ensemble = Ensemble(self.problem, pe.batch, pe.device)
