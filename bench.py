@@ -256,22 +256,28 @@ def controller_bank(prob, lo: int, hi: int, total: int):
 
 
 class HostBank:
-    """Vectorised host-side controller bank for the end-to-end (host buffers) measurement."""
+    """Vectorised host-side controller bank for the end-to-end (host buffers) measurement: u = Cd x + Dd v, x <- Ad x + Bd v
+    for every trajectory (controller.py:157-158, pre-update state in the output) as ONE contraction with the stacked matrix
+    [[Ad, Bd], [Cd, Dd]], stored trajectory-innermost like the bank itself."""
 
     def __init__(self, bank):
-        B = bank.B
-        self.Ad = bank.Ad.T.reshape(B, bank.nx, bank.nx).copy()
-        self.Bd = bank.Bd.T.reshape(B, bank.nx, bank.ny).copy()
-        self.Cd = bank.Cd.T.reshape(B, bank.nu, bank.nx).copy()
-        self.Dd = bank.Dd.T.reshape(B, bank.nu, bank.ny).copy()
-        self.x = bank.x0.T.copy()
+        B, nx, ny, nu = bank.B, bank.nx, bank.ny, bank.nu
+        M = np.zeros((nx + nu, nx + ny, B))  # M[i, j, b]
+        M[:nx, :nx] = bank.Ad.reshape(nx, nx, B)
+        M[:nx, nx:] = bank.Bd.reshape(nx, ny, B)
+        M[nx:, :nx] = bank.Cd.reshape(nu, nx, B)
+        M[nx:, nx:] = bank.Dd.reshape(nu, ny, B)
+        self.T = np.ascontiguousarray(M.transpose(1, 0, 2))  # [j, i, b]
+        self.z = np.zeros((nx + ny, B))
+        self.z[:nx] = bank.x0
+        self.nx = nx
         self.Ky, self.Fu = bank.Ky, bank.Fu
 
     def step(self, y_meas):  # y_meas [ns, B] -> u_ctrl [na, B]
-        v = (self.Ky @ y_meas).T  # [B, ny]
-        u = np.einsum("bij,bj->bi", self.Cd, self.x) + np.einsum("bij,bj->bi", self.Dd, v)
-        self.x = np.einsum("bij,bj->bi", self.Ad, self.x) + np.einsum("bij,bj->bi", self.Bd, v)
-        return np.ascontiguousarray((self.Fu @ u.T))
+        self.z[self.nx :] = self.Ky @ y_meas
+        out = np.einsum("jib,jb->ib", self.T, self.z)
+        self.z[: self.nx] = out[: self.nx]
+        return np.ascontiguousarray(self.Fu @ out[self.nx :])
 
 
 def newest_kernel_summary():

@@ -2491,7 +2491,7 @@ void destroy(fcb_context* h) {
     }
     void* ptrs[] = {h->costs, h->sp_ucols, h->sp_ginfo, h->sp_kslots, h->sp_avals, h->cn_ptr, h->cn_idx, h->cn_val, h->uctrl_prev, h->ccoef_prev, h->crow_prev, h->crow, h->ccoef, h->bc_dofs, h->cell_nodes, h->perm, h->iperm, h->Jinv, h->detJ, h->bc_shape, h->ctrl_rhs[0],
                     h->ctrl_rhs[1], h->sensor_ptr, h->sensor_idx, h->sensor_val, h->up[0], h->up[1], h->avec,
-                    h->bvec[0], h->bvec[1], h->Z, h->epart, h->uctrl, h->y, h->dE, h->diverged, h->Ad, h->Bd, h->Cd,
+                    h->bvec[0], h->bvec[1], h->Z, h->epart, h->uctrl, h->y, h->diverged, h->Ad, h->Bd, h->Cd,
                     h->Dd, h->Ky, h->Fu, h->xk[0], h->xk[1], h->series, h->useries, h->ctl, h->sweep_dbg, h->cl_dbg,
                     h->pcell_ptr, h->pcnode, h->pgeo, h->pnode_ptr, h->pnode_dst, h->mptr, h->msrc, h->mnode, h->plnode, h->pscratch, h->prow, h->mrow, h->psrc, h->pacc_rows};
     for (void* p : ptrs)
@@ -3090,8 +3090,8 @@ int create_impl(fcb_context* h, const fcb_problem* p, int B) {
     TRY(upload<double>(h, &h->epart, nullptr, (size_t)h->nblk_total * L));
     TRY(upload<double>(h, &h->uctrl, nullptr, (size_t)(h->na > 0 ? h->na : 1) * L));
     TRY(upload<double>(h, &h->uctrl_prev, nullptr, (size_t)(h->na > 0 ? h->na : 1) * L));
-    TRY(upload<double>(h, &h->y, nullptr, (size_t)(h->ns > 0 ? h->ns : 1) * L));
-    TRY(upload<double>(h, &h->dE, nullptr, L));
+    TRY(upload<double>(h, &h->y, nullptr, ((size_t)h->ns + 1) * L));  // y rows, then the dE row: one copy brings both back
+    h->dE = h->y + (size_t)h->ns * L;
     TRY(upload<int>(h, &h->diverged, nullptr, L));
     TRY(upload<RunCtl>(h, &h->ctl, nullptr, 1));
     {
@@ -3217,9 +3217,19 @@ int fcb_set_controllers(fcb_handle h, const fcb_controllers* c) {
 // stages them through pinned buffers of the handle instead, so that all transfers are asynchronous and the call
 // synchronises once
 static bool is_pageable_host(const void* p) {
+    // callers pass the same few buffers step after step: remember the last answers (a driver query costs microseconds)
+    struct Seen { const void* p; bool pageable; };
+    static thread_local Seen seen[8] = {};
+    static thread_local int next = 0;
+    for (const Seen& s : seen)
+        if (s.p == p && p) return s.pageable;
     cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return true; }
-    return at.type == cudaMemoryTypeUnregistered;
+    bool pageable = true;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) cudaGetLastError();
+    else pageable = at.type == cudaMemoryTypeUnregistered;
+    seen[next] = {p, pageable};
+    next = (next + 1) % 8;
+    return pageable;
 }
 
 int fcb_step(fcb_handle h, const double* u_ctrl, double* y_meas, double* dE, int32_t* diverged) {
@@ -3243,8 +3253,12 @@ int fcb_step(fcb_handle h, const double* u_ctrl, double* y_meas, double* dE, int
     const bool sy = y_meas && h->ns > 0 && h->pin_out && is_pageable_host(y_meas);
     const bool se = dE && h->pin_out && is_pageable_host(dE);
     const bool sd = diverged && h->pin_out && is_pageable_host(diverged);
-    if (y_meas && h->ns > 0) TRY(copy_out(h, sy ? py : y_meas, h->y, h->ns));
-    if (dE) TRY(copy_out(h, se ? pe : dE, h->dE, 1));
+    if (sy && se) {
+        TRY(copy_out(h, py, h->y, h->ns + 1));  // y rows and the dE row are adjacent on both sides: one copy
+    } else {
+        if (y_meas && h->ns > 0) TRY(copy_out(h, sy ? py : y_meas, h->y, h->ns));
+        if (dE) TRY(copy_out(h, se ? pe : dE, h->dE, 1));
+    }
     if (diverged) TRY(copy_out(h, sd ? pd : diverged, h->diverged, 1));
     CK(cudaStreamSynchronize(h->stream));
     if (sy) memcpy(y_meas, py, (size_t)h->ns * B * sizeof(double));
