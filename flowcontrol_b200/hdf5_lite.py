@@ -298,8 +298,6 @@ class _Writer:
         """entries: name -> (object header address, btree, heap) with btree = heap = None for datasets.
         Returns (object header, btree, heap) addresses of the new group."""
         names = sorted(entries)  # libhdf5 keeps symbol tables sorted by name
-        if len(names) > 2 * _LEAF_K * 2 * _INTERNAL_K:
-            raise HDF5LiteError("too many entries in one group for a single-level B-tree")
         heap_data = bytearray(8)  # offset 0: the empty string
         name_off = {}
         for nm in names:
@@ -308,7 +306,7 @@ class _Writer:
         data_addr = self.alloc(bytes(heap_data))
         heap_addr = self.alloc(b"HEAP" + struct.pack("<B3xQQQ", 0, len(heap_data), 1, data_addr))
         chunks = [names[i : i + 2 * _LEAF_K] for i in range(0, len(names), 2 * _LEAF_K)] or [[]]
-        snods, keys = [], [0]
+        nodes = []  # (address, heap offset of the largest name below)
         for chunk in chunks:
             body = b"SNOD" + struct.pack("<BBH", 1, 0, len(chunk))
             for nm in chunk:
@@ -318,13 +316,24 @@ class _Writer:
                 else:
                     body += struct.pack("<QQIIQQ", name_off[nm], obj, 1, 0, bt, hp)
             body += b"\x00" * (8 + 2 * _LEAF_K * 40 - len(body))
-            snods.append(self.alloc(body))
-            keys.append(name_off[chunk[-1]] if chunk else 0)
-        node = b"TREE" + struct.pack("<BBHQQ", 0, 0, len(snods), _UNDEF, _UNDEF) + struct.pack("<Q", keys[0])
-        for child, key in zip(snods, keys[1:]):
-            node += struct.pack("<QQ", child, key)
-        node += b"\x00" * (24 + (2 * _INTERNAL_K + 1) * 8 + 2 * _INTERNAL_K * 8 - len(node))
-        btree = self.alloc(node)
+            nodes.append((self.alloc(body), name_off[chunk[-1]] if chunk else 0))
+        level = 0
+        while True:  # B-tree levels above the symbol-table nodes: up to 2 * _INTERNAL_K children per node
+            groups = [nodes[i : i + 2 * _INTERNAL_K] for i in range(0, len(nodes), 2 * _INTERNAL_K)]
+            up = []
+            lower = 0  # key 0 of a node: the largest name to its left (the empty string for the leftmost node)
+            for grp in groups:
+                node = b"TREE" + struct.pack("<BBHQQ", 0, level, len(grp), _UNDEF, _UNDEF) + struct.pack("<Q", lower)
+                lower = grp[-1][1]
+                for child, key in grp:
+                    node += struct.pack("<QQ", child, key)
+                node += b"\x00" * (24 + (2 * _INTERNAL_K + 1) * 8 + 2 * _INTERNAL_K * 8 - len(node))
+                up.append((self.alloc(node), grp[-1][1]))
+            nodes = up
+            level += 1
+            if len(nodes) == 1:
+                break
+        btree = nodes[0][0]
         msg = _message(0x11, struct.pack("<QQ", btree, heap_addr))
         header = self.alloc(struct.pack("<BBHII4x", 1, 0, 1, 1, len(msg)) + msg)
         return header, btree, heap_addr
