@@ -37,9 +37,8 @@ def write_checkpoint(path, name: str, data: np.ndarray, time: float, append: boo
     if data.ndim == 1:
         xc.write_checkpoint(path, name, tab, data, _kind(tab, data.shape[0]), time, append=append)
         return
-    for b in range(data.shape[1]):
-        xc.write_checkpoint(path, xc.trajectory_name(name, b), tab, data[:, b], _kind(tab, data.shape[0]), time,
-                            append=append or b > 0)
+    names = [xc.trajectory_name(name, b) for b in range(data.shape[1])]
+    xc.write_checkpoints(path, names, tab, data, _kind(tab, data.shape[0]), time, append=append)
 
 
 def checkpoint_function_name(path) -> str:
@@ -64,15 +63,13 @@ def read_checkpoint(path, counter: int = -1, tab=None, name: str | None = None, 
     name = name or checkpoint_function_name(path)
     text = Path(path).read_text()
     kind = "V" if re.search(rf'Name="{re.escape(name)}" Center="Other" AttributeType="Vector"', text) else "P"
-    first = xc.read_checkpoint(path, name, tab, kind, counter)
     if batch <= 1:
-        return first
-    out = np.empty((first.size, batch))
-    out[:, 0] = first
-    for b in range(1, batch):
-        fn = xc.trajectory_name(name, b)
-        out[:, b] = xc.read_checkpoint(path, fn, tab, kind, counter) if f'<Grid Name="{fn}" GridType="Collection"' in text else first
-    return out
+        return xc.read_checkpoint(path, name, tab, kind, counter)
+    names = [xc.trajectory_name(name, b) for b in range(batch)]
+    have = [fn for fn in names if f'<Grid Name="{fn}" GridType="Collection"' in text]
+    got = xc.read_checkpoints(path, have, tab, kind, counter)  # the file is opened once for all trajectories
+    col = {fn: k for k, fn in enumerate(have)}
+    return np.stack([got[:, col.get(fn, 0)] for fn in names], axis=1)  # a file of a single run is broadcast
 
 
 class FlowExporter:
