@@ -48,12 +48,14 @@ class Supernode:
 class SymbolicFactor:
     """Ordering + supernode structure shared by every matrix on one mesh/BC set."""
 
-    def __init__(self, tab: TaylorHoodTables, free_mask: np.ndarray, leaf_cells: int = 8, amalgamate_above: int = 0):
+    def __init__(self, tab: TaylorHoodTables, free_mask: np.ndarray, leaf_cells: int = 8, amalgamate_above: int = 0,
+                 balanced: bool = False):
         """``free_mask[N]`` is True for unknowns kept in the solve (non-Dirichlet).  ``amalgamate_above`` = h > 0 merges every
-        tree node whose children have height >= h with those children (ordering.amalgamate): half the levels above height h."""
+        tree node whose children have height >= h with those children (ordering.amalgamate): half the levels above height h.
+        ``balanced`` bounds the tree depth by that of an even dissection (ordering.dissect)."""
         self.N = tab.N
         nN, nV = tab.nN, tab.nV
-        tree = amalgamate(dissect(tab, leaf_cells=leaf_cells), amalgamate_above)
+        tree = amalgamate(dissect(tab, leaf_cells=leaf_cells, balanced=balanced), amalgamate_above)
         self.amalgamate_above = int(amalgamate_above)
         po = postorder(tree)
 
@@ -373,8 +375,11 @@ def choose_clusters(sym: SymbolicFactor, in_top: np.ndarray, max_rows: int, max_
 
 
 def build_plan(fac: BlockFactor, top_levels: int = 2, cluster_rows: int = 0, cluster_height: int = 6,
-               min_tier_clusters: int = 24) -> SolvePlan:
-    """``cluster_rows`` = 0 disables the shared-memory subtree clusters (every front goes through the pull-form launches)."""
+               min_tier_clusters: int = 24, presum_height: int = 0) -> SolvePlan:
+    """``cluster_rows`` = 0 disables the shared-memory subtree clusters (every front goes through the pull-form launches).
+    ``presum_height`` = h > 0: the forward blocks of fronts of height >= h do not gather three source planes (b and two
+    update vectors) once per 32-row tile; a gather-sum right before their launch writes y_t = b_t + sum_children u_c once and
+    the tiles gather that single plane (the gathered rows are two thirds of what the sweeps move through L2)."""
     sym = fac.sym
     sns = sym.supernodes
     n = sym.n
@@ -454,6 +459,14 @@ def build_plan(fac: BlockFactor, top_levels: int = 2, cluster_rows: int = 0, clu
             a1, a2 = child_sources(i, own, ZROW)
             has_children = bool(sources[i])
             e0, e1 = child_sources(i, s.struct, -1)
+            if has_children and m > 0 and w > 0 and presum_height > 0 and h >= presum_height:
+                for k in range(w):  # y_t[k] = b + u_c1 + u_c2 in this fixed order
+                    asm_src.extend([int(r) for r in (own[k], a1[k], a2[k]) if r != ZROW])
+                    asm_ptr.append(len(asm_src))
+                    asm_dst.append(n + s.c0 + k)
+                blocks.append(dict(K=w, M=m, nsrc=1, out0=UB + int(uoff[i]), ystore=-1, i0=n + own, i1=None, i2=None,
+                                   vals=-fac.blocks[i][0], e0=e0, e1=e1))
+                continue
             blocks.append(dict(K=w, M=m, nsrc=3 if has_children else 1, out0=UB + int(uoff[i]), ystore=n + s.c0,
                                i0=own, i1=a1, i2=a2, vals=-fac.blocks[i][0], e0=e0 if has_children else None,
                                e1=e1 if has_children else None))

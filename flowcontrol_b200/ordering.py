@@ -49,15 +49,21 @@ _CUT_DIRECTIONS = [np.array((np.cos(a), np.sin(a))) for a in np.linspace(0.0, np
 
 
 def dissect(
-    tab: TaylorHoodTables, leaf_cells: int = 8, cut_fractions=(0.4, 0.45, 0.5, 0.55, 0.6)
+    tab: TaylorHoodTables, leaf_cells: int = 8, cut_fractions=(0.4, 0.45, 0.5, 0.55, 0.6), balanced: bool = False
 ) -> list[TreeNode]:
     """Return the dissection tree as a list (index 0 = root).
 
     Every bisection tries eight cut directions and a few cut positions around the
-    median and keeps the one with the fewest shared P2 nodes."""
+    median and keeps the one with the fewest shared P2 nodes.
+
+    ``balanced`` bounds the depth of the tree by D = ceil(log2(cells / leaf_cells)), the depth of a perfectly even
+    dissection: a cut is only admissible if both halves still fit ``leaf_cells * 2**(levels left)`` cells (the median
+    cut always is).  The device sweeps cost one launch per tree level (csrc/fcb200.cu: k_front_sweep), so the two or
+    three extra levels that free cuts leave below their larger halves are launches with a handful of fronts each."""
     cn = tab.cell_nodes
     cent = tab.node_xy[tab.cell_nodes[:, :3]].mean(axis=1)
     nodes: list[TreeNode] = [TreeNode(cells=np.arange(tab.nT), parent=-1, depth=0)]
+    max_depth = int(np.ceil(np.log2(max(tab.nT / leaf_cells, 1.0)))) if balanced else None
     stack = [0]
     while stack:
         t = stack.pop()
@@ -66,12 +72,14 @@ def dissect(
             continue
         c = cent[cells]
         best = None
+        cap = leaf_cells * 2 ** (max_depth - nodes[t].depth - 1) if balanced else len(cells)  # cells a child may hold
+        fractions = [f for f in cut_fractions if max(f, 1.0 - f) * len(cells) <= cap] or [0.5]
         for direction in _CUT_DIRECTIONS:
             proj = c @ direction
             order = np.argsort(proj, kind="stable")
-            for frac in cut_fractions:
+            for frac in fractions:
                 half = int(round(frac * len(cells)))
-                half = min(max(half, 1), len(cells) - 1)
+                half = min(max(half, 1, len(cells) - cap), len(cells) - 1, cap)
                 a = np.unique(cn[cells[order[:half]]].ravel())
                 b = np.unique(cn[cells[order[half:]]].ravel())
                 nshared = np.intersect1d(a, b, assume_unique=True).size

@@ -170,6 +170,24 @@ def test_multifrontal_matches_superlu_and_plan_matches_factor(small):
             if rows == 0:
                 assert pa.asm_lptr[-1] == len(pa.asm_dst) and len(pa.asm_lptr) == len(pa.launch_ptr)
                 assert len(pa.asm_dst) > (len(pa.launch_ptr) > 1 and tl) * 0  # gather-sum rows exist for the four-child fronts
+    # depth-bounded dissection: no deeper than an even dissection, leaves within the requested size, same solution
+    symb = SymbolicFactor(tab, d.free, leaf_cells=4, balanced=True)
+    assert max(s_.depth for s_ in symb.supernodes) == int(np.ceil(np.log2(tab.nT / 4)))
+    assert max(s_.depth for s_ in symb.supernodes) <= max(s_.depth for s_ in sym.supernodes)
+    assert sorted(symb.perm.tolist()) == sorted(sym.perm.tolist())
+    facb = BlockFactor(symb, A)
+    bb = rng.standard_normal((symb.n, 2))
+    xb = spla.splu(A[symb.perm][:, symb.perm].tocsc()).solve(bb)
+    for rows in (0, 80):
+        pb = build_plan(facb, top_levels=2, cluster_rows=rows, min_tier_clusters=1)
+        assert np.abs(apply_plan_host(pb, bb) - xb).max() < 1e-11 * np.abs(xb).max(), rows
+    # pre-summed gathers: above the given height every forward block reads ONE plane (y_t, written by a gather-sum)
+    for hp in (1, 3):
+        pp = build_plan(facb, top_levels=2, presum_height=hp)
+        fwd = np.arange(len(pp.blk_K)) < pp.launch_ptr[pp.n_forward_launches]
+        assert (pp.blk_nsrc[fwd] == 1).sum() > (pb.blk_nsrc[: pb.launch_ptr[pb.n_forward_launches]] == 1).sum() or hp > 1
+        assert len(pp.asm_dst) > len(pb.asm_dst) and pp.asm_lptr[-1] == len(pp.asm_dst)
+        assert np.abs(apply_plan_host(pp, bb) - xb).max() < 1e-11 * np.abs(xb).max(), hp
     plan = build_plan(fac, top_levels=2, cluster_rows=0)
     # every x row and every y row is produced exactly once; blocks of one launch never read rows
     # that the same launch writes
