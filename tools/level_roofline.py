@@ -5,9 +5,12 @@ the launch taken from the per-CTA timeline (profiles/r02_sweep_timeline.txt).  H
 
     python tools/level_roofline.py [B=256] > profiles/r02_level_roofline.txt
 """
+import os
 import re
 import sys
 from pathlib import Path
+
+os.environ.setdefault("FCB_BALANCED", "0")  # the archived timeline was taken with the free dissection (23 launches)
 
 import numpy as np
 
