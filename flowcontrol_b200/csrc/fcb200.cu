@@ -1694,6 +1694,8 @@ struct fcb_context {
     int device = 0, num_sms = 0, smem_per_sm = 0, force_nrb = 0, force_nwc = 0, max_nwc = 4, allow_ksplit = 1;
     SweepMaps zmaps[4];  // TMA descriptors of Z for CTA widths of 32, 64, 128, 256 trajectories
     double want_ctas_per_sm = 2.0;          // a launch narrows its CTAs / shortens its tiles until it has this many CTAs per SM
+    double want_ctas_fwd = 1.0;             // the same for the forward launches (FCB_SWEEP_WANT_FWD): their three-plane gathers favour wide CTAs
+                                            // and tall tiles over more CTAs (measured on B200, cylinder x 256: forward 0.282 -> 0.271 ms for 0.5..1.5)
     int kslots = 24;                        // ... and for k-split CTAs, whose 4 warps each need stages in flight (FCB_SWEEP_KSLOTS)
     int force_slots[4] = {48, 36, 12, 12};  // gathered rows per ring stage for those widths (FCB_SWEEP_SLOTS=a,b,c,d)
     unsigned long long* sweep_dbg = nullptr;  // FCB_SWEEP_DEBUG=<file>: per-CTA timeline of the sweeps of a profiled step
@@ -1845,7 +1847,7 @@ int upload_plan(fcb_context* h, DevPlan& d, const fcb_plan& p, const int32_t* pe
         };
         int nrb_cap = 4, nwc = std::min(h->max_nwc, nw_all);
         while (nw_all % nwc) nwc >>= 1;
-        const long long want = (long long)(h->want_ctas_per_sm * h->num_sms);
+        const long long want = (long long)((l < p.n_forward_launches && h->want_ctas_fwd > 0.0 ? h->want_ctas_fwd : h->want_ctas_per_sm) * h->num_sms);
         while (nwc > 1 && njobs_for(nrb_cap) * (nw_all / nwc) < want) nwc >>= 1;
         // a launch that is still too small at one 32-trajectory tile per CTA splits K over the CTA's four consumer warps
         L.ksplit = (nwc == 1 && h->allow_ksplit) ? 1 : 0;
@@ -2991,6 +2993,8 @@ int create_impl(fcb_context* h, const fcb_problem* p, int B) {
         }
         env = getenv("FCB_SWEEP_WANT");
         if (env && atof(env) > 0.0) h->want_ctas_per_sm = atof(env);
+        env = getenv("FCB_SWEEP_WANT_FWD");
+        if (env && atof(env) > 0.0) h->want_ctas_fwd = atof(env);
         env = getenv("FCB_SWEEP_KSLOTS");
         if (env && atoi(env) >= 12 && atoi(env) <= 96 && atoi(env) % 12 == 0) h->kslots = atoi(env);
         env = getenv("FCB_SWEEP_MAXWARPS");
