@@ -621,7 +621,7 @@ def test_create_rejects_inconsistent_crank_nicolson_input(cyl):
             ens.step(np.full((2, 40), 0.1 * k))
         ups.append(ens.fields(0)[:, 17].copy())
         ens.close()
-    assert rel(ups[0], ups[1]) < 1e-13
+    assert rel(ups[0], ups[1]) < 1e-12  # two summation orders of E u_n, five solves apart (field tolerance of the parity tests: 1e-9)
 
 
 def test_crank_nicolson_any_ensemble_width(cyl):
