@@ -690,6 +690,9 @@ struct RingPos {
 // acc[rb][p][0..3] = trajectories t0 + 16p + 4*(lane%4) + 0..3 of output row 8*rb + lane/4.
 // KS (k-split, narrow CTAs only): the 4 consumer warps share ONE 32-trajectory tile and take the job's stages
 // round-robin (warp kw owns stages kw, kw+4, ...); partial sums meet in shared memory and warp 0 stores.
+#ifndef FCB_KS_REDUCER
+#define FCB_KS_REDUCER 3
+#endif
 #ifndef FCB_SWEEP_SLIM
 #define FCB_SWEEP_SLIM 0  // 1: the three-plane gather and the y store become run-time branches (5 job variants per kernel instead of 20:
                           // a third of the code; measured on B200: forward 2 % faster, backward 4 % slower, step +0.6 %)
@@ -722,7 +725,10 @@ __device__ __forceinline__ void sweep_job(unsigned char* smem, uint32_t bar_full
     int xdof[NA];  // seed mode 2: canonical dof of this lane's output rows (read now: the record's stage slot is recycled later)
 #pragma unroll
     for (int rb = 0; rb < NA; ++rb) xdof[rb] = (NRB > 0 && seed == 2) ? jh[8 + rb * 8 + gid] : 0;
-    if (NRB > 0 && seed == 1 && (!KS || kw == 0)) {
+    // k-split: warp 3 owns the fewest stages (3, 7, ...: none at all in a job of up to three stages), so it is the one that
+    // waits for the seed rows, collects the partial sums and stores (FCB_KS_REDUCER picks the warp; 0 = the first)
+    constexpr int RW = KS ? FCB_KS_REDUCER : 0;
+    if (NRB > 0 && seed == 1 && (!KS || kw == RW)) {
         // the children's update rows that land on these output rows seed the accumulators
 #pragma unroll
         for (int rb = 0; rb < NRB; ++rb) {
@@ -783,8 +789,8 @@ __device__ __forceinline__ void sweep_job(unsigned char* smem, uint32_t bar_full
     if (KS && NRB > 0) {
         // k-split: warps 1..3 park their partial sums in shared memory, warp 0 adds them up
         asm volatile("bar.sync 1, 128;" ::: "memory");  // warp 0 is done reading the previous job's partials
-        if (kw > 0) {
-            double* r = red + (size_t)(kw - 1) * (NRB * 8 * 32) + lane;
+        if (kw != RW) {
+            double* r = red + (size_t)(kw < RW ? kw : kw - 1) * (NRB * 8 * 32) + lane;
 #pragma unroll
             for (int rb = 0; rb < NRB; ++rb)
 #pragma unroll
@@ -796,7 +802,7 @@ __device__ __forceinline__ void sweep_job(unsigned char* smem, uint32_t bar_full
                 }
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (kw > 0) return;
+        if (kw != RW) return;
 #pragma unroll
         for (int w = 0; w < 3; ++w) {
             const double* r = red + (size_t)w * (NRB * 8 * 32) + lane;
