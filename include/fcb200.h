@@ -67,8 +67,9 @@ typedef struct fcb_plan {
     int32_t n_forward_launches;
     /* gather-sums: Z[asm_dst[i]] = sum of Z[asm_src[j]], asm_ptr[i] <= j < asm_ptr[i+1], in that order.  Rows
      * [asm_lptr[l], asm_lptr[l+1]) run right before launch l: the right-hand side of the merged top of the elimination tree,
-     * and the "virtual" update vectors of fronts with more than two children (amalgamated levels).  asm_lptr == NULL: every
-     * row runs before launch n_forward_launches.  asm_n may be 0 */
+     * the "virtual" update vectors of fronts with more than two children (amalgamated levels), and the pre-summed
+     * y_t = b_t + sum of the children's update rows of forward blocks that gather one plane (build_plan(presum_height)).
+     * asm_lptr == NULL: every row runs before launch n_forward_launches.  asm_n may be 0 */
     int32_t asm_n;
     const int32_t* asm_ptr;  /* [asm_n+1] */
     const int32_t* asm_src;
