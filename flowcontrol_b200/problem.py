@@ -119,6 +119,7 @@ class FlowProblem:
         cluster_height: int | None = None,
         amalgamate_above: int | None = None,
         balanced: bool | None = None,
+        presum_height: int | None = None,
         factor_device: int | None = None,
         time_scheme: str = "bdf",
         symbolic: SymbolicFactor | None = None,
@@ -198,7 +199,7 @@ class FlowProblem:
             crow = int(os.environ.get("FCB_CLUSTER_ROWS", 0 if cluster_rows is None else cluster_rows))
             chgt = int(os.environ.get("FCB_CLUSTER_HEIGHT", 6 if cluster_height is None else cluster_height))
             self.plans[order] = build_plan(fac, top_levels=top_levels, cluster_rows=crow, cluster_height=chgt,
-                                           presum_height=int(os.environ.get("FCB_PRESUM", 0)))
+                                           presum_height=int(os.environ.get("FCB_PRESUM", 0 if presum_height is None else presum_height)))
             self._plan_args = (top_levels, cluster_rows is None and "FCB_CLUSTER_ROWS" not in os.environ)
             # rhs contribution per unit u_ctrl_k in solver row order: (F_k - A[:,Gamma] shape_k)[perm]
             lift = (A @ G.T).toarray().T if na else np.zeros((0, tab.N))

@@ -698,6 +698,59 @@ def test_subtree_cluster_sweeps_match_oracle(root, built_lib, rows, height):
     ens.close()
 
 
+@pytest.mark.parametrize("variant", ["free_dissection", "presummed_gathers"])
+def test_optional_solve_plans_match_oracle(root, built_lib, variant):
+    """Solve plans that are supported but not the default: the free (not depth-bounded) dissection the round started with,
+    and forward blocks that gather one pre-summed plane (gather-sums as programmatic dependent launches between the sweep
+    launches).  Same oracle comparison as the cluster test: ragged width, trajectory-dependent lid actuation."""
+    import tempfile
+    from pathlib import Path
+
+    from flowcontrol_b200.ensemble import Ensemble
+    from flowcontrol_b200.examples import lidcavity as ex
+    from flowcontrol_b200.flowfield import Field
+    from flowcontrol_b200.problem import FlowProblem
+
+    UP0 = np.load(root / "tests/golden/lidcavity_baseflow.npz")["UP0"]
+    fs = ex.LidCavityFlowSolver.make_default(Re=1000.0, path_out=Path(tempfile.mkdtemp()))
+    tab = fs.tables
+    fs._assign_steady_state(Field(UP0[: tab.Nv]), Field(UP0[tab.Nv :]))
+    kw = dict(balanced=False) if variant == "free_dissection" else dict(presum_height=1)
+    prob = FlowProblem(tab, fs.blocks, 1000.0, 0.005, fs.bc.bcu, fs.params_control.actuator_list, fs.params_control.sensor_list,
+                       UP0, pin_pressure=True, cluster_rows=0, **kw)
+    plan = prob.plans[2]
+    fwd = np.arange(len(plan.blk_K)) < plan.launch_ptr[plan.n_forward_launches]
+    if variant == "presummed_gathers":
+        assert (plan.blk_nsrc[fwd] == 1).all() and plan.asm_lptr[plan.n_forward_launches] > 0
+    else:
+        assert (plan.blk_nsrc[fwd] == 3).any()
+    case = cases.lidcavity(1000.0)
+    xy, tri = cases.load_mesh(case.mesh_file)
+    B = 72
+    probe = [0, 35, 71]
+    amp = 0.02 + 0.1 * np.arange(B) / (B - 1)
+    oracles = []
+    for b in probe:
+        orc = FlowOracle(case, xy, tri)
+        orc.set_base_flow(UP0)
+        orc.init_time_stepping()
+        oracles.append(orc)
+    ens = Ensemble(prob, B)
+    ens.set_state(oracles[0].ic[: tab.Nv], None, oracles[0].ic[tab.Nv :], order=1)
+    for k in range(6):
+        uc = (amp * np.cos(0.9 * k))[None, :]
+        ens.step(uc)
+        for orc, b in zip(oracles, probe):
+            orc.step([uc[0, b]])
+            assert np.allclose(ens.y_meas[:, b], orc.y_meas, rtol=SERIES_TOL, atol=0)
+            assert np.isclose(ens.dE[b], orc.dE, rtol=SERIES_TOL)
+    up = ens.fields(0)
+    for orc, b in zip(oracles, probe):
+        assert rel(up[: tab.Nv, b], orc.up[: tab.Nv]) < FIELD_TOL
+    assert not ens.diverged.any()
+    ens.close()
+
+
 def test_facade_ensemble_checkpoint_and_restart(root, tmp_path, built_lib):
     """Ensemble (batch = 5) through the FlowSolver facade: the XDMF/HDF5 checkpoints hold one function per trajectory, a
     restarted ensemble continues EVERY trajectory exactly where it was (the restart goes through full fields and back, so
