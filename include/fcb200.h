@@ -55,7 +55,8 @@ typedef struct fcb_plan {
     const int32_t* blk_M;      /* [nblocks] output rows (0 = store-only block)                     */
     const int32_t* blk_nsrc;   /* [nblocks] 1 or 3 gather lists                                    */
     const int32_t* blk_out0;   /* [nblocks] first output row in Z                                  */
-    const int32_t* blk_ystore; /* [nblocks] first row to store the gathered x_k to, or -1          */
+    const int32_t* blk_ystore; /* [nblocks] first row to store the gathered x_k to, or -1; -2 on a backward block of solution
+                                * rows: nobody gathers them, they are written in canonical numbering only (out0 still names them) */
     const int64_t* blk_iptr;   /* [nblocks] offsets into i0/i1/i2 (K entries per block)            */
     const int64_t* blk_vptr;   /* [nblocks] offsets into vals (row-major M x K per block)          */
     const int64_t* blk_eptr;   /* [nblocks] offsets into e0/e1 (M entries per block), or -1        */

@@ -188,6 +188,23 @@ def test_multifrontal_matches_superlu_and_plan_matches_factor(small):
         assert (pp.blk_nsrc[fwd] == 1).sum() > (pb.blk_nsrc[: pb.launch_ptr[pb.n_forward_launches]] == 1).sum() or hp > 1
         assert len(pp.asm_dst) > len(pb.asm_dst) and pp.asm_lptr[-1] == len(pp.asm_dst)
         assert np.abs(apply_plan_host(pp, bb) - xb).max() < 1e-11 * np.abs(xb).max(), hp
+    # in-place leaves: no y rows stored for them, their backward blocks read b where it lies and are marked ystore = -2
+    pl = build_plan(fac, top_levels=2, leaf_inplace=True)
+    assert np.abs(apply_plan_host(pl, b) - x).max() < 1e-12 * np.abs(x).max()
+    marked = pl.blk_ystore == -2
+    assert marked.sum() == sum(1 for i, c in enumerate(sym.children) if not c and len(sym.supernodes[i].struct) and sym.supernodes[i].c1 > sym.supernodes[i].c0)
+    assert (np.flatnonzero(marked) >= pl.launch_ptr[pl.n_forward_launches]).all()
+    first_bw = int(pl.launch_ptr[pl.n_forward_launches])
+    for q in np.flatnonzero(marked):  # in the backward sweep nobody but the block itself reads the rows it leaves as b
+        rows = np.arange(pl.blk_out0[q], pl.blk_out0[q] + pl.blk_M[q])
+        assert np.isin(rows, pl.i0[pl.blk_iptr[q] : pl.blk_iptr[q] + pl.blk_K[q]]).all()
+        for q2 in range(first_bw, len(pl.blk_K)):
+            if q2 != q:
+                assert not np.isin(pl.i0[pl.blk_iptr[q2] : pl.blk_iptr[q2] + pl.blk_K[q2]], rows).any()
+    ysl = pl.blk_ystore >= 0  # y rows are stored for every front but the in-place leaves
+    rows_yl = np.concatenate([np.arange(o, o + k) for o, k in zip(pl.blk_ystore[ysl], pl.blk_K[ysl])] + [pl.asm_dst])
+    leaf_rows = np.concatenate([np.arange(pl.blk_out0[q], pl.blk_out0[q] + pl.blk_M[q]) for q in np.flatnonzero(marked)])
+    assert sorted(rows_yl.tolist()) == sorted(set(range(sym.n, 2 * sym.n)) - set((leaf_rows + sym.n).tolist()))
     plan = build_plan(fac, top_levels=2, cluster_rows=0)
     # every x row and every y row is produced exactly once; blocks of one launch never read rows
     # that the same launch writes
