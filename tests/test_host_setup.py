@@ -191,6 +191,9 @@ def test_multifrontal_matches_superlu_and_plan_matches_factor(small):
     # in-place leaves: no y rows stored for them, their backward blocks read b where it lies and are marked ystore = -2
     pl = build_plan(fac, top_levels=2, leaf_inplace=True)
     assert np.abs(apply_plan_host(pl, b) - x).max() < 1e-12 * np.abs(x).max()
+    for rows in (80, 400):  # with subtree clusters below (the plan of ensembles of up to 32 trajectories): leaves outside clusters only
+        plc = build_plan(fac, top_levels=2, cluster_rows=rows, cluster_height=3, min_tier_clusters=1, leaf_inplace=True)
+        assert np.abs(apply_plan_host(plc, b) - x).max() < 1e-12 * np.abs(x).max(), rows
     marked = pl.blk_ystore == -2
     assert marked.sum() == sum(1 for i, c in enumerate(sym.children) if not c and len(sym.supernodes[i].struct) and sym.supernodes[i].c1 > sym.supernodes[i].c0)
     assert (np.flatnonzero(marked) >= pl.launch_ptr[pl.n_forward_launches]).all()
